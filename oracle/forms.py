@@ -1,0 +1,491 @@
+"""Pointwise weak-form coefficients of the reference's equations (oracle).
+
+Every function returns, for each equation i of the mixed system, the
+coefficient `f0[i]` multiplying the test function v_i and `f1[i]` multiplying
+grad v_i in the integrand, so that the local residual is
+
+    R_i[a] = sum_q w_q ( f0_i(q) phi_a(q) + f1_i(q) . grad phi_a(q) ).
+
+This is a restatement, in numpy, of
+
+* `mass_conservation_form`      echemfem/solver.py:1461-1733
+* `charge_conservation_form`    echemfem/solver.py:1866-2013
+* `potential_poisson_form`      echemfem/solver.py:2048-2234 (liquid, non-porous)
+* `steady_forms`                echemfem/solver.py:401-488
+
+All arithmetic is dtype-generic so that `oracle/assemble.py` can obtain the
+exact Gateaux derivative (what UFL's `derivative` gives the reference) by
+complex-step differentiation; `abs` differentiates to `sign`, `conditional`
+to a piecewise derivative, as UFL does.
+
+Closures in the problem description take numpy arrays:
+  bulk(x), U_app(x), vel(x)                 x: (..., d)
+  bulk_reaction(u, x) -> list (num_c)       u: list of field arrays [c_0.., Phi]
+  echem["reaction"](u, x) -> array
+"""
+import numpy as np
+
+
+def _cabs(a):
+    """|a| whose complex-step derivative is sign(a) (UFL: d|f| = sign(f) df)."""
+    return a * np.sign(np.real(a))
+
+
+def _pos(a):
+    """conditional(a > 0, 1, 0) evaluated on the real part."""
+    return (np.real(a) > 0).astype(float)
+
+
+def _neg(a):
+    return (np.real(a) < 0).astype(float)
+
+
+def _dot(a, b):
+    return np.sum(a * b, axis=-1)
+
+
+def _evalf(f, x):
+    """Evaluate a float-or-callable coefficient at points x (..., d)."""
+    if callable(f):
+        return f(x)
+    return f * np.ones(x.shape[:-1])
+
+
+class Problem:
+    """Physics description consumed by the oracle.
+
+    Mirrors the reference constructor's inputs (solver.py:57-71) with numpy
+    closures in place of UFL expressions.
+    """
+
+    def __init__(self, conc_params, physical_params, boundary_markers,
+                 echem_params=(), p=1, family="DG", vel=None, SUPG=False,
+                 neumann=None, variant="spectral", C_IP=10.0, p_penalty=None):
+        self.conc_params = [dict(c) for c in conc_params]
+        self.physical_params = dict(physical_params)
+        self.boundary_markers = {}
+        for k, v in boundary_markers.items():
+            self.boundary_markers[k] = (v,) if isinstance(v, int) else tuple(v)
+        self.echem_params = list(echem_params)
+        self.p = p
+        self.family = family
+        self.variant = variant
+        self.vel = vel
+        self.SUPG = SUPG
+        self.neumann = neumann
+        self.C_IP = C_IP
+        self.penalty_degree = p if p_penalty is None else p_penalty
+        flow = {k: False for k in ("advection", "diffusion", "migration",
+                                   "electroneutrality", "poisson")}
+        for f in physical_params["flow"]:
+            if f not in flow:
+                raise NotImplementedError("oracle: flow option %r" % f)
+            flow[f] = True
+        # solver.py:115-126
+        if (not flow["migration"]) and flow["electroneutrality"]:
+            raise NotImplementedError('Electroneutrality constraint requires Migration')
+        if flow["migration"] and not (flow["electroneutrality"] or flow["poisson"]):
+            raise NotImplementedError('Migration requires Electroneutrality or Poisson')
+        if flow["poisson"] and flow["electroneutrality"]:
+            raise NotImplementedError('Electroneutrality not compatible with Poisson')
+        self.flow = flow
+        self.num_c = len(conc_params)
+        self.idx_c = list(range(self.num_c))
+        self.i_el = None
+        # solver.py:148-162
+        if flow["electroneutrality"]:
+            tagged = [i for i, c in enumerate(self.conc_params) if c.get("eliminated") is not None]
+            assert len(tagged) < 2
+            self.i_el = tagged[-1] if tagged else self.num_c - 1
+            assert self.conc_params[self.i_el]["z"] != 0
+            self.idx_c.remove(self.i_el)
+        self.num_liquid = len(self.idx_c)
+        self.num_mass = self.num_liquid
+        self.has_potential = flow["electroneutrality"] or flow["poisson"]
+        self.num_fields = self.num_mass + (1 if self.has_potential else 0)
+        self.i_Ul = self.num_mass if self.has_potential else None
+        for i, k in enumerate(self.idx_c):
+            self.conc_params[k]["i_c"] = i
+
+    # -- helpers ----------------------------------------------------------
+    def penalty(self, geo):
+        """D_IP = C_IP * max(p^2, 1) / he, he = CellVolume / FacetArea (solver.py:1491-1492)."""
+        return self.C_IP * max(self.penalty_degree ** 2, 1) * geo["facet_area"] / geo["cell_volume"]
+
+    def concentrations(self, u, gu):
+        """All num_c concentrations (and gradients), eliminated one included (solver.py:1904-1916)."""
+        C = [None] * self.num_c
+        gC = [None] * self.num_c
+        for i, k in enumerate(self.idx_c):
+            C[k] = u[i]
+            gC[k] = gu[i]
+        if self.i_el is not None:
+            cp = self.conc_params
+            zel = cp[self.i_el]["z"]
+            ndel = cp[self.i_el].get("C_ND", 1.0)
+            s = 0.0
+            gs = 0.0
+            for k in self.idx_c:
+                z = cp[k]["z"]
+                if z != 0.0:
+                    nd = cp[k].get("C_ND", 1.0)
+                    s = s + z * nd * C[k]
+                    gs = gs + z * nd * gC[k]
+            C[self.i_el] = -s / zel / ndel
+            gC[self.i_el] = -gs / zel / ndel
+        return C, gC
+
+    def reaction_u(self, u):
+        """The list the reference hands to closures: split(u) (solver.py:308)."""
+        return list(u)
+
+    def K_mig(self, k):
+        pp = self.physical_params
+        cp = self.conc_params[k]
+        return cp["diffusion coefficient"] * cp["z"] * pp["F"] / pp["R"] / pp["T"]
+
+    def conductivity(self, C):
+        """K_U of the charge-conservation equation (solver.py:1920)."""
+        pp = self.physical_params
+        K_U = 0.0
+        for k in range(self.num_c):
+            cp = self.conc_params[k]
+            z = cp["z"]
+            if z != 0.0:
+                K_U = K_U + z ** 2 * pp["F"] ** 2 * cp["diffusion coefficient"] * C[k] / pp["R"] / pp["T"] * cp.get("C_ND", 1.0)
+        return K_U
+
+    def poisson_KU(self, C):
+        """K_U of the liquid Poisson equation (solver.py:2085-2093, 2136-2138)."""
+        pp = self.physical_params
+        eps_0 = pp.get("vacuum permittivity")
+        eps_r = pp.get("relative permittivity")
+        if eps_r is not None and eps_0 is not None:
+            return eps_r * eps_0
+        if pp.get("liquid conductivity"):
+            return pp["liquid conductivity"]
+        K_U = 0.0
+        for k in range(self.num_liquid):
+            cp = self.conc_params[k]
+            z = cp.get("z")
+            if z is not None and z != 0:
+                K_U = K_U + z ** 2 * pp["F"] ** 2 * cp["diffusion coefficient"] * C[k] / pp["R"] / pp["T"]
+        return K_U
+
+    def flow_vector(self, k, x, gU):
+        """`flow` of species k (solver.py:1641-1648); None if the species has no transport term."""
+        cp = self.conc_params[k]
+        adv = self.flow["advection"]
+        mig = self.flow["migration"] and cp["z"] != 0.0
+        if not (adv or mig):
+            return None
+        fl = 0.0
+        if adv:
+            fl = fl + self.vel(x)
+        if mig:
+            fl = fl - self.K_mig(k) * gU
+        return fl
+
+    # -- cell integrals ---------------------------------------------------
+    def cell(self, x, u, gu, geo):
+        nf = self.num_fields
+        d = x.shape[-1]
+        zero = np.zeros(x.shape[:-1], dtype=u[0].dtype)
+        f0 = [zero.copy() for _ in range(nf)]
+        f1 = [np.zeros(x.shape, dtype=u[0].dtype) for _ in range(nf)]
+        pp = self.physical_params
+        C, gC = self.concentrations(u, gu)
+        reactions = None
+        if pp.get("bulk reaction") is not None:
+            reactions = pp["bulk reaction"](self.reaction_u(u), x)
+        if self.has_potential:
+            U, gU = u[self.i_Ul], gu[self.i_Ul]
+        else:
+            U, gU = None, None
+        for i, k in enumerate(self.idx_c):
+            cp = self.conc_params[k]
+            D = cp["diffusion coefficient"]
+            rterm = None
+            if reactions is not None and not _is_zero(reactions[i]):
+                # solver.py:1497-1500  (note: indexed by i_c)
+                rterm = reactions[i]
+                f0[i] = f0[i] - rterm
+            if self.flow["diffusion"]:
+                f1[i] = f1[i] + D * gC[k]                                   # :1515
+            fl = self.flow_vector(k, x, gU)
+            if fl is not None:
+                f1[i] = f1[i] - C[k][..., None] * fl                        # :1649
+                if self.family != "DG" and self.SUPG:                       # :1655-1668
+                    hk = np.sqrt(2.0) * geo["cell_volume"] / geo["cell_diameter"]
+                    u_norm = _dot(fl, fl) ** 0.5
+                    Pe = hk / 2.0 * u_norm / D
+                    Pe_f = np.where(np.real(Pe) > 1, 1.0 - 1.0 / Pe, 0.0)
+                    delta_k = hk / 2.0 / u_norm * Pe_f
+                    f1[i] = f1[i] + (delta_k * _dot(fl, gC[k]))[..., None] * fl
+                    if rterm is not None:
+                        f1[i] = f1[i] - (rterm * delta_k)[..., None] * fl
+        if self.flow["electroneutrality"]:
+            iU = self.i_Ul
+            for k in self.idx_c + [self.i_el]:
+                cp = self.conc_params[k]
+                z = cp["z"]
+                if z == 0.0:
+                    continue
+                nd = cp.get("C_ND", 1.0)
+                zDF = z * cp["diffusion coefficient"] * pp["F"] * nd
+                if self.flow["diffusion"]:
+                    f1[iU] = f1[iU] + zDF * gC[k]                           # :1924
+                if reactions is not None and not _is_zero(reactions[k]):
+                    f0[iU] = f0[iU] - nd * z * pp["F"] * reactions[k]       # :1946
+            K_U = self.conductivity(C)
+            f1[iU] = f1[iU] + _bc(K_U)[..., None] * gU                      # :1978
+        elif self.flow["poisson"]:
+            iU = self.i_Ul
+            eps = pp.get("relative permittivity") is not None and pp.get("vacuum permittivity") is not None
+            for k in range(self.num_liquid):
+                cp = self.conc_params[k]
+                z = cp.get("z")
+                if z is None or z == 0:
+                    continue
+                if eps:
+                    f0[iU] = f0[iU] - pp["F"] * z * C[k]                    # :2141
+            K_U = self.poisson_KU(C)
+            f1[iU] = f1[iU] + _bc(K_U)[..., None] * gU                      # :2171
+        return f0, f1
+
+    # -- interior facets (DG) -------------------------------------------
+    def interior_facet(self, x, n, up, gup, um, gum, geop, geom):
+        """Coefficients for (v+, grad v+, v-, grad v-); n is the '+' outward normal."""
+        nf = self.num_fields
+        dt = up[0].dtype
+        zero = np.zeros(x.shape[:-1], dtype=dt)
+        zv = np.zeros(x.shape, dtype=dt)
+        f0p = [zero.copy() for _ in range(nf)]
+        f0m = [zero.copy() for _ in range(nf)]
+        f1p = [zv.copy() for _ in range(nf)]
+        f1m = [zv.copy() for _ in range(nf)]
+        if self.family != "DG":
+            return f0p, f1p, f0m, f1m
+        pp = self.physical_params
+        Cp, gCp = self.concentrations(up, gup)
+        Cm, gCm = self.concentrations(um, gum)
+        D_IPp = self.penalty(geop)
+        D_IPm = self.penalty(geom)
+        if self.has_potential:
+            Up, gUp = up[self.i_Ul], gup[self.i_Ul]
+            Um, gUm = um[self.i_Ul], gum[self.i_Ul]
+        else:
+            Up = gUp = Um = gUm = None
+
+        def sip(i, kp, km, valp, valm, gp, gm, pen):
+            """-avg(k grad w).jump(v,n) - avg(k grad v).jump(w,n) + pen jump(w) jump(v)."""
+            kp_ = _bc(kp)
+            km_ = _bc(km)
+            a = -0.5 * (kp_ * _dot(gp, n) + km_ * _dot(gm, n)) + pen * (valp - valm)
+            f0p[i] = f0p[i] + a
+            f0m[i] = f0m[i] - a
+            jw = (valp - valm)
+            f1p[i] = f1p[i] - 0.5 * (kp_ * jw)[..., None] * n
+            f1m[i] = f1m[i] - 0.5 * (km_ * jw)[..., None] * n
+
+        for i, k in enumerate(self.idx_c):
+            cp = self.conc_params[k]
+            D = cp["diffusion coefficient"]
+            if self.flow["diffusion"]:
+                pen = 0.5 * (D_IPp * D + D_IPm * D)                         # :1518-1520
+                sip(i, D, D, Cp[k], Cm[k], gCp[k], gCm[k], pen)
+            flp = self.flow_vector(k, x, gUp)
+            if flp is not None:
+                flm = self.flow_vector(k, x, gUm)
+                fnp = _dot(flp, n)
+                fnm = -_dot(flm, n)
+                flow_Np = 0.5 * (fnp + _cabs(fnp))                          # :1652
+                flow_Nm = 0.5 * (fnm + _cabs(fnm))
+                a = flow_Np * Cp[k] - flow_Nm * Cm[k]                       # :1653-1654
+                f0p[i] = f0p[i] + a
+                f0m[i] = f0m[i] - a
+        if self.flow["electroneutrality"]:
+            iU = self.i_Ul
+            for k in self.idx_c + [self.i_el]:
+                cp = self.conc_params[k]
+                z = cp["z"]
+                if z == 0.0:
+                    continue
+                zDF = z * cp["diffusion coefficient"] * pp["F"] * cp.get("C_ND", 1.0)
+                if self.flow["diffusion"]:
+                    sip(iU, zDF, zDF, Cp[k], Cm[k], gCp[k], gCm[k], 0.0)    # :1927-1930
+            D_IP2p, D_IP2m = D_IPp, D_IPm
+            KUp = self.conductivity(Cp)
+            KUm = self.conductivity(Cm)
+            pen = 0.5 * (D_IP2p * KUp + D_IP2m * KUm)                       # :1983
+            sip(iU, KUp, KUm, Up, Um, gUp, gUm, pen)
+        elif self.flow["poisson"]:
+            iU = self.i_Ul
+            KUp = self.poisson_KU(Cp)
+            KUm = self.poisson_KU(Cm)
+            pen = 0.5 * (D_IPp * KUp + D_IPm * KUm)                         # :2174-2176
+            sip(iU, KUp, KUm, Up, Um, gUp, gUm, pen)
+        return f0p, f1p, f0m, f1m
+
+    # -- exterior facets --------------------------------------------------
+    def exterior_facet(self, marker, x, n, u, gu, geo, aux):
+        """Coefficients (f0, f1) on an exterior facet carrying `marker`.
+
+        aux["U_app"]: the applied potential as the reference sees it, i.e. the
+        Vu-interpolant when U_app is an expression (solver.py:373-380).
+        """
+        nf = self.num_fields
+        dt = u[0].dtype
+        zero = np.zeros(x.shape[:-1], dtype=dt)
+        f0 = [zero.copy() for _ in range(nf)]
+        f1 = [np.zeros(x.shape, dtype=dt) for _ in range(nf)]
+        pp = self.physical_params
+        bm = self.boundary_markers
+        DG = self.family == "DG"
+
+        def on(name):
+            ids = bm.get(name)
+            return ids is not None and marker in ids
+
+        C, gC = self.concentrations(u, gu)
+        D_IP = self.penalty(geo) if DG else None
+        if self.has_potential:
+            U, gU = u[self.i_Ul], gu[self.i_Ul]
+        else:
+            U = gU = None
+        ru = self.reaction_u(u)
+
+        def nitsche(i, kcoef, w, gw, w0, pen):
+            """k (w0 - w) n.grad v - k grad w.n v + pen k (w - w0) v  (solver.py:1525-1529)."""
+            k_ = _bc(kcoef)
+            f1[i] = f1[i] + (k_ * (w0 - w))[..., None] * n
+            f0[i] = f0[i] - k_ * _dot(gw, n)
+            if pen is not None:
+                f0[i] = f0[i] + pen * k_ * (w - w0)
+
+        applied_ids = None
+        if bm.get("applied") is not None:
+            applied_ids = bm["applied"]                                    # non-porous: :1672-1680
+
+        for i, k in enumerate(self.idx_c):
+            cp = self.conc_params[k]
+            D = cp["diffusion coefficient"]
+            C_0 = _evalf(cp.get("bulk"), x) if cp.get("bulk") is not None else None
+            if self.flow["diffusion"]:
+                if on("bulk dirichlet") and DG:
+                    nitsche(i, D, C[k], gC[k], C_0, D_IP)                   # :1523-1529
+                if on("gas") and cp.get("gas") is not None and DG:
+                    nitsche(i, D, C[k], gC[k], _evalf(cp["gas"], x), D_IP)  # :1533-1538
+            fl = self.flow_vector(k, x, gU)
+            if fl is not None:
+                if applied_ids is not None and marker in applied_ids:       # :1681-1685
+                    fn = _dot(fl, n)
+                    f0[i] = f0[i] + _neg(fn) * fn * C_0 + _pos(fn) * fn * C[k]
+                if bm.get("inlet") is not None:                             # :1687-1693
+                    ids = set(bm["inlet"]) - set(applied_ids or ())
+                    if marker in ids and not _is_zero(cp.get("bulk")):
+                        vn = _dot(self.vel(x), n)
+                        f0[i] = f0[i] + _neg(vn) * vn * C_0
+                if bm.get("outlet") is not None:                            # :1695-1700
+                    ids = set(bm["outlet"]) - set(applied_ids or ())
+                    if marker in ids:
+                        vn = _dot(self.vel(x), n)
+                        f0[i] = f0[i] + _pos(vn) * vn * C[k]
+            if on("bulk") and cp.get("mass transfer coefficient") is not None:
+                f0[i] = f0[i] - cp["mass transfer coefficient"] * (C_0 - C[k])  # :1703-1706
+            for echem in self.echem_params:                                 # :1710-1717
+                if marker in bm.get(echem["boundary"], ()) and cp["name"] in echem["stoichiometry"]:
+                    nu = echem["stoichiometry"][cp["name"]]
+                    f0[i] = f0[i] - nu / echem["electrons"] / pp["F"] * echem["reaction"](ru, x)
+            if on("neumann"):                                               # :1729-1731
+                f0[i] = f0[i] - self.neumann(C[k], cp, ru, x)
+
+        if self.flow["electroneutrality"]:
+            iU = self.i_Ul
+            for k in self.idx_c + [self.i_el]:
+                cp = self.conc_params[k]
+                z = cp["z"]
+                if z == 0.0:
+                    continue
+                nd = cp.get("C_ND", 1.0)
+                C_0 = _evalf(cp.get("bulk"), x) if cp.get("bulk") is not None else None
+                zDF = z * cp["diffusion coefficient"] * pp["F"] * nd
+                if self.flow["diffusion"] and DG:
+                    if on("bulk dirichlet"):
+                        nitsche(iU, zDF, C[k], gC[k], C_0, None)           # :1933-1937
+                    if on("gas") and cp.get("gas") is not None:
+                        nitsche(iU, zDF, C[k], gC[k], _evalf(cp["gas"], x), None)
+                if on("bulk") and cp.get("mass transfer coefficient") is not None:
+                    f0[iU] = f0[iU] - nd * z * pp["F"] * cp["mass transfer coefficient"] * (C_0 - C[k])
+                for echem in self.echem_params:                             # :1955-1962
+                    if marker in bm.get(echem["boundary"], ()) and cp["name"] in echem["stoichiometry"]:
+                        nu = echem["stoichiometry"][cp["name"]]
+                        f0[iU] = f0[iU] - nd * z * nu / echem["electrons"] * echem["reaction"](ru, x)
+                if on("neumann"):
+                    f0[iU] = f0[iU] - nd * z * pp["F"] * self.neumann(C[k], cp, ru, x)
+            K_U = self.conductivity(C)
+            diric = []
+            if on("bulk"):
+                diric.append(0.0)                                           # :1992-1993
+            if on("applied"):
+                diric.append(aux["U_app"])                                  # :1994-1995
+            if on("liquid applied"):
+                diric.append(aux["U_app"])
+            for U_0 in diric:
+                if DG:
+                    nitsche(iU, K_U, U, gU, U_0, D_IP)                      # :2002-2006
+        elif self.flow["poisson"]:
+            iU = self.i_Ul
+            K_U = self.poisson_KU(C)
+            # solver.py:2188-2212: exactly one Dirichlet set, applied wins over bulk
+            if bm.get("applied") is not None:
+                if on("applied") and DG:
+                    nitsche(iU, K_U, U, gU, aux["U_app"], D_IP)
+            elif bm.get("bulk") is not None:
+                if on("bulk") and DG:
+                    nitsche(iU, K_U, U, gU, 0.0, D_IP)
+            if on("applied liquid current"):
+                f0[iU] = f0[iU] - pp["applied current density"]            # :2222-2223
+            if on("robin"):
+                f0[iU] = f0[iU] - pp["gap capacitance"] * (aux["U_app"] - U)  # :2225-2228
+            if on("poisson neumann"):
+                f0[iU] = f0[iU] - pp["surface charge density"]             # :2230-2232
+        return f0, f1
+
+    # -- strong Dirichlet sets for CG (solver.py:1531, 2008-2011, 2214-2217) --
+    def dirichlet_sets(self):
+        """List of (field, marker ids, value spec) for the DirichletBC objects.
+
+        value spec: ("bulk", k) species k's bulk; ("U_app",); ("zero",).
+        """
+        bm = self.boundary_markers
+        out = []
+        for i, k in enumerate(self.idx_c):
+            cp = self.conc_params[k]
+            if self.flow["diffusion"]:
+                if bm.get("bulk dirichlet") is not None:
+                    out.append((i, bm["bulk dirichlet"], ("bulk", k)))
+                if bm.get("gas") is not None and cp.get("gas") is not None:
+                    out.append((i, bm["gas"], ("gas", k)))
+        if self.flow["electroneutrality"]:
+            if bm.get("bulk") is not None:
+                out.append((self.i_Ul, bm["bulk"], ("zero",)))
+            if bm.get("applied") is not None:
+                out.append((self.i_Ul, bm["applied"], ("U_app",)))
+            if bm.get("liquid applied") is not None:
+                out.append((self.i_Ul, bm["liquid applied"], ("U_app",)))
+        elif self.flow["poisson"]:
+            if bm.get("applied") is not None:
+                out.append((self.i_Ul, bm["applied"], ("U_app",)))
+            elif bm.get("bulk") is not None:
+                out.append((self.i_Ul, bm["bulk"], ("zero",)))
+        return out
+
+
+def _is_zero(a):
+    return a is None or (np.isscalar(a) and a == 0)
+
+
+def _bc(a):
+    """Make a scalar-or-array broadcastable against (e, q) arrays."""
+    return np.asarray(a)
