@@ -1,0 +1,77 @@
+"""Product weak form (symbolic restatement) vs oracle weak form (numpy restatement), point by point.
+
+Two independent restatements of echemfem/solver.py:1461-1733, 1866-2013 must
+give the same f0/f1 coefficients at random point data; tolerance 1e-12 relative
+(the entry tolerance of BASELINE.json's north_star).
+"""
+import numpy as np
+import pytest
+
+from echemfem_b200.compiler import CompiledForm
+from pointwise import random_point_data, evaluate
+import mms_cases
+import product_cases
+
+RTOL = 1e-12
+
+
+def _close(a, b):
+    scale = max(np.abs(a).max(), np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() <= RTOL * scale * 50
+
+
+@pytest.mark.parametrize("vavg", [1.0, 1e5])
+def test_adm_dg_pointwise(vavg):
+    s = product_cases.AdvectionDiffusionMigrationSolver(2, vavg)
+    cf = CompiledForm(s.Form, 2, len(s._aux), 2, 1, "DG")
+    prob = mms_cases.adm_problem(vavg)
+    rng = np.random.default_rng(1)
+    npts = 64
+    dat = random_point_data(2, 1, 2, npts, rng)
+    x = dat["x"][None]
+    n = dat["n"][None]
+    u = [dat["u"][j][None] for j in range(2)]
+    gu = [dat["gu"][j][None] for j in range(2)]
+    um = [dat["um"][j][None] for j in range(2)]
+    gum = [dat["gum"][j][None] for j in range(2)]
+    # cell
+    f0, f1 = prob.cell(x, u, gu, {"cell_volume": dat["cv"][None], "cell_diameter": dat["cd"][None]})
+    for i in range(2):
+        assert _close(evaluate(cf.cell["f0"][i], dat), f0[i][0])
+        for k in range(2):
+            assert _close(evaluate(cf.cell["f1"][i][k], dat), f1[i][0, :, k])
+    # interior facet, '+' side test functions
+    geop = {"cell_volume": dat["cv"][None], "facet_area": dat["fa"][None]}
+    geom = {"cell_volume": dat["cvm"][None], "facet_area": dat["fa"][None]}
+    f0p, f1p, f0m, f1m = prob.interior_facet(x, n, u, gu, um, gum, geop, geom)
+    for i in range(2):
+        assert _close(evaluate(cf.int["f0"][i], dat), f0p[i][0])
+        for k in range(2):
+            assert _close(evaluate(cf.int["f1"][i][k], dat), f1p[i][0, :, k])
+    # +/- swap symmetry: the '-' rows are the '+' rows of the swapped facet
+    sw = dict(dat)
+    sw.update({"u": dat["um"], "um": dat["u"], "gu": dat["gum"], "gum": dat["gu"],
+               "cv": dat["cvm"], "cvm": dat["cv"], "n": -dat["n"], "a": dat["am"], "am": dat["a"]})
+    for i in range(2):
+        assert _close(evaluate(cf.int["f0"][i], sw), f0m[i][0])
+        for k in range(2):
+            assert _close(evaluate(cf.int["f1"][i][k], sw), f1m[i][0, :, k])
+    # exterior facets, every marker
+    for marker in (1, 2, 3, 4):
+        cls = cf.marker_class[marker]
+        g0, g1 = prob.exterior_facet(marker, x, n, u, gu, geop, {"U_app": dat["a"][0][None]})
+        for i in range(2):
+            assert _close(evaluate(cf.ext[cls]["f0"][i], dat), g0[i][0])
+            for k in range(2):
+                assert _close(evaluate(cf.ext[cls]["f1"][i][k], dat), g1[i][0, :, k])
+
+
+def test_block_masks_match_oracle():
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    s = product_cases.AdvectionDiffusionMigrationSolver(2, 1.0)
+    cf = CompiledForm(s.Form, 2, len(s._aux), 2, 1, "DG")
+    disc = Discretization(unit_square_mesh(3), mms_cases.adm_problem(1.0))
+    own, nbr = disc.block_mask()
+    assert np.array_equal(own, cf.own_mask)
+    assert np.array_equal(nbr, cf.nbr_mask)
