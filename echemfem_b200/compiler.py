@@ -128,7 +128,7 @@ def _bind(name, const_index):
         return "p.%s%s" % (base, side)
     if base == "fa":
         return "p.fa"
-    if base[0] == "k" and base[1:].isdigit():
+    if base[:2] == "kc" and base[2:].isdigit():
         return "p.K[%d]" % const_index[name]
     pf = S.parse_field_symbol(sp.Symbol(base))
     if pf is not None:
@@ -254,16 +254,32 @@ class CompiledForm:
         return out
 
     def _constants(self):
+        """Collect the runtime constants and rename them canonically (kc0, kc1, ...) so that the
+        generated header -- and hence the module cache key -- does not depend on how many
+        `Constant`s the process created before."""
         names = set()
         for e in self._all_exprs():
             for s in e.free_symbols:
                 if S.Constant.is_constant_symbol(s):
                     names.add(str(s))
-        self.const_names = sorted(names, key=lambda n: int(n[1:]))
+        self.const_source = sorted(names, key=lambda n: int(n[1:]))
+        self.const_names = ["kc%d" % i for i in range(len(self.const_source))]
         self.const_index = {n: i for i, n in enumerate(self.const_names)}
+        sub = {sp.Symbol(a, real=True): sp.Symbol(b, real=True) for a, b in zip(self.const_source, self.const_names)}
+
+        def ren(x):
+            if isinstance(x, list):
+                return [ren(y) for y in x]
+            return x.xreplace(sub)
+        for grp in [self.cell] + self.ext + [self.int]:
+            for key in list(grp.keys()):
+                if key in ("J", "Jp", "Jm"):
+                    grp[key] = {k: ren(v) for k, v in grp[key].items()}
+                else:
+                    grp[key] = ren(grp[key])
 
     def constant_values(self):
-        return np.array([S.Constant.lookup(sp.Symbol(n)) for n in self.const_names] or [0.0])
+        return np.array([S.Constant.lookup(sp.Symbol(n)) for n in self.const_source] or [0.0])
 
     # -- 4. code generation -----------------------------------------------------------
     def _emit(self):
@@ -301,13 +317,15 @@ class CompiledForm:
             "IM": _masks(self.int["f0"], self.int["f1"], self.int["Jm"], nf, d),
         }
         for tag, m in self.masks.items():
+            L.append("struct M%s {" % tag)
             for key in ("F0", "F1"):
-                L.append("constexpr bool %s_%s[NF] = {%s};" % (tag, key, ",".join(str(int(b)) for b in m[key])))
+                L.append("  static constexpr bool %s[NF] = {%s};" % (key, ",".join(str(int(b)) for b in m[key])))
             for key in ("G0", "G1", "G2"):
-                L.append("constexpr bool %s_%s[NF][NF] = {%s};" % (
-                    tag, key, ",".join("{" + ",".join(str(int(b)) for b in row) + "}" for row in m[key])))
-            L.append("constexpr int %s_G3[NF][NF] = {%s};" % (
-                tag, ",".join("{" + ",".join(str(int(b)) for b in row) + "}" for row in m["G3"])))
+                L.append("  static constexpr bool %s[NF][NF] = {%s};" % (
+                    key, ",".join("{" + ",".join(str(int(b)) for b in row) + "}" for row in m[key])))
+            L.append("  static constexpr int G3[NF][NF] = {%s};" % (
+                ",".join("{" + ",".join(str(int(b)) for b in row) + "}" for row in m["G3"])))
+            L.append("};")
         L.append("constexpr bool OWN_BLOCK[NF][NF] = {%s};" % ",".join(
             "{" + ",".join(str(int(b)) for b in row) + "}" for row in self.own_mask))
         L.append("constexpr bool NBR_BLOCK[NF][NF] = {%s};" % ",".join(
@@ -452,6 +470,6 @@ def _jac_outputs(J, mask, i, o, nf, d):
 def _carray(name, a):
     a = np.asarray(a, dtype=float)
     if a.ndim == 1:
-        return "__device__ constexpr double %s[%d] = {%s};" % (name, a.shape[0], ", ".join(repr(float(x)) for x in a))
+        return "__constant__ double %s[%d] = {%s};" % (name, a.shape[0], ", ".join(repr(float(x)) for x in a))
     rows = ["{" + ", ".join(repr(float(x)) for x in r) + "}" for r in a]
-    return "__device__ constexpr double %s[%d][%d] = {%s};" % (name, a.shape[0], a.shape[1], ", ".join(rows))
+    return "__constant__ double %s[%d][%d] = {%s};" % (name, a.shape[0], a.shape[1], ", ".join(rows))

@@ -1,0 +1,773 @@
+// libechem_b200.so -- C ABI of the B200 Newton step (see include/echem_b200.h).
+//
+// Holds everything that does not depend on the weak form: module binding,
+// CSR pattern construction, row constraints, SpMV, block-Jacobi/ILU(0) and
+// GMRES.  The weak-form-dependent assembly kernels live in the physics module
+// (csrc/ech_module.cu + generated header) that ech_create() binds with dlopen.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "echem_b200.h"
+#include "echem_b200_module.h"
+
+namespace {
+
+long long g_launches = 0;
+
+struct Module {
+    void *dl = nullptr;
+    int (*describe)(int32_t *, int) = nullptr;
+    int (*residual)(const ech_dg_args *, void *) = nullptr;
+    int (*jacobian)(const ech_dg_args *, void *) = nullptr;
+    int (*launches)(int) = nullptr;
+};
+
+}  // namespace
+
+struct ech_handle {
+    Module mod;
+    ech_mesh_desc mesh;
+    int32_t info[8 + 2 * 16 * 16];
+    int ninfo = 0;
+    int nf = 0, nloc = 0;
+    unsigned long long own_bits[16], nbr_bits[16];   // per equation: bit j
+    std::string err;
+};
+
+static std::string g_err;
+
+static int fail(ech_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+
+static int cuda_fail(ech_handle *h, cudaError_t e, const char *where) {
+    return fail(h, (int)e, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(h, call)                                          \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail(h, e__, #call); \
+    } while (0)
+
+static int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+// =============================================================== lifetime
+extern "C" int ech_create(const char *module_path, const ech_mesh_desc *mesh, ech_handle **out) {
+    if (!module_path || !mesh || !out) return fail(nullptr, ECH_ERR_ARG, "ech_create: null argument");
+    ech_handle *h = new ech_handle();
+    h->mesh = *mesh;
+    h->mod.dl = dlopen(module_path, RTLD_NOW | RTLD_LOCAL);
+    if (!h->mod.dl) {
+        int rc = fail(nullptr, ECH_ERR_MODULE, std::string("ech_create: dlopen failed: ") + dlerror());
+        delete h;
+        return rc;
+    }
+    h->mod.describe = (int (*)(int32_t *, int))dlsym(h->mod.dl, "ech_mod_describe");
+    h->mod.residual = (int (*)(const ech_dg_args *, void *))dlsym(h->mod.dl, "ech_mod_residual");
+    h->mod.jacobian = (int (*)(const ech_dg_args *, void *))dlsym(h->mod.dl, "ech_mod_jacobian");
+    h->mod.launches = (int (*)(int))dlsym(h->mod.dl, "ech_mod_launches");
+    if (!h->mod.describe || !h->mod.residual || !h->mod.jacobian || !h->mod.launches) {
+        int rc = fail(nullptr, ECH_ERR_MODULE, "ech_create: physics module lacks ech_mod_* symbols");
+        dlclose(h->mod.dl);
+        delete h;
+        return rc;
+    }
+    h->ninfo = h->mod.describe(h->info, (int)(sizeof(h->info) / sizeof(int32_t)));
+    if (h->ninfo <= 0) {
+        int rc = fail(nullptr, ECH_ERR_MODULE, "ech_create: module has too many fields");
+        dlclose(h->mod.dl);
+        delete h;
+        return rc;
+    }
+    const int d = h->info[0], p = h->info[1], nf = h->info[2], naux = h->info[3];
+    if (d != mesh->dim || p != mesh->degree || nf != mesh->nfields || naux != mesh->naux) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "ech_create: module (d=%d p=%d nf=%d naux=%d) does not match mesh plan (d=%d p=%d nf=%d naux=%d)", d,
+                 p, nf, naux, mesh->dim, mesh->degree, mesh->nfields, mesh->naux);
+        int rc = fail(nullptr, ECH_ERR_MISMATCH, buf);
+        dlclose(h->mod.dl);
+        delete h;
+        return rc;
+    }
+    h->nf = nf;
+    h->nloc = ipow(p + 1, d);
+    for (int i = 0; i < nf; ++i) {
+        h->own_bits[i] = h->nbr_bits[i] = 0;
+        for (int j = 0; j < nf; ++j) {
+            if (h->info[8 + i * nf + j]) h->own_bits[i] |= 1ull << j;
+            if (h->info[8 + nf * nf + i * nf + j]) h->nbr_bits[i] |= 1ull << j;
+        }
+    }
+    *out = h;
+    return ECH_OK;
+}
+
+extern "C" void ech_destroy(ech_handle *h) {
+    if (!h) return;
+    if (h->mod.dl) dlclose(h->mod.dl);
+    delete h;
+}
+
+extern "C" const char *ech_last_error(const ech_handle *h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+extern "C" int ech_describe(const ech_handle *h, int32_t *info, int capacity) {
+    if (!h || !info || capacity < h->ninfo) return ECH_ERR_ARG;
+    memcpy(info, h->info, sizeof(int32_t) * h->ninfo);
+    return h->ninfo;
+}
+
+extern "C" int64_t ech_launch_count(const ech_handle *) { return g_launches; }
+
+extern "C" int ech_num_rows(const ech_handle *h, int64_t *nrows) {
+    if (!h || !nrows) return ECH_ERR_ARG;
+    *nrows = (int64_t)h->nf * h->mesh.ncell * h->nloc;
+    return ECH_OK;
+}
+
+// =============================================================== sparsity pattern
+struct PatternPlan {
+    int nf, nloc, nlf;
+    int64_t ncell;
+    unsigned long long own_bits[16], nbr_bits[16];
+};
+
+__global__ void row_length_kernel(PatternPlan P, const uint8_t *__restrict__ ncol, int64_t *__restrict__ len) {
+    const int64_t rows_per_field = P.ncell * P.nloc;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows_per_field * P.nf) return;
+    const int i = (int)(r / rows_per_field);
+    const int64_t c = (r - i * rows_per_field) / P.nloc;
+    const int nc = ncol[c];
+    int n = 0;
+    for (int j = 0; j < P.nf; ++j) {
+        if ((P.own_bits[i] >> j) & 1) n += (((P.nbr_bits[i] >> j) & 1) ? nc : 1) * P.nloc;
+    }
+    len[r] = n;
+}
+
+__global__ void colidx_kernel(PatternPlan P, const int32_t *__restrict__ nbr, const uint8_t *__restrict__ slot,
+                              const uint8_t *__restrict__ slot_self, const uint8_t *__restrict__ ncol,
+                              const int64_t *__restrict__ rowptr, int32_t *__restrict__ colidx) {
+    const int64_t rows_per_field = P.ncell * P.nloc;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows_per_field * P.nf) return;
+    const int i = (int)(r / rows_per_field);
+    const int64_t c = (r - i * rows_per_field) / P.nloc;
+    const int nc = ncol[c];
+    int64_t cells[8];
+    cells[slot_self[c]] = c;
+    for (int lf = 0; lf < P.nlf; ++lf) {
+        const int nb = nbr[c * P.nlf + lf];
+        if (nb >= 0) cells[slot[c * P.nlf + lf]] = nb;
+    }
+    int32_t *out = colidx + rowptr[r];
+    for (int j = 0; j < P.nf; ++j) {
+        if (!((P.own_bits[i] >> j) & 1)) continue;
+        if ((P.nbr_bits[i] >> j) & 1) {
+            for (int s = 0; s < nc; ++s)
+                for (int b = 0; b < P.nloc; ++b) *out++ = (int32_t)(j * rows_per_field + cells[s] * P.nloc + b);
+        } else {
+            for (int b = 0; b < P.nloc; ++b) *out++ = (int32_t)(j * rows_per_field + c * P.nloc + b);
+        }
+    }
+}
+
+static PatternPlan make_plan(const ech_handle *h) {
+    PatternPlan P;
+    P.nf = h->nf;
+    P.nloc = h->nloc;
+    P.nlf = 2 * h->mesh.dim;
+    P.ncell = h->mesh.ncell;
+    for (int i = 0; i < 16; ++i) {
+        P.own_bits[i] = i < h->nf ? h->own_bits[i] : 0;
+        P.nbr_bits[i] = i < h->nf ? h->nbr_bits[i] : 0;
+    }
+    return P;
+}
+
+extern "C" int ech_pattern_rowptr(ech_handle *h, int64_t *rowptr, int64_t *nnz_host, void *stream) {
+    if (!h || !rowptr || !nnz_host) return fail(h, ECH_ERR_ARG, "ech_pattern_rowptr: null argument");
+    if (h->mesh.ncell != h->mesh.ncell_total)
+        return fail(h, ECH_ERR_ARG, "ech_pattern_rowptr: column numbering with ghost cells is not supported here");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t nrows;
+    ech_num_rows(h, &nrows);
+    PatternPlan P = make_plan(h);
+    int64_t *len = nullptr;
+    CK(h, cudaMalloc(&len, sizeof(int64_t) * (nrows + 1)));
+    CK(h, cudaMemsetAsync(len, 0, sizeof(int64_t) * (nrows + 1), s));
+    const int block = 256;
+    row_length_kernel<<<(unsigned)((nrows + block - 1) / block), block, 0, s>>>(P, h->mesh.ncol, len);
+    ++g_launches;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len, rowptr, nrows + 1, s);
+    void *tmp = nullptr;
+    CK(h, cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, rowptr, nrows + 1, s);
+    ++g_launches;
+    CK(h, cudaMemcpyAsync(nnz_host, rowptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    cudaFree(tmp);
+    cudaFree(len);
+    CK(h, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_pattern_colidx(ech_handle *h, const int64_t *rowptr, int32_t *colidx, void *stream) {
+    if (!h || !rowptr || !colidx) return fail(h, ECH_ERR_ARG, "ech_pattern_colidx: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t nrows;
+    ech_num_rows(h, &nrows);
+    if (nrows >= (int64_t)1 << 31) return fail(h, ECH_ERR_ARG, "ech_pattern_colidx: more than 2^31 columns");
+    PatternPlan P = make_plan(h);
+    const int block = 256;
+    colidx_kernel<<<(unsigned)((nrows + block - 1) / block), block, 0, s>>>(P, h->mesh.nbr, h->mesh.slot,
+                                                                          h->mesh.slot_self, h->mesh.ncol, rowptr,
+                                                                          colidx);
+    ++g_launches;
+    CK(h, cudaGetLastError());
+    return ECH_OK;
+}
+
+// =============================================================== SNES callbacks
+static void fill_args(const ech_handle *h, ech_dg_args &a) {
+    const ech_mesh_desc &m = h->mesh;
+    a.ncell = m.ncell;
+    a.ncell_total = m.ncell_total;
+    a.xcell = m.xcell;
+    a.nbr = m.nbr;
+    a.code = m.code;
+    a.slot = m.slot;
+    a.slot_self = m.slot_self;
+    a.ncol = m.ncol;
+    a.cell_volume = m.cell_volume;
+    a.cell_diam = m.cell_diam;
+    a.facet_area = m.facet_area;
+}
+
+extern "C" int ech_residual(ech_handle *h, const double *u, const double *aux, const double *consts, double *F,
+                            void *stream) {
+    if (!h || !u || !F) return fail(h, ECH_ERR_ARG, "ech_residual: null argument");
+    ech_dg_args a;
+    fill_args(h, a);
+    a.u = u;
+    a.aux = aux;
+    a.consts = consts;
+    a.rowptr = nullptr;
+    a.out = F;
+    int rc = h->mod.residual(&a, stream);
+    g_launches += h->mod.launches(0);
+    if (rc) return cuda_fail(h, (cudaError_t)rc, "ech_residual launch");
+    return ECH_OK;
+}
+
+extern "C" int ech_jacobian(ech_handle *h, const double *u, const double *aux, const double *consts,
+                            const int64_t *rowptr, double *vals, void *stream) {
+    if (!h || !u || !rowptr || !vals) return fail(h, ECH_ERR_ARG, "ech_jacobian: null argument");
+    ech_dg_args a;
+    fill_args(h, a);
+    a.u = u;
+    a.aux = aux;
+    a.consts = consts;
+    a.rowptr = rowptr;
+    a.out = vals;
+    int rc = h->mod.jacobian(&a, stream);
+    g_launches += h->mod.launches(1);
+    if (rc) return cuda_fail(h, (cudaError_t)rc, "ech_jacobian launch");
+    return ECH_OK;
+}
+
+__global__ void constrain_rows_kernel(int64_t nrows, const uint8_t *__restrict__ mask,
+                                      const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                      double *__restrict__ vals, double *__restrict__ F) {
+    // one warp per row
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= nrows || !mask[r]) return;
+    if (vals) {
+        for (int64_t p = rowptr[r] + lane; p < rowptr[r + 1]; p += 32) vals[p] = (colidx[p] == r) ? 1.0 : 0.0;
+    }
+    if (F && lane == 0) F[r] = 0.0;
+}
+
+extern "C" int ech_constrain_rows(int64_t nrows, const uint8_t *row_mask, const int64_t *rowptr,
+                                  const int32_t *colidx, double *vals, double *F, void *stream) {
+    if (!row_mask || (vals && (!rowptr || !colidx))) return fail(nullptr, ECH_ERR_ARG, "ech_constrain_rows: null argument");
+    if (nrows == 0) return ECH_OK;
+    const int block = 256;
+    const int64_t nthreads = nrows * 32;
+    constrain_rows_kernel<<<(unsigned)((nthreads + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+        nrows, row_mask, rowptr, colidx, vals, F);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+// =============================================================== SpMV
+// TPR lanes cooperate on one row: coalesced 8*TPR-byte value segments, shuffle reduction.
+template <int TPR>
+__global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int64_t *__restrict__ rowptr,
+                                                   const int32_t *__restrict__ colidx,
+                                                   const double *__restrict__ vals, const double *__restrict__ x,
+                                                   double *__restrict__ y) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = t / TPR;
+    const int lane = (int)(t % TPR);
+    double s = 0.0;
+    if (r < nrows) {
+        const int64_t b = rowptr[r], e = rowptr[r + 1];
+        for (int64_t p = b + lane; p < e; p += TPR) s += __ldcs(vals + p) * __ldg(x + __ldcs(colidx + p));
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, TPR);
+    if (r < nrows && lane == 0) y[r] = s;
+}
+
+extern "C" int ech_spmv(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                        const double *x, double *y, void *stream) {
+    if (nrows == 0) return ECH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int block = 256;
+    constexpr int TPR = 8;
+    const int64_t nthreads = nrows * TPR;
+    spmv_kernel<TPR><<<(unsigned)((nthreads + block - 1) / block), block, 0, s>>>(nrows, rowptr, colidx, vals, x, y);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+// =============================================================== vector kernels
+__global__ void axpby_kernel(int64_t n, double a, const double *__restrict__ x, double b, double *__restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];
+}
+
+static int grid_for(int64_t n, int block, int cap = 148 * 16) {
+    int64_t g = (n + block - 1) / block;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+extern "C" int ech_axpby(int64_t n, double a, const double *x, double b, double *y, void *stream) {
+    if (n == 0) return ECH_OK;
+    axpby_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+constexpr int DOT_BLOCKS = 592;   // 4 per SM
+constexpr int DOT_TILE = 4;
+
+// partial[(col) * DOT_BLOCKS + block] = sum over this block's rows of V[col][i] * w[i]; col == k is w.w
+__global__ void __launch_bounds__(256) multidot_kernel(int64_t n, int k, const double *__restrict__ V, int64_t ldv,
+                                                       const double *__restrict__ w, double *__restrict__ partial) {
+    const int col0 = blockIdx.y * DOT_TILE;
+    double acc[DOT_TILE];
+#pragma unroll
+    for (int t = 0; t < DOT_TILE; ++t) acc[t] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+#pragma unroll
+        for (int t = 0; t < DOT_TILE; ++t) {
+            const int col = col0 + t;
+            if (col < k)
+                acc[t] += V[col * ldv + i] * wi;
+            else if (col == k)
+                acc[t] += wi * wi;
+        }
+    }
+    __shared__ double sm[DOT_TILE][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < DOT_TILE; ++t) {
+        double v = acc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[t][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < DOT_TILE) {
+        double v = 0.0;
+        for (int q = 0; q < 8; ++q) v += sm[threadIdx.x][q];
+        const int col = col0 + threadIdx.x;
+        if (col <= k) partial[(int64_t)col * gridDim.x + blockIdx.x] = v;
+    }
+}
+
+__global__ void multidot_finish_kernel(int ncols, int nblocks, const double *__restrict__ partial,
+                                       double *__restrict__ out) {
+    const int col = blockIdx.x;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partial[(int64_t)col * nblocks + b];
+    __shared__ double sm[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += sm[q];
+        out[col] = s;
+    }
+    (void)ncols;
+}
+
+// w -= sum_j h[j] V[j]
+__global__ void multiaxpy_kernel(int64_t n, int k, const double *__restrict__ V, int64_t ldv,
+                                 const double *__restrict__ h, double *__restrict__ w, double sign) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s += h[j] * V[j * ldv + i];
+        w[i] += sign * s;
+    }
+}
+
+// hdev[0..k-1] = V^T w, hdev[k] = w.w ; copied to host (synchronises)
+static int multidot(int64_t n, int k, const double *V, const double *w, double *partial, double *hdev,
+                    double *hhost, cudaStream_t s) {
+    dim3 grid(DOT_BLOCKS, (k + 1 + DOT_TILE - 1) / DOT_TILE);
+    multidot_kernel<<<grid, 256, 0, s>>>(n, k, V, n, w, partial);
+    multidot_finish_kernel<<<k + 1, 256, 0, s>>>(k + 1, DOT_BLOCKS, partial, hdev);
+    g_launches += 2;
+    CK(nullptr, cudaMemcpyAsync(hhost, hdev, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, s));
+    CK(nullptr, cudaStreamSynchronize(s));
+    return ECH_OK;
+}
+
+extern "C" int ech_dot(int64_t n, const double *x, const double *y, double *work, double *result_host,
+                       void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        *result_host = 0.0;
+        return ECH_OK;
+    }
+    // V = x (one column), w = y : out[0] = x.y
+    double h2[2];
+    int rc = multidot(n, 1, x, y, work + 8, work, h2, s);
+    if (rc) return rc;
+    *result_host = h2[0];
+    return ECH_OK;
+}
+
+// =============================================================== block-Jacobi / ILU(0)
+struct BlockPlan {
+    int nf, nloc;
+    int64_t rows_per_field, nblocks;
+    const int64_t *cell_ptr;
+};
+
+__device__ __forceinline__ bool in_block(const BlockPlan &B, int32_t col, int64_t c0, int64_t c1) {
+    const int64_t idx = col % B.rows_per_field;
+    const int64_t cell = idx / B.nloc;
+    return cell >= c0 && cell < c1;
+}
+
+__global__ void diag_pos_kernel(int64_t nrows, const int64_t *__restrict__ rowptr,
+                                const int32_t *__restrict__ colidx, int32_t *__restrict__ diag_pos) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    const int64_t b = lo;
+    int32_t pos = -1;
+    while (lo <= hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int32_t cj = colidx[mid];
+        if (cj == r) {
+            pos = (int32_t)(mid - b);
+            break;
+        }
+        if (cj < r)
+            lo = mid + 1;
+        else
+            hi = mid - 1;
+    }
+    diag_pos[r] = pos;
+}
+
+// one warp per block; rows in ascending global order (field-major inside the block)
+__global__ void __launch_bounds__(128) ilu0_factor_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
+                                                          const int32_t *__restrict__ colidx, double *lu,
+                                                          const int32_t *__restrict__ diag_pos, int *flag) {
+    const int64_t blk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (blk >= B.nblocks) return;
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    for (int f = 0; f < B.nf; ++f) {
+        for (int64_t r = f * B.rows_per_field + c0 * B.nloc; r < f * B.rows_per_field + c1 * B.nloc; ++r) {
+            const int64_t rs = rowptr[r], re = rowptr[r + 1];
+            const int64_t rd = rs + diag_pos[r];
+            for (int64_t pk = rs; pk < rd; ++pk) {
+                const int32_t k = colidx[pk];
+                if (!in_block(B, k, c0, c1)) continue;
+                const int64_t ks = rowptr[k], ke = rowptr[k + 1];
+                const int64_t kd = ks + diag_pos[k];
+                const double l = lu[pk] / lu[kd];
+                __syncwarp();
+                if (lane == 0) lu[pk] = l;
+                for (int64_t q = kd + 1 + lane; q < ke; q += 32) {
+                    const int32_t j = colidx[q];
+                    if (!in_block(B, j, c0, c1)) continue;
+                    // find column j in row r, to the right of pk
+                    int64_t lo = pk + 1, hi = re - 1;
+                    while (lo <= hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        const int32_t cj = colidx[mid];
+                        if (cj == j) {
+                            lu[mid] -= l * lu[q];
+                            break;
+                        }
+                        if (cj < j)
+                            lo = mid + 1;
+                        else
+                            hi = mid - 1;
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane == 0 && lu[rd] == 0.0) atomicExch(flag, 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) ilu0_apply_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
+                                                         const int32_t *__restrict__ colidx,
+                                                         const double *__restrict__ lu,
+                                                         const int32_t *__restrict__ diag_pos,
+                                                         const double *__restrict__ rhs, double *z) {
+    const int64_t blk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (blk >= B.nblocks) return;
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    // forward: L y = rhs (unit diagonal)
+    for (int f = 0; f < B.nf; ++f) {
+        for (int64_t r = f * B.rows_per_field + c0 * B.nloc; r < f * B.rows_per_field + c1 * B.nloc; ++r) {
+            const int64_t rs = rowptr[r];
+            const int64_t rd = rs + diag_pos[r];
+            double s = 0.0;
+            for (int64_t p = rs + lane; p < rd; p += 32) {
+                const int32_t k = colidx[p];
+                if (in_block(B, k, c0, c1)) s += lu[p] * z[k];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) z[r] = rhs[r] - s;
+            __syncwarp();
+        }
+    }
+    // backward: U z = y
+    for (int f = B.nf - 1; f >= 0; --f) {
+        for (int64_t r = f * B.rows_per_field + c1 * B.nloc - 1; r >= f * B.rows_per_field + c0 * B.nloc; --r) {
+            const int64_t rs = rowptr[r], re = rowptr[r + 1];
+            const int64_t rd = rs + diag_pos[r];
+            double s = 0.0;
+            for (int64_t p = rd + 1 + lane; p < re; p += 32) {
+                const int32_t k = colidx[p];
+                if (in_block(B, k, c0, c1)) s += lu[p] * z[k];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) z[r] = (z[r] - s) / lu[rd];
+            __syncwarp();
+        }
+    }
+}
+
+extern "C" int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                       int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
+                                       const int32_t *colidx, const double *vals, double *lu, int32_t *diag_pos,
+                                       void *stream) {
+    if (!block_cell_ptr || !rowptr || !colidx || !vals || !lu || !diag_pos)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_factor: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t nnz = 0;
+    CK(nullptr, cudaMemcpyAsync(&nnz, rowptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(nullptr, cudaStreamSynchronize(s));
+    CK(nullptr, cudaMemcpyAsync(lu, vals, sizeof(double) * nnz, cudaMemcpyDeviceToDevice, s));
+    diag_pos_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, s>>>(nrows, rowptr, colidx, diag_pos);
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    int *flag = nullptr;
+    CK(nullptr, cudaMalloc(&flag, sizeof(int)));
+    CK(nullptr, cudaMemsetAsync(flag, 0, sizeof(int), s));
+    const int block = 128;
+    const int64_t nthreads = nblocks * 32;
+    ilu0_factor_kernel<<<(unsigned)((nthreads + block - 1) / block), block, 0, s>>>(B, rowptr, colidx, lu, diag_pos,
+                                                                                  flag);
+    g_launches += 2;
+    int hflag = 0;
+    CK(nullptr, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(nullptr, cudaStreamSynchronize(s));
+    cudaFree(flag);
+    CK(nullptr, cudaGetLastError());
+    if (hflag) return fail(nullptr, ECH_ERR_BREAKDOWN, "ech_bjacobi_ilu0_factor: zero pivot");
+    return ECH_OK;
+}
+
+static int ilu0_apply(const BlockPlan &B, const int64_t *rowptr, const int32_t *colidx, const double *lu,
+                      const int32_t *diag_pos, const double *r, double *z, cudaStream_t s) {
+    const int block = 128;
+    const int64_t nthreads = B.nblocks * 32;
+    ilu0_apply_kernel<<<(unsigned)((nthreads + block - 1) / block), block, 0, s>>>(B, rowptr, colidx, lu, diag_pos, r,
+                                                                                 z);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                      int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
+                                      const int32_t *colidx, const double *lu, const int32_t *diag_pos,
+                                      const double *r, double *z, void *stream) {
+    (void)nrows;
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    return ilu0_apply(B, rowptr, colidx, lu, diag_pos, r, z, (cudaStream_t)stream);
+}
+
+// =============================================================== GMRES
+extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                         const double *b, double *x, const ech_gmres_opts *o, double *basis, double *work,
+                         int32_t *its_host, double *rnorm_host, void *stream) {
+    if (!rowptr || !colidx || !vals || !b || !x || !o || !basis || !work)
+        return fail(nullptr, ECH_ERR_ARG, "ech_gmres: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int m = o->restart;
+    double *w = work;               // n
+    double *zt = work + n;          // n
+    double *t2 = work + 2 * n;      // n
+    double *hdev = work + 3 * n;    // m + 2 (within 4096)
+    double *partial = work + 3 * n + 4096;
+    if (m + 2 > 4096) return fail(nullptr, ECH_ERR_ARG, "ech_gmres: restart too large");
+    BlockPlan B{o->nfields, o->nloc, o->rows_per_field, o->nblocks, o->block_cell_ptr};
+    auto precond = [&](const double *in, double *out) -> int {
+        if (o->precond == 1) return ilu0_apply(B, rowptr, colidx, o->lu, o->diag_pos, in, out, s);
+        return ech_axpby(n, 1.0, in, 0.0, out, s);
+    };
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hcol(m + 2), y(m);
+    int its = 0;
+    int rc;
+    double bnorm2;
+    if ((rc = multidot(n, 0, basis, b, partial, hdev, hcol.data(), s))) return rc;
+    bnorm2 = hcol[0];
+    const double bnorm = sqrt(bnorm2);
+    const double tol = fmax(o->rtol * bnorm, o->atol);
+    double rnorm = bnorm;
+    bool converged = false;
+    while (its < o->max_it && !converged) {
+        // r = b - A x  -> V0
+        double *V0 = basis;
+        if ((rc = ech_spmv(n, rowptr, colidx, vals, x, w, s))) return rc;
+        if ((rc = ech_axpby(n, 1.0, b, 0.0, V0, s))) return rc;
+        if ((rc = ech_axpby(n, -1.0, w, 1.0, V0, s))) return rc;
+        if ((rc = multidot(n, 0, basis, V0, partial, hdev, hcol.data(), s))) return rc;
+        const double beta = sqrt(hcol[0]);
+        rnorm = beta;
+        if (o->monitor) printf("  %3d KSP Residual norm %.12e\n", its, rnorm);
+        if (beta <= tol) {
+            converged = true;
+            break;
+        }
+        if ((rc = ech_axpby(n, 0.0, V0, 1.0 / beta, V0, s))) return rc;   // V0 *= 1/beta  (a*x + b*y with x==y)
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int j = 0;
+        for (; j < m && its < o->max_it; ++j) {
+            double *Vj = basis + (int64_t)j * n;
+            double *Vn = basis + (int64_t)(j + 1) * n;
+            if ((rc = precond(Vj, zt))) return rc;
+            if ((rc = ech_spmv(n, rowptr, colidx, vals, zt, w, s))) return rc;
+            // classical Gram-Schmidt + one refinement pass
+            if ((rc = multidot(n, j + 1, basis, w, partial, hdev, hcol.data(), s))) return rc;
+            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
+            multiaxpy_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, j + 1, basis, n, hdev, w, -1.0);
+            ++g_launches;
+            if ((rc = multidot(n, j + 1, basis, w, partial, hdev, hcol.data(), s))) return rc;
+            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] += hcol[i];
+            multiaxpy_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, j + 1, basis, n, hdev, w, -1.0);
+            ++g_launches;
+            double corr = 0.0;
+            for (int i = 0; i <= j; ++i) corr += hcol[i] * hcol[i];
+            double hn2 = hcol[j + 1] - corr;
+            if (hn2 < 0.0) hn2 = 0.0;
+            // exact norm of the refined vector
+            if ((rc = multidot(n, 0, basis, w, partial, hdev, hcol.data(), s))) return rc;
+            const double hn = sqrt(hcol[0]);
+            (void)hn2;
+            H[(size_t)(j + 1) * m + j] = hn;
+            if (hn > 0.0) {
+                if ((rc = ech_axpby(n, 1.0 / hn, w, 0.0, Vn, s))) return rc;
+            }
+            // Givens
+            for (int i = 0; i < j; ++i) {
+                const double a = H[(size_t)i * m + j], bb = H[(size_t)(i + 1) * m + j];
+                H[(size_t)i * m + j] = cs[i] * a + sn[i] * bb;
+                H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs[i] * bb;
+            }
+            const double a = H[(size_t)j * m + j], bb = H[(size_t)(j + 1) * m + j];
+            const double den = hypot(a, bb);
+            cs[j] = den == 0.0 ? 1.0 : a / den;
+            sn[j] = den == 0.0 ? 0.0 : bb / den;
+            H[(size_t)j * m + j] = den;
+            H[(size_t)(j + 1) * m + j] = 0.0;
+            g[j + 1] = -sn[j] * g[j];
+            g[j] = cs[j] * g[j];
+            ++its;
+            rnorm = fabs(g[j + 1]);
+            if (o->monitor) printf("  %3d KSP Residual norm %.12e\n", its, rnorm);
+            if (rnorm <= tol || hn == 0.0) {
+                ++j;
+                converged = rnorm <= tol;
+                break;
+            }
+        }
+        // solve the triangular system, x += M^-1 V y
+        const int k = j;
+        for (int i = k - 1; i >= 0; --i) {
+            double sum = g[i];
+            for (int l = i + 1; l < k; ++l) sum -= H[(size_t)i * m + l] * y[l];
+            y[i] = sum / H[(size_t)i * m + i];
+        }
+        CK(nullptr, cudaMemcpyAsync(hdev, y.data(), sizeof(double) * k, cudaMemcpyHostToDevice, s));
+        CK(nullptr, cudaMemsetAsync(t2, 0, sizeof(double) * n, s));
+        multiaxpy_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, k, basis, n, hdev, t2, 1.0);
+        ++g_launches;
+        if ((rc = precond(t2, zt))) return rc;
+        if ((rc = ech_axpby(n, 1.0, zt, 1.0, x, s))) return rc;
+        CK(nullptr, cudaStreamSynchronize(s));
+        if (!converged && k == 0) break;
+    }
+    if (its_host) *its_host = its;
+    if (rnorm_host) *rnorm_host = rnorm;
+    CK(nullptr, cudaGetLastError());
+    return converged ? ECH_OK : ECH_ERR_NOT_CONVERGED;
+}
+
+// =============================================================== host-buffer boundary
+extern "C" int ech_assemble_host(ech_handle *h, const double *u_host, double *u_dev, const double *aux,
+                                 const double *consts, const int64_t *rowptr, double *vals, double *F_dev,
+                                 double *F_host, void *stream) {
+    if (!h || !u_host || !u_dev || !F_dev || !F_host) return fail(h, ECH_ERR_ARG, "ech_assemble_host: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t nrows;
+    ech_num_rows(h, &nrows);
+    const int64_t nstate = (int64_t)h->nf * h->mesh.ncell_total * h->nloc;
+    CK(h, cudaMemcpyAsync(u_dev, u_host, sizeof(double) * nstate, cudaMemcpyHostToDevice, s));
+    int rc = ech_residual(h, u_dev, aux, consts, F_dev, stream);
+    if (rc) return rc;
+    if (vals) {
+        rc = ech_jacobian(h, u_dev, aux, consts, rowptr, vals, stream);
+        if (rc) return rc;
+    }
+    CK(h, cudaMemcpyAsync(F_host, F_dev, sizeof(double) * nrows, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    return ECH_OK;
+}

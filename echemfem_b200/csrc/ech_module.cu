@@ -1,0 +1,39 @@
+// Translation unit of one physics module: generated integrands + hand-written DG skeleton.
+// Built by echemfem_b200/build.py as
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
+//        -include <generated header> ech_module.cu -o libech_phys_<key>.so
+#include "ech_dg.cuh"
+
+extern "C" {
+
+int ech_mod_describe(int32_t *info, int capacity) {
+    using namespace echgen;
+    const int need = 8 + 2 * NF * NF;
+    if (capacity < need) return -need;
+    info[0] = D;
+    info[1] = P;
+    info[2] = NF;
+    info[3] = ECH_NAUX;
+    info[4] = ECH_NCONST;
+    info[5] = NQ;
+    info[6] = ECH_NCLS;
+    info[7] = ECH_FAMILY_DG;
+    for (int i = 0; i < NF; ++i)
+        for (int j = 0; j < NF; ++j) {
+            info[8 + i * NF + j] = OWN_BLOCK[i][j];
+            info[8 + NF * NF + i * NF + j] = NBR_BLOCK[i][j];
+        }
+    return need;
+}
+
+int ech_mod_residual(const ech_dg_args *a, void *stream) {
+    return echdg::launch_residual(a, (cudaStream_t)stream);
+}
+
+int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
+    return echdg::launch_jacobian(a, (cudaStream_t)stream);
+}
+
+int ech_mod_launches(int which) { return which == 0 ? 1 : echgen::NF; }
+
+}  // extern "C"

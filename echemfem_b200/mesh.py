@@ -122,8 +122,11 @@ class Mesh:
         """(nbr int32, code uint8, slot uint8, slot_self uint8, ncol uint8)."""
         nc, nlf = self.nbr_cell.shape
         nbr = self.nbr_cell.copy()
-        cls = np.vectorize(lambda m: marker_class.get(int(m), 0), otypes=[np.int64])(self.ext_marker) \
-            if nc else self.ext_marker
+        lut = np.zeros(int(self.ext_marker.max()) + 2 if nc else 1, dtype=np.int64)
+        for m, k in marker_class.items():
+            if 0 <= int(m) < len(lut):
+                lut[int(m)] = k
+        cls = lut[self.ext_marker]
         bnd = nbr < 0
         nbr[bnd] = -(1 + cls[bnd])
         code = (self.nbr_lf | (self.nbr_orient << 3)).astype(np.uint8)
@@ -169,6 +172,7 @@ def TensorMesh(axes, name="tensor", marker_of_facet=None, layers=None):
         marker_of_facet = _box_markers([a[0] for a in axes], [a[-1] for a in axes])
     m = Mesh(coords, cells, marker_of_facet, name=name, layers=layers)
     m.shape = tuple(n - 1 for n in nv)
+    m.axes = axes
     return m
 
 
@@ -208,3 +212,66 @@ def ExtrudedMesh(base, layers, layer_height=None, **kw):
         axes = base.axes
     z = np.arange(layers + 1) * float(layer_height)
     return TensorMesh(list(axes) + [z], name=base.name + "_extruded", layers=layers)
+
+
+def _shape_derivs(d, xi):
+    """Vertex shape functions and reference derivatives at points xi (npts, d)."""
+    npts = xi.shape[0]
+    N = np.ones((npts, 2 ** d))
+    dN = np.ones((npts, 2 ** d, d))
+    for v in range(2 ** d):
+        for k in range(d):
+            bit = (v >> (d - 1 - k)) & 1
+            val = xi[:, k] if bit else 1.0 - xi[:, k]
+            N[:, v] *= val
+            for l in range(d):
+                dN[:, v, l] *= (1.0 if bit else -1.0) if l == k else val
+    return N, dN
+
+
+def cell_geometry(mesh, chunk=1 << 18):
+    """CellVolume, FacetArea (per cell and local facet) and CellDiameter.
+
+    Volumes and areas are integrated with a 3-point Gauss rule per direction,
+    exact for multilinear cells with planar facets; the diameter is the largest
+    vertex distance.
+    """
+    from .tables import gauss_points
+    d = mesh.dim
+    gp, gw = gauss_points(3)
+    grids = np.meshgrid(*([np.arange(3)] * d), indexing="ij")
+    qi = np.stack([g.reshape(-1) for g in grids], axis=1)
+    xi = gp[qi]
+    w = np.prod(gw[qi], axis=1)
+    _, dN = _shape_derivs(d, xi)
+    X = mesh.cell_coords()
+    nc = mesh.num_cells
+    vol = np.empty(nc)
+    area = np.empty((nc, 2 * d))
+    diam = np.empty(nc)
+    if d > 1:
+        gridf = np.meshgrid(*([np.arange(3)] * (d - 1)), indexing="ij")
+        qf = np.stack([g.reshape(-1) for g in gridf], axis=1)
+        wf = np.prod(gw[qf], axis=1)
+    else:
+        qf = np.zeros((1, 0), dtype=int)
+        wf = np.ones(1)
+    for s0 in range(0, nc, chunk):
+        Xc = X[s0:s0 + chunk]
+        J = np.einsum("qvl,cvk->cqkl", dN, Xc)
+        vol[s0:s0 + chunk] = np.einsum("q,cq->c", w, np.abs(np.linalg.det(J)))
+        for lf in range(2 * d):
+            k, s = divmod(lf, 2)
+            xif = np.empty((qf.shape[0], d))
+            xif[:, k] = float(s)
+            rest = [m for m in range(d) if m != k]
+            for a, m in enumerate(rest):
+                xif[:, m] = gp[qf[:, a]]
+            _, dNf = _shape_derivs(d, xif)
+            Jf = np.einsum("qvl,cvk->cqkl", dNf, Xc)
+            Jinv = np.linalg.inv(Jf)
+            nrm = np.sqrt((Jinv[..., k, :] ** 2).sum(-1))
+            area[s0:s0 + chunk, lf] = np.einsum("q,cq->c", wf, np.abs(np.linalg.det(Jf)) * nrm)
+        diff = Xc[:, :, None, :] - Xc[:, None, :, :]
+        diam[s0:s0 + chunk] = np.sqrt((diff ** 2).sum(-1)).max(axis=(1, 2))
+    return vol, area, diam

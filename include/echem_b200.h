@@ -1,0 +1,141 @@
+/* echem_b200 -- C ABI of the B200 Newton-step library (libechem_b200.so).
+ *
+ * Drop-in boundary.  In the reference the hot path sits behind
+ *     NonlinearVariationalProblem(Form, u, bcs) / NonlinearVariationalSolver(...).solve()
+ * (echemfem/solver.py:714-718, 725) and, below that, behind the two PETSc SNES
+ * callbacks  F(X) -> Vec  and  J(X) -> Mat(AIJ)  plus KSPSolve.  The entry
+ * points below are what a binding for that path calls instead; each one cites
+ * the reference-side operation it replaces.  Python binds them with ctypes
+ * (echemfem_b200/capi.py; INTEGRATION.md shows the stub a maintainer would add
+ * to the reference).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless the name ends in `_host`.
+ *  - The caller owns every buffer (state, matrix values, Krylov basis); the
+ *    handle owns only plans.  No hot call allocates.
+ *  - All work is enqueued on the caller's stream (a cudaStream_t passed as
+ *    void*); only calls documented as synchronising read back a scalar.
+ *  - Every function returns 0 on success, a negative ech_* code or a positive
+ *    cudaError_t otherwise; ech_last_error() describes the last failure.
+ *    Nothing throws across this boundary.  One handle per (GPU, stream); not
+ *    re-entrant.
+ *  - FP64 throughout; column indices int32, row pointers int64.
+ */
+#ifndef ECHEM_B200_H
+#define ECHEM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECH_OK 0
+#define ECH_ERR_ARG (-1)
+#define ECH_ERR_MODULE (-2)
+#define ECH_ERR_MISMATCH (-3)
+#define ECH_ERR_BREAKDOWN (-4)
+#define ECH_ERR_NOT_CONVERGED (-5)
+
+typedef struct ech_handle ech_handle;
+
+/* Mesh / discretisation plan: per-cell connectivity of a DG tensor-product space
+ * (what Firedrake's cell_node_map + interior/exterior facet maps + coordinates
+ * provide below solver.py:714). */
+typedef struct ech_mesh_desc {
+    int32_t dim, degree, nfields, naux;
+    int64_t ncell;            /* owned cells: rows are produced for these            */
+    int64_t ncell_total;      /* owned + ghost cells: state / geometry cover these   */
+    const double *xcell;      /* [ncell_total][2^dim][dim]                            */
+    const int32_t *nbr;       /* [ncell][2 dim]  neighbour or -(1 + boundary class)   */
+    const uint8_t *code;      /* [ncell][2 dim]  neighbour facet | orientation << 3   */
+    const uint8_t *slot;      /* [ncell][2 dim]                                       */
+    const uint8_t *slot_self; /* [ncell]                                              */
+    const uint8_t *ncol;      /* [ncell]                                              */
+    const double *cell_volume;/* [ncell_total]  CellVolume  (solver.py:1491)          */
+    const double *cell_diam;  /* [ncell_total]  CellDiameter (solver.py:1657)         */
+    const double *facet_area; /* [ncell][2 dim] FacetArea   (solver.py:1491)          */
+} ech_mesh_desc;
+
+/* -- lifetime ---------------------------------------------------------------- */
+/* Binds a compiled physics module (the weak form: replaces Form + derivative(F,u) +
+ * the TSFC kernels of NonlinearVariationalProblem, solver.py:714) to a mesh plan. */
+int ech_create(const char *module_path, const ech_mesh_desc *mesh, ech_handle **out);
+void ech_destroy(ech_handle *h);
+const char *ech_last_error(const ech_handle *h);
+/* d, p, nf, naux, nconst, nq, nclasses, family, own[nf*nf], nbr[nf*nf] */
+int ech_describe(const ech_handle *h, int32_t *info, int capacity);
+
+/* -- sparsity (PyOP2 Sparsity + MatSeqAIJ preallocation; "mat_type": "aij", solver.py:943) */
+int ech_num_rows(const ech_handle *h, int64_t *nrows);
+/* fills rowptr[nrows+1]; *nnz_host receives the total. Synchronises the stream. */
+int ech_pattern_rowptr(ech_handle *h, int64_t *rowptr, int64_t *nnz_host, void *stream);
+int ech_pattern_colidx(ech_handle *h, const int64_t *rowptr, int32_t *colidx, void *stream);
+
+/* -- SNES callbacks --------------------------------------------------------------- */
+/* form_function: F = assemble(Form) at state u (SNESFunctionEval; solver.py:725). */
+int ech_residual(ech_handle *h, const double *u, const double *aux, const double *consts, double *F,
+                 void *stream);
+/* form_jacobian: CSR values of assemble(derivative(Form, u)) (SNESJacobianEval + MatSetValuesLocal). */
+int ech_jacobian(ech_handle *h, const double *u, const double *aux, const double *consts,
+                 const int64_t *rowptr, double *vals, void *stream);
+/* Rows flagged in row_mask[nrows] become identity rows and F is zeroed there: strong
+ * DirichletBC rows (solver.py:1531, 2009) and the frozen concentration rows of the potential
+ * pre-solve (solver.py:645-662). F and/or vals may be NULL. */
+int ech_constrain_rows(int64_t nrows, const uint8_t *row_mask, const int64_t *rowptr, const int32_t *colidx,
+                       double *vals, double *F, void *stream);
+
+/* -- linear algebra (PETSc MatMult / Vec ops / PC bjacobi + sub ilu(0) / KSP gmres; solver.py:1179-1189) */
+int ech_spmv(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *x,
+             double *y, void *stream);
+/* y = a x + b y */
+int ech_axpby(int64_t n, double a, const double *x, double b, double *y, void *stream);
+/* *result_host = x . y ; synchronises. `work` holds >= 1024 doubles. */
+int ech_dot(int64_t n, const double *x, const double *y, double *work, double *result_host, void *stream);
+
+/* Block-Jacobi with ILU(0) inside each block.  Block b owns the cells
+ * [block_cell_ptr[b], block_cell_ptr[b+1]) (all fields of those cells); couplings
+ * between blocks are dropped.  nblocks = 1 is PETSc's default "one block per rank". */
+int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                            int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
+                            const int32_t *colidx, const double *vals, double *lu, int32_t *diag_pos,
+                            void *stream);
+int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                           int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
+                           const int32_t *colidx, const double *lu, const int32_t *diag_pos, const double *r,
+                           double *z, void *stream);
+
+typedef struct ech_gmres_opts {
+    double rtol, atol;
+    int32_t restart, max_it;
+    int32_t precond;          /* 0 none, 1 block-Jacobi/ILU(0) (factor must be current) */
+    int32_t monitor;          /* print residual norms */
+    /* preconditioner plan (precond == 1) */
+    int32_t nfields, nloc;
+    int64_t rows_per_field, nblocks;
+    const int64_t *block_cell_ptr;
+    const double *lu;
+    const int32_t *diag_pos;
+} ech_gmres_opts;
+
+/* Right-preconditioned restarted GMRES (classical Gram-Schmidt with one refinement, unpreconditioned
+ * residual norm: PETSc fgmres + fixed PC, solver.py:1181-1189).  basis: (restart+1) * nrows doubles,
+ * work: 3 * nrows + 4096 + 2*(restart+2)*1024 doubles.  Synchronises once per iteration
+ * (Hessenberg column read-back).  its_host / rnorm_host receive iteration count and final norm. */
+int ech_gmres(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *b,
+              double *x, const ech_gmres_opts *opts, double *basis, double *work, int32_t *its_host,
+              double *rnorm_host, void *stream);
+
+/* -- host-buffer boundary: what a binding inside the reference's SNES callbacks would call ------- */
+/* u_host -> device, residual (and Jacobian values into the device-resident matrix), F -> F_host.
+ * vals stays on the device (the linear solve consumes it there). Synchronises. */
+int ech_assemble_host(ech_handle *h, const double *u_host, double *u_dev, const double *aux,
+                      const double *consts, const int64_t *rowptr, double *vals, double *F_dev,
+                      double *F_host, void *stream);
+
+/* number of kernels launched by this library (and the bound module) since ech_create */
+int64_t ech_launch_count(const ech_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,49 @@
+/* ABI between libechem_b200.so and a compiled physics module (libech_phys_<key>.so).
+ *
+ * A physics module is the generated pointwise-integrand header (one per weak
+ * form, see echemfem_b200/compiler.py) compiled together with the hand-written
+ * kernel skeleton csrc/ech_dg.cuh.  It plays the role the TSFC-generated element
+ * kernels + PyOP2 wrapper loops play below the reference's
+ * NonlinearVariationalSolver (echemfem/solver.py:714-718).
+ *
+ * All pointers are DEVICE pointers.  Nothing here allocates.
+ */
+#ifndef ECHEM_B200_MODULE_H
+#define ECHEM_B200_MODULE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ech_dg_args {
+    int64_t ncell;            /* cells owned by this rank (rows are assembled for these) */
+    int64_t ncell_total;      /* owned + ghost cells (state/geometry arrays cover these)  */
+    const double *xcell;      /* [ncell_total][2^d][d] vertex coordinates per cell        */
+    const int32_t *nbr;       /* [ncell][2d]  neighbour cell, or -(1+class) on the boundary */
+    const uint8_t *code;      /* [ncell][2d]  neighbour local facet | orientation << 3     */
+    const uint8_t *slot;      /* [ncell][2d]  column-block rank of the neighbour in a row   */
+    const uint8_t *slot_self; /* [ncell]                                                    */
+    const uint8_t *ncol;      /* [ncell]      number of cell blocks per coupled field       */
+    const double *cell_volume;/* [ncell_total]                                              */
+    const double *cell_diam;  /* [ncell_total]                                              */
+    const double *facet_area; /* [ncell][2d]                                                */
+    const double *u;          /* [nf][ncell_total * n] state, field-blocked                 */
+    const double *aux;        /* [naux][ncell_total * n] data fields                        */
+    const double *consts;     /* [nconst] runtime constants                                 */
+    const int64_t *rowptr;    /* [nf * ncell * n + 1] (Jacobian only)                       */
+    double *out;              /* residual [nf][ncell*n]  or CSR values [nnz]                */
+} ech_dg_args;
+
+/* info[0..7] = d, p, nf, naux, nconst, nq, nclasses, family(1=DG); then nf*nf own-block flags,
+ * nf*nf neighbour-block flags. Returns the number of ints written. */
+int ech_mod_describe(int32_t *info, int capacity);
+int ech_mod_residual(const ech_dg_args *a, void *stream);
+int ech_mod_jacobian(const ech_dg_args *a, void *stream);
+/* number of kernel launches one residual / Jacobian call makes */
+int ech_mod_launches(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

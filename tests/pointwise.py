@@ -35,8 +35,11 @@ def _value(name, dat):
     return dat["g" + kind + side][j][:, comp]
 
 
-def evaluate(expr, dat):
+def evaluate(expr, dat, form=None):
     expr = sp.sympify(expr)
+    if form is not None:
+        expr = expr.xreplace({sp.Symbol(b, real=True): sp.Symbol(a, real=True)
+                              for a, b in zip(form.const_source, form.const_names)})
     syms = sorted(expr.free_symbols, key=str)
     npts = dat["x"].shape[0]
     if not syms:

@@ -37,33 +37,33 @@ def test_adm_dg_pointwise(vavg):
     # cell
     f0, f1 = prob.cell(x, u, gu, {"cell_volume": dat["cv"][None], "cell_diameter": dat["cd"][None]})
     for i in range(2):
-        assert _close(evaluate(cf.cell["f0"][i], dat), f0[i][0])
+        assert _close(evaluate(cf.cell["f0"][i], dat, cf), f0[i][0])
         for k in range(2):
-            assert _close(evaluate(cf.cell["f1"][i][k], dat), f1[i][0, :, k])
+            assert _close(evaluate(cf.cell["f1"][i][k], dat, cf), f1[i][0, :, k])
     # interior facet, '+' side test functions
     geop = {"cell_volume": dat["cv"][None], "facet_area": dat["fa"][None]}
     geom = {"cell_volume": dat["cvm"][None], "facet_area": dat["fa"][None]}
     f0p, f1p, f0m, f1m = prob.interior_facet(x, n, u, gu, um, gum, geop, geom)
     for i in range(2):
-        assert _close(evaluate(cf.int["f0"][i], dat), f0p[i][0])
+        assert _close(evaluate(cf.int["f0"][i], dat, cf), f0p[i][0])
         for k in range(2):
-            assert _close(evaluate(cf.int["f1"][i][k], dat), f1p[i][0, :, k])
+            assert _close(evaluate(cf.int["f1"][i][k], dat, cf), f1p[i][0, :, k])
     # +/- swap symmetry: the '-' rows are the '+' rows of the swapped facet
     sw = dict(dat)
     sw.update({"u": dat["um"], "um": dat["u"], "gu": dat["gum"], "gum": dat["gu"],
                "cv": dat["cvm"], "cvm": dat["cv"], "n": -dat["n"], "a": dat["am"], "am": dat["a"]})
     for i in range(2):
-        assert _close(evaluate(cf.int["f0"][i], sw), f0m[i][0])
+        assert _close(evaluate(cf.int["f0"][i], sw, cf), f0m[i][0])
         for k in range(2):
-            assert _close(evaluate(cf.int["f1"][i][k], sw), f1m[i][0, :, k])
+            assert _close(evaluate(cf.int["f1"][i][k], sw, cf), f1m[i][0, :, k])
     # exterior facets, every marker
     for marker in (1, 2, 3, 4):
         cls = cf.marker_class[marker]
         g0, g1 = prob.exterior_facet(marker, x, n, u, gu, geop, {"U_app": dat["a"][0][None]})
         for i in range(2):
-            assert _close(evaluate(cf.ext[cls]["f0"][i], dat), g0[i][0])
+            assert _close(evaluate(cf.ext[cls]["f0"][i], dat, cf), g0[i][0])
             for k in range(2):
-                assert _close(evaluate(cf.ext[cls]["f1"][i][k], dat), g1[i][0, :, k])
+                assert _close(evaluate(cf.ext[cls]["f1"][i][k], dat, cf), g1[i][0, :, k])
 
 
 def test_block_masks_match_oracle():

@@ -1,0 +1,79 @@
+"""CUDA assembly vs oracle: sparsity bit-exact, residual and Jacobian entries to 1e-12 (north_star tolerance).
+
+Entry tolerance: |a - b| <= 1e-12 * max(|a|, |b|, tau) with tau the largest
+magnitude in the compared array block (pure relative error is meaningless for entries that
+cancel to ~0).
+"""
+import numpy as np
+import pytest
+import torch
+
+import mms_cases
+import product_cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _state(disc, seed=0):
+    """Nodal interpolant of the exact fields + deterministic perturbation."""
+    x = disc.node_coords
+    pert = 1e-3 * np.sin(7 * x[:, 0] + 3 * x[:, 1])
+    return np.concatenate([mms_cases.C1ex(x) + pert, mms_cases.Uex(x) - pert])
+
+
+def _assert_close(a, b, what):
+    tau = max(np.abs(a).max(), np.abs(b).max())
+    err = np.abs(a - b).max()
+    assert err <= RTOL * tau * 10, "%s: max abs err %.3e vs scale %.3e" % (what, err, tau)
+
+
+@pytest.mark.parametrize("N,vavg", [(1, 1.0), (3, 1.0), (6, 1e5)])
+def test_adm_dg_q1_assembly_matches_oracle(N, vavg):
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    from echemfem_b200.newton import NewtonEngine
+
+    disc = Discretization(unit_square_mesh(N), mms_cases.adm_problem(vavg))
+    s = product_cases.AdvectionDiffusionMigrationSolver(N, vavg)
+    eng = NewtonEngine(s)
+    u = _state(disc)
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+
+    # sparsity: bit-exact
+    indptr, indices = disc.pattern()
+    rp, ci, _ = eng.csr_host()
+    assert np.array_equal(rp, indptr)
+    assert np.array_equal(ci, indices)
+
+    F = eng.residual(s.u.tensor).cpu().numpy()
+    _assert_close(F, disc.residual(u), "residual")
+
+    eng.jacobian(s.u.tensor)
+    vals = eng.vals.cpu().numpy()
+    J = disc.jacobian(u)
+    _assert_close(vals, J.data, "jacobian")
+
+    # SpMV against scipy on the same matrix
+    x = np.cos(np.arange(disc.ndof) * 0.37)
+    y = torch.empty(disc.ndof, dtype=torch.float64, device="cuda")
+    eng.spmv(torch.from_numpy(x).cuda(), y)
+    _assert_close(y.cpu().numpy(), J @ x, "spmv")
+
+
+def test_newton_solution_matches_oracle():
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    from oracle.newton import solve_problem
+
+    N = 8
+    disc = Discretization(unit_square_mesh(N), mms_cases.adm_problem(1.0))
+    u_ref, info = solve_problem(disc)
+    s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0)
+    s.setup_solver()
+    s.solve()
+    u = s.u.numpy()
+    Ns = disc.ndof_scalar
+    for f in range(2):
+        a, b = u[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
+        assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
