@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Headline benchmark: residual + Jacobian assembly throughput (MDOF/s) of the DG Nernst-Planck MMS case.
+
+Workload (BASELINE.json configs[1]; SURVEY.md 8d "cfg2"): 2D electroneutral Nernst-Planck MMS,
+UnitSquareMesh(N, N) quadrilaterals, DG Q1, fields (C1, Phi), D = (0.5e-5, 1e-5) as in
+examples/mms_scaling.py:90-93, N = 1408 -> 15.86 M dofs, 634 M non-zeros.
+State: nodal interpolant of the exact fields + 1e-3 sin(7x + 3y).
+
+One "step" = one residual evaluation + one Jacobian evaluation (what SNES does once per Newton
+iteration, echemfem/solver.py:725).  Prints ONE JSON line (see the task contract).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "assembly_throughput_residual_plus_jacobian"
+UNIT = "MDOF/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(mesh, nf, nloc, nnz):
+    ndof = nf * mesh.num_cells * nloc
+    nvert = mesh.coords.shape[0]
+    d = mesh.dim
+    BJ = 8 * nnz + 8 * ndof + 8 * d * nvert + 10 * mesh.num_interior_facets + 5 * mesh.num_exterior_facets
+    BF = 16 * ndof + 8 * d * nvert + 10 * mesh.num_interior_facets + 5 * mesh.num_exterior_facets
+    BS = 12 * nnz + 20 * ndof + 4
+    return BJ, BF, BS
+
+
+def cpu_baseline(sample_n, reps=1):
+    """The oracle (numpy port of the reference algorithm) on this host: residual + Jacobian, one core."""
+    import mms_cases
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    import numpy as np
+    disc = Discretization(unit_square_mesh(sample_n), mms_cases.adm_problem(1.0, D1=0.5e-5, D2=1.0e-5))
+    x = disc.node_coords
+    u = np.concatenate([mms_cases.C1ex(x), mms_cases.Uex(x)]) + 1e-3 * np.tile(np.sin(7 * x[:, 0] + 3 * x[:, 1]), 2)
+    disc.block_mask()
+    disc.pattern()
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        disc.residual(u)
+        disc.jacobian(u)
+        best = min(best, time.perf_counter() - t0)
+    return disc.ndof / best / 1e6, best, disc.ndof
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.sample_n
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(n)
+    t0 = time.perf_counter()
+    ndof = 0
+    for _ in range(args.steps):
+        v, t, ndof = cpu_baseline(n)
+        vals.append(t)
+    total = time.perf_counter() - t0
+    value = ndof * args.steps / sum(vals) / 1e6
+    sample = "UnitSquareMesh(%d,%d) DG Q1, %d dofs per step (numpy oracle, complex-step Jacobian)" % (n, n, ndof)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(vals) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2 MMS 2D DG Q1 electroneutral Nernst-Planck (bounded CPU sample)",
+                       "sample_N": n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": total}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--N", type=int, default=1408, help="cells per direction (cfg2 P1: 1408)")
+    ap.add_argument("--sample-n", dest="sample_n", type=int, default=96, help="CPU baseline sample mesh")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time SpMV")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import ctypes as C
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import product_cases
+    from echemfem_b200.newton import NewtonEngine
+    from echemfem_b200 import capi
+    from echemfem_b200.capi import ptr
+
+    W = max(args.warmup, 3)
+    N = args.N
+    # one mesh replica per rank: the path shards by cells; per-GPU work is fixed (weak scaling)
+    s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5)
+    eng = NewtonEngine(s)
+    mesh = s.mesh
+    x = s.V.node_coords()
+    pert = 1e-3 * np.sin(7 * x[:, 0] + 3 * x[:, 1])
+    u_host = np.concatenate([np.cos(x[:, 0]) + np.sin(x[:, 1]) + 3 + pert, np.sin(x[:, 0]) + np.cos(x[:, 1]) + 3 + pert])
+    u = s.u.tensor
+    u.copy_(torch.from_numpy(u_host).cuda())
+    aux = eng._aux_tensor()
+    consts = eng._consts()
+    lib = eng.lib
+    st = eng._stream()
+    ndof = eng.ndof
+
+    def step():
+        capi.check(lib.ech_residual(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.F), st), eng.h)
+        capi.check(lib.ech_jacobian(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr), ptr(eng.vals), st), eng.h)
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+
+    # per-kernel timings (events on the launching stream)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    launches0 = lib.ech_launch_count(eng.h)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        evs[k][0].record()
+        capi.check(lib.ech_residual(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.F), st), eng.h)
+        evs[k][1].record()
+        capi.check(lib.ech_jacobian(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr), ptr(eng.vals), st), eng.h)
+        evs[k][2].record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = lib.ech_launch_count(eng.h) - launches0
+    tF = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    tJ = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    t_step = evs[0][0].elapsed_time(evs[-1][2]) / args.steps
+
+    # end to end through the host-buffer C ABI: pinned host state in, residual out, every step
+    uh = torch.from_numpy(u_host).pin_memory()
+    Fh = torch.empty(ndof, dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        capi.check(lib.ech_assemble_host(eng.h, ptr(uh), ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr),
+                                         ptr(eng.vals), ptr(eng.F), ptr(Fh), st), eng.h)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        capi.check(lib.ech_assemble_host(eng.h, ptr(uh), ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr),
+                                         ptr(eng.vals), ptr(eng.F), ptr(Fh), st), eng.h)
+    e1.record()
+    torch.cuda.synchronize()
+    t_e2e = e0.elapsed_time(e1) / args.steps
+
+    extras = {}
+    if args.extras:
+        xv = torch.from_numpy(np.cos(np.arange(ndof) * 0.37)).cuda()
+        yv = torch.empty_like(xv)
+        for _ in range(3):
+            eng.spmv(xv, yv)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            eng.spmv(xv, yv)
+        a1.record()
+        torch.cuda.synchronize()
+        extras["spmv_ms"] = a0.elapsed_time(a1) / args.steps
+
+    times = torch.tensor([t_step, tF, tJ, t_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_step, tF, tJ, t_e2e = [float(v) for v in times.cpu()]
+
+    if rank == 0:
+        BJ, BF, BS = algorithmic_bytes(mesh, eng.nf, eng.nloc, eng.nnz)
+        peak, peak_src = measured_peak()
+        achieved = BJ / (tJ * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * ndof / (t_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2 MMS 2D DG Q1 electroneutral Nernst-Planck, UnitSquareMesh(%d,%d) quads" % (N, N),
+                       "cells_per_gpu": mesh.num_cells, "dofs_per_gpu": ndof, "nnz_per_gpu": eng.nnz,
+                       "l2_policy": "outputs (%.1f GB CSR values) exceed the 126 MB L2 every step" % (8 * eng.nnz / 1e9),
+                       "parallelism": "one mesh replica per GPU, no data-path collective (halo exchange not in round 1)"},
+            "residual_ms": tF, "jacobian_ms": tJ,
+            "residual_MDOFs": ndof / (tF * 1e-3) / 1e6, "jacobian_MDOFs": ndof / (tJ * 1e-3) / 1e6,
+            "roofline": {"bound": "hbm", "kernel": "jacobian_kernel<I> (%d launches per step)" % eng.nf,
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "algorithmic_bytes": BJ, "traffic": None,
+                         "residual_achieved_GBs": BF / (tF * 1e-3) / 1e9},
+            "e2e": {"value": world * ndof / (t_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": t_e2e,
+                    "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
+            "module_compile_s": eng.t_compile,
+        }
+        line.update(extras)
+        if extras.get("spmv_ms"):
+            line["spmv_GBs"] = BS / (extras["spmv_ms"] * 1e-3) / 1e9
+        if not args.no_cpu:
+            v, t, nd = cpu_baseline(args.sample_n)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "UnitSquareMesh(%d,%d) DG Q1, %d dofs, one residual + one Jacobian "
+                                              "(numpy oracle, complex-step Jacobian), %.1f s" % (args.sample_n, args.sample_n, nd, t)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

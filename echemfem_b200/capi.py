@@ -33,6 +33,7 @@ EXPORTS = {
     "ech_destroy": (None, [c_p]),
     "ech_last_error": (C.c_char_p, [c_p]),
     "ech_describe": (C.c_int, [c_p, C.POINTER(c_i32), C.c_int]),
+    "ech_cell_geometry": (C.c_int, [c_i32, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "ech_num_rows": (C.c_int, [c_p, C.POINTER(c_i64)]),
     "ech_pattern_rowptr": (C.c_int, [c_p, c_p, C.POINTER(c_i64), c_p]),
     "ech_pattern_colidx": (C.c_int, [c_p, c_p, c_p, c_p]),

@@ -240,6 +240,117 @@ extern "C" int ech_pattern_colidx(ech_handle *h, const int64_t *rowptr, int32_t 
     return ECH_OK;
 }
 
+// =============================================================== cell geometry
+// CellVolume / FacetArea / CellDiameter of multilinear cells: 3-point Gauss per
+// direction (exact for multilinear maps with planar facets), largest vertex distance.
+template <int D>
+__global__ void cell_geometry_kernel(int64_t ncell, const double *__restrict__ xcell, double *__restrict__ vol,
+                                     double *__restrict__ area, double *__restrict__ diam) {
+    constexpr int NV = 1 << D;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    double X[NV][D];
+    for (int v = 0; v < NV; ++v)
+        for (int a = 0; a < D; ++a) X[v][a] = xcell[(c * NV + v) * D + a];
+    const double gp[3] = {0.5 - 0.5 * 0.7745966692414834, 0.5, 0.5 + 0.5 * 0.7745966692414834};
+    const double gw[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+    auto jac = [&](const double (&xi)[D], double (&J)[D][D]) {
+        for (int a = 0; a < D; ++a)
+            for (int m = 0; m < D; ++m) J[a][m] = 0.0;
+        for (int v = 0; v < NV; ++v) {
+            double dN[D];
+            for (int m = 0; m < D; ++m) dN[m] = 1.0;
+            for (int k = 0; k < D; ++k) {
+                const bool bit = (v >> (D - 1 - k)) & 1;
+                const double val = bit ? xi[k] : 1.0 - xi[k];
+                for (int m = 0; m < D; ++m) dN[m] *= (m == k) ? (bit ? 1.0 : -1.0) : val;
+            }
+            for (int a = 0; a < D; ++a)
+                for (int m = 0; m < D; ++m) J[a][m] += dN[m] * X[v][a];
+        }
+    };
+    auto det_and_cof = [&](const double (&J)[D][D], int k, double &det, double &cofnorm) {
+        // cofnorm = |det| * |J^{-T} e_k| = norm of the k-th cofactor column
+        if constexpr (D == 2) {
+            det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            const double c0 = (k == 0) ? J[1][1] : -J[1][0];
+            const double c1 = (k == 0) ? -J[0][1] : J[0][0];
+            cofnorm = sqrt(c0 * c0 + c1 * c1);
+        } else {
+            double cf[3][3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                    cf[i][j] = J[i1][j1] * J[i2][j2] - J[i1][j2] * J[i2][j1];
+                }
+            det = J[0][0] * cf[0][0] + J[0][1] * cf[0][1] + J[0][2] * cf[0][2];
+            cofnorm = sqrt(cf[0][k] * cf[0][k] + cf[1][k] * cf[1][k] + cf[2][k] * cf[2][k]);
+        }
+    };
+    constexpr int NQ3 = (D == 2) ? 9 : 27;
+    double v = 0.0;
+    for (int q = 0; q < NQ3; ++q) {
+        double xi[D], w = 1.0, J[D][D], det, cn;
+        int r = q;
+        for (int k = D - 1; k >= 0; --k) {
+            xi[k] = gp[r % 3];
+            w *= gw[r % 3];
+            r /= 3;
+        }
+        jac(xi, J);
+        det_and_cof(J, 0, det, cn);
+        v += w * fabs(det);
+    }
+    vol[c] = v;
+    constexpr int NQF3 = (D == 2) ? 3 : 9;
+    for (int lf = 0; lf < 2 * D; ++lf) {
+        const int kf = lf >> 1;
+        double s = 0.0;
+        for (int q = 0; q < NQF3; ++q) {
+            double xi[D], w = 1.0, J[D][D], det, cn;
+            int r = q;
+            for (int k = D - 1; k >= 0; --k) {
+                if (k == kf) {
+                    xi[k] = (double)(lf & 1);
+                } else {
+                    xi[k] = gp[r % 3];
+                    w *= gw[r % 3];
+                    r /= 3;
+                }
+            }
+            jac(xi, J);
+            det_and_cof(J, kf, det, cn);
+            s += w * cn;
+        }
+        area[c * 2 * D + lf] = s;
+    }
+    double dm = 0.0;
+    for (int a = 0; a < NV; ++a)
+        for (int b = a + 1; b < NV; ++b) {
+            double d2 = 0.0;
+            for (int k = 0; k < D; ++k) d2 += (X[a][k] - X[b][k]) * (X[a][k] - X[b][k]);
+            dm = fmax(dm, d2);
+        }
+    diam[c] = sqrt(dm);
+}
+
+extern "C" int ech_cell_geometry(int32_t dim, int64_t ncell, const double *xcell, double *vol, double *area,
+                                 double *diam, void *stream) {
+    if (!xcell || !vol || !area || !diam) return fail(nullptr, ECH_ERR_ARG, "ech_cell_geometry: null argument");
+    if (ncell == 0) return ECH_OK;
+    const int block = 128;
+    const unsigned grid = (unsigned)((ncell + block - 1) / block);
+    if (dim == 2)
+        cell_geometry_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(ncell, xcell, vol, area, diam);
+    else if (dim == 3)
+        cell_geometry_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(ncell, xcell, vol, area, diam);
+    else
+        return fail(nullptr, ECH_ERR_ARG, "ech_cell_geometry: dim must be 2 or 3");
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== SNES callbacks
 static void fill_args(const ech_handle *h, ech_dg_args &a) {
     const ech_mesh_desc &m = h->mesh;

@@ -22,7 +22,6 @@ import torch
 from . import build, capi
 from .capi import ptr
 from .compiler import CompiledForm
-from .mesh import cell_geometry
 
 
 class ConvergenceError(RuntimeError):
@@ -84,12 +83,16 @@ class NewtonEngine:
     def _upload_mesh(self, mesh):
         dev = self.dev
         nbr, code, slot, slot_self, ncol = mesh.connectivity(self.form.marker_class)
-        vol, area, diam = cell_geometry(mesh)
         f = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
+        nc = mesh.num_cells
         self.m = {
             "xcell": f(mesh.cell_coords(), torch.float64), "nbr": f(nbr, torch.int32), "code": f(code, torch.uint8),
             "slot": f(slot, torch.uint8), "slot_self": f(slot_self, torch.uint8), "ncol": f(ncol, torch.uint8),
-            "vol": f(vol, torch.float64), "diam": f(diam, torch.float64), "area": f(area, torch.float64)}
+            "vol": torch.empty(nc, dtype=torch.float64, device=dev),
+            "diam": torch.empty(nc, dtype=torch.float64, device=dev),
+            "area": torch.empty(nc * 2 * mesh.dim, dtype=torch.float64, device=dev)}
+        capi.check(self.lib.ech_cell_geometry(mesh.dim, nc, ptr(self.m["xcell"]), ptr(self.m["vol"]),
+                                              ptr(self.m["area"]), ptr(self.m["diam"]), self._stream()))
 
     def _create(self):
         mesh = self.solver.mesh

@@ -65,6 +65,11 @@ const char *ech_last_error(const ech_handle *h);
 /* d, p, nf, naux, nconst, nq, nclasses, family, own[nf*nf], nbr[nf*nf] */
 int ech_describe(const ech_handle *h, int32_t *info, int capacity);
 
+/* CellVolume / FacetArea / CellDiameter of every cell (the UFL geometric quantities of
+ * solver.py:1491, 1657) from the per-cell vertex coordinates [ncell][2^dim][dim]. */
+int ech_cell_geometry(int32_t dim, int64_t ncell, const double *xcell, double *vol, double *area, double *diam,
+                      void *stream);
+
 /* -- sparsity (PyOP2 Sparsity + MatSeqAIJ preallocation; "mat_type": "aij", solver.py:943) */
 int ech_num_rows(const ech_handle *h, int64_t *nrows);
 /* fills rowptr[nrows+1]; *nnz_host receives the total. Synchronises the stream. */
