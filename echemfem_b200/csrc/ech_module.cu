@@ -2,7 +2,7 @@
 // Built by echemfem_b200/build.py as
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
 //        -include <generated header> ech_module.cu -o libech_phys_<key>.so
-#include "ech_dg.cuh"
+#include "ech_dg_coop.cuh"
 
 extern "C" {
 
@@ -26,14 +26,24 @@ int ech_mod_describe(int32_t *info, int capacity) {
     return need;
 }
 
+// variant 0 (default): cooperative kernels (one cell per NLOC lanes, shared quadrature work);
+// variant 1: row-per-thread kernels (kept for elements with more than 32 local nodes and as a cross-check)
+static int g_variant = 0;
+
+void ech_mod_set_variant(int v) { g_variant = v; }
+
+static bool use_coop() { return echdg::COOP_OK && g_variant == 0; }
+
 int ech_mod_residual(const ech_dg_args *a, void *stream) {
+    if (use_coop()) return echdg::launch_residual_coop(a, (cudaStream_t)stream);
     return echdg::launch_residual(a, (cudaStream_t)stream);
 }
 
 int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
+    if (use_coop()) return echdg::launch_jacobian_coop(a, (cudaStream_t)stream);
     return echdg::launch_jacobian(a, (cudaStream_t)stream);
 }
 
-int ech_mod_launches(int which) { return which == 0 ? 1 : echgen::NF; }
+int ech_mod_launches(int which) { return (which == 0 || use_coop()) ? 1 : echgen::NF; }
 
 }  // extern "C"

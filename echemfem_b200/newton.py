@@ -105,6 +105,13 @@ class NewtonEngine:
         capi.check(self.lib.ech_create(self.module.encode(), C.byref(self.desc), C.byref(h)))
         self.h = h
 
+    def set_variant(self, v):
+        """0: cooperative kernels (default); 1: row-per-thread kernels (cross-check / large elements)."""
+        mod = C.CDLL(self.module)
+        mod.ech_mod_set_variant.argtypes = [C.c_int]
+        mod.ech_mod_set_variant.restype = None
+        mod.ech_mod_set_variant(int(v))
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

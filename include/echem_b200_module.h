@@ -40,6 +40,8 @@ typedef struct ech_dg_args {
 int ech_mod_describe(int32_t *info, int capacity);
 int ech_mod_residual(const ech_dg_args *a, void *stream);
 int ech_mod_jacobian(const ech_dg_args *a, void *stream);
+/* 0: cooperative kernels (default), 1: row-per-thread kernels */
+void ech_mod_set_variant(int variant);
 /* number of kernel launches one residual / Jacobian call makes */
 int ech_mod_launches(int which);
 

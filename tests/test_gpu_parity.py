@@ -28,8 +28,9 @@ def _assert_close(a, b, what):
     assert err <= RTOL * tau * 10, "%s: max abs err %.3e vs scale %.3e" % (what, err, tau)
 
 
-@pytest.mark.parametrize("N,vavg", [(1, 1.0), (3, 1.0), (6, 1e5)])
-def test_adm_dg_q1_assembly_matches_oracle(N, vavg):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("N,vavg", [(1, 1.0), (3, 1.0), (6, 1e5), (11, 1.0)])
+def test_adm_dg_q1_assembly_matches_oracle(N, vavg, variant):
     from oracle.mesh import unit_square_mesh
     from oracle.assemble import Discretization
     from echemfem_b200.newton import NewtonEngine
@@ -37,6 +38,7 @@ def test_adm_dg_q1_assembly_matches_oracle(N, vavg):
     disc = Discretization(unit_square_mesh(N), mms_cases.adm_problem(vavg))
     s = product_cases.AdvectionDiffusionMigrationSolver(N, vavg)
     eng = NewtonEngine(s)
+    eng.set_variant(variant)
     u = _state(disc)
     s.u.tensor.copy_(torch.from_numpy(u).cuda())
 
@@ -59,6 +61,7 @@ def test_adm_dg_q1_assembly_matches_oracle(N, vavg):
     y = torch.empty(disc.ndof, dtype=torch.float64, device="cuda")
     eng.spmv(torch.from_numpy(x).cuda(), y)
     _assert_close(y.cpu().numpy(), J @ x, "spmv")
+    eng.set_variant(0)
 
 
 def test_newton_solution_matches_oracle():
