@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 MODDIR = os.path.join(LIBDIR, "modules")
 CORE_LIB = os.path.join(LIBDIR, "libechem_b200.so")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-shared", "-Xcompiler", "-fPIC", "-I" + INCLUDE, "-I" + CSRC]
 
 
@@ -61,14 +61,18 @@ def skeleton_hash():
     return h.hexdigest()[:8]
 
 
-def module_path(key):
-    return os.path.join(MODDIR, "libech_phys_%s_%s.so" % (key, skeleton_hash()))
+def module_path(key, extra_flags=()):
+    tag = skeleton_hash()
+    if extra_flags:
+        tag += "_" + hashlib.sha1(" ".join(extra_flags).encode()).hexdigest()[:6]
+    return os.path.join(MODDIR, "libech_phys_%s_%s.so" % (key, tag))
 
 
 def build_module(header_text, key, force=False, extra_flags=()):
     """Compile one physics module; returns the path of the shared object."""
     os.makedirs(MODDIR, exist_ok=True)
-    out = module_path(key)
+    extra_flags = tuple(extra_flags) or tuple(os.environ.get("ECH_MODULE_FLAGS", "").split())
+    out = module_path(key, extra_flags)
     if os.path.exists(out) and not force:
         return out
     hdr = os.path.join(MODDIR, "ech_gen_%s.cuh" % key)

@@ -28,35 +28,73 @@ constexpr int CPW = COOP_OK ? 32 / NLOC : 1;           // cells per warp
 constexpr int NTASK = NQC + NLF * NQF;
 constexpr int NROUND = (NTASK + G - 1) / G;
 
-// record layout (in doubles)
-constexpr int ROWJ_LEN = NF * (1 + 2 * D + D * D);
+// ---- record layout (in doubles).  A record holds the trial bases of both sides followed by the
+// weight-scaled coefficients g0..g3 of every equation, COMPACTED by the compile-time coupling masks.
+template <class M>
+struct Layout {
+    int o0[NF][NF], o1[NF][NF], o2[NF][NF], o3[NF][NF];
+    int len;
+    __host__ __device__ constexpr Layout() : o0{}, o1{}, o2{}, o3{}, len(0) {
+        int n = 0;
+        for (int i = 0; i < NF; ++i)
+            for (int j = 0; j < NF; ++j) {
+                o0[i][j] = o1[i][j] = o2[i][j] = o3[i][j] = -1;
+                if (M::G0[i][j]) { o0[i][j] = n; n += 1; }
+                if (M::G1[i][j]) { o1[i][j] = n; n += D; }
+                if (M::G2[i][j]) { o2[i][j] = n; n += D; }
+                if (M::G3[i][j] == 1) { o3[i][j] = n; n += 1; }
+                if (M::G3[i][j] == 2) { o3[i][j] = n; n += D * D; }
+            }
+        len = n;
+    }
+};
+constexpr Layout<MC> LAY_C{};
+constexpr Layout<ME> LAY_E{};
+constexpr Layout<MIP> LAY_IP{};
+constexpr Layout<MIM> LAY_IM{};
+template <class M> struct LayoutOf;
+template <> struct LayoutOf<MC> { static __host__ __device__ constexpr const Layout<MC> &get() { return LAY_C; } };
+template <> struct LayoutOf<ME> { static __host__ __device__ constexpr const Layout<ME> &get() { return LAY_E; } };
+template <> struct LayoutOf<MIP> { static __host__ __device__ constexpr const Layout<MIP> &get() { return LAY_IP; } };
+template <> struct LayoutOf<MIM> { static __host__ __device__ constexpr const Layout<MIM> &get() { return LAY_IM; } };
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int OFF_PHI = 0;
 constexpr int OFF_GPHI = NLOC;
 constexpr int OFF_PHI2 = NLOC * (1 + D);
 constexpr int OFF_GPHI2 = NLOC * (2 + D);
 constexpr int OFF_JP = 2 * NLOC * (1 + D);
-constexpr int OFF_JM = OFF_JP + NF * ROWJ_LEN;
-constexpr int JREC_LEN = (OFF_JM + NF * ROWJ_LEN) | 1;
-constexpr int RREC_LEN = (NLOC * (1 + D) + NF * (1 + D)) | 1;
+constexpr int OFF_JM = OFF_JP + LAY_IP.len;
+constexpr int JREC_LEN = OFF_JP + cmax(cmax(LAY_C.len, LAY_E.len), LAY_IP.len + LAY_IM.len);
+constexpr int RREC_LEN = NLOC * (1 + D) + NF * (1 + D);
 
-__host__ __device__ constexpr int o_g0(int j) { return j; }
-__host__ __device__ constexpr int o_g1(int j, int l) { return NF + j * D + l; }
-__host__ __device__ constexpr int o_g2(int j, int k) { return NF + NF * D + j * D + k; }
-__host__ __device__ constexpr int o_g3(int j, int k, int l) { return NF + 2 * NF * D + (j * D + k) * D + l; }
+// neighbour data staged per (cell, facet): vertex coordinates, state, aux, volume, diameter
+constexpr int NBD_X = 0;
+constexpr int NBD_U = NV * D;
+constexpr int NBD_A = NBD_U + NF * NLOC;
+constexpr int NBD_CV = NBD_A + ECH_NAUX * NLOC;
+constexpr int NBD_LEN = (NBD_CV + 2) | 1;
+// per-cell facet metadata (ints): nbr, code, slot
+constexpr int META_LEN = 3 * NLF;
 
+__host__ __device__ constexpr int warp_smem_doubles(int reclen) { return reclen * 32 + CPW * NLF * NBD_LEN + (CPW * META_LEN + 1) / 2; }
 constexpr int coop_warps(int reclen) {
-    const int per_warp = reclen * 32 * 8;               // bytes: G * CPW <= 32 records
-    int w = (100 * 1024) / per_warp;
+    const int per_warp = warp_smem_doubles(reclen) * 8;
+#ifdef ECH_COOP_WARPS
+    return ECH_COOP_WARPS + 0 * per_warp;
+#else
+    int w = (56 * 1024) / per_warp;
     return w < 1 ? 1 : (w > 4 ? 4 : w);
+#endif
 }
 constexpr int JWARPS = coop_warps(JREC_LEN);
 constexpr int RWARPS = coop_warps(RREC_LEN);
 
-// accessor of one record: field k of (slot s, cell g) of this warp
+// accessor of one record: field k of (slot s, cell g) lives at k*32 + s*CPW + g, so that the lanes of
+// a warp write / read consecutive words (no bank conflicts; same-cell lanes broadcast)
 struct RecRef {
     double *base;   // warp base + g
-    int reclen;
-    __device__ __forceinline__ double &operator()(int slot, int k) const { return base[(slot * reclen + k) * CPW]; }
+    __device__ __forceinline__ double &operator()(int slot, int k) const { return base[k * 32 + slot * CPW]; }
 };
 
 // evaluation context of one lane
@@ -70,21 +108,24 @@ template <class M, int I>
 __device__ __forceinline__ void put_rowj(const RecRef &R, int slot, int off, const RowJ &r, double w) {
     static_for<0, NF>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
-        if constexpr (M::G0[I][j]) R(slot, off + o_g0(j)) = w * r.g0[j];
-        if constexpr (M::G1[I][j]) {
+        constexpr int p0 = LayoutOf<M>::get().o0[I][j], p1 = LayoutOf<M>::get().o1[I][j];
+        constexpr int p2 = LayoutOf<M>::get().o2[I][j], p3 = LayoutOf<M>::get().o3[I][j];
+        constexpr int h3 = M::G3[I][j];
+        if constexpr (p0 >= 0) R(slot, off + p0) = w * r.g0[j];
+        if constexpr (p1 >= 0) {
 #pragma unroll
-            for (int l = 0; l < D; ++l) R(slot, off + o_g1(j, l)) = w * r.g1[j][l];
+            for (int l = 0; l < D; ++l) R(slot, off + p1 + l) = w * r.g1[j][l];
         }
-        if constexpr (M::G2[I][j]) {
+        if constexpr (p2 >= 0) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) R(slot, off + o_g2(j, k)) = w * r.g2[j][k];
+            for (int k = 0; k < D; ++k) R(slot, off + p2 + k) = w * r.g2[j][k];
         }
-        if constexpr (M::G3[I][j] == 1) R(slot, off + o_g3(j, 0, 0)) = w * r.g3[j][0][0];
-        if constexpr (M::G3[I][j] == 2) {
+        if constexpr (h3 == 1) R(slot, off + p3) = w * r.g3[j][0][0];
+        if constexpr (h3 == 2) {
 #pragma unroll
             for (int k = 0; k < D; ++k)
 #pragma unroll
-                for (int l = 0; l < D; ++l) R(slot, off + o_g3(j, k, l)) = w * r.g3[j][k][l];
+                for (int l = 0; l < D; ++l) R(slot, off + p3 + k * D + l) = w * r.g3[j][k][l];
         }
     });
 }
@@ -99,48 +140,50 @@ __device__ __forceinline__ void put_basis(const RecRef &R, int slot, int off_phi
     }
 }
 
-// rows (I, a) += record, for the trial basis stored at (off_phi, off_gphi) and coefficients at off
+// rows (I, a) += record, for the trial basis (phi, gphi) and the coefficients stored at off
 template <class M, int I>
 __device__ __forceinline__ void take_rowj(const RecRef &R, int slot, int off, double phia, const double (&gphia)[D],
                                           const double (&phi)[NLOC], const double (&gphi)[NLOC][D],
                                           double (&acc)[NF][NLOC]) {
     static_for<0, NF>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
-        constexpr bool h0 = M::G0[I][j], h1 = M::G1[I][j], h2 = M::G2[I][j];
+        constexpr int p0 = LayoutOf<M>::get().o0[I][j], p1 = LayoutOf<M>::get().o1[I][j];
+        constexpr int p2 = LayoutOf<M>::get().o2[I][j], p3 = LayoutOf<M>::get().o3[I][j];
+        constexpr bool h0 = p0 >= 0, h1 = p1 >= 0, h2 = p2 >= 0;
         constexpr int h3 = M::G3[I][j];
         if constexpr (h0 || h1 || h2 || h3 != 0) {
             double Aj = 0.0, Bj[D];
 #pragma unroll
             for (int l = 0; l < D; ++l) Bj[l] = 0.0;
-            if constexpr (h0) Aj += R(slot, off + o_g0(j)) * phia;
+            if constexpr (h0) Aj += R(slot, off + p0) * phia;
             if constexpr (h2) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) Aj += R(slot, off + o_g2(j, k)) * gphia[k];
+                for (int k = 0; k < D; ++k) Aj += R(slot, off + p2 + k) * gphia[k];
             }
             if constexpr (h1) {
 #pragma unroll
-                for (int l = 0; l < D; ++l) Bj[l] += R(slot, off + o_g1(j, l)) * phia;
+                for (int l = 0; l < D; ++l) Bj[l] += R(slot, off + p1 + l) * phia;
             }
             if constexpr (h3 == 1) {
-                const double s = R(slot, off + o_g3(j, 0, 0));
+                const double sc = R(slot, off + p3);
 #pragma unroll
-                for (int l = 0; l < D; ++l) Bj[l] += s * gphia[l];
+                for (int l = 0; l < D; ++l) Bj[l] += sc * gphia[l];
             }
             if constexpr (h3 == 2) {
 #pragma unroll
                 for (int l = 0; l < D; ++l)
 #pragma unroll
-                    for (int k = 0; k < D; ++k) Bj[l] += R(slot, off + o_g3(j, k, l)) * gphia[k];
+                    for (int k = 0; k < D; ++k) Bj[l] += R(slot, off + p3 + k * D + l) * gphia[k];
             }
 #pragma unroll
             for (int b = 0; b < NLOC; ++b) {
-                double s = acc[j][b];
-                if constexpr (h0 || h2) s += Aj * phi[b];
+                double sacc = acc[j][b];
+                if constexpr (h0 || h2) sacc += Aj * phi[b];
                 if constexpr (h1 || h3 != 0) {
 #pragma unroll
-                    for (int l = 0; l < D; ++l) s += Bj[l] * gphi[b][l];
+                    for (int l = 0; l < D; ++l) sacc += Bj[l] * gphi[b][l];
                 }
-                acc[j][b] = s;
+                acc[j][b] = sacc;
             }
         }
     });
@@ -157,7 +200,97 @@ __device__ __forceinline__ void get_basis(const RecRef &R, int slot, int off_phi
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg_args A) {
+// per-warp shared memory: [records | neighbour data | facet metadata]
+struct WarpSmem {
+    double *rec;     // reclen * 32
+    double *nbd;     // [CPW][NLF][NBD_LEN]
+    int *meta;       // [CPW][3][NLF]   nbr, code, slot
+};
+
+__device__ __forceinline__ WarpSmem warp_smem(double *smem, int warp, int reclen) {
+    double *base = smem + (size_t)warp * warp_smem_doubles(reclen);
+    WarpSmem w;
+    w.rec = base;
+    w.nbd = base + reclen * 32;
+    w.meta = reinterpret_cast<int *>(w.nbd + CPW * NLF * NBD_LEN);
+    return w;
+}
+
+// stage facet metadata and the neighbours' data of my cell (lanes of a cell split the facets);
+// all global loads are issued back to back, so their latency is paid once per warp
+__device__ __forceinline__ void stage_neighbours(const ech_dg_args &A, const WarpSmem &W, int g, int a, int64_t c,
+                                                 bool active, int64_t fstride) {
+    if (active) {
+        for (int lf = a; lf < NLF; lf += G) {
+            const int nb = A.nbr[c * NLF + lf];
+            int *m = W.meta + g * META_LEN;
+            m[lf] = nb;
+            m[NLF + lf] = A.code[c * NLF + lf];
+            m[2 * NLF + lf] = A.slot[c * NLF + lf];
+            double *d = W.nbd + (g * NLF + lf) * NBD_LEN;
+            if (nb >= 0) {
+                const double2 *px = reinterpret_cast<const double2 *>(A.xcell + (int64_t)nb * (NV * D));
+#pragma unroll
+                for (int i = 0; i < NV * D / 2; ++i) {
+                    const double2 v = __ldg(px + i);
+                    d[NBD_X + 2 * i] = v.x;
+                    d[NBD_X + 2 * i + 1] = v.y;
+                }
+#pragma unroll
+                for (int j = 0; j < NF; ++j)
+#pragma unroll
+                    for (int b = 0; b < NLOC; ++b) d[NBD_U + j * NLOC + b] = __ldg(A.u + j * fstride + (int64_t)nb * NLOC + b);
+                if constexpr (NAUX > 0) {
+#pragma unroll
+                    for (int j = 0; j < NAUX; ++j)
+#pragma unroll
+                        for (int b = 0; b < NLOC; ++b)
+                            d[NBD_A + j * NLOC + b] = __ldg(A.aux + j * fstride + (int64_t)nb * NLOC + b);
+                }
+                d[NBD_CV] = A.cell_volume[nb];
+                d[NBD_CV + 1] = A.cell_diam[nb];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int NFLD>
+__device__ __forceinline__ void read_fields(const double *d, double (&U)[NFLD][NLOC]) {
+#pragma unroll
+    for (int j = 0; j < NFLD; ++j)
+#pragma unroll
+        for (int b = 0; b < NLOC; ++b) U[j][b] = d[j * NLOC + b];
+}
+
+// evaluate the neighbour side of a facet point from the staged data
+__device__ __forceinline__ void neighbour_side(const double *d, int code, const int (&tt)[D > 1 ? D - 1 : 1], Pt &p,
+                                               double (&phi2)[NLOC], double (&gphi2)[NLOC][D]) {
+    double X2[NV][D], U2[NF][NLOC];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < D; ++k) X2[v][k] = d[NBD_X + v * D + k];
+    read_fields<NF>(d + NBD_U, U2);
+    p.cvm = d[NBD_CV];
+    p.cdm = d[NBD_CV + 1];
+    int idx2[D];
+    neighbour_point(code, tt, idx2);
+    Geo g2;
+    geometry(X2, idx2, g2);
+    basis(idx2, g2.invJ, phi2, gphi2);
+    interpolate<NF>(U2, phi2, gphi2, p.um, p.gum);
+    if constexpr (NAUX > 0) {
+        double AX2[ECH_NA1][NLOC];
+        read_fields<ECH_NA1>(d + NBD_A, AX2);
+        interpolate<ECH_NA1>(AX2, phi2, gphi2, p.am, p.gam);
+    }
+}
+
+#ifndef ECH_JMINB
+#define ECH_JMINB 1
+#endif
+__global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(const ech_dg_args A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / G, a = lane - g * G;
@@ -165,11 +298,15 @@ __global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg
     const int64_t c = ((int64_t)blockIdx.x * JWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
-    RecRef R{smem + (size_t)warp * (G * JREC_LEN * CPW) + (active_lane ? g : 0), JREC_LEN};
+    const int64_t rows_per_field = A.ncell * NLOC;
+    const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
+    const RecRef R{W.rec + (active_lane ? g : 0)};
+    const int *meta = W.meta + (active_lane ? g : 0) * META_LEN;
 
     CellCtx cx;
     double cv = 0.0, cd = 0.0;
     int ncol = 0;
+    int64_t rp[NF];
     if (active) {
         load_cell_coords(A.xcell, c, cx.X);
         load_cell_fields<NF>(A.u, fstride, c, cx.U);
@@ -177,7 +314,11 @@ __global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg
         cv = A.cell_volume[c];
         cd = A.cell_diam[c];
         ncol = A.ncol[c];
+#pragma unroll
+        for (int i = 0; i < NF; ++i) rp[i] = A.rowptr[(int64_t)i * rows_per_field + c * NLOC + a];
     }
+    const int pos_self = active ? A.slot_self[c] : 0;
+    stage_neighbours(A, W, g, a, c, active, fstride);
 
     double acc[NF][NF][NLOC], accn[NF][NF][NLOC];
     static_for<0, NF>([&](auto ic) {
@@ -195,8 +336,6 @@ __global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg
             }
         });
     });
-
-    const int64_t rows_per_field = A.ncell * NLOC;
 
     for (int round = 0; round < NROUND; ++round) {
         // ---------------- evaluate my task of this round
@@ -224,12 +363,12 @@ __global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg
                     constexpr int I = decltype(ic)::value;
                     RowJ rj;
                     cell_jac<I>(p, rj);
-                    put_rowj<MC, I>(R, a, OFF_JP + I * ROWJ_LEN, rj, w);
+                    put_rowj<MC, I>(R, a, OFF_JP, rj, w);
                 });
             } else {
                 const int ft = task - NQC;
                 const int lf = ft / NQF, qf = ft - lf * NQF;
-                const int nb = A.nbr[c * NLF + lf];
+                const int nb = meta[lf];
                 p.fa = A.facet_area[c * NLF + lf];
                 int tt[D > 1 ? D - 1 : 1];
                 double ds;
@@ -249,31 +388,19 @@ __global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg
                         constexpr int I = decltype(ic)::value;
                         RowJ rj;
                         efacet_jac<I>(cls, p, rj);
-                        put_rowj<ME, I>(R, a, OFF_JP + I * ROWJ_LEN, rj, w);
+                        put_rowj<ME, I>(R, a, OFF_JP, rj, w);
                     });
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
-                        double X2[NV][D], U2[NF][NLOC], AX2[ECH_NA1][NLOC];
-                        load_cell_coords(A.xcell, nb, X2);
-                        load_cell_fields<NF>(A.u, fstride, nb, U2);
-                        if constexpr (NAUX > 0) load_cell_fields<ECH_NA1>(A.aux, fstride, nb, AX2);
-                        p.cvm = A.cell_volume[nb];
-                        p.cdm = A.cell_diam[nb];
-                        int idx2[D];
-                        neighbour_point(A.code[c * NLF + lf], tt, idx2);
-                        Geo g2;
                         double phi2[NLOC], gphi2[NLOC][D];
-                        geometry(X2, idx2, g2);
-                        basis(idx2, g2.invJ, phi2, gphi2);
-                        interpolate<NF>(U2, phi2, gphi2, p.um, p.gum);
-                        if constexpr (NAUX > 0) interpolate<ECH_NA1>(AX2, phi2, gphi2, p.am, p.gam);
+                        neighbour_side(W.nbd + (g * NLF + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
                         put_basis(R, a, OFF_PHI2, OFF_GPHI2, phi2, gphi2);
                         static_for<0, NF>([&](auto ic) {
                             constexpr int I = decltype(ic)::value;
                             RowJ rj, rjm;
                             ifacet_jac<I>(p, rj, rjm);
-                            put_rowj<MIP, I>(R, a, OFF_JP + I * ROWJ_LEN, rj, w);
-                            put_rowj<MIM, I>(R, a, OFF_JM + I * ROWJ_LEN, rjm, w);
+                            put_rowj<MIP, I>(R, a, OFF_JP, rj, w);
+                            put_rowj<MIM, I>(R, a, OFF_JM, rjm, w);
                         });
                     }
                 }
@@ -293,34 +420,33 @@ __global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg
                 if (tk < NQC) {
                     static_for<0, NF>([&](auto ic) {
                         constexpr int I = decltype(ic)::value;
-                        take_rowj<MC, I>(R, s, OFF_JP + I * ROWJ_LEN, phia, gphia, phi, gphi, acc[I]);
+                        take_rowj<MC, I>(R, s, OFF_JP, phia, gphia, phi, gphi, acc[I]);
                     });
                 } else {
                     const int ft = tk - NQC;
                     const int lf = ft / NQF, qf = ft - lf * NQF;
-                    const int nb = A.nbr[c * NLF + lf];
+                    const int nb = meta[lf];
                     if (nb < 0) {
                         static_for<0, NF>([&](auto ic) {
                             constexpr int I = decltype(ic)::value;
-                            take_rowj<ME, I>(R, s, OFF_JP + I * ROWJ_LEN, phia, gphia, phi, gphi, acc[I]);
+                            take_rowj<ME, I>(R, s, OFF_JP, phia, gphia, phi, gphi, acc[I]);
                         });
                     } else {
                         if constexpr (ECH_FAMILY_DG) {
                             static_for<0, NF>([&](auto ic) {
                                 constexpr int I = decltype(ic)::value;
-                                take_rowj<MIP, I>(R, s, OFF_JP + I * ROWJ_LEN, phia, gphia, phi, gphi, acc[I]);
+                                take_rowj<MIP, I>(R, s, OFF_JP, phia, gphia, phi, gphi, acc[I]);
                             });
                             get_basis(R, s, OFF_PHI2, OFF_GPHI2, phi, gphi);
                             static_for<0, NF>([&](auto ic) {
                                 constexpr int I = decltype(ic)::value;
-                                take_rowj<MIM, I>(R, s, OFF_JM + I * ROWJ_LEN, phia, gphia, phi, gphi, accn[I]);
+                                take_rowj<MIM, I>(R, s, OFF_JM, phia, gphia, phi, gphi, accn[I]);
                             });
                             if (qf == NQF - 1) {
-                                const int pos = A.slot[c * NLF + lf];
+                                const int pos = meta[2 * NLF + lf];
                                 static_for<0, NF>([&](auto ic) {
                                     constexpr int I = decltype(ic)::value;
-                                    double *__restrict__ vals =
-                                        A.out + A.rowptr[(int64_t)I * rows_per_field + c * NLOC + a];
+                                    double *__restrict__ vals = A.out + rp[I];
                                     static_for<0, NF>([&](auto jc) {
                                         constexpr int j = decltype(jc)::value;
                                         constexpr bool nbj = NBR_BLOCK[I][j];
@@ -340,14 +466,13 @@ __global__ void __launch_bounds__(JWARPS * 32) jacobian_coop_kernel(const ech_dg
         __syncwarp();
     }
     if (active) {
-        const int pos = A.slot_self[c];
         static_for<0, NF>([&](auto ic) {
             constexpr int I = decltype(ic)::value;
-            double *__restrict__ vals = A.out + A.rowptr[(int64_t)I * rows_per_field + c * NLOC + a];
+            double *__restrict__ vals = A.out + rp[I];
             static_for<0, NF>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 constexpr bool own = OWN_BLOCK[I][j];
-                if constexpr (own) store_block(vals + block_offset<I, j>(ncol, pos), acc[I][j]);
+                if constexpr (own) store_block(vals + block_offset<I, j>(ncol, pos_self), acc[I][j]);
             });
         });
     }
@@ -385,7 +510,9 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
     const int64_t c = ((int64_t)blockIdx.x * RWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
-    RecRef R{smem + (size_t)warp * (G * RREC_LEN * CPW) + (active_lane ? g : 0), RREC_LEN};
+    const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
+    const RecRef R{W.rec + (active_lane ? g : 0)};
+    const int *meta = W.meta + (active_lane ? g : 0) * META_LEN;
 
     CellCtx cx;
     double cv = 0.0, cd = 0.0;
@@ -396,6 +523,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
         cv = A.cell_volume[c];
         cd = A.cell_diam[c];
     }
+    stage_neighbours(A, W, g, a, c, active, fstride);
     double r[NF];
 #pragma unroll
     for (int i = 0; i < NF; ++i) r[i] = 0.0;
@@ -426,7 +554,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
             } else {
                 const int ft = task - NQC;
                 const int lf = ft / NQF, qf = ft - lf * NQF;
-                const int nb = A.nbr[c * NLF + lf];
+                const int nb = meta[lf];
                 p.fa = A.facet_area[c * NLF + lf];
                 int tt[D > 1 ? D - 1 : 1];
                 double ds;
@@ -444,20 +572,8 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
                     put_res<ME>(R, a, o, w * ds);
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
-                        double X2[NV][D], U2[NF][NLOC], AX2[ECH_NA1][NLOC];
-                        load_cell_coords(A.xcell, nb, X2);
-                        load_cell_fields<NF>(A.u, fstride, nb, U2);
-                        if constexpr (NAUX > 0) load_cell_fields<ECH_NA1>(A.aux, fstride, nb, AX2);
-                        p.cvm = A.cell_volume[nb];
-                        p.cdm = A.cell_diam[nb];
-                        int idx2[D];
-                        neighbour_point(A.code[c * NLF + lf], tt, idx2);
-                        Geo g2;
                         double phi2[NLOC], gphi2[NLOC][D];
-                        geometry(X2, idx2, g2);
-                        basis(idx2, g2.invJ, phi2, gphi2);
-                        interpolate<NF>(U2, phi2, gphi2, p.um, p.gum);
-                        if constexpr (NAUX > 0) interpolate<ECH_NA1>(AX2, phi2, gphi2, p.am, p.gam);
+                        neighbour_side(W.nbd + (g * NLF + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
                         ifacet_res(p, o);
                         put_res<MIP>(R, a, o, w * ds);
                     }
@@ -491,14 +607,15 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int JSMEM = JWARPS * warp_smem_doubles(JREC_LEN) * 8;
+constexpr int RSMEM = RWARPS * warp_smem_doubles(RREC_LEN) * 8;
+
 inline int coop_setup() {
     static int done = 0;
     if (done) return 0;
-    cudaError_t e = cudaFuncSetAttribute(jacobian_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         JWARPS * G * JREC_LEN * CPW * 8);
+    cudaError_t e = cudaFuncSetAttribute(jacobian_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(residual_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             RWARPS * G * RREC_LEN * CPW * 8);
+    e = cudaFuncSetAttribute(residual_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM);
     if (e != cudaSuccess) return (int)e;
     done = 1;
     return 0;
@@ -510,7 +627,7 @@ inline int launch_jacobian_coop(const ech_dg_args *a, cudaStream_t s) {
     if (e) return e;
     const int64_t cells_per_block = (int64_t)JWARPS * CPW;
     const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
-    jacobian_coop_kernel<<<(unsigned)grid, JWARPS * 32, JWARPS * G * JREC_LEN * CPW * 8, s>>>(*a);
+    jacobian_coop_kernel<<<(unsigned)grid, JWARPS * 32, JSMEM, s>>>(*a);
     return (int)cudaGetLastError();
 }
 
@@ -520,7 +637,7 @@ inline int launch_residual_coop(const ech_dg_args *a, cudaStream_t s) {
     if (e) return e;
     const int64_t cells_per_block = (int64_t)RWARPS * CPW;
     const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
-    residual_coop_kernel<<<(unsigned)grid, RWARPS * 32, RWARPS * G * RREC_LEN * CPW * 8, s>>>(*a);
+    residual_coop_kernel<<<(unsigned)grid, RWARPS * 32, RSMEM, s>>>(*a);
     return (int)cudaGetLastError();
 }
 
