@@ -77,7 +77,8 @@ constexpr int NBD_LEN = (NBD_CV + 2) | 1;
 // per-cell facet metadata (ints): nbr, code, slot
 constexpr int META_LEN = 3 * NLF;
 
-__host__ __device__ constexpr int warp_smem_doubles(int reclen) { return reclen * 32 + CPW * NLF * NBD_LEN + (CPW * META_LEN + 1) / 2; }
+constexpr int NBD_SLOTS = NLF + 1;   // neighbours + the cell itself
+__host__ __device__ constexpr int warp_smem_doubles(int reclen) { return reclen * 32 + CPW * NBD_SLOTS * NBD_LEN + (CPW * META_LEN + 1) / 2; }
 constexpr int coop_warps(int reclen) {
     const int per_warp = warp_smem_doubles(reclen) * 8;
 #ifdef ECH_COOP_WARPS
@@ -212,7 +213,7 @@ __device__ __forceinline__ WarpSmem warp_smem(double *smem, int warp, int reclen
     WarpSmem w;
     w.rec = base;
     w.nbd = base + reclen * 32;
-    w.meta = reinterpret_cast<int *>(w.nbd + CPW * NLF * NBD_LEN);
+    w.meta = reinterpret_cast<int *>(w.nbd + CPW * NBD_SLOTS * NBD_LEN);
     return w;
 }
 
@@ -221,13 +222,18 @@ __device__ __forceinline__ WarpSmem warp_smem(double *smem, int warp, int reclen
 __device__ __forceinline__ void stage_neighbours(const ech_dg_args &A, const WarpSmem &W, int g, int a, int64_t c,
                                                  bool active, int64_t fstride) {
     if (active) {
-        for (int lf = a; lf < NLF; lf += G) {
-            const int nb = A.nbr[c * NLF + lf];
-            int *m = W.meta + g * META_LEN;
-            m[lf] = nb;
-            m[NLF + lf] = A.code[c * NLF + lf];
-            m[2 * NLF + lf] = A.slot[c * NLF + lf];
-            double *d = W.nbd + (g * NLF + lf) * NBD_LEN;
+        for (int lf = a; lf < NBD_SLOTS; lf += G) {
+            int nb;
+            if (lf < NLF) {
+                nb = A.nbr[c * NLF + lf];
+                int *m = W.meta + g * META_LEN;
+                m[lf] = nb;
+                m[NLF + lf] = A.code[c * NLF + lf];
+                m[2 * NLF + lf] = A.slot[c * NLF + lf];
+            } else {
+                nb = (int)c;
+            }
+            double *d = W.nbd + (g * NBD_SLOTS + lf) * NBD_LEN;
             if (nb >= 0) {
                 const double2 *px = reinterpret_cast<const double2 *>(A.xcell + (int64_t)nb * (NV * D));
 #pragma unroll
@@ -253,6 +259,35 @@ __device__ __forceinline__ void stage_neighbours(const ech_dg_args &A, const War
         }
     }
     __syncwarp();
+}
+
+// own-side evaluation at a table point from the staged cell data
+__device__ __forceinline__ void own_side(const double *d, const int (&idx)[D], Pt &p, Geo &gm, double (&phi)[NLOC],
+                                         double (&gphi)[NLOC][D]) {
+    double X[NV][D], U[NF][NLOC];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < D; ++k) X[v][k] = d[NBD_X + v * D + k];
+#pragma unroll
+    for (int j = 0; j < NF; ++j)
+#pragma unroll
+        for (int b = 0; b < NLOC; ++b) U[j][b] = d[NBD_U + j * NLOC + b];
+    p.cv = d[NBD_CV];
+    p.cd = d[NBD_CV + 1];
+    geometry(X, idx, gm);
+    basis(idx, gm.invJ, phi, gphi);
+    interpolate<NF>(U, phi, gphi, p.u, p.gu);
+    if constexpr (NAUX > 0) {
+        double AX[ECH_NA1][NLOC];
+#pragma unroll
+        for (int j = 0; j < ECH_NA1; ++j)
+#pragma unroll
+            for (int b = 0; b < NLOC; ++b) AX[j][b] = d[NBD_A + j * NLOC + b];
+        interpolate<ECH_NA1>(AX, phi, gphi, p.a, p.ga);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) p.x[k] = gm.x[k];
 }
 
 template <int NFLD>
@@ -290,6 +325,54 @@ __device__ __forceinline__ void neighbour_side(const double *d, int code, const 
 #ifndef ECH_JMINB
 #define ECH_JMINB 1
 #endif
+// all records of a facet fall into one round, and rounds do not mix cell and facet records
+constexpr bool FACET_IN_ROUND = (NQC % G == 0) && (G % NQF == 0);
+
+template <class M>
+__device__ __forceinline__ void take_all(const RecRef &R, int s, int off, double phia, const double (&gphia)[D],
+                                         const double (&phi)[NLOC], const double (&gphi)[NLOC][D],
+                                         double (&acc)[NF][NF][NLOC]) {
+    static_for<0, NF>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        take_rowj<M, I>(R, s, off, phia, gphia, phi, gphi, acc[I]);
+    });
+}
+
+template <bool OWN>
+__device__ __forceinline__ void zero_blocks(double (&acc)[NF][NF][NLOC]) {
+    static_for<0, NF>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        static_for<0, NF>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr bool on = OWN ? OWN_BLOCK[I][j] : NBR_BLOCK[I][j];
+            if constexpr (on) {
+#pragma unroll
+                for (int b = 0; b < NLOC; ++b) acc[I][j][b] = 0.0;
+            }
+        });
+    });
+}
+
+template <bool OWN>
+__device__ __forceinline__ void store_blocks(double *__restrict__ out, const int64_t (&rp)[NF], int ncol, int pos,
+                                             const double (&acc)[NF][NF][NLOC]) {
+    static_for<0, NF>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        double *__restrict__ vals = out + rp[I];
+        static_for<0, NF>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr bool on = OWN ? OWN_BLOCK[I][j] : NBR_BLOCK[I][j];
+            if constexpr (on) store_block(vals + block_offset<I, j>(ncol, pos), acc[I][j]);
+        });
+    });
+}
+
+__device__ __forceinline__ void test_basis(const RecRef &R, int s, int a, double &phia, double (&gphia)[D]) {
+    phia = R(s, OFF_PHI + a);
+#pragma unroll
+    for (int k = 0; k < D; ++k) gphia[k] = R(s, OFF_GPHI + a * D + k);
+}
+
 __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(const ech_dg_args A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -301,62 +384,42 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int64_t rows_per_field = A.ncell * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
     const RecRef R{W.rec + (active_lane ? g : 0)};
-    const int *meta = W.meta + (active_lane ? g : 0) * META_LEN;
+    const int gg = active_lane ? g : 0;
+    const int *meta = W.meta + gg * META_LEN;
+    const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
 
-    CellCtx cx;
-    double cv = 0.0, cd = 0.0;
-    int ncol = 0;
+    int ncol = 0, pos_self = 0;
     int64_t rp[NF];
     if (active) {
-        load_cell_coords(A.xcell, c, cx.X);
-        load_cell_fields<NF>(A.u, fstride, c, cx.U);
-        if constexpr (NAUX > 0) load_cell_fields<ECH_NA1>(A.aux, fstride, c, cx.AX);
-        cv = A.cell_volume[c];
-        cd = A.cell_diam[c];
         ncol = A.ncol[c];
+        pos_self = A.slot_self[c];
 #pragma unroll
         for (int i = 0; i < NF; ++i) rp[i] = A.rowptr[(int64_t)i * rows_per_field + c * NLOC + a];
     }
-    const int pos_self = active ? A.slot_self[c] : 0;
     stage_neighbours(A, W, g, a, c, active, fstride);
 
-    double acc[NF][NF][NLOC], accn[NF][NF][NLOC];
-    static_for<0, NF>([&](auto ic) {
-        constexpr int I = decltype(ic)::value;
-        static_for<0, NF>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            constexpr bool own = OWN_BLOCK[I][j], nb = NBR_BLOCK[I][j];
-            if constexpr (own) {
-#pragma unroll
-                for (int b = 0; b < NLOC; ++b) acc[I][j][b] = 0.0;
-            }
-            if constexpr (nb) {
-#pragma unroll
-                for (int b = 0; b < NLOC; ++b) accn[I][j][b] = 0.0;
-            }
-        });
-    });
+    double acc[NF][NF][NLOC];
+    zero_blocks<true>(acc);
+    double accn_persist[FACET_IN_ROUND ? 1 : NF][FACET_IN_ROUND ? 1 : NF][FACET_IN_ROUND ? 1 : NLOC];
+    if constexpr (!FACET_IN_ROUND) zero_blocks<false>(reinterpret_cast<double(&)[NF][NF][NLOC]>(accn_persist));
 
     for (int round = 0; round < NROUND; ++round) {
         // ---------------- evaluate my task of this round
         const int task = round * G + a;
+#ifdef ECH_DBG_NO_EVAL
+        if (false) {
+#else
         if (active && task < NTASK) {
+#endif
             Pt p;
             p.K = A.consts;
-            p.cv = cv;
-            p.cd = cd;
             Geo gm;
             double phi[NLOC], gphi[NLOC][D];
             int idx[D];
             double w;
             if (task < NQC) {
                 cell_point(task, idx, w);
-                geometry(cx.X, idx, gm);
-                basis(idx, gm.invJ, phi, gphi);
-                interpolate<NF>(cx.U, phi, gphi, p.u, p.gu);
-                if constexpr (NAUX > 0) interpolate<ECH_NA1>(cx.AX, phi, gphi, p.a, p.ga);
-#pragma unroll
-                for (int k = 0; k < D; ++k) p.x[k] = gm.x[k];
+                own_side(own, idx, p, gm, phi, gphi);
                 w *= fabs(gm.detJ);
                 put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
                 static_for<0, NF>([&](auto ic) {
@@ -369,17 +432,19 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                 const int ft = task - NQC;
                 const int lf = ft / NQF, qf = ft - lf * NQF;
                 const int nb = meta[lf];
-                p.fa = A.facet_area[c * NLF + lf];
                 int tt[D > 1 ? D - 1 : 1];
                 double ds;
                 facet_point(lf, qf, idx, tt, w);
-                geometry(cx.X, idx, gm);
-                basis(idx, gm.invJ, phi, gphi);
-                interpolate<NF>(cx.U, phi, gphi, p.u, p.gu);
-                if constexpr (NAUX > 0) interpolate<ECH_NA1>(cx.AX, phi, gphi, p.a, p.ga);
+                if (nb >= 0) {
+                    if constexpr (ECH_FAMILY_DG) {
+                        double phi2[NLOC], gphi2[NLOC][D];
+                        neighbour_side(W.nbd + (gg * NBD_SLOTS + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
+                        put_basis(R, a, OFF_PHI2, OFF_GPHI2, phi2, gphi2);
+                    }
+                }
+                own_side(own, idx, p, gm, phi, gphi);
+                p.fa = A.facet_area[c * NLF + lf];
                 facet_normal(gm, lf, p.n, ds);
-#pragma unroll
-                for (int k = 0; k < D; ++k) p.x[k] = gm.x[k];
                 w *= ds;
                 put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
                 if (nb < 0) {
@@ -392,9 +457,6 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                     });
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
-                        double phi2[NLOC], gphi2[NLOC][D];
-                        neighbour_side(W.nbd + (g * NLF + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
-                        put_basis(R, a, OFF_PHI2, OFF_GPHI2, phi2, gphi2);
                         static_for<0, NF>([&](auto ic) {
                             constexpr int I = decltype(ic)::value;
                             RowJ rj, rjm;
@@ -408,55 +470,81 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
         }
         __syncwarp();
         // ---------------- accumulate the records of my cell into my rows
+#ifdef ECH_DBG_NO_ACCUM
+        if (false) {
+#else
         if (active) {
-            for (int s = 0; s < G; ++s) {
-                const int tk = round * G + s;
-                if (tk >= NTASK) break;
-                double phi[NLOC], gphi[NLOC][D], phia, gphia[D];
-                get_basis(R, s, OFF_PHI, OFF_GPHI, phi, gphi);
-                phia = R(s, OFF_PHI + a);
+#endif
+            if constexpr (FACET_IN_ROUND) {
+                if (round < NQC / G) {
 #pragma unroll
-                for (int k = 0; k < D; ++k) gphia[k] = R(s, OFF_GPHI + a * D + k);
-                if (tk < NQC) {
-                    static_for<0, NF>([&](auto ic) {
-                        constexpr int I = decltype(ic)::value;
-                        take_rowj<MC, I>(R, s, OFF_JP, phia, gphia, phi, gphi, acc[I]);
-                    });
+                    for (int s = 0; s < G; ++s) {
+                        double phi[NLOC], gphi[NLOC][D], phia, gphia[D];
+                        get_basis(R, s, OFF_PHI, OFF_GPHI, phi, gphi);
+                        test_basis(R, s, a, phia, gphia);
+                        take_all<MC>(R, s, OFF_JP, phia, gphia, phi, gphi, acc);
+                    }
                 } else {
-                    const int ft = tk - NQC;
-                    const int lf = ft / NQF, qf = ft - lf * NQF;
-                    const int nb = meta[lf];
-                    if (nb < 0) {
-                        static_for<0, NF>([&](auto ic) {
-                            constexpr int I = decltype(ic)::value;
-                            take_rowj<ME, I>(R, s, OFF_JP, phia, gphia, phi, gphi, acc[I]);
-                        });
-                    } else {
-                        if constexpr (ECH_FAMILY_DG) {
-                            static_for<0, NF>([&](auto ic) {
-                                constexpr int I = decltype(ic)::value;
-                                take_rowj<MIP, I>(R, s, OFF_JP, phia, gphia, phi, gphi, acc[I]);
-                            });
-                            get_basis(R, s, OFF_PHI2, OFF_GPHI2, phi, gphi);
-                            static_for<0, NF>([&](auto ic) {
-                                constexpr int I = decltype(ic)::value;
-                                take_rowj<MIM, I>(R, s, OFF_JM, phia, gphia, phi, gphi, accn[I]);
-                            });
-                            if (qf == NQF - 1) {
-                                const int pos = meta[2 * NLF + lf];
-                                static_for<0, NF>([&](auto ic) {
-                                    constexpr int I = decltype(ic)::value;
-                                    double *__restrict__ vals = A.out + rp[I];
-                                    static_for<0, NF>([&](auto jc) {
-                                        constexpr int j = decltype(jc)::value;
-                                        constexpr bool nbj = NBR_BLOCK[I][j];
-                                        if constexpr (nbj) {
-                                            store_block(vals + block_offset<I, j>(ncol, pos), accn[I][j]);
+                    const int lf0 = (round * G - NQC) / NQF;
 #pragma unroll
-                                            for (int b = 0; b < NLOC; ++b) accn[I][j][b] = 0.0;
-                                        }
-                                    });
-                                });
+                    for (int fi = 0; fi < G / NQF; ++fi) {
+                        const int lf = lf0 + fi;
+                        if (lf < NLF) {
+                            const int nb = meta[lf];
+                            if (nb < 0) {
+#pragma unroll
+                                for (int qf = 0; qf < NQF; ++qf) {
+                                    const int s = fi * NQF + qf;
+                                    double phi[NLOC], gphi[NLOC][D], phia, gphia[D];
+                                    get_basis(R, s, OFF_PHI, OFF_GPHI, phi, gphi);
+                                    test_basis(R, s, a, phia, gphia);
+                                    take_all<ME>(R, s, OFF_JP, phia, gphia, phi, gphi, acc);
+                                }
+                            } else {
+                                if constexpr (ECH_FAMILY_DG) {
+                                    double accn[NF][NF][NLOC];
+                                    zero_blocks<false>(accn);
+#pragma unroll
+                                    for (int qf = 0; qf < NQF; ++qf) {
+                                        const int s = fi * NQF + qf;
+                                        double phi[NLOC], gphi[NLOC][D], phia, gphia[D];
+                                        test_basis(R, s, a, phia, gphia);
+                                        get_basis(R, s, OFF_PHI2, OFF_GPHI2, phi, gphi);
+                                        take_all<MIM>(R, s, OFF_JM, phia, gphia, phi, gphi, accn);
+                                        get_basis(R, s, OFF_PHI, OFF_GPHI, phi, gphi);
+                                        take_all<MIP>(R, s, OFF_JP, phia, gphia, phi, gphi, acc);
+                                    }
+                                    store_blocks<false>(A.out, rp, ncol, meta[2 * NLF + lf], accn);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                double(&accn)[NF][NF][NLOC] = reinterpret_cast<double(&)[NF][NF][NLOC]>(accn_persist);
+                for (int s = 0; s < G; ++s) {
+                    const int tk = round * G + s;
+                    if (tk >= NTASK) break;
+                    double phi[NLOC], gphi[NLOC][D], phia, gphia[D];
+                    get_basis(R, s, OFF_PHI, OFF_GPHI, phi, gphi);
+                    test_basis(R, s, a, phia, gphia);
+                    if (tk < NQC) {
+                        take_all<MC>(R, s, OFF_JP, phia, gphia, phi, gphi, acc);
+                    } else {
+                        const int ft = tk - NQC;
+                        const int lf = ft / NQF, qf = ft - lf * NQF;
+                        const int nb = meta[lf];
+                        if (nb < 0) {
+                            take_all<ME>(R, s, OFF_JP, phia, gphia, phi, gphi, acc);
+                        } else {
+                            if constexpr (ECH_FAMILY_DG) {
+                                take_all<MIP>(R, s, OFF_JP, phia, gphia, phi, gphi, acc);
+                                get_basis(R, s, OFF_PHI2, OFF_GPHI2, phi, gphi);
+                                take_all<MIM>(R, s, OFF_JM, phia, gphia, phi, gphi, accn);
+                                if (qf == NQF - 1) {
+                                    store_blocks<false>(A.out, rp, ncol, meta[2 * NLF + lf], accn);
+                                    zero_blocks<false>(accn);
+                                }
                             }
                         }
                     }
@@ -465,17 +553,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
         }
         __syncwarp();
     }
-    if (active) {
-        static_for<0, NF>([&](auto ic) {
-            constexpr int I = decltype(ic)::value;
-            double *__restrict__ vals = A.out + rp[I];
-            static_for<0, NF>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                constexpr bool own = OWN_BLOCK[I][j];
-                if constexpr (own) store_block(vals + block_offset<I, j>(ncol, pos_self), acc[I][j]);
-            });
-        });
-    }
+    if (active) store_blocks<true>(A.out, rp, ncol, pos_self, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,17 +590,9 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
     const RecRef R{W.rec + (active_lane ? g : 0)};
-    const int *meta = W.meta + (active_lane ? g : 0) * META_LEN;
-
-    CellCtx cx;
-    double cv = 0.0, cd = 0.0;
-    if (active) {
-        load_cell_coords(A.xcell, c, cx.X);
-        load_cell_fields<NF>(A.u, fstride, c, cx.U);
-        if constexpr (NAUX > 0) load_cell_fields<ECH_NA1>(A.aux, fstride, c, cx.AX);
-        cv = A.cell_volume[c];
-        cd = A.cell_diam[c];
-    }
+    const int gg = active_lane ? g : 0;
+    const int *meta = W.meta + gg * META_LEN;
+    const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
     stage_neighbours(A, W, g, a, c, active, fstride);
     double r[NF];
 #pragma unroll
@@ -533,8 +603,6 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
         if (active && task < NTASK) {
             Pt p;
             p.K = A.consts;
-            p.cv = cv;
-            p.cd = cd;
             Geo gm;
             double phi[NLOC], gphi[NLOC][D];
             int idx[D];
@@ -542,12 +610,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
             Res o;
             if (task < NQC) {
                 cell_point(task, idx, w);
-                geometry(cx.X, idx, gm);
-                basis(idx, gm.invJ, phi, gphi);
-                interpolate<NF>(cx.U, phi, gphi, p.u, p.gu);
-                if constexpr (NAUX > 0) interpolate<ECH_NA1>(cx.AX, phi, gphi, p.a, p.ga);
-#pragma unroll
-                for (int k = 0; k < D; ++k) p.x[k] = gm.x[k];
+                own_side(own, idx, p, gm, phi, gphi);
                 cell_res(p, o);
                 put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
                 put_res<MC>(R, a, o, w * fabs(gm.detJ));
@@ -559,13 +622,8 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
                 int tt[D > 1 ? D - 1 : 1];
                 double ds;
                 facet_point(lf, qf, idx, tt, w);
-                geometry(cx.X, idx, gm);
-                basis(idx, gm.invJ, phi, gphi);
-                interpolate<NF>(cx.U, phi, gphi, p.u, p.gu);
-                if constexpr (NAUX > 0) interpolate<ECH_NA1>(cx.AX, phi, gphi, p.a, p.ga);
+                own_side(own, idx, p, gm, phi, gphi);
                 facet_normal(gm, lf, p.n, ds);
-#pragma unroll
-                for (int k = 0; k < D; ++k) p.x[k] = gm.x[k];
                 put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
                 if (nb < 0) {
                     efacet_res(-nb - 1, p, o);
@@ -573,7 +631,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
                         double phi2[NLOC], gphi2[NLOC][D];
-                        neighbour_side(W.nbd + (g * NLF + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
+                        neighbour_side(W.nbd + (gg * NBD_SLOTS + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
                         ifacet_res(p, o);
                         put_res<MIP>(R, a, o, w * ds);
                     }
