@@ -454,7 +454,14 @@ __device__ __forceinline__ void accum_row(const RowJ &r, double w, double phia, 
 }
 
 __device__ __forceinline__ void store_block(double *__restrict__ dst, const double (&v)[NLOC]) {
-    if constexpr (NLOC % 2 == 0) {
+    if constexpr (NLOC % 4 == 0) {
+        // one 256-bit store per 4 entries (STG.E.ENL2.256): row blocks start on 32-byte boundaries
+#pragma unroll
+        for (int b = 0; b < NLOC; b += 4)
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + b), "d"(v[b]), "d"(v[b + 1]),
+                         "d"(v[b + 2]), "d"(v[b + 3])
+                         : "memory");
+    } else if constexpr (NLOC % 2 == 0) {
 #pragma unroll
         for (int b = 0; b < NLOC; b += 2) reinterpret_cast<double2 *>(dst)[b / 2] = make_double2(v[b], v[b + 1]);
     } else {

@@ -39,11 +39,12 @@ struct Layout {
         for (int i = 0; i < NF; ++i)
             for (int j = 0; j < NF; ++j) {
                 o0[i][j] = o1[i][j] = o2[i][j] = o3[i][j] = -1;
+                // scalars first would leave holes; D-vectors start on even offsets (128-bit shared access)
+                if (M::G1[i][j]) { n = (D == 2) ? ((n + 1) & ~1) : n; o1[i][j] = n; n += D; }
+                if (M::G2[i][j]) { n = (D == 2) ? ((n + 1) & ~1) : n; o2[i][j] = n; n += D; }
+                if (M::G3[i][j] == 2) { n = (D == 2) ? ((n + 1) & ~1) : n; o3[i][j] = n; n += D * D; }
                 if (M::G0[i][j]) { o0[i][j] = n; n += 1; }
-                if (M::G1[i][j]) { o1[i][j] = n; n += D; }
-                if (M::G2[i][j]) { o2[i][j] = n; n += D; }
                 if (M::G3[i][j] == 1) { o3[i][j] = n; n += 1; }
-                if (M::G3[i][j] == 2) { o3[i][j] = n; n += D * D; }
             }
         len = n;
     }
@@ -64,9 +65,9 @@ constexpr int OFF_GPHI = NLOC;
 constexpr int OFF_PHI2 = NLOC * (1 + D);
 constexpr int OFF_GPHI2 = NLOC * (2 + D);
 constexpr int OFF_JP = 2 * NLOC * (1 + D);
-constexpr int OFF_JM = OFF_JP + LAY_IP.len;
-constexpr int JREC_LEN = OFF_JP + cmax(cmax(LAY_C.len, LAY_E.len), LAY_IP.len + LAY_IM.len);
-constexpr int RREC_LEN = NLOC * (1 + D) + NF * (1 + D);
+constexpr int OFF_JM = OFF_JP + ((LAY_IP.len + 1) & ~1);
+constexpr int JREC_LEN = (cmax(cmax(OFF_JP + LAY_C.len, OFF_JP + LAY_E.len), OFF_JM + LAY_IM.len) + 1) & ~1;
+constexpr int RREC_LEN = (NLOC * (1 + D) + NF * (1 + D) + 1) & ~1;
 
 // neighbour data staged per (cell, facet): vertex coordinates, state, aux, volume, diameter
 constexpr int NBD_X = 0;
@@ -94,8 +95,18 @@ constexpr int RWARPS = coop_warps(RREC_LEN);
 // accessor of one record: field k of (slot s, cell g) lives at k*32 + s*CPW + g, so that the lanes of
 // a warp write / read consecutive words (no bank conflicts; same-cell lanes broadcast)
 struct RecRef {
-    double *base;   // warp base + g
-    __device__ __forceinline__ double &operator()(int slot, int k) const { return base[k * 32 + slot * CPW]; }
+    double *base;   // warp base + 2 * g
+    // fields are stored in pairs: (k even, k odd) adjacent, pairs strided by 32 lanes
+    __device__ __forceinline__ double &operator()(int slot, int k) const {
+        return base[((k >> 1) * 32 + slot * CPW) * 2 + (k & 1)];
+    }
+    // 128-bit access to the pair (k, k+1), k even
+    __device__ __forceinline__ double2 pair(int slot, int k) const {
+        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2);
+    }
+    __device__ __forceinline__ void set_pair(int slot, int k, double x, double y) const {
+        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2) = make_double2(x, y);
+    }
 };
 
 // evaluation context of one lane
@@ -114,12 +125,20 @@ __device__ __forceinline__ void put_rowj(const RecRef &R, int slot, int off, con
         constexpr int h3 = M::G3[I][j];
         if constexpr (p0 >= 0) R(slot, off + p0) = w * r.g0[j];
         if constexpr (p1 >= 0) {
+            if constexpr (D == 2) {
+                R.set_pair(slot, off + p1, w * r.g1[j][0], w * r.g1[j][1]);
+            } else {
 #pragma unroll
-            for (int l = 0; l < D; ++l) R(slot, off + p1 + l) = w * r.g1[j][l];
+                for (int l = 0; l < D; ++l) R(slot, off + p1 + l) = w * r.g1[j][l];
+            }
         }
         if constexpr (p2 >= 0) {
+            if constexpr (D == 2) {
+                R.set_pair(slot, off + p2, w * r.g2[j][0], w * r.g2[j][1]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < D; ++k) R(slot, off + p2 + k) = w * r.g2[j][k];
+                for (int k = 0; k < D; ++k) R(slot, off + p2 + k) = w * r.g2[j][k];
+            }
         }
         if constexpr (h3 == 1) R(slot, off + p3) = w * r.g3[j][0][0];
         if constexpr (h3 == 2) {
@@ -133,11 +152,20 @@ __device__ __forceinline__ void put_rowj(const RecRef &R, int slot, int off, con
 
 __device__ __forceinline__ void put_basis(const RecRef &R, int slot, int off_phi, int off_gphi,
                                           const double (&phi)[NLOC], const double (&gphi)[NLOC][D]) {
+    // off_phi and off_gphi are even when NLOC is even; both blocks are then written as pairs
+    if constexpr (NLOC % 2 == 0) {
 #pragma unroll
-    for (int b = 0; b < NLOC; ++b) {
-        R(slot, off_phi + b) = phi[b];
+        for (int b = 0; b < NLOC; b += 2) R.set_pair(slot, off_phi + b, phi[b], phi[b + 1]);
+        const double *gp = &gphi[0][0];
 #pragma unroll
-        for (int k = 0; k < D; ++k) R(slot, off_gphi + b * D + k) = gphi[b][k];
+        for (int m = 0; m < NLOC * D; m += 2) R.set_pair(slot, off_gphi + m, gp[m], gp[m + 1]);
+    } else {
+#pragma unroll
+        for (int b = 0; b < NLOC; ++b) {
+            R(slot, off_phi + b) = phi[b];
+#pragma unroll
+            for (int k = 0; k < D; ++k) R(slot, off_gphi + b * D + k) = gphi[b][k];
+        }
     }
 }
 
@@ -158,12 +186,24 @@ __device__ __forceinline__ void take_rowj(const RecRef &R, int slot, int off, do
             for (int l = 0; l < D; ++l) Bj[l] = 0.0;
             if constexpr (h0) Aj += R(slot, off + p0) * phia;
             if constexpr (h2) {
+                if constexpr (D == 2) {
+                    const double2 v = R.pair(slot, off + p2);
+                    Aj += v.x * gphia[0];
+                    Aj += v.y * gphia[1];
+                } else {
 #pragma unroll
-                for (int k = 0; k < D; ++k) Aj += R(slot, off + p2 + k) * gphia[k];
+                    for (int k = 0; k < D; ++k) Aj += R(slot, off + p2 + k) * gphia[k];
+                }
             }
             if constexpr (h1) {
+                if constexpr (D == 2) {
+                    const double2 v = R.pair(slot, off + p1);
+                    Bj[0] += v.x * phia;
+                    Bj[1] += v.y * phia;
+                } else {
 #pragma unroll
-                for (int l = 0; l < D; ++l) Bj[l] += R(slot, off + p1 + l) * phia;
+                    for (int l = 0; l < D; ++l) Bj[l] += R(slot, off + p1 + l) * phia;
+                }
             }
             if constexpr (h3 == 1) {
                 const double sc = R(slot, off + p3);
@@ -192,11 +232,27 @@ __device__ __forceinline__ void take_rowj(const RecRef &R, int slot, int off, do
 
 __device__ __forceinline__ void get_basis(const RecRef &R, int slot, int off_phi, int off_gphi, double (&phi)[NLOC],
                                           double (&gphi)[NLOC][D]) {
+    if constexpr (NLOC % 2 == 0) {
 #pragma unroll
-    for (int b = 0; b < NLOC; ++b) {
-        phi[b] = R(slot, off_phi + b);
+        for (int b = 0; b < NLOC; b += 2) {
+            const double2 v = R.pair(slot, off_phi + b);
+            phi[b] = v.x;
+            phi[b + 1] = v.y;
+        }
+        double *gp = &gphi[0][0];
 #pragma unroll
-        for (int k = 0; k < D; ++k) gphi[b][k] = R(slot, off_gphi + b * D + k);
+        for (int m = 0; m < NLOC * D; m += 2) {
+            const double2 v = R.pair(slot, off_gphi + m);
+            gp[m] = v.x;
+            gp[m + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < NLOC; ++b) {
+            phi[b] = R(slot, off_phi + b);
+#pragma unroll
+            for (int k = 0; k < D; ++k) gphi[b][k] = R(slot, off_gphi + b * D + k);
+        }
     }
 }
 
@@ -383,7 +439,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
-    const RecRef R{W.rec + (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
@@ -589,7 +645,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
-    const RecRef R{W.rec + (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
