@@ -116,38 +116,51 @@ struct CellCtx {
     double AX[ECH_NA1][NLOC];
 };
 
-template <class M, int I>
-__device__ __forceinline__ void put_rowj(const RecRef &R, int slot, int off, const RowJ &r, double w) {
+// the producer assembles its record in registers (compile-time offsets) and flushes it as 128-bit pairs,
+// so that every shared-memory store of a warp is conflict-free
+template <class M, int I, int LEN>
+__device__ __forceinline__ void put_rowj(double (&buf)[LEN], int off, const RowJ &r, double w) {
     static_for<0, NF>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         constexpr int p0 = LayoutOf<M>::get().o0[I][j], p1 = LayoutOf<M>::get().o1[I][j];
         constexpr int p2 = LayoutOf<M>::get().o2[I][j], p3 = LayoutOf<M>::get().o3[I][j];
         constexpr int h3 = M::G3[I][j];
-        if constexpr (p0 >= 0) R(slot, off + p0) = w * r.g0[j];
+        if constexpr (p0 >= 0) buf[off + p0] = w * r.g0[j];
         if constexpr (p1 >= 0) {
-            if constexpr (D == 2) {
-                R.set_pair(slot, off + p1, w * r.g1[j][0], w * r.g1[j][1]);
-            } else {
 #pragma unroll
-                for (int l = 0; l < D; ++l) R(slot, off + p1 + l) = w * r.g1[j][l];
-            }
+            for (int l = 0; l < D; ++l) buf[off + p1 + l] = w * r.g1[j][l];
         }
         if constexpr (p2 >= 0) {
-            if constexpr (D == 2) {
-                R.set_pair(slot, off + p2, w * r.g2[j][0], w * r.g2[j][1]);
-            } else {
 #pragma unroll
-                for (int k = 0; k < D; ++k) R(slot, off + p2 + k) = w * r.g2[j][k];
-            }
+            for (int k = 0; k < D; ++k) buf[off + p2 + k] = w * r.g2[j][k];
         }
-        if constexpr (h3 == 1) R(slot, off + p3) = w * r.g3[j][0][0];
+        if constexpr (h3 == 1) buf[off + p3] = w * r.g3[j][0][0];
         if constexpr (h3 == 2) {
 #pragma unroll
             for (int k = 0; k < D; ++k)
 #pragma unroll
-                for (int l = 0; l < D; ++l) R(slot, off + p3 + k * D + l) = w * r.g3[j][k][l];
+                for (int l = 0; l < D; ++l) buf[off + p3 + k * D + l] = w * r.g3[j][k][l];
         }
     });
+}
+
+template <int LEN>
+__device__ __forceinline__ void flush_record(const RecRef &R, int slot, const double (&buf)[LEN], int from, int to) {
+#pragma unroll
+    for (int m = 0; m < LEN; m += 2) {
+        if (m >= from && m < to) R.set_pair(slot, m, buf[m], buf[m + 1]);
+    }
+}
+
+template <int LEN>
+__device__ __forceinline__ void buf_basis(double (&buf)[LEN], int off_phi, int off_gphi, const double (&phi)[NLOC],
+                                          const double (&gphi)[NLOC][D]) {
+#pragma unroll
+    for (int b = 0; b < NLOC; ++b) {
+        buf[off_phi + b] = phi[b];
+#pragma unroll
+        for (int k = 0; k < D; ++k) buf[off_gphi + b * D + k] = gphi[b][k];
+    }
 }
 
 __device__ __forceinline__ void put_basis(const RecRef &R, int slot, int off_phi, int off_gphi,
@@ -473,17 +486,22 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
             double phi[NLOC], gphi[NLOC][D];
             int idx[D];
             double w;
+            double buf[JREC_LEN];
+#pragma unroll
+            for (int m = 0; m < JREC_LEN; ++m) buf[m] = 0.0;
             if (task < NQC) {
                 cell_point(task, idx, w);
                 own_side(own, idx, p, gm, phi, gphi);
                 w *= fabs(gm.detJ);
-                put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
+                buf_basis(buf, OFF_PHI, OFF_GPHI, phi, gphi);
                 static_for<0, NF>([&](auto ic) {
                     constexpr int I = decltype(ic)::value;
                     RowJ rj;
                     cell_jac<I>(p, rj);
-                    put_rowj<MC, I>(R, a, OFF_JP, rj, w);
+                    put_rowj<MC, I>(buf, OFF_JP, rj, w);
                 });
+                flush_record(R, a, buf, OFF_PHI, OFF_PHI2);
+                flush_record(R, a, buf, OFF_JP, OFF_JP + ((LAY_C.len + 1) & ~1));
             } else {
                 const int ft = task - NQC;
                 const int lf = ft / NQF, qf = ft - lf * NQF;
@@ -495,31 +513,34 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                     if constexpr (ECH_FAMILY_DG) {
                         double phi2[NLOC], gphi2[NLOC][D];
                         neighbour_side(W.nbd + (gg * NBD_SLOTS + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
-                        put_basis(R, a, OFF_PHI2, OFF_GPHI2, phi2, gphi2);
+                        buf_basis(buf, OFF_PHI2, OFF_GPHI2, phi2, gphi2);
                     }
                 }
                 own_side(own, idx, p, gm, phi, gphi);
                 p.fa = A.facet_area[c * NLF + lf];
                 facet_normal(gm, lf, p.n, ds);
                 w *= ds;
-                put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
+                buf_basis(buf, OFF_PHI, OFF_GPHI, phi, gphi);
                 if (nb < 0) {
                     const int cls = -nb - 1;
                     static_for<0, NF>([&](auto ic) {
                         constexpr int I = decltype(ic)::value;
                         RowJ rj;
                         efacet_jac<I>(cls, p, rj);
-                        put_rowj<ME, I>(R, a, OFF_JP, rj, w);
+                        put_rowj<ME, I>(buf, OFF_JP, rj, w);
                     });
+                    flush_record(R, a, buf, OFF_PHI, OFF_PHI2);
+                    flush_record(R, a, buf, OFF_JP, OFF_JP + ((LAY_E.len + 1) & ~1));
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
                         static_for<0, NF>([&](auto ic) {
                             constexpr int I = decltype(ic)::value;
                             RowJ rj, rjm;
                             ifacet_jac<I>(p, rj, rjm);
-                            put_rowj<MIP, I>(R, a, OFF_JP, rj, w);
-                            put_rowj<MIM, I>(R, a, OFF_JM, rjm, w);
+                            put_rowj<MIP, I>(buf, OFF_JP, rj, w);
+                            put_rowj<MIM, I>(buf, OFF_JM, rjm, w);
                         });
+                        flush_record(R, a, buf, 0, JREC_LEN);
                     }
                 }
             }
@@ -617,21 +638,21 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
 constexpr int RO_F0 = NLOC * (1 + D);
 constexpr int RO_F1 = RO_F0 + NF;
 
-template <class M>
-__device__ __forceinline__ void put_res(const RecRef &R, int slot, const Res &o, double w) {
+template <class M, int LEN>
+__device__ __forceinline__ void put_res(double (&buf)[LEN], const Res &o, double w) {
     static_for<0, NF>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         constexpr bool h0 = M::F0[i], h1 = M::F1[i];
         if constexpr (h0)
-            R(slot, RO_F0 + i) = w * o.f0[i];
+            buf[RO_F0 + i] = w * o.f0[i];
         else
-            R(slot, RO_F0 + i) = 0.0;
+            buf[RO_F0 + i] = 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             if constexpr (h1)
-                R(slot, RO_F1 + i * D + k) = w * o.f1[i][k];
+                buf[RO_F1 + i * D + k] = w * o.f1[i][k];
             else
-                R(slot, RO_F1 + i * D + k) = 0.0;
+                buf[RO_F1 + i * D + k] = 0.0;
         }
     });
 }
@@ -664,12 +685,15 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
             int idx[D];
             double w;
             Res o;
+            double buf[RREC_LEN];
+#pragma unroll
+            for (int m = 0; m < RREC_LEN; ++m) buf[m] = 0.0;
             if (task < NQC) {
                 cell_point(task, idx, w);
                 own_side(own, idx, p, gm, phi, gphi);
                 cell_res(p, o);
-                put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
-                put_res<MC>(R, a, o, w * fabs(gm.detJ));
+                buf_basis(buf, OFF_PHI, OFF_GPHI, phi, gphi);
+                put_res<MC>(buf, o, w * fabs(gm.detJ));
             } else {
                 const int ft = task - NQC;
                 const int lf = ft / NQF, qf = ft - lf * NQF;
@@ -680,19 +704,20 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
                 facet_point(lf, qf, idx, tt, w);
                 own_side(own, idx, p, gm, phi, gphi);
                 facet_normal(gm, lf, p.n, ds);
-                put_basis(R, a, OFF_PHI, OFF_GPHI, phi, gphi);
+                buf_basis(buf, OFF_PHI, OFF_GPHI, phi, gphi);
                 if (nb < 0) {
                     efacet_res(-nb - 1, p, o);
-                    put_res<ME>(R, a, o, w * ds);
+                    put_res<ME>(buf, o, w * ds);
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
                         double phi2[NLOC], gphi2[NLOC][D];
                         neighbour_side(W.nbd + (gg * NBD_SLOTS + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
                         ifacet_res(p, o);
-                        put_res<MIP>(R, a, o, w * ds);
+                        put_res<MIP>(buf, o, w * ds);
                     }
                 }
             }
+            flush_record(R, a, buf, 0, RREC_LEN);
         }
         __syncwarp();
         if (active) {
