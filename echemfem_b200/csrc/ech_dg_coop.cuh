@@ -95,17 +95,18 @@ constexpr int RWARPS = coop_warps(RREC_LEN);
 // accessor of one record: field k of (slot s, cell g) lives at k*32 + s*CPW + g, so that the lanes of
 // a warp write / read consecutive words (no bank conflicts; same-cell lanes broadcast)
 struct RecRef {
-    double *base;   // warp base + 2 * g
-    // fields are stored in pairs: (k even, k odd) adjacent, pairs strided by 32 lanes
+    double *base;   // warp base + 2 * (g * G): records of a warp are indexed by the producing lane
+    // pair (k even, k odd) of the record produced by lane (g, slot) lives at 16 * ((k/2) * 32 + g*G + slot):
+    // a warp-wide 128-bit store is contiguous, and the 128-bit loads of one quarter-warp (two cells)
+    // fall into different halves of a 128-byte bank row
     __device__ __forceinline__ double &operator()(int slot, int k) const {
-        return base[((k >> 1) * 32 + slot * CPW) * 2 + (k & 1)];
+        return base[((k >> 1) * 32 + slot) * 2 + (k & 1)];
     }
-    // 128-bit access to the pair (k, k+1), k even
     __device__ __forceinline__ double2 pair(int slot, int k) const {
-        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2);
+        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot) * 2);
     }
     __device__ __forceinline__ void set_pair(int slot, int k, double x, double y) const {
-        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2) = make_double2(x, y);
+        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot) * 2) = make_double2(x, y);
     }
 };
 
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
-    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * G * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
-    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * G * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
