@@ -95,18 +95,17 @@ constexpr int RWARPS = coop_warps(RREC_LEN);
 // accessor of one record: field k of (slot s, cell g) lives at k*32 + s*CPW + g, so that the lanes of
 // a warp write / read consecutive words (no bank conflicts; same-cell lanes broadcast)
 struct RecRef {
-    double *base;   // warp base + 2 * (g * G): records of a warp are indexed by the producing lane
-    // pair (k even, k odd) of the record produced by lane (g, slot) lives at 16 * ((k/2) * 32 + g*G + slot):
-    // a warp-wide 128-bit store is contiguous, and the 128-bit loads of one quarter-warp (two cells)
-    // fall into different halves of a 128-byte bank row
-    __device__ __forceinline__ double &operator()(int slot, int k) const {
-        return base[((k >> 1) * 32 + slot) * 2 + (k & 1)];
-    }
+    double *base;   // warp base + g
+    // field k of the record in slot s of cell g lives at word k*32 + s*CPW + g.  With lanes numbered
+    // cell-minor (g = lane % CPW, a = lane / CPW) a warp-wide 64-bit store of field k is one contiguous
+    // 256-byte row, and a load of slot s touches CPW consecutive words (same-cell lanes broadcast).
+    __device__ __forceinline__ double &operator()(int slot, int k) const { return base[k * 32 + slot * CPW]; }
     __device__ __forceinline__ double2 pair(int slot, int k) const {
-        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot) * 2);
+        return make_double2(base[k * 32 + slot * CPW], base[(k + 1) * 32 + slot * CPW]);
     }
     __device__ __forceinline__ void set_pair(int slot, int k, double x, double y) const {
-        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot) * 2) = make_double2(x, y);
+        base[k * 32 + slot * CPW] = x;
+        base[(k + 1) * 32 + slot * CPW] = y;
     }
 };
 
@@ -446,14 +445,14 @@ __device__ __forceinline__ void test_basis(const RecRef &R, int s, int a, double
 __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(const ech_dg_args A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / G, a = lane - g * G;
-    const bool active_lane = g < CPW;
+    const int g = lane % CPW, a = lane / CPW;       // cell-minor lane numbering
+    const bool active_lane = a < G;
     const int64_t c = ((int64_t)blockIdx.x * JWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
-    const RecRef R{W.rec + 2 * G * (active_lane ? g : 0)};
+    const RecRef R{W.rec + (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
@@ -661,13 +660,13 @@ __device__ __forceinline__ void put_res(double (&buf)[LEN], const Res &o, double
 __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg_args A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / G, a = lane - g * G;
-    const bool active_lane = g < CPW;
+    const int g = lane % CPW, a = lane / CPW;       // cell-minor lane numbering
+    const bool active_lane = a < G;
     const int64_t c = ((int64_t)blockIdx.x * RWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
-    const RecRef R{W.rec + 2 * G * (active_lane ? g : 0)};
+    const RecRef R{W.rec + (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
