@@ -94,21 +94,28 @@ constexpr int RWARPS = coop_warps(RREC_LEN);
 
 // accessor of one record: field k of (slot s, cell g) lives at k*32 + s*CPW + g, so that the lanes of
 // a warp write / read consecutive words (no bank conflicts; same-cell lanes broadcast)
+// Record addressing.  Fields are stored as 16-byte pairs; pair m of the record produced in slot s of
+// cell g lives at 16 * (m*32 + ridx(g, s)) bytes with
+//     ridx(g, s) = (g / GPQ) * (GPQ * G) + s * GPQ + g % GPQ,        GPQ = cells per quarter-warp.
+// Lanes are numbered cell-major (g = lane / G, a = lane % G).  Then
+//  * a warp-wide 128-bit STORE (lane (g, a) writes slot a) is a permutation inside each quarter-warp's
+//    own 128-byte row: conflict-free;
+//  * a 128-bit LOAD of slot s by a quarter-warp touches GPQ adjacent pairs (same-cell lanes
+//    broadcast).
+// Measured on the accumulate / evaluate phases (ms): 64-bit words 2.15 / 0.54; pairs with cell-minor
+// lanes 2.2 / 0.53; pairs, cell-major lanes, cell-minor records 1.69 / 0.89.
+constexpr int GPQ = (G <= 8 && 8 % G == 0) ? 8 / G : 1;
+__host__ __device__ constexpr int ridx_cell(int g) { return (g / GPQ) * (GPQ * G) + g % GPQ; }
 struct RecRef {
-    double *base;   // warp base + 2 * g
-    // Fields are stored as 16-byte pairs; pair m of the record in slot s of cell g lives at
-    // 16 * (m*32 + s*CPW + g) bytes.  Lanes are numbered cell-minor (g = lane % CPW, a = lane / CPW),
-    // so a warp-wide 128-bit store of pair m is one contiguous 512-byte row (each quarter-warp one
-    // 128-byte bank row), and a 128-bit load of slot s touches CPW consecutive pairs (same-cell lanes
-    // broadcast).  Measured: 1.69 ms vs 2.15 ms for the accumulate phase against 64-bit records.
+    double *base;   // warp base + 2 * ridx_cell(g)
     __device__ __forceinline__ double &operator()(int slot, int k) const {
-        return base[((k >> 1) * 32 + slot * CPW) * 2 + (k & 1)];
+        return base[((k >> 1) * 32 + slot * GPQ) * 2 + (k & 1)];
     }
     __device__ __forceinline__ double2 pair(int slot, int k) const {
-        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2);
+        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot * GPQ) * 2);
     }
     __device__ __forceinline__ void set_pair(int slot, int k, double x, double y) const {
-        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2) = make_double2(x, y);
+        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot * GPQ) * 2) = make_double2(x, y);
     }
 };
 
@@ -448,14 +455,14 @@ __device__ __forceinline__ void test_basis(const RecRef &R, int s, int a, double
 __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(const ech_dg_args A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane % CPW, a = lane / CPW;       // cell-minor lane numbering
-    const bool active_lane = a < G;
+    const int g = lane / G, a = lane - g * G;       // cell-major lane numbering
+    const bool active_lane = g < CPW;
     const int64_t c = ((int64_t)blockIdx.x * JWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
-    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * ridx_cell(active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
@@ -663,13 +670,13 @@ __device__ __forceinline__ void put_res(double (&buf)[LEN], const Res &o, double
 __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg_args A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane % CPW, a = lane / CPW;       // cell-minor lane numbering
-    const bool active_lane = a < G;
+    const int g = lane / G, a = lane - g * G;       // cell-major lane numbering
+    const bool active_lane = g < CPW;
     const int64_t c = ((int64_t)blockIdx.x * RWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
-    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * ridx_cell(active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
     const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
