@@ -94,28 +94,24 @@ constexpr int RWARPS = coop_warps(RREC_LEN);
 
 // accessor of one record: field k of (slot s, cell g) lives at k*32 + s*CPW + g, so that the lanes of
 // a warp write / read consecutive words (no bank conflicts; same-cell lanes broadcast)
-// Record addressing.  Fields are stored as 16-byte pairs; pair m of the record produced in slot s of
-// cell g lives at 16 * (m*32 + ridx(g, s)) bytes with
-//     ridx(g, s) = (g / GPQ) * (GPQ * G) + s * GPQ + g % GPQ,        GPQ = cells per quarter-warp.
-// Lanes are numbered cell-major (g = lane / G, a = lane % G).  Then
-//  * a warp-wide 128-bit STORE (lane (g, a) writes slot a) is a permutation inside each quarter-warp's
-//    own 128-byte row: conflict-free;
-//  * a 128-bit LOAD of slot s by a quarter-warp touches GPQ adjacent pairs (same-cell lanes
-//    broadcast).
-// Measured on the accumulate / evaluate phases (ms): 64-bit words 2.15 / 0.54; pairs with cell-minor
-// lanes 2.2 / 0.53; pairs, cell-major lanes, cell-minor records 1.69 / 0.89.
-constexpr int GPQ = (G <= 8 && 8 % G == 0) ? 8 / G : 1;
-__host__ __device__ constexpr int ridx_cell(int g) { return (g / GPQ) * (GPQ * G) + g % GPQ; }
+// Record addressing.  Fields are stored as 16-byte pairs; pair m of the record in slot s of cell g
+// lives at 16 * (m*32 + s*CPW + g) bytes.
+//  * PRODUCER role (evaluate): lane L evaluates slot L / CPW of cell L % CPW, so a warp-wide 128-bit
+//    store of pair m is one contiguous 512-byte row -> conflict-free.
+//  * CONSUMER role (accumulate): lane L owns test node L % G of cell L / G; a 128-bit load of slot s
+//    touches the CPW consecutive pairs of one 128-byte row, same-cell lanes broadcast.
+// Measured (accumulate / evaluate phase, ms): 64-bit words 2.15 / 0.54; one lane numbering for both
+// roles: cell-minor 2.2 / 0.53, cell-major 0.9 / 0.89; split roles: see profiles/.
 struct RecRef {
-    double *base;   // warp base + 2 * ridx_cell(g)
+    double *base;   // warp base + 2 * g
     __device__ __forceinline__ double &operator()(int slot, int k) const {
-        return base[((k >> 1) * 32 + slot * GPQ) * 2 + (k & 1)];
+        return base[((k >> 1) * 32 + slot * CPW) * 2 + (k & 1)];
     }
     __device__ __forceinline__ double2 pair(int slot, int k) const {
-        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot * GPQ) * 2);
+        return *reinterpret_cast<const double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2);
     }
     __device__ __forceinline__ void set_pair(int slot, int k, double x, double y) const {
-        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot * GPQ) * 2) = make_double2(x, y);
+        *reinterpret_cast<double2 *>(base + ((k >> 1) * 32 + slot * CPW) * 2) = make_double2(x, y);
     }
 };
 
@@ -462,10 +458,16 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
-    const RecRef R{W.rec + 2 * ridx_cell(active_lane ? g : 0)};
+    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
-    const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
+    // producer role: this lane evaluates slot ae of cell ge of the warp
+    const int ge = lane % CPW, ae = lane / CPW;
+    const int64_t ce = ((int64_t)blockIdx.x * JWARPS + warp) * CPW + ge;
+    const bool active_e = ae < G && ce < A.ncell;
+    const RecRef RE{W.rec + 2 * ge};
+    const int *meta_e = W.meta + ge * META_LEN;
+    const double *own = W.nbd + (ge * NBD_SLOTS + NLF) * NBD_LEN;
 
     int ncol = 0, pos_self = 0;
     int64_t rp[NF];
@@ -484,11 +486,11 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
 
     for (int round = 0; round < NROUND; ++round) {
         // ---------------- evaluate my task of this round
-        const int task = round * G + a;
+        const int task = round * G + ae;
 #ifdef ECH_DBG_NO_EVAL
         if (false) {
 #else
-        if (active && task < NTASK) {
+        if (active_e && task < NTASK) {
 #endif
             Pt p;
             p.K = A.consts;
@@ -510,24 +512,24 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                     cell_jac<I>(p, rj);
                     put_rowj<MC, I>(buf, OFF_JP, rj, w);
                 });
-                flush_record(R, a, buf, OFF_PHI, OFF_PHI2);
-                flush_record(R, a, buf, OFF_JP, OFF_JP + ((LAY_C.len + 1) & ~1));
+                flush_record(RE, ae, buf, OFF_PHI, OFF_PHI2);
+                flush_record(RE, ae, buf, OFF_JP, OFF_JP + ((LAY_C.len + 1) & ~1));
             } else {
                 const int ft = task - NQC;
                 const int lf = ft / NQF, qf = ft - lf * NQF;
-                const int nb = meta[lf];
+                const int nb = meta_e[lf];
                 int tt[D > 1 ? D - 1 : 1];
                 double ds;
                 facet_point(lf, qf, idx, tt, w);
                 if (nb >= 0) {
                     if constexpr (ECH_FAMILY_DG) {
                         double phi2[NLOC], gphi2[NLOC][D];
-                        neighbour_side(W.nbd + (gg * NBD_SLOTS + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
+                        neighbour_side(W.nbd + (ge * NBD_SLOTS + lf) * NBD_LEN, meta_e[NLF + lf], tt, p, phi2, gphi2);
                         buf_basis(buf, OFF_PHI2, OFF_GPHI2, phi2, gphi2);
                     }
                 }
                 own_side(own, idx, p, gm, phi, gphi);
-                p.fa = A.facet_area[c * NLF + lf];
+                p.fa = A.facet_area[ce * NLF + lf];
                 facet_normal(gm, lf, p.n, ds);
                 w *= ds;
                 buf_basis(buf, OFF_PHI, OFF_GPHI, phi, gphi);
@@ -539,8 +541,8 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                         efacet_jac<I>(cls, p, rj);
                         put_rowj<ME, I>(buf, OFF_JP, rj, w);
                     });
-                    flush_record(R, a, buf, OFF_PHI, OFF_PHI2);
-                    flush_record(R, a, buf, OFF_JP, OFF_JP + ((LAY_E.len + 1) & ~1));
+                    flush_record(RE, ae, buf, OFF_PHI, OFF_PHI2);
+                    flush_record(RE, ae, buf, OFF_JP, OFF_JP + ((LAY_E.len + 1) & ~1));
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
                         static_for<0, NF>([&](auto ic) {
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                             put_rowj<MIP, I>(buf, OFF_JP, rj, w);
                             put_rowj<MIM, I>(buf, OFF_JM, rjm, w);
                         });
-                        flush_record(R, a, buf, 0, JREC_LEN);
+                        flush_record(RE, ae, buf, 0, JREC_LEN);
                     }
                 }
             }
@@ -676,18 +678,21 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
-    const RecRef R{W.rec + 2 * ridx_cell(active_lane ? g : 0)};
-    const int gg = active_lane ? g : 0;
-    const int *meta = W.meta + gg * META_LEN;
-    const double *own = W.nbd + (gg * NBD_SLOTS + NLF) * NBD_LEN;
+    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
+    const int ge = lane % CPW, ae = lane / CPW;     // producer role (see RecRef)
+    const int64_t ce = ((int64_t)blockIdx.x * RWARPS + warp) * CPW + ge;
+    const bool active_e = ae < G && ce < A.ncell;
+    const RecRef RE{W.rec + 2 * ge};
+    const int *meta_e = W.meta + ge * META_LEN;
+    const double *own = W.nbd + (ge * NBD_SLOTS + NLF) * NBD_LEN;
     stage_neighbours(A, W, g, a, c, active, fstride);
     double r[NF];
 #pragma unroll
     for (int i = 0; i < NF; ++i) r[i] = 0.0;
 
     for (int round = 0; round < NROUND; ++round) {
-        const int task = round * G + a;
-        if (active && task < NTASK) {
+        const int task = round * G + ae;
+        if (active_e && task < NTASK) {
             Pt p;
             p.K = A.consts;
             Geo gm;
@@ -707,8 +712,8 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
             } else {
                 const int ft = task - NQC;
                 const int lf = ft / NQF, qf = ft - lf * NQF;
-                const int nb = meta[lf];
-                p.fa = A.facet_area[c * NLF + lf];
+                const int nb = meta_e[lf];
+                p.fa = A.facet_area[ce * NLF + lf];
                 int tt[D > 1 ? D - 1 : 1];
                 double ds;
                 facet_point(lf, qf, idx, tt, w);
@@ -721,13 +726,13 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
                 } else {
                     if constexpr (ECH_FAMILY_DG) {
                         double phi2[NLOC], gphi2[NLOC][D];
-                        neighbour_side(W.nbd + (gg * NBD_SLOTS + lf) * NBD_LEN, meta[NLF + lf], tt, p, phi2, gphi2);
+                        neighbour_side(W.nbd + (ge * NBD_SLOTS + lf) * NBD_LEN, meta_e[NLF + lf], tt, p, phi2, gphi2);
                         ifacet_res(p, o);
                         put_res<MIP>(buf, o, w * ds);
                     }
                 }
             }
-            flush_record(R, a, buf, 0, RREC_LEN);
+            flush_record(RE, ae, buf, 0, RREC_LEN);
         }
         __syncwarp();
         if (active) {
