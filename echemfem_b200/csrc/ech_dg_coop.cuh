@@ -437,7 +437,11 @@ __device__ __forceinline__ void store_blocks(double *__restrict__ out, const int
         static_for<0, NF>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             constexpr bool on = OWN ? OWN_BLOCK[I][j] : NBR_BLOCK[I][j];
+#ifdef ECH_DBG_NO_STORE
+            if constexpr (on) { if (acc[I][j][0] == 1.2345e300) store_block(vals + block_offset<I, j>(ncol, pos), acc[I][j]); }
+#else
             if constexpr (on) store_block(vals + block_offset<I, j>(ncol, pos), acc[I][j]);
+#endif
         });
     });
 }

@@ -18,7 +18,7 @@ def Uex(x):
 
 def make_vel(vavg, d=2):
     def vel(x):
-        v = np.zeros(x.shape, dtype=x.dtype)
+        v = np.zeros(x.shape, dtype=float)
         y = x[..., 1]
         v[..., 0] = 6.0 * vavg * y * (1.0 - y)
         return v
@@ -41,7 +41,7 @@ def forcing(vavg, D1=0.5, D2=1.0, z1=2.0, z2=-2.0):
     return f
 
 
-def adm_problem(vavg, family="DG", p=1, D1=0.5, D2=1.0, variant="spectral"):
+def adm_problem(vavg, family="DG", p=1, D1=0.5, D2=1.0, variant="spectral", markers=None):
     """AdvectionDiffusionMigrationSolver of the reference test, for the oracle."""
     from oracle.forms import Problem
     conc_params = [
@@ -53,6 +53,7 @@ def adm_problem(vavg, family="DG", p=1, D1=0.5, D2=1.0, variant="spectral"):
         "F": 1.0, "R": 1.0, "T": 1.0, "U_app": Uex,
         "bulk reaction": forcing(vavg, D1, D2),
     }
-    markers = {"applied": (1, 2, 3, 4), "bulk dirichlet": (1, 2, 3, 4)}
+    if markers is None:
+        markers = {"applied": (1, 2, 3, 4), "bulk dirichlet": (1, 2, 3, 4)}
     return Problem(conc_params, physical_params, markers, p=p, family=family,
                    vel=make_vel(vavg), variant=variant)

@@ -80,3 +80,55 @@ def test_newton_solution_matches_oracle():
     for f in range(2):
         a, b = u[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
         assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
+
+
+def _compare(disc, s, tag):
+    from echemfem_b200.newton import NewtonEngine
+    eng = NewtonEngine(s)
+    u = _state(disc)
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+    indptr, indices = disc.pattern()
+    rp, ci, _ = eng.csr_host()
+    assert np.array_equal(rp, indptr), tag
+    assert np.array_equal(ci, indices), tag
+    for variant in (0, 1):
+        eng.set_variant(variant)
+        F = eng.residual(s.u.tensor).cpu().numpy()
+        _assert_close(F, disc.residual(u), "%s residual v%d" % (tag, variant))
+        eng.vals.zero_()
+        eng.jacobian(s.u.tensor)
+        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "%s jacobian v%d" % (tag, variant))
+    eng.set_variant(0)
+
+
+@pytest.mark.parametrize("p,N", [(2, 3), (3, 3)])
+def test_higher_order_dg_matches_oracle(p, N):
+    """DG Q2 / Q3 (cfg2 sweep P1-P3): under-integrated rule degree p+1 kept."""
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    disc = Discretization(unit_square_mesh(N), mms_cases.adm_problem(1.0, p=p))
+    s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, p=p)
+    _compare(disc, s, "Q%d" % p)
+
+
+def test_graded_mesh_matches_oracle():
+    """Non-uniform tensor mesh (the Bortels meshes are graded; cell volumes / facet areas vary)."""
+    from oracle.mesh import tensor_mesh
+    from oracle.assemble import Discretization
+    from echemfem_b200.mesh import TensorMesh
+    ax = [np.array([0.0, 0.1, 0.35, 0.7, 1.0]), np.array([0.0, 0.2, 0.25, 0.6, 0.8, 1.0])]
+    disc = Discretization(tensor_mesh(ax), mms_cases.adm_problem(10.0))
+    s = product_cases.AdvectionDiffusionMigrationSolver(0, 10.0, mesh=TensorMesh(ax))
+    _compare(disc, s, "graded")
+
+
+def test_extruded_3d_matches_oracle():
+    """3D hexahedra, DQ1 x DG1 (cfg4 element); side walls carry ids 1-4, top/bottom are natural."""
+    from oracle.mesh import unit_cube_mesh
+    from oracle.assemble import Discretization
+    from echemfem_b200.mesh import UnitSquareMesh, ExtrudedMesh
+    disc = Discretization(unit_cube_mesh(3, 2, 2), mms_cases.adm_problem(1.0))
+    base = UnitSquareMesh(3, 2)
+    mesh = ExtrudedMesh(base, 2, 0.5)
+    s = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, mesh=mesh)
+    _compare(disc, s, "hex")
