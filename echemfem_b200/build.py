@@ -79,7 +79,9 @@ def build_module(header_text, key, force=False, extra_flags=()):
     with open(hdr, "w") as f:
         f.write(header_text)
     tmp = out + ".tmp.%d" % os.getpid()
-    _run([_nvcc()] + NVCC_FLAGS + list(extra_flags) +
-         ["-include", hdr, os.path.join(CSRC, "ech_module.cu"), "-o", tmp])
+    # physics modules are dlopen'ed side by side and define the same C++ names: no STB_GNU_UNIQUE
+    # symbols (inline-function statics would otherwise be shared between modules)
+    _run([_nvcc()] + NVCC_FLAGS + ["-Xcompiler", "-fno-gnu-unique", "-Xcompiler", "-fvisibility=hidden"] +
+         list(extra_flags) + ["-include", hdr, os.path.join(CSRC, "ech_module.cu"), "-o", tmp])
     os.replace(tmp, out)
     return out

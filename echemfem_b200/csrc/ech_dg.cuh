@@ -33,7 +33,13 @@
 namespace echdg {
 using namespace echgen;
 
-__host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+// iterative on purpose: a recursive helper that is not inlined makes the stack size unknowable and
+// caps the kernel at cudaLimitStackSize
+__host__ __device__ constexpr int ipow(int b, int e) {
+    int r = 1;
+    for (int i = 0; i < e; ++i) r *= b;
+    return r;
+}
 constexpr int NV = 1 << D;
 constexpr int NLF = 2 * D;
 constexpr int NLOC = ipow(N1, D);
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const ech_dg_args A) {
 }
 
 // ---------------------------------------------------------------- launches
-inline int launch_residual(const ech_dg_args *a, cudaStream_t s) {
+static int launch_residual(const ech_dg_args *a, cudaStream_t s) {
     const int64_t nthreads = a->ncell * NLOC;
     if (nthreads == 0) return 0;
     const int block = 128;
@@ -618,7 +624,7 @@ inline int launch_residual(const ech_dg_args *a, cudaStream_t s) {
 }
 
 template <int I>
-inline int launch_jacobian_rows(const ech_dg_args *a, cudaStream_t s) {
+static int launch_jacobian_rows(const ech_dg_args *a, cudaStream_t s) {
     if constexpr (I < NF) {
         const int64_t nthreads = a->ncell * NLOC;
         const int block = 128;
@@ -632,7 +638,7 @@ inline int launch_jacobian_rows(const ech_dg_args *a, cudaStream_t s) {
     }
 }
 
-inline int launch_jacobian(const ech_dg_args *a, cudaStream_t s) {
+static int launch_jacobian(const ech_dg_args *a, cudaStream_t s) {
     if (a->ncell == 0) return 0;
     return launch_jacobian_rows<0>(a, s);
 }

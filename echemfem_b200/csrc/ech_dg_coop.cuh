@@ -18,6 +18,7 @@
 // is used.  Everything else (owner-computes rows, exactly-once vector stores, constant-memory
 // 1D tables, compile-time coupling masks) is as in ech_dg.cuh.
 #pragma once
+#include <stdio.h>
 #include "ech_dg.cuh"
 
 namespace echdg {
@@ -79,7 +80,7 @@ constexpr int NBD_LEN = (NBD_CV + 2) | 1;
 constexpr int META_LEN = 3 * NLF;
 
 constexpr int NBD_SLOTS = NLF + 1;   // neighbours + the cell itself
-__host__ __device__ constexpr int warp_smem_doubles(int reclen) { return reclen * 32 + CPW * NBD_SLOTS * NBD_LEN + (CPW * META_LEN + 1) / 2; }
+__host__ __device__ constexpr int warp_smem_doubles(int reclen) { return (reclen * 32 + CPW * NBD_SLOTS * NBD_LEN + (CPW * META_LEN + 1) / 2 + 1) & ~1; }
 constexpr int coop_warps(int reclen) {
     const int per_warp = warp_smem_doubles(reclen) * 8;
 #ifdef ECH_COOP_WARPS
@@ -768,35 +769,49 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
 constexpr int JSMEM = JWARPS * warp_smem_doubles(JREC_LEN) * 8;
 constexpr int RSMEM = RWARPS * warp_smem_doubles(RREC_LEN) * 8;
 
-inline int coop_setup() {
+static int coop_setup() {
     static int done = 0;
     if (done) return 0;
     cudaError_t e = cudaFuncSetAttribute(jacobian_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) {
+        fprintf(stderr, "echem_b200: cudaFuncSetAttribute(jacobian_coop_kernel, %d B) failed: %s\n", JSMEM,
+                cudaGetErrorString(e));
+        return (int)e;
+    }
     e = cudaFuncSetAttribute(residual_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) {
+        fprintf(stderr, "echem_b200: cudaFuncSetAttribute(residual_coop_kernel, %d B) failed: %s\n", RSMEM,
+                cudaGetErrorString(e));
+        return (int)e;
+    }
     done = 1;
     return 0;
 }
 
-inline int launch_jacobian_coop(const ech_dg_args *a, cudaStream_t s) {
+static int launch_jacobian_coop(const ech_dg_args *a, cudaStream_t s) {
     if (a->ncell == 0) return 0;
     int e = coop_setup();
     if (e) return e;
     const int64_t cells_per_block = (int64_t)JWARPS * CPW;
     const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
     jacobian_coop_kernel<<<(unsigned)grid, JWARPS * 32, JSMEM, s>>>(*a);
-    return (int)cudaGetLastError();
+    e = (int)cudaGetLastError();
+    if (e) fprintf(stderr, "echem_b200: jacobian_coop_kernel<<<%lld, %d, %d>>> failed: %s\n", (long long)grid,
+                   JWARPS * 32, JSMEM, cudaGetErrorString((cudaError_t)e));
+    return e;
 }
 
-inline int launch_residual_coop(const ech_dg_args *a, cudaStream_t s) {
+static int launch_residual_coop(const ech_dg_args *a, cudaStream_t s) {
     if (a->ncell == 0) return 0;
     int e = coop_setup();
     if (e) return e;
     const int64_t cells_per_block = (int64_t)RWARPS * CPW;
     const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
     residual_coop_kernel<<<(unsigned)grid, RWARPS * 32, RSMEM, s>>>(*a);
-    return (int)cudaGetLastError();
+    e = (int)cudaGetLastError();
+    if (e) fprintf(stderr, "echem_b200: residual_coop_kernel<<<%lld, %d, %d>>> failed: %s\n", (long long)grid,
+                   RWARPS * 32, RSMEM, cudaGetErrorString((cudaError_t)e));
+    return e;
 }
 
 }  // namespace echdg

@@ -37,13 +37,14 @@ typedef struct ech_dg_args {
 
 /* info[0..7] = d, p, nf, naux, nconst, nq, nclasses, family(1=DG); then nf*nf own-block flags,
  * nf*nf neighbour-block flags. Returns the number of ints written. */
-int ech_mod_describe(int32_t *info, int capacity);
-int ech_mod_residual(const ech_dg_args *a, void *stream);
-int ech_mod_jacobian(const ech_dg_args *a, void *stream);
+#define ECH_MOD_EXPORT __attribute__((visibility("default")))
+ECH_MOD_EXPORT int ech_mod_describe(int32_t *info, int capacity);
+ECH_MOD_EXPORT int ech_mod_residual(const ech_dg_args *a, void *stream);
+ECH_MOD_EXPORT int ech_mod_jacobian(const ech_dg_args *a, void *stream);
 /* 0: cooperative kernels (default), 1: row-per-thread kernels */
-void ech_mod_set_variant(int variant);
+ECH_MOD_EXPORT void ech_mod_set_variant(int variant);
 /* number of kernel launches one residual / Jacobian call makes */
-int ech_mod_launches(int which);
+ECH_MOD_EXPORT int ech_mod_launches(int which);
 
 #ifdef __cplusplus
 }
