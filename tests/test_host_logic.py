@@ -1,0 +1,107 @@
+"""Host-side logic of the product: mesh connectivity, tables, symbolic layer, contract validation."""
+import numpy as np
+import pytest
+
+from echemfem_b200 import symbolic as S
+from echemfem_b200.fd import *  # noqa: F401,F403
+from echemfem_b200 import EchemSolver
+from echemfem_b200.mesh import TensorMesh
+from echemfem_b200.tables import ElementTables, lobatto_nodes
+
+
+def test_connectivity_matches_oracle_mesh():
+    from oracle.mesh import tensor_mesh
+    ax = [np.linspace(0, 1, 4), np.linspace(0, 2, 3), np.linspace(0, 1, 3)]
+    m = TensorMesh(ax)
+    o = tensor_mesh(ax)
+    assert m.num_cells == o.num_cells
+    assert np.array_equal(m.nbr_cell, o.nbr)
+    mask = o.nbr >= 0
+    assert np.array_equal(m.nbr_lf[mask], o.nbr_lf[mask])
+    assert m.num_interior_facets == o.int_facets.shape[0]
+    assert np.all(m.nbr_orient == 0)               # tensor meshes are consistently oriented
+    for f, (c, lf) in enumerate(o.ext_facets):
+        assert m.ext_marker[c, lf] == o.ext_marker[f]
+
+
+def test_connectivity_slots_are_sorted_ranks():
+    m = UnitSquareMesh(3, 3)
+    nbr, code, slot, slot_self, ncol = m.connectivity({1: 1, 2: 1, 3: 2, 4: 2})
+    for c in range(m.num_cells):
+        cells = {int(slot_self[c]): c}
+        for lf in range(4):
+            if nbr[c, lf] >= 0:
+                cells[int(slot[c, lf])] = int(nbr[c, lf])
+        assert sorted(cells) == list(range(ncol[c]))
+        assert [cells[k] for k in sorted(cells)] == sorted(cells.values())
+    assert set(np.unique(nbr[nbr < 0])) == {-2, -3}        # boundary classes 1 and 2
+
+
+def test_tables_against_oracle_fem():
+    from oracle import fem
+    for p in (1, 2, 3):
+        for fam in ("DG", "CG"):
+            t = ElementTables(p, fam)
+            assert np.allclose(t.nodes, fem.nodes_1d(p, fam), atol=1e-15)
+            L, dL = fem.lagrange_1d(fem.nodes_1d(p, fam), t.pts)
+            assert np.allclose(t.L, L, atol=1e-13) and np.allclose(t.dL, dL, atol=1e-12)
+            assert t.q == fem.num_quad_points(p)
+    assert np.allclose(lobatto_nodes(3), [0, 0.5, 1])
+
+
+def test_symbolic_restriction_and_grad():
+    S.set_geometric_dimension(2)
+    u = S.FieldRef("u", 0, 2)
+    v = S.FieldRef("v", 0, 2)
+    n = S.facet_normal(2)
+    j = jump(v, n)
+    assert str(j.v[0]) in ("n0*v0_p - n0*v0_m", "-n0*v0_m + n0*v0_p")
+    g = grad(u * u)
+    assert g.v[1] == 2 * S.sym("u0") * S.sym("gu0_1")
+    x = S.coordinate(2)
+    assert div(as_vector((x[0] ** 2, x[0] * x[1]))).v == 3 * S.sym("x0")
+    k = Constant(2.0)
+    assert float(k) == 2.0
+    k.assign(5.0)
+    assert float(k) == 5.0
+    with pytest.raises(NotImplementedError):
+        grad(grad(u)[0])
+
+
+class _Bad(EchemSolver):
+    def __init__(self, flow, family="DG"):
+        mesh = UnitSquareMesh(2, 2)
+        cp = [{"name": "A", "diffusion coefficient": 1.0, "z": 1.0, "bulk": 1.0},
+              {"name": "B", "diffusion coefficient": 1.0, "z": -1.0, "bulk": 1.0}]
+        pp = {"flow": flow, "F": 1.0, "R": 1.0, "T": 1.0}
+        super().__init__(cp, pp, mesh, family=family)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk": 1}
+
+
+@pytest.mark.parametrize("flow,msg", [
+    (["diffusion", "electroneutrality"], "Electroneutrality constraint requires Migration"),
+    (["diffusion", "migration"], "Migration requires Electroneutrality or Poisson"),
+    (["diffusion", "migration", "poisson", "electroneutrality"], "Electroneutrality not compatible with Poisson"),
+    (["diffusion", "finite size"], "finite size effects only implemented with CG"),
+    (["diffusion", "darcy"], "Darcy requires a porous model"),
+])
+def test_invalid_flow_combinations_raise(flow, msg):
+    """Same NotImplementedError messages as the reference (echemfem/solver.py:115-142)."""
+    with pytest.raises(NotImplementedError, match=msg):
+        _Bad(flow)
+
+
+def test_contract_attributes():
+    import product_cases
+    s = product_cases.AdvectionDiffusionMigrationSolver(2, 1.0)
+    assert s.num_c == 2 and s.num_liquid == 1 and s.num_mass == 1 and s.i_el == 1
+    assert s.i_c == {"C1": 0} and s.i_Ul == 1 and s.idx_c == [0]
+    assert s.boundary_markers["applied"] == (1, 2, 3, 4)
+    assert s.solver_parameters["pc_type"] == "lu" and s.solver_parameters["snes_max_it"] == 50
+    s.init_solver_parameters(pc_type="ilu")
+    assert s.solver_parameters["ksp_type"] == "fgmres" and s.solver_parameters["ksp_gmres_restart"] == 1000
+    with pytest.raises(NotImplementedError):
+        s.init_solver_parameters(pc_type="gmg")
+    assert s.W.dim() == 2 * 16 and len(s.u.subfunctions) == 2
