@@ -57,3 +57,41 @@ def adm_problem(vavg, family="DG", p=1, D1=0.5, D2=1.0, variant="spectral", mark
         markers = {"applied": (1, 2, 3, 4), "bulk dirichlet": (1, 2, 3, 4)}
     return Problem(conc_params, physical_params, markers, p=p, family=family,
                    vel=make_vel(vavg), variant=variant)
+
+
+def bortels_problem(U_app_factor=1.0):
+    """examples/bortels_threeion_nondim.py for the oracle: Butler-Volmer electrodes as numpy closures."""
+    from oracle.forms import Problem
+    import product_cases
+    P = product_cases.bortels_parameters()
+    U_app = P["U_app_hat"] * U_app_factor
+    conc_params = [
+        {"name": "Cu", "diffusion coefficient": P["D_Cu_hat"], "z": 2., "bulk": 1., "C_ND": 1.},
+        {"name": "SO4", "diffusion coefficient": P["D_SO4_hat"], "z": -2., "bulk": 1., "C_ND": P["C_SO4"]},
+        {"name": "H", "diffusion coefficient": P["D_H_hat"], "z": 1., "bulk": 1., "C_ND": P["C_H"]},
+    ]
+    physical_params = {"flow": ["advection", "diffusion", "migration", "electroneutrality"],
+                       "F": 1.0, "R": 1.0, "T": 1.0, "U_app": U_app}
+
+    def reaction(V):
+        def r(u, x):
+            eta = V - u[2]
+            return P["J0_hat"] * (np.exp(eta) - u[0] * np.exp(-eta))
+        return r
+    echem_params = [
+        {"reaction": reaction(0.0), "electrons": 2, "stoichiometry": {"Cu": 1}, "boundary": "cathode"},
+        {"reaction": reaction(U_app), "electrons": 2, "stoichiometry": {"Cu": 1}, "boundary": "anode"},
+    ]
+    markers = {"inlet": (10,), "outlet": (11,), "anode": (12,), "cathode": (13,)}
+    return Problem(conc_params, physical_params, markers, echem_params=echem_params, vel=make_vel(1.0))
+
+
+def bortels_oracle_mesh(n_in, n_el, n_out, n_y):
+    from oracle.mesh import tensor_mesh
+    from echemfem_b200.meshes import bortels_axes, bortels_markers
+    x, y = bortels_axes(n_in, n_el, n_out, n_y)
+    fn = bortels_markers()
+
+    def marker(xv):
+        return int(fn(xv[None], None)[0])
+    return tensor_mesh([x, y], boundary_id_fn=marker)

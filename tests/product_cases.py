@@ -43,3 +43,57 @@ class AdvectionDiffusionMigrationSolver(EchemSolver):
         h = 1.0
         comps = [6. * self.physical_params["v_avg"] / h**2 * y * (h - y)] + [Constant(0.)] * (len(xs) - 1)
         self.vel = as_vector(comps)
+
+
+def bortels_parameters():
+    """Non-dimensional three-ion parameters of examples/bortels_threeion_nondim.py:28-47."""
+    D_Cu, J0, C_Cu = 7.2e-10, 30., 10.
+    D_SO4, C_SO4 = 10.65e-10, 1010.
+    D_H, C_H = 93.12e-10, 2000.
+    F, R, T = 96485.3329, 8.3144598, 273.15 + 25.
+    U_app, v_avg, L = 0.006, 0.03, 0.01
+    return {"D_Cu_hat": D_Cu / L / v_avg, "D_SO4_hat": D_SO4 / L / v_avg, "D_H_hat": D_H / L / v_avg,
+            "J0_hat": J0 / v_avg / C_Cu / F, "U_app_hat": F / R / T * U_app,
+            "C_SO4": C_SO4 / C_Cu, "C_H": C_H / C_Cu}
+
+
+class BortelsSolver(EchemSolver):
+    """examples/bortels_threeion_nondim.py:24-135 of the reference (BASELINE.json configs[0])."""
+
+    def __init__(self, mesh, U_app_factor=1.0):
+        P = bortels_parameters()
+        conc_params = [
+            {"name": "Cu", "diffusion coefficient": P["D_Cu_hat"], "z": 2., "bulk": 1., "C_ND": 1.},
+            {"name": "SO4", "diffusion coefficient": P["D_SO4_hat"], "z": -2., "bulk": 1., "C_ND": P["C_SO4"]},
+            {"name": "H", "diffusion coefficient": P["D_H_hat"], "z": 1., "bulk": 1., "C_ND": P["C_H"]},
+        ]
+        physical_params = {"flow": ["advection", "diffusion", "migration", "electroneutrality"],
+                           "F": 1.0, "R": 1.0, "T": 1.0, "U_app": P["U_app_hat"] * U_app_factor, "v_avg": 1.0}
+
+        def reaction(u, V):
+            C = u[0]
+            U = u[2]
+            C_b = conc_params[0]["bulk"]
+            F, R, T = physical_params["F"], physical_params["R"], physical_params["T"]
+            eta = V - U
+            return P["J0_hat"] * (exp(F / R / T * (eta)) - (C / C_b) * exp(-F / R / T * (eta)))
+
+        def reaction_cathode(u):
+            return reaction(u, Constant(0))
+
+        def reaction_anode(u):
+            return reaction(u, Constant(physical_params["U_app"]))
+
+        echem_params = [
+            {"reaction": reaction_cathode, "electrons": 2, "stoichiometry": {"Cu": 1}, "boundary": "cathode"},
+            {"reaction": reaction_anode, "electrons": 2, "stoichiometry": {"Cu": 1}, "boundary": "anode"},
+        ]
+        super().__init__(conc_params, physical_params, mesh, echem_params=echem_params)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"inlet": (10,), "outlet": (11,), "anode": (12,), "cathode": (13,)}
+
+    def set_velocity(self):
+        y = SpatialCoordinate(self.mesh)[1]
+        h = 1.0
+        self.vel = as_vector((6. * self.physical_params["v_avg"] / h**2 * y * (h - y), Constant(0.)))

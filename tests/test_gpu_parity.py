@@ -133,3 +133,48 @@ def test_extruded_3d_matches_oracle():
     mesh = ExtrudedMesh(base, 2, 0.5)
     s = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, mesh=mesh)
     _compare(disc, s, "hex")
+
+
+def test_bortels_three_ion_matches_oracle():
+    """BASELINE configs[0]: 3 ions (H eliminated), Butler-Volmer electrodes, inlet/outlet, graded mesh.
+
+    Also checks the block structure: 7 of the 9 field blocks exist (no Cu-SO4 coupling)."""
+    from oracle.assemble import Discretization
+    from echemfem_b200.meshes import BortelsMesh
+    from echemfem_b200.newton import NewtonEngine
+    n = (5, 6, 4, 5)
+    disc = Discretization(mms_cases.bortels_oracle_mesh(*n), mms_cases.bortels_problem())
+    s = product_cases.BortelsSolver(BortelsMesh(*n))
+    eng = NewtonEngine(s)
+    assert eng.form.own_mask.sum() == 7 and not eng.form.own_mask[0, 1] and not eng.form.own_mask[1, 0]
+    x = disc.node_coords
+    pert = 1e-2 * np.sin(3 * x[:, 0] + 5 * x[:, 1])
+    u = np.concatenate([1.0 + pert, 1.0 - 0.5 * pert, 0.1 + pert])
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+    indptr, indices = disc.pattern()
+    rp, ci, _ = eng.csr_host()
+    assert np.array_equal(rp, indptr) and np.array_equal(ci, indices)
+    for variant in (0, 1):
+        eng.set_variant(variant)
+        _assert_close(eng.residual(s.u.tensor).cpu().numpy(), disc.residual(u), "bortels residual")
+        eng.jacobian(s.u.tensor)
+        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "bortels jacobian")
+    eng.set_variant(0)
+
+
+def test_bortels_newton_solution_matches_oracle():
+    """setup_solver() (bulk guess + potential pre-solve) + solve() vs the oracle, 1e-8 relative per field."""
+    from oracle.assemble import Discretization
+    from oracle.newton import solve_problem
+    from echemfem_b200.meshes import BortelsMesh
+    n = (6, 8, 6, 6)
+    disc = Discretization(mms_cases.bortels_oracle_mesh(*n), mms_cases.bortels_problem())
+    u_ref, info = solve_problem(disc)
+    s = product_cases.BortelsSolver(BortelsMesh(*n))
+    s.setup_solver()
+    s.solve()
+    u = s.u.numpy()
+    Ns = disc.ndof_scalar
+    for f in range(3):
+        a, b = u[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
+        assert np.linalg.norm(a - b) <= 1e-8 * max(np.linalg.norm(b), 1e-3), "field %d" % f
