@@ -61,6 +61,17 @@ def skeleton_hash():
     return h.hexdigest()[:8]
 
 
+def _prune_stale():
+    """Drop modules built against an older kernel skeleton (they would never be loaded again)."""
+    tag = "_" + skeleton_hash()
+    for name in os.listdir(MODDIR):
+        if name.startswith("libech_phys_") and name.endswith(".so") and tag not in name:
+            try:
+                os.remove(os.path.join(MODDIR, name))
+            except OSError:
+                pass
+
+
 def module_path(key, extra_flags=()):
     tag = skeleton_hash()
     if extra_flags:
@@ -71,6 +82,7 @@ def module_path(key, extra_flags=()):
 def build_module(header_text, key, force=False, extra_flags=()):
     """Compile one physics module; returns the path of the shared object."""
     os.makedirs(MODDIR, exist_ok=True)
+    _prune_stale()
     extra_flags = tuple(extra_flags) or tuple(os.environ.get("ECH_MODULE_FLAGS", "").split())
     out = module_path(key, extra_flags)
     if os.path.exists(out) and not force:
