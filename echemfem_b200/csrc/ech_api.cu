@@ -131,23 +131,27 @@ extern "C" int64_t ech_launch_count(const ech_handle *) { return g_launches; }
 
 extern "C" int ech_num_rows(const ech_handle *h, int64_t *nrows) {
     if (!h || !nrows) return ECH_ERR_ARG;
-    *nrows = (int64_t)h->nf * h->mesh.ncell * h->nloc;
+    *nrows = (int64_t)h->nf * h->mesh.ncell_total * h->nloc;   // ghost rows exist and are empty
     return ECH_OK;
 }
 
 // =============================================================== sparsity pattern
 struct PatternPlan {
     int nf, nloc, nlf;
-    int64_t ncell;
+    int64_t ncell, ncell_total;
     unsigned long long own_bits[16], nbr_bits[16];
 };
 
 __global__ void row_length_kernel(PatternPlan P, const uint8_t *__restrict__ ncol, int64_t *__restrict__ len) {
-    const int64_t rows_per_field = P.ncell * P.nloc;
+    const int64_t rows_per_field = P.ncell_total * P.nloc;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows_per_field * P.nf) return;
     const int i = (int)(r / rows_per_field);
     const int64_t c = (r - i * rows_per_field) / P.nloc;
+    if (c >= P.ncell) {          // ghost cell: its rows belong to another rank
+        len[r] = 0;
+        return;
+    }
     const int nc = ncol[c];
     int n = 0;
     for (int j = 0; j < P.nf; ++j) {
@@ -159,11 +163,12 @@ __global__ void row_length_kernel(PatternPlan P, const uint8_t *__restrict__ nco
 __global__ void colidx_kernel(PatternPlan P, const int32_t *__restrict__ nbr, const uint8_t *__restrict__ slot,
                               const uint8_t *__restrict__ slot_self, const uint8_t *__restrict__ ncol,
                               const int64_t *__restrict__ rowptr, int32_t *__restrict__ colidx) {
-    const int64_t rows_per_field = P.ncell * P.nloc;
+    const int64_t rows_per_field = P.ncell_total * P.nloc;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows_per_field * P.nf) return;
     const int i = (int)(r / rows_per_field);
     const int64_t c = (r - i * rows_per_field) / P.nloc;
+    if (c >= P.ncell) return;
     const int nc = ncol[c];
     int64_t cells[8];
     cells[slot_self[c]] = c;
@@ -189,6 +194,7 @@ static PatternPlan make_plan(const ech_handle *h) {
     P.nloc = h->nloc;
     P.nlf = 2 * h->mesh.dim;
     P.ncell = h->mesh.ncell;
+    P.ncell_total = h->mesh.ncell_total;
     for (int i = 0; i < 16; ++i) {
         P.own_bits[i] = i < h->nf ? h->own_bits[i] : 0;
         P.nbr_bits[i] = i < h->nf ? h->nbr_bits[i] : 0;
@@ -198,8 +204,6 @@ static PatternPlan make_plan(const ech_handle *h) {
 
 extern "C" int ech_pattern_rowptr(ech_handle *h, int64_t *rowptr, int64_t *nnz_host, void *stream) {
     if (!h || !rowptr || !nnz_host) return fail(h, ECH_ERR_ARG, "ech_pattern_rowptr: null argument");
-    if (h->mesh.ncell != h->mesh.ncell_total)
-        return fail(h, ECH_ERR_ARG, "ech_pattern_rowptr: column numbering with ghost cells is not supported here");
     cudaStream_t s = (cudaStream_t)stream;
     int64_t nrows;
     ech_num_rows(h, &nrows);

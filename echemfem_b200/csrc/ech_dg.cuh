@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128) residual_kernel(const ech_dg_args A) {
             }
         }
     }
-    const int64_t ostride = A.ncell * NLOC;
+    const int64_t ostride = A.ncell_total * NLOC;     // ghost rows exist (empty) so every vector shares one layout
 #pragma unroll
     for (int i = 0; i < NF; ++i) A.out[i * ostride + t] = r[i];
 }
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(128) jacobian_kernel(const ech_dg_args A) {
     const int64_t c = t / NLOC;
     const int a = (int)(t - c * NLOC);
     const int64_t fstride = A.ncell_total * NLOC;
-    const int64_t row = (int64_t)I * A.ncell * NLOC + t;
+    const int64_t row = (int64_t)I * A.ncell_total * NLOC + t;
     double *__restrict__ vals = A.out + A.rowptr[row];
     const int ncol = A.ncol[c];
 

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int64_t c = ((int64_t)blockIdx.x * JWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
-    const int64_t rows_per_field = A.ncell * NLOC;
+    const int64_t rows_per_field = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
     const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
         __syncwarp();
     }
     if (active) {
-        const int64_t ostride = A.ncell * NLOC;
+        const int64_t ostride = A.ncell_total * NLOC;
 #pragma unroll
         for (int i = 0; i < NF; ++i) A.out[i * ostride + c * NLOC + a] = r[i];
     }

@@ -63,8 +63,11 @@ class NewtonEngine:
         if V.family != "DG":
             raise NotImplementedError("the device path currently covers DG spaces")
         self.nloc = V.n
-        self.N = V.num_nodes
+        self.N = V.num_nodes                                   # per-field stride: owned + ghost cells
         self.ndof = self.nf * self.N
+        self.ncell_total = mesh.num_cells
+        self.ncell = getattr(mesh, "num_owned", mesh.num_cells)
+        self.halo = None
         t0 = time.time()
         self.form = CompiledForm(solver.Form, self.nf, self.naux, mesh.dim, V.degree, V.family)
         self.module = build.build_module(self.form.header, self.form.key)
@@ -72,6 +75,10 @@ class NewtonEngine:
         self._upload_mesh(mesh)
         self._create()
         self._pattern()
+        plan = getattr(mesh, "halo_plan", None)
+        if plan is not None and plan.size > 1:
+            from .partition import HaloExchange
+            self.halo = HaloExchange(plan, self.nf, self.nloc, self.ncell_total, self.dev)
         self.snes = _Snes(self)
         self.last = {"snes_its": 0, "ksp_its": 0, "history": [], "ksp_its_per_step": []}
         self.timers = {k: 0.0 for k in ("SNESSolve", "KSPSolve", "PCSetUp", "PCApply", "JacobianEval", "FunctionEval")}
@@ -84,7 +91,7 @@ class NewtonEngine:
         dev = self.dev
         nbr, code, slot, slot_self, ncol = mesh.connectivity(self.form.marker_class)
         f = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
-        nc = mesh.num_cells
+        nc = self.ncell_total
         self.m = {
             "xcell": f(mesh.cell_coords(), torch.float64), "nbr": f(nbr, torch.int32), "code": f(code, torch.uint8),
             "slot": f(slot, torch.uint8), "slot_self": f(slot_self, torch.uint8), "ncol": f(ncol, torch.uint8),
@@ -98,7 +105,7 @@ class NewtonEngine:
         mesh = self.solver.mesh
         m = self.m
         self.desc = capi.MeshDesc(mesh.dim, self.solver.W.scalar.degree, self.nf, self.naux,
-                                  mesh.num_cells, mesh.num_cells,
+                                  self.ncell, self.ncell_total,
                                   ptr(m["xcell"]), ptr(m["nbr"]), ptr(m["code"]), ptr(m["slot"]),
                                   ptr(m["slot_self"]), ptr(m["ncol"]), ptr(m["vol"]), ptr(m["diam"]), ptr(m["area"]))
         h = C.c_void_p()
@@ -126,7 +133,7 @@ class NewtonEngine:
         self.colidx = torch.empty(self.nnz, dtype=torch.int32, device=self.dev)
         capi.check(self.lib.ech_pattern_colidx(self.h, ptr(self.rowptr), ptr(self.colidx), self._stream()), self.h)
         self.vals = torch.empty(self.nnz, dtype=torch.float64, device=self.dev)
-        self.F = torch.empty(self.ndof, dtype=torch.float64, device=self.dev)
+        self.F = torch.zeros(self.ndof, dtype=torch.float64, device=self.dev)
 
     # -- device state -----------------------------------------------------------------
     def _aux_tensor(self):
@@ -142,12 +149,16 @@ class NewtonEngine:
         out = self.F if out is None else out
         aux = self._aux_tensor() if aux is None else aux
         consts = self._consts() if consts is None else consts
+        if self.halo is not None:
+            self.halo.exchange(u)
         capi.check(self.lib.ech_residual(self.h, ptr(u), ptr(aux), ptr(consts), ptr(out), self._stream()), self.h)
         return out
 
     def jacobian(self, u, aux=None, consts=None):
         aux = self._aux_tensor() if aux is None else aux
         consts = self._consts() if consts is None else consts
+        if self.halo is not None:
+            self.halo.exchange(u)
         capi.check(self.lib.ech_jacobian(self.h, ptr(u), ptr(aux), ptr(consts), ptr(self.rowptr), ptr(self.vals),
                                          self._stream()), self.h)
         return self.vals
@@ -165,10 +176,11 @@ class NewtonEngine:
     def _linear_plan(self, restart):
         if self._lin is not None and self._lin["restart"] >= restart:
             return self._lin
-        ncell = self.solver.mesh.num_cells
+        ncell = self.ncell
         nblocks = self.nblocks
         if nblocks is None:
-            nblocks = max(1, min(ncell, 148 * 32) if ncell > 4096 else 1)
+            # one warp factors / solves one block: enough blocks to fill the machine, >= ~64 cells each
+            nblocks = int(max(1, min(ncell // 64, 148 * 32)))
         edges = np.linspace(0, ncell, nblocks + 1).astype(np.int64)
         free, _ = torch.cuda.mem_get_info()
         cap = self.max_basis_bytes if self.max_basis_bytes is not None else int(0.5 * free)

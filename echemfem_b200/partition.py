@@ -1,0 +1,197 @@
+"""Cell partition and ghost-dof halo exchange (multi-GPU, one process per GPU).
+
+Stands in for what the reference gets from DMPlex distribution with a one-facet overlap, PetscSF halo
+updates and MPI reductions (`mpiexec -n N python example.py`).  Cells are partitioned;
+rows are owned with their cell; every cut facet is evaluated by both owners, each keeping its own rows,
+so no matrix entry is ever communicated.  Per residual / Jacobian / SpMV the only exchange is the state
+of the ghost cells (grouped send/recv, NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+Local numbering: owned cells first (in global order), then ghost cells (by owner rank, then global id).
+Ghost rows exist in every local vector and matrix but are empty, so all arrays of a rank share one
+layout with field stride `ncell_total * n`.
+"""
+import numpy as np
+
+from .mesh import TensorMesh, _box_markers
+
+
+class LocalMesh:
+    """The part of a mesh one rank sees: owned + ghost cells, duck-typing `mesh.Mesh` for the engine."""
+
+    def __init__(self, ext_mesh, order, num_owned, global_ids, ghost_owner, name=None, global_num_cells=None):
+        # `order`: indices into ext_mesh cells, owned first then ghosts
+        self.dim = ext_mesh.dim
+        self.name = name or ext_mesh.name
+        self.layers = ext_mesh.layers
+        self.num_owned = int(num_owned)
+        self.num_cells = int(len(order))                  # owned + ghost: host-side sizing covers both
+        self.global_ids = np.asarray(global_ids, dtype=np.int64)          # per local cell
+        self.ghost_owner = np.asarray(ghost_owner, dtype=np.int64)        # per ghost cell (local index - num_owned)
+        self.global_num_cells = global_num_cells
+        inv = -np.ones(ext_mesh.num_cells, dtype=np.int64)
+        inv[order] = np.arange(len(order))
+        self._coords = ext_mesh.cell_coords()[order]
+        owned = order[:num_owned]
+        nb = ext_mesh.nbr_cell[owned]
+        loc = np.where(nb >= 0, inv[np.maximum(nb, 0)], -1)
+        if np.any((nb >= 0) & (loc < 0)):
+            raise ValueError("an owned cell has a neighbour that is neither owned nor ghost")
+        self.nbr_cell = loc
+        self.nbr_lf = ext_mesh.nbr_lf[owned]
+        self.nbr_orient = ext_mesh.nbr_orient[owned]
+        self.ext_marker = ext_mesh.ext_marker[owned]
+        self.coords = ext_mesh.coords
+        self.num_interior_facets = int((self.nbr_cell >= 0).sum())       # facets seen from owned cells
+        self.num_exterior_facets = int((self.nbr_cell < 0).sum())
+
+    def topological_dimension(self):
+        return self.dim
+
+    def geometric_dimension(self):
+        return self.dim
+
+    @property
+    def cell_set(self):
+        class _S:
+            size = self.num_owned
+        return _S
+
+    def cell_coords(self):
+        return np.ascontiguousarray(self._coords)
+
+    def connectivity(self, marker_class):
+        nc, nlf = self.nbr_cell.shape
+        nbr = self.nbr_cell.copy()
+        lut = np.zeros(int(self.ext_marker.max()) + 2 if nc else 1, dtype=np.int64)
+        for m, k in marker_class.items():
+            if 0 <= int(m) < len(lut):
+                lut[int(m)] = k
+        cls = lut[self.ext_marker]
+        bnd = nbr < 0
+        nbr[bnd] = -(1 + cls[bnd])
+        code = (self.nbr_lf | (self.nbr_orient << 3)).astype(np.uint8)
+        big = np.iinfo(np.int64).max
+        allc = np.concatenate([np.arange(nc)[:, None], np.where(bnd, big, self.nbr_cell)], axis=1)
+        rank = np.argsort(np.argsort(allc, axis=1, kind="stable"), axis=1, kind="stable")
+        return (nbr.astype(np.int32), code, rank[:, 1:].astype(np.uint8), rank[:, 0].astype(np.uint8),
+                (1 + (~bnd).sum(axis=1)).astype(np.uint8))
+
+
+class HaloPlan:
+    """Who sends which owned cells to whom, and where received cells land (local cell indices)."""
+
+    def __init__(self, rank, size, send, recv):
+        self.rank, self.size = rank, size
+        self.send = send          # {peer: int64 array of local owned cell ids, sorted by global id}
+        self.recv = recv          # {peer: int64 array of local ghost cell ids, sorted by global id}
+
+    def peers(self):
+        return sorted(set(self.send) | set(self.recv))
+
+
+def _halo_plan(local, owner_of_ext_nbr, rank, size):
+    """Build the exchange lists of a LocalMesh; `owner_of_ext_nbr(local ghost index) -> owner rank`."""
+    no = local.num_owned
+    recv = {}
+    if len(local.ghost_owner) == 0:
+        return HaloPlan(rank, size, {}, {})
+    for peer in np.unique(local.ghost_owner):
+        g = np.nonzero(local.ghost_owner == peer)[0] + no
+        recv[int(peer)] = g[np.argsort(local.global_ids[g], kind="stable")]
+    send = {}
+    nb = local.nbr_cell
+    is_ghost = nb >= no
+    for peer in recv:
+        mask = np.zeros(no, dtype=bool)
+        gmask = is_ghost & (local.ghost_owner[np.maximum(nb - no, 0)] == peer)
+        mask |= gmask.any(axis=1)
+        s = np.nonzero(mask)[0]
+        send[peer] = s[np.argsort(local.global_ids[s], kind="stable")]
+    return HaloPlan(rank, size, send, recv)
+
+
+def partition_mesh(mesh, rank, size, edges=None):
+    """Contiguous-range partition of an existing (global) mesh; returns (LocalMesh, HaloPlan)."""
+    nc = mesh.num_cells
+    if edges is None:
+        edges = np.linspace(0, nc, size + 1).astype(np.int64)
+    c0, c1 = int(edges[rank]), int(edges[rank + 1])
+    owned = np.arange(c0, c1)
+    nb = mesh.nbr_cell[owned]
+    ghosts = np.unique(nb[(nb >= 0) & ((nb < c0) | (nb >= c1))])
+    owner = np.searchsorted(edges, ghosts, side="right") - 1
+    o = np.lexsort((ghosts, owner))
+    ghosts, owner = ghosts[o], owner[o]
+    order = np.concatenate([owned, ghosts])
+    local = LocalMesh(mesh, order, len(owned), order, owner, global_num_cells=nc)
+    local.halo_plan = _halo_plan(local, None, rank, size)
+    return local, local.halo_plan
+
+
+def strip_partition(axes, rank, size, name="strip"):
+    """Rank `rank`'s part of the tensor mesh over `axes`, split into strips along the first direction,
+    built WITHOUT the global mesh (weak-scaling benchmarks): the strip plus one ghost layer per side."""
+    axes = [np.asarray(a, dtype=float) for a in axes]
+    nx = len(axes[0]) - 1
+    edges = np.linspace(0, nx, size + 1).astype(np.int64)
+    i0, i1 = int(edges[rank]), int(edges[rank + 1])
+    lo, hi = max(i0 - 1, 0), min(i1 + 1, nx)
+    sub = [axes[0][lo:hi + 1]] + axes[1:]
+    marker = _box_markers([a[0] for a in axes], [a[-1] for a in axes])
+    ext = TensorMesh(sub, name=name, marker_of_facet=marker)
+    per_col = int(np.prod([len(a) - 1 for a in axes[1:]]))
+    col = np.arange(ext.num_cells) // per_col + lo                 # global column of every ext cell
+    owned_mask = (col >= i0) & (col < i1)
+    gid = (col * per_col + np.arange(ext.num_cells) % per_col).astype(np.int64)
+    owned = np.nonzero(owned_mask)[0]
+    ghosts = np.nonzero(~owned_mask)[0]
+    gowner = np.where(col[ghosts] < i0, rank - 1, rank + 1)
+    o = np.lexsort((gid[ghosts], gowner))
+    ghosts, gowner = ghosts[o], gowner[o]
+    order = np.concatenate([owned, ghosts])
+    local = LocalMesh(ext, order, len(owned), gid[order], gowner, name=name, global_num_cells=nx * per_col)
+    local.halo_plan = _halo_plan(local, None, rank, size)
+    return local, local.halo_plan
+
+
+class HaloExchange:
+    """Ghost-cell state exchange for vectors laid out [nf][ncell_total * n] (torch.distributed P2P)."""
+
+    def __init__(self, plan, nf, nloc, ncell_total, device):
+        import torch
+        self.plan, self.nf, self.nloc, self.ntot = plan, nf, nloc, ncell_total
+        self.device = device
+        self.bytes_per_exchange = 0
+        self._send_idx, self._recv_idx, self._sbuf, self._rbuf = {}, {}, {}, {}
+        for peer, cells in plan.send.items():
+            self._send_idx[peer] = self._dof_index(cells).to(device)
+            self._sbuf[peer] = torch.empty(len(cells) * nf * nloc, dtype=torch.float64, device=device)
+        for peer, cells in plan.recv.items():
+            self._recv_idx[peer] = self._dof_index(cells).to(device)
+            self._rbuf[peer] = torch.empty(len(cells) * nf * nloc, dtype=torch.float64, device=device)
+            self.bytes_per_exchange += 8 * len(cells) * nf * nloc
+
+    def _dof_index(self, cells):
+        import torch
+        cells = np.asarray(cells, dtype=np.int64)
+        dof = (cells[:, None] * self.nloc + np.arange(self.nloc)[None, :]).reshape(-1)
+        idx = (np.arange(self.nf)[:, None] * (self.ntot * self.nloc) + dof[None, :]).reshape(-1)
+        return torch.from_numpy(idx)
+
+    def exchange(self, u):
+        """Fill the ghost-cell entries of `u` with the owners' values."""
+        import torch
+        import torch.distributed as dist
+        if self.plan.size == 1 or not self.plan.peers():
+            return
+        ops = []
+        for peer in self.plan.peers():
+            if peer in self._send_idx:
+                torch.index_select(u, 0, self._send_idx[peer], out=self._sbuf[peer])
+                ops.append(dist.P2POp(dist.isend, self._sbuf[peer], peer))
+            if peer in self._recv_idx:
+                ops.append(dist.P2POp(dist.irecv, self._rbuf[peer], peer))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for peer, idx in self._recv_idx.items():
+            u.index_copy_(0, idx, self._rbuf[peer])

@@ -1,0 +1,108 @@
+"""Partition + halo exchange host logic; the N > 1 path is exercised with world_size-2 gloo on CPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from echemfem_b200.mesh import TensorMesh, UnitSquareMesh
+from echemfem_b200.partition import partition_mesh, strip_partition, HaloExchange
+
+
+def _check_local(mesh, local):
+    """Local connectivity, mapped back to global ids, is the global connectivity of the owned cells."""
+    gid = local.global_ids
+    no = local.num_owned
+    for lc in range(no):
+        g = gid[lc]
+        for lf in range(2 * mesh.dim):
+            ln = local.nbr_cell[lc, lf]
+            gn = mesh.nbr_cell[g, lf]
+            assert (ln < 0) == (gn < 0)
+            if ln >= 0:
+                assert gid[ln] == gn
+            else:
+                assert local.ext_marker[lc, lf] == mesh.ext_marker[g, lf]
+    assert np.allclose(local.cell_coords(), mesh.cell_coords()[gid])
+
+
+@pytest.mark.parametrize("size", [1, 2, 3])
+def test_partition_covers_mesh(size):
+    mesh = UnitSquareMesh(6, 4)
+    owned = []
+    for r in range(size):
+        local, plan = partition_mesh(mesh, r, size)
+        _check_local(mesh, local)
+        owned += list(local.global_ids[:local.num_owned])
+        for peer, cells in plan.recv.items():
+            assert np.all(cells >= local.num_owned)
+        for peer, cells in plan.send.items():
+            assert np.all(cells < local.num_owned)
+    assert sorted(owned) == list(range(mesh.num_cells))
+
+
+def test_strip_partition_equals_global_partition():
+    ax = [np.linspace(0, 3, 10), np.linspace(0, 1, 5)]
+    mesh = TensorMesh(ax)
+    for size in (2, 3):
+        for r in range(size):
+            local, plan = strip_partition(ax, r, size)
+            edges = np.linspace(0, 9, size + 1).astype(np.int64) * 4
+            ref, rplan = partition_mesh(mesh, r, size, edges=edges)
+            assert np.array_equal(local.global_ids, ref.global_ids)
+            assert np.array_equal(local.nbr_cell, ref.nbr_cell)
+            assert np.array_equal(local.ext_marker, ref.ext_marker)
+            for peer in rplan.peers():
+                assert np.array_equal(plan.send[peer], rplan.send[peer])
+                assert np.array_equal(plan.recv[peer], rplan.recv[peer])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        mesh = UnitSquareMesh(6, 4)
+        local, plan = partition_mesh(mesh, rank, size)
+        nf, nloc = 2, 4
+        ntot = local.num_cells
+        hx = HaloExchange(plan, nf, nloc, ntot, torch.device("cpu"))
+        gid = torch.from_numpy(local.global_ids)
+        # value of dof (field f, global cell g, node b)
+        val = (torch.arange(nf)[:, None, None] * 1000.0 + gid[None, :, None] * 10.0 + torch.arange(nloc)[None, None, :])
+        u = val.clone().double()
+        u[:, local.num_owned:, :] = -1.0                         # ghosts unknown before the exchange
+        u = u.reshape(-1).contiguous()
+        hx.exchange(u)
+        assert torch.equal(u, val.double().reshape(-1))
+        # allreduce as used for Krylov dots
+        t = torch.tensor([float(local.num_owned)], dtype=torch.float64)
+        dist.all_reduce(t)
+        assert int(t.item()) == mesh.num_cells
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_gloo_world2():
+    size = 2
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * size)
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, size, port, ok)) for r in range(size)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert list(ok) == [1] * size
