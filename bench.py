@@ -280,7 +280,7 @@ def main():
                                           eng.halo.bytes_per_exchange if eng.halo is not None else 0)},
             "residual_ms": tF, "jacobian_ms": tJ,
             "residual_MDOFs": ndof / (tF * 1e-3) / 1e6, "jacobian_MDOFs": ndof / (tJ * 1e-3) / 1e6,
-            "roofline": {"bound": "hbm", "kernel": "jacobian_kernel<I> (%d launches per step)" % eng.nf,
+            "roofline": {"bound": "hbm", "kernel": "echdg::jacobian_coop_kernel (1 launch per step)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes": BJ, "traffic": None,
