@@ -18,7 +18,9 @@ class MeshDesc(C.Structure):
     _fields_ = [("dim", c_i32), ("degree", c_i32), ("nfields", c_i32), ("naux", c_i32),
                 ("ncell", c_i64), ("ncell_total", c_i64),
                 ("xcell", c_p), ("nbr", c_p), ("code", c_p), ("slot", c_p), ("slot_self", c_p), ("ncol", c_p),
-                ("cell_volume", c_p), ("cell_diam", c_p), ("facet_area", c_p)]
+                ("cell_volume", c_p), ("cell_diam", c_p), ("facet_area", c_p),
+                ("nnodes", c_i64), ("cell_nodes", c_p), ("inc_ptr", c_p), ("inc_cell", c_p), ("inc_loc", c_p),
+                ("colslot", c_p), ("adj_count", c_p)]
 
 
 class GmresOpts(C.Structure):

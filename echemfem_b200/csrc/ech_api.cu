@@ -131,7 +131,10 @@ extern "C" int64_t ech_launch_count(const ech_handle *) { return g_launches; }
 
 extern "C" int ech_num_rows(const ech_handle *h, int64_t *nrows) {
     if (!h || !nrows) return ECH_ERR_ARG;
-    *nrows = (int64_t)h->nf * h->mesh.ncell_total * h->nloc;   // ghost rows exist and are empty
+    if (h->info[7] == 0)
+        *nrows = (int64_t)h->nf * h->mesh.nnodes;                 // continuous space
+    else
+        *nrows = (int64_t)h->nf * h->mesh.ncell_total * h->nloc;  // ghost rows exist and are empty
     return ECH_OK;
 }
 
@@ -369,6 +372,13 @@ static void fill_args(const ech_handle *h, ech_dg_args &a) {
     a.cell_volume = m.cell_volume;
     a.cell_diam = m.cell_diam;
     a.facet_area = m.facet_area;
+    a.nnodes = m.nnodes;
+    a.cell_nodes = m.cell_nodes;
+    a.inc_ptr = m.inc_ptr;
+    a.inc_cell = m.inc_cell;
+    a.inc_loc = m.inc_loc;
+    a.colslot = m.colslot;
+    a.adj_count = m.adj_count;
 }
 
 extern "C" int ech_residual(ech_handle *h, const double *u, const double *aux, const double *consts, double *F,
@@ -874,7 +884,7 @@ extern "C" int ech_assemble_host(ech_handle *h, const double *u_host, double *u_
     cudaStream_t s = (cudaStream_t)stream;
     int64_t nrows;
     ech_num_rows(h, &nrows);
-    const int64_t nstate = (int64_t)h->nf * h->mesh.ncell_total * h->nloc;
+    const int64_t nstate = nrows;
     CK(h, cudaMemcpyAsync(u_dev, u_host, sizeof(double) * nstate, cudaMemcpyHostToDevice, s));
     int rc = ech_residual(h, u_dev, aux, consts, F_dev, stream);
     if (rc) return rc;

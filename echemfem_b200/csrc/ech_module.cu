@@ -2,7 +2,11 @@
 // Built by echemfem_b200/build.py as
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
 //        -include <generated header> ech_module.cu -o libech_phys_<key>.so
+#if ECH_FAMILY_DG
 #include "ech_dg_coop.cuh"
+#else
+#include "ech_cg.cuh"
+#endif
 
 extern "C" {
 
@@ -32,6 +36,7 @@ static int g_variant = 0;
 
 void ech_mod_set_variant(int v) { g_variant = v; }
 
+#if ECH_FAMILY_DG
 static bool use_coop() { return echdg::COOP_OK && g_variant == 0; }
 
 int ech_mod_residual(const ech_dg_args *a, void *stream) {
@@ -45,5 +50,15 @@ int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
 }
 
 int ech_mod_launches(int which) { return (which == 0 || use_coop()) ? 1 : echgen::NF; }
+#else
+int ech_mod_residual(const ech_dg_args *a, void *stream) {
+    (void)g_variant;
+    return echcg::launch_cg_residual(a, (cudaStream_t)stream);
+}
+
+int ech_mod_jacobian(const ech_dg_args *a, void *stream) { return echcg::launch_cg_jacobian(a, (cudaStream_t)stream); }
+
+int ech_mod_launches(int which) { return which == 0 ? 1 : echgen::NF; }
+#endif
 
 }  // extern "C"

@@ -60,8 +60,7 @@ class NewtonEngine:
         self.nf = W.num_sub_spaces()
         self.naux = len(solver._aux)
         V = W.scalar
-        if V.family != "DG":
-            raise NotImplementedError("the device path currently covers DG spaces")
+        self.family = V.family
         self.nloc = V.n
         self.N = V.num_nodes                                   # per-field stride: owned + ghost cells
         self.ndof = self.nf * self.N
@@ -73,8 +72,10 @@ class NewtonEngine:
         self.module = build.build_module(self.form.header, self.form.key)
         self.t_compile = time.time() - t0
         self._upload_mesh(mesh)
+        self.cg = self._cg_plan(V) if self.family == "CG" else None
         self._create()
         self._pattern()
+        self.bc_mask, self.bc_vals = self._dirichlet(V) if self.family == "CG" else (None, None)
         plan = getattr(mesh, "halo_plan", None)
         if plan is not None and plan.size > 1:
             from .partition import HaloExchange
@@ -101,13 +102,101 @@ class NewtonEngine:
         capi.check(self.lib.ech_cell_geometry(mesh.dim, nc, ptr(self.m["xcell"]), ptr(self.m["vol"]),
                                               ptr(self.m["area"]), ptr(self.m["diam"]), self._stream()))
 
+    # -- continuous spaces: node-owner gather plan --------------------------------------
+    def _cg_plan(self, V):
+        """cell->node map, its transpose, the node adjacency (row pattern) and column slots (host, numpy)."""
+        import scipy.sparse as sp
+        cn = V.cell_nodes.astype(np.int64)
+        nc, n = cn.shape
+        Nn = V.num_nodes
+        flat = cn.reshape(-1)
+        order = np.argsort(flat, kind="stable")
+        inc_cell = (order // n).astype(np.int32)
+        inc_loc = (order % n).astype(np.uint8)
+        inc_ptr = np.concatenate([[0], np.cumsum(np.bincount(flat, minlength=Nn))]).astype(np.int64)
+        rows = np.repeat(cn, n, axis=1).reshape(-1)
+        cols = np.tile(cn, (1, n)).reshape(-1)
+        Aadj = sp.csr_matrix((np.ones(len(rows), dtype=np.int8), (rows, cols)), shape=(Nn, Nn))
+        Aadj.sum_duplicates()
+        Aadj.sort_indices()
+        adj_ptr = Aadj.indptr.astype(np.int64)
+        adj = Aadj.indices.astype(np.int64)
+        adj_count = np.diff(adj_ptr).astype(np.int32)
+        keys = np.repeat(np.arange(Nn, dtype=np.int64), adj_count) * Nn + adj
+        inc_node = flat[order]
+        want = inc_node[:, None] * Nn + cn[inc_cell]                          # (ninc, n)
+        pos = np.searchsorted(keys, want.reshape(-1)).reshape(want.shape) - adj_ptr[inc_node][:, None]
+        f = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev, dtype=dt)
+        return {"Nn": Nn, "adj_ptr": adj_ptr, "adj": adj, "adj_count_h": adj_count,
+                "cell_nodes": f(cn, torch.int32), "inc_ptr": f(inc_ptr, torch.int64), "inc_cell": f(inc_cell, torch.int32),
+                "inc_loc": f(inc_loc, torch.uint8), "colslot": f(pos.astype(np.uint8), torch.uint8),
+                "adj_count": f(adj_count, torch.int32)}
+
+    def _cg_pattern(self):
+        """Field-blocked AIJ pattern of the CG space: row (i, r) couples, for every field j
+        the Jacobian form couples to, the nodes of all cells around node r, ascending."""
+        cg = self.cg
+        Nn, adj_ptr, adj, cnt = cg["Nn"], cg["adj_ptr"], cg["adj"], cg["adj_count_h"].astype(np.int64)
+        own = self.form.own_mask
+        lens = np.concatenate([own[i].sum() * cnt for i in range(self.nf)])
+        rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        colidx = np.empty(int(rowptr[-1]), dtype=np.int32)
+        within = np.arange(len(adj), dtype=np.int64) - np.repeat(adj_ptr[:-1], cnt)
+        for i in range(self.nf):
+            start = np.repeat(rowptr[i * Nn:(i + 1) * Nn], cnt)
+            seg = 0
+            for j in range(self.nf):
+                if own[i, j]:
+                    colidx[start + seg * np.repeat(cnt, cnt) + within] = (j * Nn + adj).astype(np.int32)
+                    seg += 1
+        return rowptr, colidx
+
+    def _dirichlet(self, V):
+        """Strong DirichletBC dofs and values from the solver's bcs list (solver.py:1531, 2009, 2215)."""
+        from .function import evaluate_expression, Function
+        from . import symbolic as S
+        mesh = self.solver.mesh
+        d = mesh.dim
+        Nn = V.num_nodes
+        mask = np.zeros(self.ndof, dtype=np.uint8)
+        vals = np.zeros(self.ndof)
+        ref = V.ref_nodes()
+        coords = V.node_coords()
+        for kind, field, value, ids in self.solver.bcs:
+            if kind != "dirichlet" or ids is None:
+                continue
+            ids = (ids,) if isinstance(ids, int) else tuple(ids)
+            on = (mesh.nbr_cell < 0) & np.isin(mesh.ext_marker, ids)
+            cs, lfs = np.nonzero(on)
+            for lf in np.unique(lfs):
+                k, sde = divmod(int(lf), 2)
+                loc = np.nonzero(np.abs(ref[:, k] - sde) < 1e-14)[0]
+                nodes = np.unique(V.cell_nodes[cs[lfs == lf]][:, loc].reshape(-1))
+                if isinstance(value, Function):
+                    v = value.numpy()[nodes]
+                elif isinstance(value, (int, float)):
+                    v = np.full(len(nodes), float(value))
+                else:
+                    v = evaluate_expression(value, coords[nodes])
+                mask[field * Nn + nodes] = 1
+                vals[field * Nn + nodes] = v
+        if not mask.any():
+            return None, None
+        return torch.from_numpy(mask).to(self.dev), torch.from_numpy(vals).to(self.dev)
+
     def _create(self):
         mesh = self.solver.mesh
         m = self.m
+        cg = self.cg
+        z = None
         self.desc = capi.MeshDesc(mesh.dim, self.solver.W.scalar.degree, self.nf, self.naux,
                                   self.ncell, self.ncell_total,
                                   ptr(m["xcell"]), ptr(m["nbr"]), ptr(m["code"]), ptr(m["slot"]),
-                                  ptr(m["slot_self"]), ptr(m["ncol"]), ptr(m["vol"]), ptr(m["diam"]), ptr(m["area"]))
+                                  ptr(m["slot_self"]), ptr(m["ncol"]), ptr(m["vol"]), ptr(m["diam"]), ptr(m["area"]),
+                                  cg["Nn"] if cg else 0, ptr(cg["cell_nodes"]) if cg else z,
+                                  ptr(cg["inc_ptr"]) if cg else z, ptr(cg["inc_cell"]) if cg else z,
+                                  ptr(cg["inc_loc"]) if cg else z, ptr(cg["colslot"]) if cg else z,
+                                  ptr(cg["adj_count"]) if cg else z)
         h = C.c_void_p()
         capi.check(self.lib.ech_create(self.module.encode(), C.byref(self.desc), C.byref(h)))
         self.h = h
@@ -126,12 +215,18 @@ class NewtonEngine:
         n = C.c_int64()
         capi.check(self.lib.ech_num_rows(self.h, C.byref(n)), self.h)
         assert n.value == self.ndof
-        self.rowptr = torch.empty(self.ndof + 1, dtype=torch.int64, device=self.dev)
-        nnz = C.c_int64()
-        capi.check(self.lib.ech_pattern_rowptr(self.h, ptr(self.rowptr), C.byref(nnz), self._stream()), self.h)
-        self.nnz = nnz.value
-        self.colidx = torch.empty(self.nnz, dtype=torch.int32, device=self.dev)
-        capi.check(self.lib.ech_pattern_colidx(self.h, ptr(self.rowptr), ptr(self.colidx), self._stream()), self.h)
+        if self.cg is not None:
+            rp, ci = self._cg_pattern()
+            self.rowptr = torch.from_numpy(rp).to(self.dev)
+            self.colidx = torch.from_numpy(ci).to(self.dev)
+            self.nnz = int(rp[-1])
+        else:
+            self.rowptr = torch.empty(self.ndof + 1, dtype=torch.int64, device=self.dev)
+            nnz = C.c_int64()
+            capi.check(self.lib.ech_pattern_rowptr(self.h, ptr(self.rowptr), C.byref(nnz), self._stream()), self.h)
+            self.nnz = nnz.value
+            self.colidx = torch.empty(self.nnz, dtype=torch.int32, device=self.dev)
+            capi.check(self.lib.ech_pattern_colidx(self.h, ptr(self.rowptr), ptr(self.colidx), self._stream()), self.h)
         self.vals = torch.empty(self.nnz, dtype=torch.float64, device=self.dev)
         self.F = torch.zeros(self.ndof, dtype=torch.float64, device=self.dev)
 
@@ -176,12 +271,15 @@ class NewtonEngine:
     def _linear_plan(self, restart):
         if self._lin is not None and self._lin["restart"] >= restart:
             return self._lin
-        ncell = self.ncell
+        # preconditioner blocks are ranges of "units": cells (all dofs of the cell) for DG, nodes for CG
+        nunits = self.ncell if self.cg is None else self.N
+        per = 64 if self.cg is None else 256
         nblocks = self.nblocks
         if nblocks is None:
-            # one warp factors / solves one block: enough blocks to fill the machine, >= ~64 cells each
-            nblocks = int(max(1, min(ncell // 64, 148 * 32)))
-        edges = np.linspace(0, ncell, nblocks + 1).astype(np.int64)
+            # one warp factors / solves one block: enough blocks to fill the machine, >= ~256 rows per field each
+            nblocks = int(max(1, min(nunits // per, 148 * 32)))
+        edges = np.linspace(0, nunits, nblocks + 1).astype(np.int64)
+        self._unit = self.nloc if self.cg is None else 1
         free, _ = torch.cuda.mem_get_info()
         cap = self.max_basis_bytes if self.max_basis_bytes is not None else int(0.5 * free)
         m = int(max(2, min(restart, cap // (8 * self.ndof) - 1)))
@@ -203,12 +301,12 @@ class NewtonEngine:
         """Solve J dx = rhs with right-preconditioned GMRES; returns (dx, iterations)."""
         L = self._linear_plan(restart)
         t0 = time.time()
-        capi.check(self.lib.ech_bjacobi_ilu0_factor(self.ndof, self.nf, self.N, self.nloc, L["nblocks"],
+        capi.check(self.lib.ech_bjacobi_ilu0_factor(self.ndof, self.nf, self.N, self._unit, L["nblocks"],
                                                     ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
                                                     ptr(self.vals), ptr(L["lu"]), ptr(L["diag"]), self._stream()))
         torch.cuda.synchronize()
         self.timers["PCSetUp"] += time.time() - t0
-        opts = capi.GmresOpts(rtol, atol, L["restart"], max_it, 1, 1 if monitor else 0, self.nf, self.nloc,
+        opts = capi.GmresOpts(rtol, atol, L["restart"], max_it, 1, 1 if monitor else 0, self.nf, self._unit,
                               self.N, L["nblocks"], ptr(L["block_ptr"]), ptr(L["lu"]), ptr(L["diag"]))
         L["dx"].zero_()
         its = C.c_int32()
@@ -258,6 +356,14 @@ class NewtonEngine:
             mask = torch.zeros(self.ndof, dtype=torch.uint8, device=self.dev)
             for f in frozen_fields:
                 mask[f * self.N:(f + 1) * self.N] = 1
+        if self.bc_mask is not None:
+            # strong Dirichlet rows (CG): the state carries the boundary values, the rows become identity
+            sel = self.bc_mask.bool()
+            if frozen_fields:
+                for f in frozen_fields:
+                    sel[f * self.N:(f + 1) * self.N] = False
+            u[sel] = self.bc_vals[sel]
+            mask = self.bc_mask.clone() if mask is None else torch.maximum(mask, self.bc_mask)
         st = self._stream()
 
         def resid(x, out):

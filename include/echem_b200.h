@@ -54,6 +54,15 @@ typedef struct ech_mesh_desc {
     const double *cell_volume;/* [ncell_total]  CellVolume  (solver.py:1491)          */
     const double *cell_diam;  /* [ncell_total]  CellDiameter (solver.py:1657)         */
     const double *facet_area; /* [ncell][2 dim] FacetArea   (solver.py:1491)          */
+    /* continuous (CG) spaces: cell -> node map and its transpose (NULL / 0 for DG);
+     * the CSR pattern of a CG space is passed to ech_jacobian by the caller */
+    int64_t nnodes;
+    const int32_t *cell_nodes;/* [ncell][n]                                            */
+    const int64_t *inc_ptr;   /* [nnodes+1]                                            */
+    const int32_t *inc_cell;  /* [ninc]                                                */
+    const uint8_t *inc_loc;   /* [ninc]                                                */
+    const uint8_t *colslot;   /* [ninc][n]                                             */
+    const int32_t *adj_count; /* [nnodes]                                              */
 } ech_mesh_desc;
 
 /* -- lifetime ---------------------------------------------------------------- */

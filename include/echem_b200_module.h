@@ -32,7 +32,15 @@ typedef struct ech_dg_args {
     const double *aux;        /* [naux][ncell_total * n] data fields                        */
     const double *consts;     /* [nconst] runtime constants                                 */
     const int64_t *rowptr;    /* [nf * ncell * n + 1] (Jacobian only)                       */
-    double *out;              /* residual [nf][ncell*n]  or CSR values [nnz]                */
+    double *out;              /* residual [nf][ncell_total*n] (DG) / [nf][nnodes] (CG), or CSR values [nnz] */
+    /* continuous spaces only (family CG): dofs are shared between cells, assembly gathers per node */
+    int64_t nnodes;           /* nodes of the scalar space; field stride of u / aux / out    */
+    const int32_t *cell_nodes;/* [ncell][n]  cell -> node map                                 */
+    const int64_t *inc_ptr;   /* [nnodes+1]  node -> incident (cell, local node) pairs         */
+    const int32_t *inc_cell;  /* [ninc]                                                        */
+    const uint8_t *inc_loc;   /* [ninc]      local index of the node in that cell              */
+    const uint8_t *colslot;   /* [ninc][n]   position of the cell's b-th node in the row's sorted column nodes */
+    const int32_t *adj_count; /* [nnodes]    number of column nodes of a row                   */
 } ech_dg_args;
 
 /* info[0..7] = d, p, nf, naux, nconst, nq, nclasses, family(1=DG); then nf*nf own-block flags,

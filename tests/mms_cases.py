@@ -95,3 +95,26 @@ def bortels_oracle_mesh(n_in, n_el, n_out, n_y):
     def marker(xv):
         return int(fn(xv[None], None)[0])
     return tensor_mesh([x, y], boundary_id_fn=marker)
+
+
+def supg_C1ex(x):
+    return np.sin(x[..., 0]) + np.cos(x[..., 1])
+
+
+def supg_C2ex(x):
+    return np.cos(x[..., 0]) + np.sin(x[..., 1])
+
+
+def supg_problem(D, SUPG=True, family="CG"):
+    """tests/test_SUPG.py:6-66 of the reference for the oracle (forcing expanded by hand, div vel = 0)."""
+    from oracle.forms import Problem
+
+    def f(u, x):
+        X, Y = x[..., 0], x[..., 1]
+        vx = 6.0 * Y * (1.0 - Y)
+        return [vx * np.cos(X) + D * (np.sin(X) + np.cos(Y)), -vx * np.sin(X) + D * (np.cos(X) + np.sin(Y))]
+    conc_params = [{"name": "C1", "diffusion coefficient": D, "z": 0.0, "bulk": supg_C1ex},
+                   {"name": "C2", "diffusion coefficient": D, "z": 0.0, "bulk": supg_C2ex}]
+    physical_params = {"flow": ["diffusion", "advection"], "bulk reaction": f}
+    markers = {"inlet": (1, 2, 3, 4), "outlet": (1, 2, 3, 4), "bulk dirichlet": (1, 2, 3, 4)}
+    return Problem(conc_params, physical_params, markers, family=family, vel=make_vel(1.0), SUPG=SUPG)

@@ -97,3 +97,36 @@ class BortelsSolver(EchemSolver):
         y = SpatialCoordinate(self.mesh)[1]
         h = 1.0
         self.vel = as_vector((6. * self.physical_params["v_avg"] / h**2 * y * (h - y), Constant(0.)))
+
+
+class AdvectionDiffusionSolver(EchemSolver):
+    """tests/test_SUPG.py:6-66 of the reference: CG advection-diffusion of two species with SUPG."""
+
+    def __init__(self, N, D, SUPG=True, family="CG", mesh=None):
+        if mesh is None:
+            mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        C1ex = sin(x) + cos(y)
+        C2ex = cos(x) + sin(y)
+        self.C1ex = C1ex
+        self.C2ex = C2ex
+
+        def f(C):
+            f1 = div(self.vel * C1ex - D * grad(C1ex))
+            f2 = div(self.vel * C2ex - D * grad(C2ex))
+            return [f1, f2]
+
+        conc_params = [{"name": "C1", "diffusion coefficient": D, "bulk": C1ex},
+                       {"name": "C2", "diffusion coefficient": D, "bulk": C2ex}]
+        physical_params = {"flow": ["diffusion", "advection"], "bulk reaction": f, "v_avg": 1.0}
+        super().__init__(conc_params, physical_params, mesh, family=family, SUPG=SUPG)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"inlet": (1, 2, 3, 4), "outlet": (1, 2, 3, 4), "bulk dirichlet": (1, 2, 3, 4)}
+
+    def set_velocity(self):
+        xs = SpatialCoordinate(self.mesh)
+        y = xs[1]
+        h = 1.0
+        x_vel = 6. * self.physical_params["v_avg"] / h**2 * y * (h - y)
+        self.vel = as_vector([x_vel] + [Constant(0.)] * (len(xs) - 1))
