@@ -251,6 +251,9 @@ class Problem:
                     f0[iU] = f0[iU] - pp["F"] * z * C[k]                    # :2141
             K_U = self.poisson_KU(C)
             f1[iU] = f1[iU] + _bc(K_U)[..., None] * gU                      # :2171
+            n_r = self.num_liquid                                           # :2178-2186 ("for test only")
+            if reactions is not None and len(reactions) > n_r and not _is_zero(reactions[n_r]):
+                f0[iU] = f0[iU] - reactions[n_r]
         return f0, f1
 
     # -- interior facets (DG) -------------------------------------------

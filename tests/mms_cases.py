@@ -118,3 +118,34 @@ def supg_problem(D, SUPG=True, family="CG"):
     physical_params = {"flow": ["diffusion", "advection"], "bulk reaction": f}
     markers = {"inlet": (1, 2, 3, 4), "outlet": (1, 2, 3, 4), "bulk dirichlet": (1, 2, 3, 4)}
     return Problem(conc_params, physical_params, markers, family=family, vel=make_vel(1.0), SUPG=SUPG)
+
+
+def poisson_C2ex(x):
+    return np.cos(x[..., 0]) - np.sin(x[..., 1]) + 3.0
+
+
+def poisson_problem(family="DG"):
+    """tests/test_diffusion_migration_poisson.py:6-57 of the reference for the oracle."""
+    from oracle.forms import Problem
+
+    def f(u, x):
+        X, Y = x[..., 0], x[..., 1]
+        D1, D2, z1, z2, K = 0.5, 1.0, 2.0, -2.0, 2e-1
+        C1 = np.cos(X) + np.sin(Y) + 3.0
+        C2 = np.cos(X) - np.sin(Y) + 3.0
+        g1 = (-np.sin(X), np.cos(Y))
+        g2 = (-np.sin(X), -np.cos(Y))
+        l1 = -np.cos(X) - np.sin(Y)
+        l2 = -np.cos(X) + np.sin(Y)
+        gU = (np.cos(X), -np.sin(Y))
+        lU = -np.sin(X) - np.cos(Y)
+        f1 = -D1 * z1 * (g1[0] * gU[0] + g1[1] * gU[1] + C1 * lU) - D1 * l1
+        f2 = -D2 * z2 * (g2[0] * gU[0] + g2[1] * gU[1] + C2 * lU) - D2 * l2
+        f3 = -K * lU - z1 * C1 - z2 * C2
+        return [f1, f2, f3]
+    conc_params = [{"name": "C1", "diffusion coefficient": 0.5, "z": 2.0, "bulk": C1ex},
+                   {"name": "C2", "diffusion coefficient": 1.0, "z": -2.0, "bulk": poisson_C2ex}]
+    physical_params = {"flow": ["diffusion", "migration", "poisson"], "F": 1.0, "R": 1.0, "T": 1.0,
+                       "vacuum permittivity": 2.0, "relative permittivity": 1e-1, "U_app": Uex, "bulk reaction": f}
+    markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4)}
+    return Problem(conc_params, physical_params, markers, family=family)

@@ -130,3 +130,32 @@ class AdvectionDiffusionSolver(EchemSolver):
         h = 1.0
         x_vel = 6. * self.physical_params["v_avg"] / h**2 * y * (h - y)
         self.vel = as_vector([x_vel] + [Constant(0.)] * (len(xs) - 1))
+
+
+class DiffusionMigrationPoissonSolver(EchemSolver):
+    """tests/test_diffusion_migration_poisson.py:6-57 of the reference: Nernst-Planck + true Poisson."""
+
+    def __init__(self, N, family="DG"):
+        mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        C1ex = cos(x) + sin(y) + 3
+        C2ex = cos(x) - sin(y) + 3
+        Uex = sin(x) + cos(y) + 3
+        self.C1ex, self.C2ex, self.Uex = C1ex, C2ex, Uex
+
+        def f(C):
+            D1, D2, z1, z2, K = 0.5, 1.0, 2.0, -2.0, 2e-1
+            f1 = div((- D1 * z1 * grad(Uex)) * C1ex) - div(D1 * grad(C1ex))
+            f2 = div((- D2 * z2 * grad(Uex)) * C2ex) - div(D2 * grad(C2ex))
+            f3 = div((-K * grad(Uex))) - z1 * C1ex - z2 * C2ex
+            return [f1, f2, f3]
+
+        conc_params = [{"name": "C1", "diffusion coefficient": 0.5, "z": 2., "bulk": C1ex},
+                       {"name": "C2", "diffusion coefficient": 1.0, "z": -2., "bulk": C2ex}]
+        physical_params = {"flow": ["diffusion", "migration", "poisson"], "F": 1.0, "R": 1.0, "T": 1.0,
+                           "vacuum permittivity": 2.0, "relative permittivity": 1e-1, "U_app": Uex,
+                           "bulk reaction": f}
+        super().__init__(conc_params, physical_params, mesh, family=family)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,), "applied": (1, 2, 3, 4,)}

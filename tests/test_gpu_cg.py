@@ -77,3 +77,27 @@ def test_cg_newton_solutions_match_oracle():
         for f in range(2):
             a, b = u[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
             assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("family", ["DG", "CG"])
+def test_poisson_coupled_matches_oracle(family):
+    """Poisson-coupled Nernst-Planck (potential_poisson_form, solver.py:2048-2234), three fields."""
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    from oracle.newton import solve_problem
+    N = 4
+    disc = Discretization(unit_square_mesh(N), mms_cases.poisson_problem(family))
+    s = product_cases.DiffusionMigrationPoissonSolver(N, family=family)
+    x = disc.node_coords
+    pert = 1e-2 * np.sin(7 * x[:, 0] + 3 * x[:, 1])
+    u = np.concatenate([mms_cases.C1ex(x) + pert, mms_cases.poisson_C2ex(x) - pert, mms_cases.Uex(x) + 0.5 * pert])
+    _compare_raw(disc, s, u, "poisson " + family)
+    u_ref, info = solve_problem(disc)
+    s2 = product_cases.DiffusionMigrationPoissonSolver(N, family=family)
+    s2.setup_solver()
+    s2.solve()
+    un = s2.u.numpy()
+    Ns = disc.ndof_scalar
+    for f in range(3):
+        a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
+        assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
