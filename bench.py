@@ -141,7 +141,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--N", type=int, default=1408, help="cells per direction (cfg2 P1: 1408)")
+    ap.add_argument("--N", type=int, default=0, help="cells per direction (cfg2: 1408 / 944 / 704 for Q1 / Q2 / Q3)")
+    ap.add_argument("--degree", type=int, default=1, help="polynomial degree (the headline number is Q1)")
     ap.add_argument("--sample-n", dest="sample_n", type=int, default=96, help="CPU baseline sample mesh")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extras", action="store_true", help="also time SpMV")
@@ -167,7 +168,8 @@ def main():
     from echemfem_b200.capi import ptr
 
     W = max(args.warmup, 3)
-    N = args.N
+    N = args.N or {1: 1408, 2: 944, 3: 704}[args.degree]
+    deg = args.degree
     # The path shards by cells.  Weak scaling: the global mesh is (world*N) x N cells on [0, world] x [0, 1],
     # rank r owns the r-th strip of N x N cells plus one ghost column per cut; per step the ghost-cell
     # state is exchanged (NCCL send/recv) before the residual and Jacobian kernels run.
@@ -175,9 +177,9 @@ def main():
         from echemfem_b200.partition import strip_partition
         lmesh, plan = strip_partition([np.linspace(0.0, float(world), world * N + 1), np.linspace(0.0, 1.0, N + 1)],
                                       rank, world)
-        s = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, D1=0.5e-5, D2=1.0e-5, mesh=lmesh)
+        s = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, D1=0.5e-5, D2=1.0e-5, mesh=lmesh, p=deg)
     else:
-        s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5)
+        s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5, p=deg)
     eng = NewtonEngine(s)
     mesh = s.mesh
     x = s.V.node_coords()
@@ -272,7 +274,7 @@ def main():
             "metric": METRIC, "value": world * ndof / (t_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 MMS 2D DG Q1 electroneutral Nernst-Planck, UnitSquareMesh(%d,%d) quads" % (N, N),
+            "config": {"workload": "cfg2 MMS 2D DG Q%d electroneutral Nernst-Planck, UnitSquareMesh(%d,%d) quads" % (deg, N, N),
                        "cells_per_gpu": getattr(mesh, "num_owned", mesh.num_cells), "dofs_per_gpu": ndof, "nnz_per_gpu": eng.nnz,
                        "l2_policy": "outputs (%.1f GB CSR values) exceed the 126 MB L2 every step" % (8 * eng.nnz / 1e9),
                        "parallelism": "cells partitioned in strips, one per GPU; ghost-cell state exchanged by NCCL "
