@@ -357,7 +357,9 @@ class NewtonEngine:
             for f in frozen_fields:
                 mask[f * self.N:(f + 1) * self.N] = 1
         if self.bc_mask is not None:
-            # strong Dirichlet rows (CG): the state carries the boundary values, the rows become identity
+            # strong Dirichlet rows (CG): the state carries the boundary values, the rows become identity;
+            # values are re-evaluated because they may depend on Constants (time, applied potential)
+            self.bc_mask, self.bc_vals = self._dirichlet(self.solver.W.scalar)
             sel = self.bc_mask.bool()
             if frozen_fields:
                 for f in frozen_fields:

@@ -135,6 +135,12 @@ class Discretization:
         geo = {"cell_volume": self.cell_volume[cells][:, None],
                "cell_diameter": self.cell_diameter[cells][:, None]}
         f0, f1 = self.prob.cell(x, u, gu, geo)
+        tr = getattr(self.prob, "transient", None)
+        if tr is not None:
+            # backward Euler accumulation term (C - C_old)/dt v dx of TransientEchemSolver (solver.py:2693)
+            Uold = self._local(tr["u_old"], cells)
+            for i in range(self.prob.num_mass):
+                f0[i] = f0[i] + (u[i] - np.einsum("eb,qb->eq", Uold[:, i], phi)) / tr["dt"]
         return self._test(f0, f1, w, phi, gphi)
 
     def _test(self, f0, f1, w, phi, gphi):

@@ -149,3 +149,23 @@ def poisson_problem(family="DG"):
                        "vacuum permittivity": 2.0, "relative permittivity": 1e-1, "U_app": Uex, "bulk reaction": f}
     markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4)}
     return Problem(conc_params, physical_params, markers, family=family)
+
+
+def heat_problem(t, dt, u_old, family="DG"):
+    """tests/test_heat_equation.py:7-42 at time t with a backward-Euler step of size dt from u_old."""
+    from oracle.forms import Problem
+
+    def c1(x):
+        return (np.sin(x[..., 0]) + np.cos(x[..., 1])) * np.exp(t)
+
+    def c2(x):
+        return (np.cos(x[..., 0]) + np.sin(x[..., 1])) * np.exp(-t)
+
+    def f(u, x):
+        return [2.0 * c1(x), 0.0 * c2(x)]          # C1ex - lap C1ex = 2 C1ex ; -C2ex - lap C2ex = 0
+    conc_params = [{"name": "C1", "diffusion coefficient": 1.0, "z": 0.0, "bulk": c1},
+                   {"name": "C2", "diffusion coefficient": 1.0, "z": 0.0, "bulk": c2}]
+    prob = Problem(conc_params, {"flow": ["diffusion"], "bulk reaction": f}, {"bulk dirichlet": (1, 2, 3, 4)},
+                   family=family)
+    prob.transient = {"dt": dt, "u_old": u_old}
+    return prob, c1, c2

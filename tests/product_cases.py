@@ -159,3 +159,32 @@ class DiffusionMigrationPoissonSolver(EchemSolver):
 
     def set_boundary_markers(self):
         self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,), "applied": (1, 2, 3, 4,)}
+
+
+from echemfem_b200 import TransientEchemSolver  # noqa: E402
+
+
+class HeatEquationSolver(TransientEchemSolver):
+    """tests/test_heat_equation.py:7-42 of the reference: transient diffusion of two species, backward Euler."""
+
+    def __init__(self, N, family="DG"):
+        mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        self.time = Constant(0)
+        t = self.time
+        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        C1ex = (sin(x) + cos(y)) * exp(t)
+        C2ex = (cos(x) + sin(y)) * exp(-t)
+        self.C1ex, self.C2ex = C1ex, C2ex
+
+        def f(C):
+            f1 = C1ex - div(grad(C1ex))
+            f2 = -C2ex - div(grad(C2ex))
+            return [f1, f2]
+
+        conc_params = [{"name": "C1", "diffusion coefficient": 1.0, "bulk": C1ex},
+                       {"name": "C2", "diffusion coefficient": 1.0, "bulk": C2ex}]
+        physical_params = {"flow": ["diffusion"], "bulk reaction": f}
+        super().__init__(conc_params, physical_params, mesh, family=family)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,)}
