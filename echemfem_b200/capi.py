@@ -45,6 +45,8 @@ EXPORTS = {
     "ech_spmv": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_axpby": (C.c_int, [c_i64, C.c_double, c_p, C.c_double, c_p, c_p]),
     "ech_dot": (C.c_int, [c_i64, c_p, c_p, c_p, C.POINTER(C.c_double), c_p]),
+    "ech_multidot": (C.c_int, [c_i64, c_i32, c_p, c_p, c_p, c_p, c_p]),
+    "ech_multiaxpy": (C.c_int, [c_i64, c_i32, c_p, c_p, C.c_double, c_p, c_p]),
     "ech_bjacobi_ilu0_factor": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_apply": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_gmres": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_p, C.POINTER(GmresOpts), c_p, c_p,

@@ -570,6 +570,31 @@ static int multidot(int64_t n, int k, const double *V, const double *w, double *
     return ECH_OK;
 }
 
+// device-resident variants used by the distributed (multi-GPU) Krylov loop: the caller all-reduces
+// out[0..k] over the ranks before reading it
+extern "C" int ech_multidot(int64_t n, int32_t k, const double *V, const double *w, double *work, double *out,
+                            void *stream) {
+    if (!w || !work || !out || (k > 0 && !V)) return fail(nullptr, ECH_ERR_ARG, "ech_multidot: null argument");
+    if (n == 0) return ECH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(DOT_BLOCKS, (k + 1 + DOT_TILE - 1) / DOT_TILE);
+    multidot_kernel<<<grid, 256, 0, s>>>(n, k, V, n, w, work);
+    multidot_finish_kernel<<<k + 1, 256, 0, s>>>(k + 1, DOT_BLOCKS, work, out);
+    g_launches += 2;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_multiaxpy(int64_t n, int32_t k, const double *V, const double *h, double sign, double *w,
+                             void *stream) {
+    if (!V || !h || !w) return fail(nullptr, ECH_ERR_ARG, "ech_multiaxpy: null argument");
+    if (n == 0 || k == 0) return ECH_OK;
+    multiaxpy_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, k, V, n, h, w, sign);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 extern "C" int ech_dot(int64_t n, const double *x, const double *y, double *work, double *result_host,
                        void *stream) {
     cudaStream_t s = (cudaStream_t)stream;

@@ -306,6 +306,12 @@ class NewtonEngine:
                                                     ptr(self.vals), ptr(L["lu"]), ptr(L["diag"]), self._stream()))
         torch.cuda.synchronize()
         self.timers["PCSetUp"] += time.time() - t0
+        if self.halo is not None:
+            t0 = time.time()
+            out = self._dist_gmres(rhs, rtol, atol, max_it, monitor)
+            torch.cuda.synchronize()
+            self.timers["KSPSolve"] += time.time() - t0
+            return out
         opts = capi.GmresOpts(rtol, atol, L["restart"], max_it, 1, 1 if monitor else 0, self.nf, self._unit,
                               self.N, L["nblocks"], ptr(L["block_ptr"]), ptr(L["lu"]), ptr(L["diag"]))
         L["dx"].zero_()
@@ -321,8 +327,119 @@ class NewtonEngine:
             capi.check(rc)
         return L["dx"], its.value, rc == 0
 
+    def _dist_gmres(self, b, rtol, atol, max_it, monitor=False):
+        """Right-preconditioned restarted GMRES across ranks: the same algorithm as `ech_gmres`, with the
+        ghost-dof exchange in front of every SpMV and the Gram-Schmidt dot products all-reduced over NCCL
+        (PETSc: VecScatter + MPI_Allreduce inside KSPSolve).  Preconditioner blocks never cross ranks."""
+        import torch.distributed as dist
+        L = self._lin
+        n, m = self.ndof, L["restart"]
+        lib, st = self.lib, self._stream()
+        V = L["basis"]
+        work = L["work"]
+        w, zt, t2 = work[:n], work[n:2 * n], work[2 * n:3 * n]
+        hdev = work[3 * n:3 * n + m + 2]
+        partial = work[3 * n + 4096:]
+        x = L["dx"]
+        x.zero_()
+
+        def mdot(k, vec):
+            capi.check(lib.ech_multidot(n, k, ptr(V), ptr(vec), ptr(partial), ptr(hdev), st))
+            dist.all_reduce(hdev[:k + 1])
+            return hdev[:k + 1].cpu().numpy()
+
+        def precond(src, dst):
+            dst.zero_()
+            capi.check(lib.ech_bjacobi_ilu0_apply(n, self.nf, self.N, self._unit, L["nblocks"], ptr(L["block_ptr"]),
+                                                  ptr(self.rowptr), ptr(self.colidx), ptr(L["lu"]), ptr(L["diag"]),
+                                                  ptr(src), ptr(dst), st))
+
+        def matvec(src, dst):
+            self.halo.exchange(src)
+            capi.check(lib.ech_spmv(n, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(src), ptr(dst), st))
+
+        bnorm = math.sqrt(max(mdot(0, b)[0], 0.0))
+        tol = max(rtol * bnorm, atol)
+        its, rnorm, converged = 0, bnorm, False
+        H = np.zeros((m + 1, m))
+        cs, sn, g = np.zeros(m), np.zeros(m), np.zeros(m + 1)
+        while its < max_it and not converged:
+            V0 = V[:n]
+            t2.copy_(x)
+            matvec(t2, w)
+            torch.sub(b, w, out=V0)
+            beta = math.sqrt(max(mdot(0, V0)[0], 0.0))
+            rnorm = beta
+            if monitor and self.halo.plan.rank == 0:
+                print("  %3d KSP Residual norm %.12e" % (its, rnorm))
+            if beta <= tol:
+                converged = True
+                break
+            V0.mul_(1.0 / beta)
+            g[:] = 0.0
+            g[0] = beta
+            j = 0
+            while j < m and its < max_it:
+                Vj, Vn = V[j * n:(j + 1) * n], V[(j + 1) * n:(j + 2) * n]
+                precond(Vj, zt)
+                matvec(zt, w)
+                h = mdot(j + 1, w)
+                H[:j + 1, j] = h[:j + 1]
+                capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
+                h = mdot(j + 1, w)                                   # one refinement pass
+                H[:j + 1, j] += h[:j + 1]
+                capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
+                hn = math.sqrt(max(mdot(0, w)[0], 0.0))
+                H[j + 1, j] = hn
+                if hn > 0.0:
+                    torch.mul(w, 1.0 / hn, out=Vn)
+                for i in range(j):
+                    a_, b_ = H[i, j], H[i + 1, j]
+                    H[i, j] = cs[i] * a_ + sn[i] * b_
+                    H[i + 1, j] = -sn[i] * a_ + cs[i] * b_
+                a_, b_ = H[j, j], H[j + 1, j]
+                den = math.hypot(a_, b_)
+                cs[j], sn[j] = (1.0, 0.0) if den == 0.0 else (a_ / den, b_ / den)
+                H[j, j], H[j + 1, j] = den, 0.0
+                g[j + 1] = -sn[j] * g[j]
+                g[j] = cs[j] * g[j]
+                its += 1
+                rnorm = abs(g[j + 1])
+                if monitor and self.halo.plan.rank == 0:
+                    print("  %3d KSP Residual norm %.12e" % (its, rnorm))
+                j += 1
+                if rnorm <= tol or hn == 0.0:
+                    converged = rnorm <= tol
+                    break
+            k = j
+            if k == 0:
+                break
+            y = np.linalg.solve(np.triu(H[:k, :k]), g[:k])
+            hdev[:k].copy_(torch.from_numpy(y).to(self.dev))
+            t2.zero_()
+            capi.check(lib.ech_multiaxpy(n, k, ptr(V), ptr(hdev), 1.0, ptr(t2), st))
+            precond(t2, zt)
+            x.add_(zt)
+        x.mul_(self._owned_mask())          # ghost entries of the update are refreshed by the next exchange
+        return x, its, converged
+
     # -- Newton -----------------------------------------------------------------------------
+    def _owned_mask(self):
+        if not hasattr(self, "_owned"):
+            w = torch.zeros(self.ndof, dtype=torch.float64, device=self.dev)
+            no = self.ncell * self.nloc
+            for f in range(self.nf):
+                w[f * self.N:f * self.N + no] = 1.0
+            self._owned = w
+        return self._owned
+
     def _norm(self, v):
+        if self.halo is not None:
+            # owned entries only, summed over the ranks (PETSc VecNorm on an MPI Vec)
+            import torch.distributed as dist
+            t = (v * v * self._owned_mask()).sum().reshape(1)
+            dist.all_reduce(t)
+            return math.sqrt(max(float(t.item()), 0.0))
         r = C.c_double()
         if self._lin is not None:
             work = self._lin["work"]
@@ -387,9 +504,9 @@ class NewtonEngine:
             print("  %d SNES Function norm %.12e" % (0, fnorm))
         reason = None
         its = 0
-        W1 = torch.empty_like(u)
-        F1 = torch.empty_like(u)
-        F2 = torch.empty_like(u)
+        W1 = torch.zeros_like(u)
+        F1 = torch.zeros_like(u)
+        F2 = torch.zeros_like(u)
         if fnorm < atol:
             reason = "CONVERGED_FNORM_ABS"
         while reason is None and its < max_it:

@@ -106,6 +106,13 @@ int ech_axpby(int64_t n, double a, const double *x, double b, double *y, void *s
 /* *result_host = x . y ; synchronises. `work` holds >= 1024 doubles. */
 int ech_dot(int64_t n, const double *x, const double *y, double *work, double *result_host, void *stream);
 
+/* Building blocks of the multi-GPU Krylov loop (results stay on the device so that the caller can
+ * all-reduce them over NCCL before reading them; PETSc: VecMDot / VecMAXPY + MPI_Allreduce):
+ * out[j] = V_j . w for j < k and out[k] = w . w, V column-major with leading dimension n;
+ * work holds >= (k + 1) * 1024 doubles.   w += sign * sum_j h[j] V_j. */
+int ech_multidot(int64_t n, int32_t k, const double *V, const double *w, double *work, double *out, void *stream);
+int ech_multiaxpy(int64_t n, int32_t k, const double *V, const double *h, double sign, double *w, void *stream);
+
 /* Block-Jacobi with ILU(0) inside each block.  Block b owns the cells
  * [block_cell_ptr[b], block_cell_ptr[b+1]) (all fields of those cells); couplings
  * between blocks are dropped.  nblocks = 1 is PETSc's default "one block per rank". */
