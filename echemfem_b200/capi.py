@@ -41,6 +41,7 @@ EXPORTS = {
     "ech_pattern_colidx": (C.c_int, [c_p, c_p, c_p, c_p]),
     "ech_residual": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_jacobian": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ech_residual_jacobian": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_constrain_rows": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_spmv": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_axpby": (C.c_int, [c_i64, C.c_double, c_p, C.c_double, c_p, c_p]),

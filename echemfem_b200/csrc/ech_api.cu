@@ -391,6 +391,7 @@ extern "C" int ech_residual(ech_handle *h, const double *u, const double *aux, c
     a.consts = consts;
     a.rowptr = nullptr;
     a.out = F;
+    a.out2 = nullptr;
     int rc = h->mod.residual(&a, stream);
     g_launches += h->mod.launches(0);
     if (rc) return cuda_fail(h, (cudaError_t)rc, "ech_residual launch");
@@ -407,9 +408,27 @@ extern "C" int ech_jacobian(ech_handle *h, const double *u, const double *aux, c
     a.consts = consts;
     a.rowptr = rowptr;
     a.out = vals;
+    a.out2 = nullptr;
     int rc = h->mod.jacobian(&a, stream);
     g_launches += h->mod.launches(1);
     if (rc) return cuda_fail(h, (cudaError_t)rc, "ech_jacobian launch");
+    return ECH_OK;
+}
+
+extern "C" int ech_residual_jacobian(ech_handle *h, const double *u, const double *aux, const double *consts,
+                                     const int64_t *rowptr, double *vals, double *F, void *stream) {
+    if (!h || !u || !rowptr || !vals || !F) return fail(h, ECH_ERR_ARG, "ech_residual_jacobian: null argument");
+    ech_dg_args a;
+    fill_args(h, a);
+    a.u = u;
+    a.aux = aux;
+    a.consts = consts;
+    a.rowptr = rowptr;
+    a.out = vals;
+    a.out2 = F;
+    int rc = h->mod.jacobian(&a, stream);
+    g_launches += h->mod.launches(2);
+    if (rc) return cuda_fail(h, (cudaError_t)rc, "ech_residual_jacobian launch");
     return ECH_OK;
 }
 
@@ -911,12 +930,9 @@ extern "C" int ech_assemble_host(ech_handle *h, const double *u_host, double *u_
     ech_num_rows(h, &nrows);
     const int64_t nstate = nrows;
     CK(h, cudaMemcpyAsync(u_dev, u_host, sizeof(double) * nstate, cudaMemcpyHostToDevice, s));
-    int rc = ech_residual(h, u_dev, aux, consts, F_dev, stream);
+    int rc = vals ? ech_residual_jacobian(h, u_dev, aux, consts, rowptr, vals, F_dev, stream)
+                  : ech_residual(h, u_dev, aux, consts, F_dev, stream);
     if (rc) return rc;
-    if (vals) {
-        rc = ech_jacobian(h, u_dev, aux, consts, rowptr, vals, stream);
-        if (rc) return rc;
-    }
     CK(h, cudaMemcpyAsync(F_host, F_dev, sizeof(double) * nrows, cudaMemcpyDeviceToHost, s));
     CK(h, cudaStreamSynchronize(s));
     return ECH_OK;

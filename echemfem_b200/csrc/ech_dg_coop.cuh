@@ -453,7 +453,28 @@ __device__ __forceinline__ void test_basis(const RecRef &R, int s, int a, double
     for (int k = 0; k < D; ++k) gphia[k] = R(s, OFF_GPHI + a * D + k);
 }
 
+// WITH_RES: fused evaluation of the residual at the same state (one Newton step needs F(u) and J(u);
+// geometry, bases, state interpolation and staging are shared, the residual costs 6 more record words)
+constexpr int RES_LEN = (NF * (1 + D) + 1) & ~1;
+constexpr int OFF_RES = JREC_LEN;
+constexpr int JFREC_LEN = JREC_LEN + RES_LEN;
+
+template <class M, int LEN>
+__device__ __forceinline__ void put_res_at(double (&buf)[LEN], const Res &o, double w) {
+    static_for<0, NF>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr bool h0 = M::F0[i], h1 = M::F1[i];
+        if constexpr (h0) buf[OFF_RES + i] = w * o.f0[i];
+        if constexpr (h1) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) buf[OFF_RES + NF + i * D + k] = w * o.f1[i][k];
+        }
+    });
+}
+
+template <bool WITH_RES>
 __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(const ech_dg_args A) {
+    constexpr int RECLEN = WITH_RES ? JFREC_LEN : JREC_LEN;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / G, a = lane - g * G;       // cell-major lane numbering
@@ -462,7 +483,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell_total * NLOC;
-    const WarpSmem W = warp_smem(smem, warp, JREC_LEN);
+    const WarpSmem W = warp_smem(smem, warp, RECLEN);
     const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
     const int *meta = W.meta + gg * META_LEN;
@@ -486,6 +507,9 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
 
     double acc[NF][NF][NLOC];
     zero_blocks<true>(acc);
+    double res[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) res[i] = 0.0;
     double accn_persist[FACET_IN_ROUND ? 1 : NF][FACET_IN_ROUND ? 1 : NF][FACET_IN_ROUND ? 1 : NLOC];
     if constexpr (!FACET_IN_ROUND) zero_blocks<false>(reinterpret_cast<double(&)[NF][NF][NLOC]>(accn_persist));
 
@@ -503,9 +527,9 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
             double phi[NLOC], gphi[NLOC][D];
             int idx[D];
             double w;
-            double buf[JREC_LEN];
+            double buf[RECLEN];
 #pragma unroll
-            for (int m = 0; m < JREC_LEN; ++m) buf[m] = 0.0;
+            for (int m = 0; m < RECLEN; ++m) buf[m] = 0.0;
             if (task < NQC) {
                 cell_point(task, idx, w);
                 own_side(own, idx, p, gm, phi, gphi);
@@ -517,6 +541,12 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                     cell_jac<I>(p, rj);
                     put_rowj<MC, I>(buf, OFF_JP, rj, w);
                 });
+                if constexpr (WITH_RES) {
+                    Res o;
+                    cell_res(p, o);
+                    put_res_at<MC>(buf, o, w);
+                    flush_record(RE, ae, buf, OFF_RES, OFF_RES + RES_LEN);
+                }
                 flush_record(RE, ae, buf, OFF_PHI, OFF_PHI2);
                 flush_record(RE, ae, buf, OFF_JP, OFF_JP + ((LAY_C.len + 1) & ~1));
             } else {
@@ -546,6 +576,12 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                         efacet_jac<I>(cls, p, rj);
                         put_rowj<ME, I>(buf, OFF_JP, rj, w);
                     });
+                    if constexpr (WITH_RES) {
+                        Res o;
+                        efacet_res(cls, p, o);
+                        put_res_at<ME>(buf, o, w);
+                        flush_record(RE, ae, buf, OFF_RES, OFF_RES + RES_LEN);
+                    }
                     flush_record(RE, ae, buf, OFF_PHI, OFF_PHI2);
                     flush_record(RE, ae, buf, OFF_JP, OFF_JP + ((LAY_E.len + 1) & ~1));
                 } else {
@@ -557,7 +593,12 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
                             put_rowj<MIP, I>(buf, OFF_JP, rj, w);
                             put_rowj<MIM, I>(buf, OFF_JM, rjm, w);
                         });
-                        flush_record(RE, ae, buf, 0, JREC_LEN);
+                        if constexpr (WITH_RES) {
+                            Res o;
+                            ifacet_res(p, o);
+                            put_res_at<MIP>(buf, o, w);
+                        }
+                        flush_record(RE, ae, buf, 0, RECLEN);
                     }
                 }
             }
@@ -569,6 +610,21 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
 #else
         if (active) {
 #endif
+            if constexpr (WITH_RES) {
+                // residual rows (all equations, test node a): every record of my cell contributes
+                for (int s = 0; s < G; ++s) {
+                    if (round * G + s >= NTASK) break;
+                    double phia, gphia[D];
+                    test_basis(R, s, a, phia, gphia);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        double t = R(s, OFF_RES + i) * phia;
+#pragma unroll
+                        for (int k2 = 0; k2 < D; ++k2) t += R(s, OFF_RES + NF + i * D + k2) * gphia[k2];
+                        res[i] += t;
+                    }
+                }
+            }
             if constexpr (FACET_IN_ROUND) {
                 if (round < NQC / G) {
 #pragma unroll
@@ -647,7 +703,13 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
         }
         __syncwarp();
     }
-    if (active) store_blocks<true>(A.out, rp, ncol, pos_self, acc);
+    if (active) {
+        store_blocks<true>(A.out, rp, ncol, pos_self, acc);
+        if constexpr (WITH_RES) {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) A.out2[i * rows_per_field + c * NLOC + a] = res[i];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -767,12 +829,15 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
 
 // ------------------------------------------------------------------------------------------------
 constexpr int JSMEM = JWARPS * warp_smem_doubles(JREC_LEN) * 8;
+constexpr int JFSMEM = JWARPS * warp_smem_doubles(JFREC_LEN) * 8;
 constexpr int RSMEM = RWARPS * warp_smem_doubles(RREC_LEN) * 8;
 
 static int coop_setup() {
     static int done = 0;
     if (done) return 0;
-    cudaError_t e = cudaFuncSetAttribute(jacobian_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
+    cudaError_t e = cudaFuncSetAttribute(jacobian_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, JFSMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(jacobian_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, JSMEM);
     if (e != cudaSuccess) {
         fprintf(stderr, "echem_b200: cudaFuncSetAttribute(jacobian_coop_kernel, %d B) failed: %s\n", JSMEM,
                 cudaGetErrorString(e));
@@ -794,7 +859,10 @@ static int launch_jacobian_coop(const ech_dg_args *a, cudaStream_t s) {
     if (e) return e;
     const int64_t cells_per_block = (int64_t)JWARPS * CPW;
     const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
-    jacobian_coop_kernel<<<(unsigned)grid, JWARPS * 32, JSMEM, s>>>(*a);
+    if (a->out2)
+        jacobian_coop_kernel<true><<<(unsigned)grid, JWARPS * 32, JFSMEM, s>>>(*a);
+    else
+        jacobian_coop_kernel<false><<<(unsigned)grid, JWARPS * 32, JSMEM, s>>>(*a);
     e = (int)cudaGetLastError();
     if (e) fprintf(stderr, "echem_b200: jacobian_coop_kernel<<<%lld, %d, %d>>> failed: %s\n", (long long)grid,
                    JWARPS * 32, JSMEM, cudaGetErrorString((cudaError_t)e));

@@ -45,20 +45,41 @@ int ech_mod_residual(const ech_dg_args *a, void *stream) {
 }
 
 int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
-    if (use_coop()) return echdg::launch_jacobian_coop(a, (cudaStream_t)stream);
+    if (use_coop()) return echdg::launch_jacobian_coop(a, (cudaStream_t)stream);   // fused when a->out2 is set
+    if (a->out2) {
+        ech_dg_args r = *a;
+        r.out = a->out2;
+        r.out2 = nullptr;
+        int e = echdg::launch_residual(&r, (cudaStream_t)stream);
+        if (e) return e;
+    }
     return echdg::launch_jacobian(a, (cudaStream_t)stream);
 }
 
-int ech_mod_launches(int which) { return (which == 0 || use_coop()) ? 1 : echgen::NF; }
+// which: 0 residual, 1 Jacobian, 2 fused residual + Jacobian
+int ech_mod_launches(int which) {
+    if (which == 0) return 1;
+    if (use_coop()) return 1;
+    return echgen::NF + (which == 2 ? 1 : 0);
+}
 #else
 int ech_mod_residual(const ech_dg_args *a, void *stream) {
     (void)g_variant;
     return echcg::launch_cg_residual(a, (cudaStream_t)stream);
 }
 
-int ech_mod_jacobian(const ech_dg_args *a, void *stream) { return echcg::launch_cg_jacobian(a, (cudaStream_t)stream); }
+int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
+    if (a->out2) {
+        ech_dg_args r = *a;
+        r.out = a->out2;
+        r.out2 = nullptr;
+        int e = echcg::launch_cg_residual(&r, (cudaStream_t)stream);
+        if (e) return e;
+    }
+    return echcg::launch_cg_jacobian(a, (cudaStream_t)stream);
+}
 
-int ech_mod_launches(int which) { return which == 0 ? 1 : echgen::NF; }
+int ech_mod_launches(int which) { return which == 0 ? 1 : echgen::NF + (which == 2 ? 1 : 0); }
 #endif
 
 }  // extern "C"

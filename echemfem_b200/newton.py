@@ -258,6 +258,17 @@ class NewtonEngine:
                                          self._stream()), self.h)
         return self.vals
 
+    def residual_jacobian(self, u, out=None, aux=None, consts=None):
+        """F(u) and J(u) in one pass (`ech_residual_jacobian`)."""
+        out = self.F if out is None else out
+        aux = self._aux_tensor() if aux is None else aux
+        consts = self._consts() if consts is None else consts
+        if self.halo is not None:
+            self.halo.exchange(u)
+        capi.check(self.lib.ech_residual_jacobian(self.h, ptr(u), ptr(aux), ptr(consts), ptr(self.rowptr),
+                                                  ptr(self.vals), ptr(out), self._stream()), self.h)
+        return out, self.vals
+
     def spmv(self, x, y):
         capi.check(self.lib.ech_spmv(self.ndof, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(x), ptr(y),
                                      self._stream()))

@@ -92,6 +92,10 @@ int ech_residual(ech_handle *h, const double *u, const double *aux, const double
 /* form_jacobian: CSR values of assemble(derivative(Form, u)) (SNESJacobianEval + MatSetValuesLocal). */
 int ech_jacobian(ech_handle *h, const double *u, const double *aux, const double *consts,
                  const int64_t *rowptr, double *vals, void *stream);
+/* Both callbacks at the same state in one pass (a Newton iteration needs F(u_k) and J(u_k)): geometry,
+ * bases, state interpolation and staging are shared; for DG the two are one kernel. */
+int ech_residual_jacobian(ech_handle *h, const double *u, const double *aux, const double *consts,
+                          const int64_t *rowptr, double *vals, double *F, void *stream);
 /* Rows flagged in row_mask[nrows] become identity rows and F is zeroed there: strong
  * DirichletBC rows (solver.py:1531, 2009) and the frozen concentration rows of the potential
  * pre-solve (solver.py:645-662). F and/or vals may be NULL. */

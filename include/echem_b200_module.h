@@ -33,6 +33,8 @@ typedef struct ech_dg_args {
     const double *consts;     /* [nconst] runtime constants                                 */
     const int64_t *rowptr;    /* [nf * ncell * n + 1] (Jacobian only)                       */
     double *out;              /* residual [nf][ncell_total*n] (DG) / [nf][nnodes] (CG), or CSR values [nnz] */
+    double *out2;             /* Jacobian call only: if non-NULL, the residual at the same state is written
+                                 here by the same kernel (fused evaluation); NULL otherwise               */
     /* continuous spaces only (family CG): dofs are shared between cells, assembly gathers per node */
     int64_t nnodes;           /* nodes of the scalar space; field stride of u / aux / out    */
     const int32_t *cell_nodes;/* [ncell][n]  cell -> node map                                 */

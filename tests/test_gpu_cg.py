@@ -28,6 +28,11 @@ def _compare_raw(disc, s, u, tag):
     _assert_close(eng.residual(s.u.tensor).cpu().numpy(), disc.residual(u), tag + " residual")
     eng.jacobian(s.u.tensor)
     _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, tag + " jacobian")
+    eng.vals.zero_()
+    Ff = torch.zeros_like(s.u.tensor)
+    eng.residual_jacobian(s.u.tensor, out=Ff)
+    _assert_close(Ff.cpu().numpy(), disc.residual(u), tag + " fused residual")
+    _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, tag + " fused jacobian")
     return eng
 
 

@@ -99,6 +99,12 @@ def _compare(disc, s, tag):
         eng.vals.zero_()
         eng.jacobian(s.u.tensor)
         _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "%s jacobian v%d" % (tag, variant))
+        # fused evaluation of both at the same state
+        eng.vals.zero_()
+        Ff = torch.zeros_like(s.u.tensor)
+        eng.residual_jacobian(s.u.tensor, out=Ff)
+        _assert_close(Ff.cpu().numpy(), disc.residual(u), "%s fused residual v%d" % (tag, variant))
+        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "%s fused jacobian v%d" % (tag, variant))
     eng.set_variant(0)
 
 
