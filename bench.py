@@ -149,6 +149,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly one JSON line; everything the solver prints goes to stderr
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
 
     import numpy as np
     import torch
@@ -308,7 +311,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "UnitSquareMesh(%d,%d) DG Q1, %d dofs, one residual + one Jacobian "
                                               "(numpy oracle, complex-step Jacobian), %.1f s" % (args.sample_n, args.sample_n, nd, t)}
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
