@@ -35,47 +35,65 @@ def measured_peak():
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms; only samples inside the timed region count."""
+
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        q = "timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            deadline = time.time() + 5.0
+            while not self.rows and time.time() < deadline:      # wait until the sampler is live
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            parts = [p.strip() for p in r.split(",")]
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                parts = [p.strip() for p in r.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except Exception:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, reasons
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.04]
+        sm, mx, reasons = parse(inside if inside else self.rows)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 def algorithmic_bytes(mesh, nf, nloc, nnz):
@@ -211,11 +229,12 @@ def main():
     # per-kernel timings (events on the launching stream)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     sampler = ClockSampler(local)
+    sampler.start()
     launches0 = lib.ech_launch_count(eng.h)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark_begin()
     t_wall = time.perf_counter()
     for k in range(args.steps):
         evs[k][0].record()
@@ -225,6 +244,7 @@ def main():
     if dist is not None:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = lib.ech_launch_count(eng.h) - launches0
     t_step = evs[0][0].elapsed_time(evs[-1][1]) / args.steps
