@@ -39,6 +39,9 @@ class _Printer(C99CodePrinter):
             return "(1.0/(%s))" % self._print(b)
         return "pow((double)(%s), (double)(%s))" % (self._print(b), self._print(e))
 
+    def _print_rpow(self, expr):
+        return "pow((double)(%s), (double)(%s))" % (self._print(expr.args[0]), self._print(expr.args[1]))
+
     def _print_sign(self, expr):
         a = self._print(expr.args[0])
         return "(((%s) > 0.0) ? 1.0 : (((%s) < 0.0) ? -1.0 : 0.0))" % (a, a)

@@ -39,6 +39,42 @@ def sym(name):
     return sp.Symbol(name, real=True)
 
 
+class rpow(sp.Function):
+    """Real power base**expo for a non-integer exponent.
+
+    sympy treats x**1.5 of a real symbol as possibly complex, which leaks re()/im() into derivatives of
+    |.| (e.g. the upwind flux with Bruggeman coefficients eps**1.5).  UFL's `Power` is real-valued;
+    this function keeps that semantics."""
+    nargs = 2
+    is_real = True
+    is_extended_real = True
+
+    @classmethod
+    def eval(cls, base, expo):
+        if base.is_Number and expo.is_Number:
+            return sp.Float(float(base) ** float(expo))
+        if expo.is_Integer:
+            return base ** expo
+        return None
+
+    def fdiff(self, argindex=1):
+        base, expo = self.args
+        if argindex == 1:
+            return expo * rpow(base, expo - 1)
+        return self * sp.log(base)
+
+
+def _power(a, b):
+    a, b = sp.sympify(a), sp.sympify(b)
+    if b.is_Integer or (a.is_Number and b.is_Number):
+        return a ** b
+    if b.is_Number and not a.is_Number:
+        if a.is_nonnegative:
+            return a ** b
+        return rpow(a, b)
+    return a ** b
+
+
 class Expr:
     """Tensor of sympy scalars with UFL-like operators."""
     __array_priority__ = 100
@@ -90,8 +126,8 @@ class Expr:
     def __rsub__(self, o): return self._bin(o, lambda a, b: b - a)
     def __truediv__(self, o): return self._bin(o, lambda a, b: a / b)
     def __rtruediv__(self, o): return self._bin(o, lambda a, b: b / a)
-    def __pow__(self, o): return self._bin(o, lambda a, b: a ** b)
-    def __rpow__(self, o): return self._bin(o, lambda a, b: b ** a)
+    def __pow__(self, o): return self._bin(o, _power)
+    def __rpow__(self, o): return self._bin(o, lambda a, b: _power(b, a))
     def __neg__(self): return self._map(lambda e: -e)
     def __pos__(self): return self
     def __abs__(self): return Expr(sp.Abs(self.v))

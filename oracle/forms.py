@@ -76,7 +76,7 @@ class Problem:
         self.C_IP = C_IP
         self.penalty_degree = p if p_penalty is None else p_penalty
         flow = {k: False for k in ("advection", "diffusion", "migration",
-                                   "electroneutrality", "poisson")}
+                                   "electroneutrality", "poisson", "porous")}
         for f in physical_params["flow"]:
             if f not in flow:
                 raise NotImplementedError("oracle: flow option %r" % f)
@@ -104,6 +104,10 @@ class Problem:
         self.has_potential = flow["electroneutrality"] or flow["poisson"]
         self.num_fields = self.num_mass + (1 if self.has_potential else 0)
         self.i_Ul = self.num_mass if self.has_potential else None
+        self.i_Us = None
+        if flow["porous"] and self.has_potential:              # solver.py:264-267, 327-330
+            self.i_Us = self.num_mass + 1
+            self.num_fields += 1
         for i, k in enumerate(self.idx_c):
             self.conc_params[k]["i_c"] = i
 
@@ -139,10 +143,21 @@ class Problem:
         """The list the reference hands to closures: split(u) (solver.py:308)."""
         return list(u)
 
+    def effective(self, D, phase="liquid"):
+        """Bruggeman correlation (solver.py:1276-1286); saturation 1 (no gas phase in the oracle)."""
+        if not self.flow["porous"]:
+            return D
+        eps = self.physical_params["porosity"]
+        frac = {"solid": 1.0 - eps, "liquid": eps}[phase]
+        return D * frac ** 1.5
+
+    def Dk(self, k):
+        return self.effective(self.conc_params[k]["diffusion coefficient"])
+
     def K_mig(self, k):
         pp = self.physical_params
         cp = self.conc_params[k]
-        return cp["diffusion coefficient"] * cp["z"] * pp["F"] / pp["R"] / pp["T"]
+        return self.Dk(k) * cp["z"] * pp["F"] / pp["R"] / pp["T"]
 
     def conductivity(self, C):
         """K_U of the charge-conservation equation (solver.py:1920)."""
@@ -152,8 +167,11 @@ class Problem:
             cp = self.conc_params[k]
             z = cp["z"]
             if z != 0.0:
-                K_U = K_U + z ** 2 * pp["F"] ** 2 * cp["diffusion coefficient"] * C[k] / pp["R"] / pp["T"] * cp.get("C_ND", 1.0)
+                K_U = K_U + z ** 2 * pp["F"] ** 2 * self.Dk(k) * C[k] / pp["R"] / pp["T"] * cp.get("C_ND", 1.0)
         return K_U
+
+    def solid_KU(self):
+        return self.effective(self.physical_params["solid conductivity"], "solid")      # :2082-2084
 
     def poisson_KU(self, C):
         """K_U of the liquid Poisson equation (solver.py:2085-2093, 2136-2138)."""
@@ -169,7 +187,7 @@ class Problem:
             cp = self.conc_params[k]
             z = cp.get("z")
             if z is not None and z != 0:
-                K_U = K_U + z ** 2 * pp["F"] ** 2 * cp["diffusion coefficient"] * C[k] / pp["R"] / pp["T"]
+                K_U = K_U + z ** 2 * pp["F"] ** 2 * self.Dk(k) * C[k] / pp["R"] / pp["T"]
         return K_U
 
     def flow_vector(self, k, x, gU):
@@ -204,7 +222,7 @@ class Problem:
             U, gU = None, None
         for i, k in enumerate(self.idx_c):
             cp = self.conc_params[k]
-            D = cp["diffusion coefficient"]
+            D = self.Dk(k)
             rterm = None
             if reactions is not None and not _is_zero(reactions[i]):
                 # solver.py:1497-1500  (note: indexed by i_c)
@@ -232,13 +250,19 @@ class Problem:
                 if z == 0.0:
                     continue
                 nd = cp.get("C_ND", 1.0)
-                zDF = z * cp["diffusion coefficient"] * pp["F"] * nd
+                zDF = z * self.Dk(k) * pp["F"] * nd
                 if self.flow["diffusion"]:
                     f1[iU] = f1[iU] + zDF * gC[k]                           # :1924
                 if reactions is not None and not _is_zero(reactions[k]):
                     f0[iU] = f0[iU] - nd * z * pp["F"] * reactions[k]       # :1946
             K_U = self.conductivity(C)
             f1[iU] = f1[iU] + _bc(K_U)[..., None] * gU                      # :1978
+            if self.i_Us is not None:                                       # solid Poisson, :2162-2186
+                iS = self.i_Us
+                f1[iS] = f1[iS] + self.solid_KU() * gu[iS]
+                n_r = self.num_liquid + 1
+                if reactions is not None and len(reactions) > n_r and not _is_zero(reactions[n_r]):
+                    f0[iS] = f0[iS] - reactions[n_r]
         elif self.flow["poisson"]:
             iU = self.i_Ul
             eps = pp.get("relative permittivity") is not None and pp.get("vacuum permittivity") is not None
@@ -293,7 +317,7 @@ class Problem:
 
         for i, k in enumerate(self.idx_c):
             cp = self.conc_params[k]
-            D = cp["diffusion coefficient"]
+            D = self.Dk(k)
             if self.flow["diffusion"]:
                 pen = 0.5 * (D_IPp * D + D_IPm * D)                         # :1518-1520
                 sip(i, D, D, Cp[k], Cm[k], gCp[k], gCm[k], pen)
@@ -314,7 +338,7 @@ class Problem:
                 z = cp["z"]
                 if z == 0.0:
                     continue
-                zDF = z * cp["diffusion coefficient"] * pp["F"] * cp.get("C_ND", 1.0)
+                zDF = z * self.Dk(k) * pp["F"] * cp.get("C_ND", 1.0)
                 if self.flow["diffusion"]:
                     sip(iU, zDF, zDF, Cp[k], Cm[k], gCp[k], gCm[k], 0.0)    # :1927-1930
             D_IP2p, D_IP2m = D_IPp, D_IPm
@@ -322,6 +346,10 @@ class Problem:
             KUm = self.conductivity(Cm)
             pen = 0.5 * (D_IP2p * KUp + D_IP2m * KUm)                       # :1983
             sip(iU, KUp, KUm, Up, Um, gUp, gUm, pen)
+            if self.i_Us is not None:                                       # :2171-2176
+                iS = self.i_Us
+                Ks = self.solid_KU()
+                sip(iS, Ks, Ks, up[iS], um[iS], gup[iS], gum[iS], 0.5 * (D_IPp * Ks + D_IPm * Ks))
         elif self.flow["poisson"]:
             iU = self.i_Ul
             KUp = self.poisson_KU(Cp)
@@ -367,12 +395,15 @@ class Problem:
                 f0[i] = f0[i] + pen * k_ * (w - w0)
 
         applied_ids = None
-        if bm.get("applied") is not None:
-            applied_ids = bm["applied"]                                    # non-porous: :1672-1680
+        if self.flow["porous"]:
+            if bm.get("liquid applied") is not None:
+                applied_ids = bm["liquid applied"]                         # :1672-1680
+        elif bm.get("applied") is not None:
+            applied_ids = bm["applied"]
 
         for i, k in enumerate(self.idx_c):
             cp = self.conc_params[k]
-            D = cp["diffusion coefficient"]
+            D = self.Dk(k)
             C_0 = _evalf(cp.get("bulk"), x) if cp.get("bulk") is not None else None
             if self.flow["diffusion"]:
                 if on("bulk dirichlet") and DG:
@@ -412,7 +443,7 @@ class Problem:
                     continue
                 nd = cp.get("C_ND", 1.0)
                 C_0 = _evalf(cp.get("bulk"), x) if cp.get("bulk") is not None else None
-                zDF = z * cp["diffusion coefficient"] * pp["F"] * nd
+                zDF = z * self.Dk(k) * pp["F"] * nd
                 if self.flow["diffusion"] and DG:
                     if on("bulk dirichlet"):
                         nitsche(iU, zDF, C[k], gC[k], C_0, None)           # :1933-1937
@@ -430,13 +461,24 @@ class Problem:
             diric = []
             if on("bulk"):
                 diric.append(0.0)                                           # :1992-1993
-            if on("applied"):
+            if on("applied") and not self.flow["porous"]:
                 diric.append(aux["U_app"])                                  # :1994-1995
             if on("liquid applied"):
                 diric.append(aux["U_app"])
             for U_0 in diric:
                 if DG:
                     nitsche(iU, K_U, U, gU, U_0, D_IP)                      # :2002-2006
+            if self.i_Us is not None:                                       # solid: applied > inlet (:2188-2212)
+                iS = self.i_Us
+                tgt = None
+                if bm.get("applied") is not None:
+                    tgt = "applied"
+                elif bm.get("inlet") is not None:
+                    tgt = "inlet"
+                if tgt is not None and on(tgt) and DG:
+                    nitsche(iS, self.solid_KU(), u[iS], gu[iS], aux["U_app"], D_IP)
+                if on("applied solid current"):
+                    f0[iS] = f0[iS] - pp["applied current density"]
         elif self.flow["poisson"]:
             iU = self.i_Ul
             K_U = self.poisson_KU(C)
@@ -473,10 +515,15 @@ class Problem:
         if self.flow["electroneutrality"]:
             if bm.get("bulk") is not None:
                 out.append((self.i_Ul, bm["bulk"], ("zero",)))
-            if bm.get("applied") is not None:
+            if bm.get("applied") is not None and not self.flow["porous"]:
                 out.append((self.i_Ul, bm["applied"], ("U_app",)))
             if bm.get("liquid applied") is not None:
                 out.append((self.i_Ul, bm["liquid applied"], ("U_app",)))
+            if self.i_Us is not None:
+                if bm.get("applied") is not None:
+                    out.append((self.i_Us, bm["applied"], ("U_app",)))
+                elif bm.get("inlet") is not None:
+                    out.append((self.i_Us, bm["inlet"], ("U_app",)))
         elif self.flow["poisson"]:
             if bm.get("applied") is not None:
                 out.append((self.i_Ul, bm["applied"], ("U_app",)))

@@ -98,11 +98,15 @@ def solve_problem(disc, initial_guess=True, initial_solve=True, monitor=None, u0
         if prob.has_potential:
             iU = prob.i_Ul
             ua = prob.physical_params.get("U_app")
+            nU = 1
             U0 = np.zeros(N)
-            if ua is not None:
+            if prob.i_Us is not None:                              # solver.py:609-643: both potentials
+                nU = 2
+                U0 = np.concatenate([np.zeros(N), disc.interpolate(ua)])
+            elif ua is not None:
                 U0 = disc.interpolate(ua) / 2.0                    # solver.py:646-648
             if initial_solve:                                      # solver.py:649-662
-                sl = slice(iU * N, (iU + 1) * N)
+                sl = slice(iU * N, (iU + nU) * N)
                 fx = None if fixed is None else fixed[sl]
 
                 def rU(U):
@@ -115,7 +119,7 @@ def solve_problem(disc, initial_guess=True, initial_solve=True, monitor=None, u0
                 if fx is not None:
                     U0[fx] = gvals[sl][fx]
                 U0, _ = newton(rU, jU, U0, rtol=1e-8, atol=1e-50, stol=1e-8, max_it=20, fixed=fx)
-            u[iU * N:(iU + 1) * N] = U0
+            u[iU * N:(iU + nU) * N] = U0
     if fixed is not None:
         u[fixed] = gvals[fixed]
     return newton(disc.residual, disc.jacobian, u, fixed=fixed, monitor=monitor)

@@ -169,3 +169,32 @@ def heat_problem(t, dt, u_old, family="DG"):
                    family=family)
     prob.transient = {"dt": dt, "u_old": u_old}
     return prob, c1, c2
+
+
+def porous_problem(vavg):
+    """tests/test_advection_diffusion_migration_porous.py:6-70 of the reference for the oracle (DG)."""
+    from oracle.forms import Problem
+    eps = 0.5
+    De = lambda D: D * eps ** 1.5
+    Ks = 1.0 * (1.0 - eps) ** 1.5
+
+    def f(u, x):
+        X, Y = x[..., 0], x[..., 1]
+        C = np.cos(X) + np.sin(Y) + 3.0
+        Cx, Cy = -np.sin(X), np.cos(Y)
+        lapC = -np.cos(X) - np.sin(Y)
+        Ux, Uy = np.cos(X), -np.sin(Y)
+        lapU = -np.sin(X) - np.cos(Y)
+        vx = 6.0 * vavg * Y * (1.0 - Y)
+        out = []
+        for D, z in ((0.5, 2.0), (1.0, -2.0)):
+            out.append(vx * Cx - De(D) * z * (Cx * Ux + Cy * Uy + C * lapU) - De(D) * lapC)
+        out.append(-Ks * lapU)
+        return out
+    conc_params = [{"name": "C1", "diffusion coefficient": 0.5, "z": 2.0, "bulk": C1ex},
+                   {"name": "C2", "diffusion coefficient": 1.0, "z": -2.0, "bulk": C1ex}]
+    physical_params = {"flow": ["diffusion", "advection", "migration", "electroneutrality", "porous"],
+                       "F": 1.0, "R": 1.0, "T": 1.0, "U_app": Uex, "bulk reaction": f, "porosity": eps,
+                       "solid conductivity": 1.0, "specific surface area": 1.0}
+    markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4), "liquid applied": (1, 2, 3, 4)}
+    return Problem(conc_params, physical_params, markers, vel=make_vel(vavg))

@@ -188,3 +188,43 @@ class HeatEquationSolver(TransientEchemSolver):
 
     def set_boundary_markers(self):
         self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,)}
+
+
+class PorousSolver(EchemSolver):
+    """tests/test_advection_diffusion_migration_porous.py:6-70 of the reference: porous electrode model,
+    liquid + solid potentials, Bruggeman effective coefficients."""
+
+    def __init__(self, N, vavg):
+        mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        C1ex = cos(x) + sin(y) + 3
+        C2ex = C1ex
+        U1ex = sin(x) + cos(y) + 3
+        U2ex = sin(x) + cos(y) + 3
+        self.C1ex, self.C2ex, self.U1ex, self.U2ex = C1ex, C2ex, U1ex, U2ex
+
+        def f(C):
+            D1, D2, z1, z2, K = 0.5, 1.0, 2.0, -2.0, 1.0
+            f1 = div((self.vel - self.effective_diffusion(D1) * z1 * grad(U1ex)) * C1ex) - \
+                div(self.effective_diffusion(D1) * grad(C1ex))
+            f2 = div((self.vel - self.effective_diffusion(D2) * z2 * grad(U1ex)) * C2ex) - \
+                div(self.effective_diffusion(D2) * grad(C2ex))
+            f3 = div(- self.effective_diffusion(K, phase="solid") * grad(U2ex))
+            return [f1, f2, f3]
+
+        conc_params = [{"name": "C1", "diffusion coefficient": 0.5, "z": 2., "bulk": C1ex},
+                       {"name": "C2", "diffusion coefficient": 1.0, "z": -2., "bulk": C2ex}]
+        physical_params = {"flow": ["diffusion", "advection", "migration", "electroneutrality", "porous"],
+                           "F": 1.0, "R": 1.0, "T": 1.0, "U_app": U1ex, "bulk reaction": f, "v_avg": vavg,
+                           "porosity": 0.5, "solid conductivity": 1., "specific surface area": 1.,
+                           "standard potential": 0.}
+        super().__init__(conc_params, physical_params, mesh)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,), "applied": (1, 2, 3, 4,),
+                                 "liquid applied": (1, 2, 3, 4)}
+
+    def set_velocity(self):
+        y = SpatialCoordinate(self.mesh)[1]
+        h = 1.0
+        self.vel = as_vector((6. * self.physical_params["v_avg"] / h**2 * y * (h - y), Constant(0.)))

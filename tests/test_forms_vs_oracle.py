@@ -75,3 +75,31 @@ def test_block_masks_match_oracle():
     own, nbr = disc.block_mask()
     assert np.array_equal(own, cf.own_mask)
     assert np.array_equal(nbr, cf.nbr_mask)
+
+
+def test_porous_pointwise():
+    """Porous model (two potentials, Bruggeman coefficients): product vs oracle forms at random points."""
+    s = product_cases.PorousSolver(2, 2.0)
+    cf = CompiledForm(s.Form, 3, len(s._aux), 2, 1, "DG")
+    prob = mms_cases.porous_problem(2.0)
+    rng = np.random.default_rng(2)
+    dat = random_point_data(3, 1, 2, 48, rng)
+    x, n = dat["x"][None], dat["n"][None]
+    u = [dat["u"][j][None] for j in range(3)]
+    gu = [dat["gu"][j][None] for j in range(3)]
+    um = [dat["um"][j][None] for j in range(3)]
+    gum = [dat["gum"][j][None] for j in range(3)]
+    f0, f1 = prob.cell(x, u, gu, {"cell_volume": dat["cv"][None], "cell_diameter": dat["cd"][None]})
+    geop = {"cell_volume": dat["cv"][None], "facet_area": dat["fa"][None]}
+    geom = {"cell_volume": dat["cvm"][None], "facet_area": dat["fa"][None]}
+    f0p, f1p, _, _ = prob.interior_facet(x, n, u, gu, um, gum, geop, geom)
+    g0, g1 = prob.exterior_facet(1, x, n, u, gu, geop, {"U_app": dat["a"][0][None]})
+    cls = cf.marker_class[1]
+    for i in range(3):
+        assert _close(evaluate(cf.cell["f0"][i], dat, cf), f0[i][0])
+        assert _close(evaluate(cf.int["f0"][i], dat, cf), f0p[i][0])
+        assert _close(evaluate(cf.ext[cls]["f0"][i], dat, cf), g0[i][0])
+        for k in range(2):
+            assert _close(evaluate(cf.cell["f1"][i][k], dat, cf), f1[i][0, :, k])
+            assert _close(evaluate(cf.int["f1"][i][k], dat, cf), f1p[i][0, :, k])
+            assert _close(evaluate(cf.ext[cls]["f1"][i][k], dat, cf), g1[i][0, :, k])

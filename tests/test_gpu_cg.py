@@ -106,3 +106,26 @@ def test_poisson_coupled_matches_oracle(family):
     for f in range(3):
         a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
         assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
+
+
+def test_porous_two_potentials_matches_oracle():
+    """Porous electrode model (cfg5 ingredients): liquid + solid potential, coupled pre-solve."""
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    from oracle.newton import solve_problem
+    N = 4
+    disc = Discretization(unit_square_mesh(N), mms_cases.porous_problem(2.0))
+    s = product_cases.PorousSolver(N, 2.0)
+    x = disc.node_coords
+    pert = 1e-2 * np.sin(7 * x[:, 0] + 3 * x[:, 1])
+    u = np.concatenate([mms_cases.C1ex(x) + pert, mms_cases.Uex(x) - pert, mms_cases.Uex(x) + 0.5 * pert])
+    _compare_raw(disc, s, u, "porous")
+    u_ref, info = solve_problem(disc)
+    s2 = product_cases.PorousSolver(N, 2.0)
+    s2.setup_solver()
+    s2.solve()
+    un = s2.u.numpy()
+    Ns = disc.ndof_scalar
+    for f in range(3):
+        a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
+        assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
