@@ -53,7 +53,7 @@ def build_core(force=False):
 
 def skeleton_hash():
     h = hashlib.sha1()
-    for name in ("ech_dg.cuh", "ech_dg_coop.cuh", "ech_cg.cuh", "ech_module.cu"):
+    for name in ("ech_dg.cuh", "ech_dg_coop.cuh", "ech_dg_coop2.cuh", "ech_cg.cuh", "ech_module.cu"):
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(f.read())
     with open(os.path.join(INCLUDE, "echem_b200_module.h"), "rb") as f:

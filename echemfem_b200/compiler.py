@@ -306,6 +306,9 @@ class CompiledForm:
         L.append(_carray("TAB_DL", T.dL))
         L.append(_carray("TAB_W", T.gw))
         L.append(_carray("TAB_X", T.pts))
+        # compile-time copies: reference bases of own-side points become immediates in ech_dg_coop2.cuh
+        L.append(_carray("CT_L", T.L, "constexpr"))
+        L.append(_carray("CT_DL", T.dL, "constexpr"))
         L.append("struct Pt { double x[D], n[D], u[NF], gu[NF][D], um[NF], gum[NF][D], "
                  "a[ECH_NA1], ga[ECH_NA1][D], am[ECH_NA1], gam[ECH_NA1][D], cv, cvm, cd, cdm, fa; "
                  "const double* __restrict__ K; };")
@@ -470,9 +473,9 @@ def _jac_outputs(J, mask, i, o, nf, d):
     return outs
 
 
-def _carray(name, a):
+def _carray(name, a, qual="__constant__"):
     a = np.asarray(a, dtype=float)
     if a.ndim == 1:
-        return "__constant__ double %s[%d] = {%s};" % (name, a.shape[0], ", ".join(repr(float(x)) for x in a))
+        return "%s double %s[%d] = {%s};" % (qual, name, a.shape[0], ", ".join(repr(float(x)) for x in a))
     rows = ["{" + ", ".join(repr(float(x)) for x in r) + "}" for r in a]
-    return "__constant__ double %s[%d][%d] = {%s};" % (name, a.shape[0], a.shape[1], ", ".join(rows))
+    return "%s double %s[%d][%d] = {%s};" % (qual, name, a.shape[0], a.shape[1], ", ".join(rows))

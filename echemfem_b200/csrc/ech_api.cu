@@ -802,6 +802,100 @@ extern "C" int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t ro
     return ilu0_apply(B, rowptr, colidx, lu, diag_pos, r, z, (cudaStream_t)stream);
 }
 
+// =============================================================== coarse space (two-level preconditioner)
+// Piecewise-constant aggregation: fine dof r belongs to coarse dof agg[r].  Ac = P^T A P is accumulated
+// with warp-level pre-reduction (entries of a row that hit the same coarse column are summed with
+// shuffles before one atomicAdd), r_c = P^T r likewise, z += P y_c is a gather.
+__global__ void __launch_bounds__(256) galerkin_kernel(int64_t nrows, const int64_t *__restrict__ rowptr,
+                                                       const int32_t *__restrict__ colidx,
+                                                       const double *__restrict__ vals,
+                                                       const int32_t *__restrict__ agg, int32_t nc,
+                                                       double *__restrict__ Ac) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    const int64_t b = rowptr[r], e = rowptr[r + 1];
+    const int I = agg[r];
+    for (int64_t p0 = b; p0 < e; p0 += 32) {
+        const int64_t p = p0 + lane;
+        const bool in = p < e;
+        int key = in ? agg[colidx[p]] : -1;
+        double v = in ? vals[p] : 0.0;
+        unsigned todo = __ballot_sync(0xffffffffu, in);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int k = __shfl_sync(0xffffffffu, key, leader);
+            const bool mine = in && key == k;
+            double s = mine ? v : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == leader) atomicAdd(Ac + (int64_t)I * nc + k, s);
+            todo &= ~__ballot_sync(0xffffffffu, mine);
+        }
+    }
+}
+
+__global__ void restrict_kernel(int64_t n, const int32_t *__restrict__ agg, const double *__restrict__ v,
+                                double *__restrict__ rc) {
+    // consecutive dofs mostly share an aggregate: reduce runs inside the warp, one atomic per run
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in = i < n;
+    const int key = in ? agg[i] : -1;
+    const double val = in ? v[i] : 0.0;
+    unsigned todo = __ballot_sync(0xffffffffu, in);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int k = __shfl_sync(0xffffffffu, key, leader);
+        const bool mine = in && key == k;
+        double s = mine ? val : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == leader) atomicAdd(rc + k, s);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
+__global__ void prolong_add_kernel(int64_t n, const int32_t *__restrict__ agg, const double *__restrict__ yc,
+                                   double *__restrict__ z) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        z[i] += yc[agg[i]];
+}
+
+extern "C" int ech_coarse_galerkin(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                                   const int32_t *agg, int32_t nc, double *Ac, void *stream) {
+    if (!rowptr || !colidx || !vals || !agg || !Ac) return fail(nullptr, ECH_ERR_ARG, "ech_coarse_galerkin: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(nullptr, cudaMemsetAsync(Ac, 0, sizeof(double) * (size_t)nc * nc, s));
+    if (nrows == 0) return ECH_OK;
+    const int64_t nthreads = nrows * 32;
+    galerkin_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, s>>>(nrows, rowptr, colidx, vals, agg, nc, Ac);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_coarse_restrict(int64_t n, const int32_t *agg, int32_t nc, const double *v, double *rc,
+                                   void *stream) {
+    if (!agg || !v || !rc) return fail(nullptr, ECH_ERR_ARG, "ech_coarse_restrict: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(nullptr, cudaMemsetAsync(rc, 0, sizeof(double) * nc, s));
+    if (n == 0) return ECH_OK;
+    restrict_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, agg, v, rc);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_coarse_prolong_add(int64_t n, const int32_t *agg, const double *yc, double *z, void *stream) {
+    if (!agg || !yc || !z) return fail(nullptr, ECH_ERR_ARG, "ech_coarse_prolong_add: null argument");
+    if (n == 0) return ECH_OK;
+    prolong_add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, agg, yc, z);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== GMRES
 extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx, const double *vals,
                          const double *b, double *x, const ech_gmres_opts *o, double *basis, double *work,

@@ -1,0 +1,734 @@
+// Cooperative DG Jacobian (+ fused residual) kernel, second generation: REFERENCE-SPACE records.
+//
+// ncu on the first cooperative kernel (ech_dg_coop.cuh, profiles/r1f_*) shows the LSU data pipe as
+// the limiter: one wavefront per 128 B of shared-memory record traffic plus one per 32-byte sector
+// of the CSR stores.  A third of every record was the physical trial/test bases of the point.  Here
+// the producer folds the inverse Jacobians of the test side (always the own cell) and of the trial
+// side (own cell or neighbour) into the pointwise coefficients,
+//
+//     g1^[n]    = w * sum_l  Jt^-1[n][l] g1[l]            (trial gradient)
+//     g2^[m]    = w * sum_k  Jo^-1[m][k] g2[k]            (test gradient)
+//     g3^[m][n] = w * sum_kl Jo^-1[m][k] g3[k][l] Jt^-1[n][l]
+//
+// so that the consumer contracts them with REFERENCE-element bases.  Those are compile-time
+// constants for every own-side point (cell points and own-facet points are compile-time task
+// numbers once the slot loop is unrolled): no basis values travel through shared memory, and
+// structurally zero basis values (Gauss-Legendre DQ nodes are collocated with the cell rule;
+// basis functions off a facet vanish on it) drop out of the accumulation at compile time.  Only
+// the neighbour-side trial basis of an interior-facet point (its local facet and orientation are
+// run-time mesh data) is still carried by the record, in reference space (table products, no
+// geometry).  The test-side values of a lane come from 1D factors it keeps in registers.
+//
+// Same ownership / store discipline as ech_dg_coop.cuh (every CSR value written exactly once).
+#pragma once
+#include "ech_dg_coop.cuh"
+
+namespace echdg {
+namespace v2 {
+
+// ---------------------------------------------------------------- compile-time task geometry
+struct TaskPt {
+    int kind;        // 0 cell point, 1 facet point
+    int lf, qf;
+    int idx[D];      // 1D table index per direction
+};
+
+__host__ __device__ constexpr TaskPt task_point(int tk) {
+    TaskPt t{};
+    if (tk < NQC) {
+        t.kind = 0;
+        t.lf = -1;
+        t.qf = tk;
+        for (int k = 0; k < D; ++k) t.idx[k] = (tk / ipow(NQ, D - 1 - k)) % NQ;
+    } else {
+        const int ft = tk - NQC;
+        t.kind = 1;
+        t.lf = ft / NQF;
+        t.qf = ft % NQF;
+        const int kf = t.lf >> 1, s = t.lf & 1;
+        int tt[2] = {0, 0};
+        for (int m = 0; m < D - 1; ++m) tt[m] = (t.qf / ipow(NQ, D - 2 - m)) % NQ;
+        for (int k = 0; k < D; ++k) {
+            const int m = (k < kf) ? k : k - 1;
+            t.idx[k] = (k == kf) ? NQ + s : (m == 0 ? tt[0] : tt[1]);
+        }
+    }
+    return t;
+}
+
+__host__ __device__ constexpr double ref_phi(const TaskPt &t, int b) {
+    double v = 1.0;
+    for (int k = 0; k < D; ++k) v *= CT_L[t.idx[k]][digit(b, k)];
+    return v;
+}
+__host__ __device__ constexpr double ref_dphi(const TaskPt &t, int b, int m) {
+    double v = 1.0;
+    for (int k = 0; k < D; ++k) v *= (k == m) ? CT_DL[t.idx[k]][digit(b, k)] : CT_L[t.idx[k]][digit(b, k)];
+    return v;
+}
+
+// ---------------------------------------------------------------- record layout (doubles)
+template <class M>
+struct Layout2 {
+    int o0[NF][NF], o1[NF][NF], o2[NF][NF], o3[NF][NF];
+    int rowbeg[NF + 1];     // coefficients of equation i occupy [rowbeg[i], rowbeg[i+1]), even bounds (flushed per equation)
+    int klen;               // [0, klen): K = Jo^-1 Jt^-T, shared by every isotropic (scalar g3) coupling of the record
+    int len;
+    __host__ __device__ constexpr Layout2() : o0{}, o1{}, o2{}, o3{}, rowbeg{}, klen(0), len(0) {
+        bool iso = false;
+        for (int i = 0; i < NF; ++i)
+            for (int j = 0; j < NF; ++j) iso = iso || M::G3[i][j] == 1;
+        klen = iso ? ((D * D + 1) & ~1) : 0;
+        int n = klen;
+        for (int i = 0; i < NF; ++i) {
+            n = (n + 1) & ~1;
+            rowbeg[i] = n;
+            for (int j = 0; j < NF; ++j) {
+                o0[i][j] = o1[i][j] = o2[i][j] = o3[i][j] = -1;
+                if (M::G1[i][j]) { n = (D == 2) ? ((n + 1) & ~1) : n; o1[i][j] = n; n += D; }
+                if (M::G2[i][j]) { n = (D == 2) ? ((n + 1) & ~1) : n; o2[i][j] = n; n += D; }
+                if (M::G3[i][j] == 2) { n = (D == 2) ? ((n + 1) & ~1) : n; o3[i][j] = n; n += D * D; }
+                if (M::G0[i][j]) { o0[i][j] = n; n += 1; }
+                if (M::G3[i][j] == 1) { o3[i][j] = n; n += 1; }
+            }
+        }
+        n = (n + 1) & ~1;
+        rowbeg[NF] = n;
+        len = n;
+    }
+};
+constexpr Layout2<MC> L2_C{};
+constexpr Layout2<ME> L2_E{};
+constexpr Layout2<MIP> L2_IP{};
+constexpr Layout2<MIM> L2_IM{};
+template <class M> struct L2Of;
+template <> struct L2Of<MC> { static __host__ __device__ constexpr const Layout2<MC> &get() { return L2_C; } };
+template <> struct L2Of<ME> { static __host__ __device__ constexpr const Layout2<ME> &get() { return L2_E; } };
+template <> struct L2Of<MIP> { static __host__ __device__ constexpr const Layout2<MIP> &get() { return L2_IP; } };
+template <> struct L2Of<MIM> { static __host__ __device__ constexpr const Layout2<MIM> &get() { return L2_IM; } };
+
+constexpr int even(int n) { return (n + 1) & ~1; }
+
+template <bool WITH_RES>
+struct Rec {
+    static constexpr int OFF_RES = 0;
+    static constexpr int RLEN = WITH_RES ? even(NF * (1 + D)) : 0;
+    static constexpr int OFF_JP = RLEN;
+    static constexpr int END_C = OFF_JP + even(L2_C.len);
+    static constexpr int END_E = OFF_JP + even(L2_E.len);
+    static constexpr int OFF_JM = OFF_JP + even(L2_IP.len);
+    static constexpr int END_I = OFF_JM + even(L2_IM.len);
+    static constexpr int LEN = cmax(cmax(END_C, END_E), ECH_FAMILY_DG ? END_I : 2);
+};
+
+constexpr int J2WARPS = coop_warps(Rec<true>::LEN);
+
+// ---------------------------------------------------------------- producer helpers
+__device__ __forceinline__ void basis_ref(const int (&idx)[D], double (&phi)[NLOC], double (&dref)[NLOC][D]) {
+    double L[D][N1], dL[D][N1];
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int m = 0; m < N1; ++m) {
+            L[k][m] = TAB_L[idx[k]][m];
+            dL[k][m] = TAB_DL[idx[k]][m];
+        }
+#pragma unroll
+    for (int b = 0; b < NLOC; ++b) {
+        double v = 1.0, dr[D];
+#pragma unroll
+        for (int m = 0; m < D; ++m) dr[m] = 1.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int bk = digit(b, k);
+            v *= L[k][bk];
+#pragma unroll
+            for (int m = 0; m < D; ++m) dr[m] *= (m == k) ? dL[k][bk] : L[k][bk];
+        }
+        phi[b] = v;
+#pragma unroll
+        for (int m = 0; m < D; ++m) dref[b][m] = dr[m];
+    }
+}
+
+// value and PHYSICAL gradient of NFLD fields from the reference basis: grad[a] = sum_m invJ[m][a] * (sum_b U_b dref_b[m])
+template <int NFLD>
+__device__ __forceinline__ void interp_ref(const double *d, const double (&phi)[NLOC], const double (&dref)[NLOC][D],
+                                           const double (&invJ)[D][D], double (&u)[NFLD], double (&gu)[NFLD][D]) {
+#pragma unroll
+    for (int j = 0; j < NFLD; ++j) {
+        double s = 0.0, gr[D];
+#pragma unroll
+        for (int m = 0; m < D; ++m) gr[m] = 0.0;
+#pragma unroll
+        for (int b = 0; b < NLOC; ++b) {
+            const double ub = d[j * NLOC + b];
+            s += ub * phi[b];
+#pragma unroll
+            for (int m = 0; m < D; ++m) gr[m] += ub * dref[b][m];
+        }
+        u[j] = s;
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double g = 0.0;
+#pragma unroll
+            for (int m = 0; m < D; ++m) g += invJ[m][a] * gr[m];
+            gu[j][a] = g;
+        }
+    }
+}
+
+__device__ __forceinline__ void read_coords(const double *d, double (&X)[NV][D]) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < D; ++k) X[v][k] = d[NBD_X + v * D + k];
+}
+
+// own side of a point from the staged cell data
+__device__ __forceinline__ void own_side2(const double *d, const int (&idx)[D], Pt &p, Geo &gm) {
+    double X[NV][D];
+    read_coords(d, X);
+    p.cv = d[NBD_CV];
+    p.cd = d[NBD_CV + 1];
+    geometry(X, idx, gm);
+    double phi[NLOC], dref[NLOC][D];
+    basis_ref(idx, phi, dref);
+    interp_ref<NF>(d + NBD_U, phi, dref, gm.invJ, p.u, p.gu);
+    if constexpr (NAUX > 0) interp_ref<ECH_NA1>(d + NBD_A, phi, dref, gm.invJ, p.a, p.ga);
+#pragma unroll
+    for (int k = 0; k < D; ++k) p.x[k] = gm.x[k];
+}
+
+// neighbour side of a facet point: state for the physics, inverse Jacobian for the folding
+__device__ __forceinline__ void neighbour_side2(const double *d, int code, const int (&tt)[D > 1 ? D - 1 : 1], Pt &p,
+                                                double (&invJn)[D][D]) {
+    double X2[NV][D];
+    read_coords(d, X2);
+    p.cvm = d[NBD_CV];
+    p.cdm = d[NBD_CV + 1];
+    int idx2[D];
+    neighbour_point(code, tt, idx2);
+    Geo g2;
+    geometry(X2, idx2, g2);
+    double phi2[NLOC], dref2[NLOC][D];
+    basis_ref(idx2, phi2, dref2);
+    interp_ref<NF>(d + NBD_U, phi2, dref2, g2.invJ, p.um, p.gum);
+    if constexpr (NAUX > 0) interp_ref<ECH_NA1>(d + NBD_A, phi2, dref2, g2.invJ, p.am, p.gam);
+#pragma unroll
+    for (int m = 0; m < D; ++m)
+#pragma unroll
+        for (int a = 0; a < D; ++a) invJn[m][a] = g2.invJ[m][a];
+}
+
+// K[m][n] = sum_k Jo[m][k] Jt[n][k], stored once per record when the mask has isotropic couplings
+template <class M, int LEN>
+__device__ __forceinline__ void put_k(double (&buf)[LEN], int off, const double (&Jo)[D][D], const double (&Jt)[D][D]) {
+    if constexpr (L2Of<M>::get().klen > 0) {
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int n = 0; n < D; ++n) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) s += Jo[m][k] * Jt[n][k];
+                buf[off + m * D + n] = s;
+            }
+    }
+}
+
+// coefficients of equation I -> reference space, weight folded in.  Jo: test side, Jt: trial side.
+template <class M, int I, int LEN>
+__device__ __forceinline__ void put_rowj2(double (&buf)[LEN], int off, const RowJ &r, double w, const double (&Jo)[D][D],
+                                          const double (&Jt)[D][D]) {
+    static_for<0, NF>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int p0 = L2Of<M>::get().o0[I][j], p1 = L2Of<M>::get().o1[I][j];
+        constexpr int p2 = L2Of<M>::get().o2[I][j], p3 = L2Of<M>::get().o3[I][j];
+        constexpr int h3 = M::G3[I][j];
+        if constexpr (p0 >= 0) buf[off + p0] = w * r.g0[j];
+        if constexpr (p1 >= 0) {
+#pragma unroll
+            for (int n = 0; n < D; ++n) {
+                double s = 0.0;
+#pragma unroll
+                for (int l = 0; l < D; ++l) s += Jt[n][l] * r.g1[j][l];
+                buf[off + p1 + n] = w * s;
+            }
+        }
+        if constexpr (p2 >= 0) {
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) s += Jo[m][k] * r.g2[j][k];
+                buf[off + p2 + m] = w * s;
+            }
+        }
+        if constexpr (h3 == 1) buf[off + p3] = w * r.g3[j][0][0];
+        if constexpr (h3 == 2) {
+            double t[D][D];    // t[k][n] = sum_l g3[k][l] Jt[n][l]
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+#pragma unroll
+                for (int n = 0; n < D; ++n) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < D; ++l) s += r.g3[j][k][l] * Jt[n][l];
+                    t[k][n] = s;
+                }
+#pragma unroll
+            for (int m = 0; m < D; ++m)
+#pragma unroll
+                for (int n = 0; n < D; ++n) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s += Jo[m][k] * t[k][n];
+                    buf[off + p3 + m * D + n] = w * s;
+                }
+        }
+    });
+}
+
+template <class M, int LEN>
+__device__ __forceinline__ void put_res2(double (&buf)[LEN], const Res &o, double w, const double (&Jo)[D][D]) {
+    static_for<0, NF>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if constexpr (M::F0[i]) buf[i] = w * o.f0[i];
+        if constexpr (M::F1[i]) {
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) s += Jo[m][k] * o.f1[i][k];
+                buf[NF + i * D + m] = w * s;
+            }
+        }
+    });
+}
+
+// ---------------------------------------------------------------- consumer helpers
+// rows (I, a) += one record.  TK >= 0: trial basis = compile-time reference basis of own-side task TK;
+// TK < 0: trial basis (phi2, d2) read from the record (neighbour side).
+template <class M, int I, int TK>
+__device__ __forceinline__ void take_rowj2(const RecRef &R, int slot, int off, double pa, const double (&da)[D],
+                                           const double (&Kd)[D], const double (&phi2)[NLOC],
+                                           const double (&d2)[NLOC][D], double (&acc)[NF][NLOC]) {
+    static_for<0, NF>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int p0 = L2Of<M>::get().o0[I][j], p1 = L2Of<M>::get().o1[I][j];
+        constexpr int p2 = L2Of<M>::get().o2[I][j], p3 = L2Of<M>::get().o3[I][j];
+        constexpr bool h0 = p0 >= 0, h1 = p1 >= 0, h2 = p2 >= 0, h3 = p3 >= 0;
+        constexpr bool iso = M::G3[I][j] == 1;
+        if constexpr (h0 || h1 || h2 || h3) {
+            double Aj = 0.0, Bj[D];
+#pragma unroll
+            for (int n = 0; n < D; ++n) Bj[n] = 0.0;
+            if constexpr (h0) Aj += R(slot, off + p0) * pa;
+            if constexpr (h2) {
+                if constexpr (D == 2) {
+                    const double2 v = R.pair(slot, off + p2);
+                    Aj += v.x * da[0];
+                    Aj += v.y * da[1];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < D; ++m) Aj += R(slot, off + p2 + m) * da[m];
+                }
+            }
+            if constexpr (h1) {
+                if constexpr (D == 2) {
+                    const double2 v = R.pair(slot, off + p1);
+                    Bj[0] += v.x * pa;
+                    Bj[1] += v.y * pa;
+                } else {
+#pragma unroll
+                    for (int n = 0; n < D; ++n) Bj[n] += R(slot, off + p1 + n) * pa;
+                }
+            }
+            if constexpr (iso) {
+                const double sc = R(slot, off + p3);
+#pragma unroll
+                for (int n = 0; n < D; ++n) Bj[n] += sc * Kd[n];
+            }
+            if constexpr (h3 && !iso) {
+                if constexpr (D == 2) {
+                    const double2 r0 = R.pair(slot, off + p3), r1 = R.pair(slot, off + p3 + 2);
+                    Bj[0] += r0.x * da[0];
+                    Bj[1] += r0.y * da[0];
+                    Bj[0] += r1.x * da[1];
+                    Bj[1] += r1.y * da[1];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < D; ++m)
+#pragma unroll
+                        for (int n = 0; n < D; ++n) Bj[n] += R(slot, off + p3 + m * D + n) * da[m];
+                }
+            }
+            if constexpr (TK >= 0) {
+                static_for<0, NLOC>([&](auto bc) {
+                    constexpr int b = decltype(bc)::value;
+                    constexpr double pb = ref_phi(task_point(TK >= 0 ? TK : 0), b);
+                    if constexpr ((h0 || h2) && pb != 0.0) acc[j][b] += Aj * pb;
+                    if constexpr (h1 || h3) {
+                        static_for<0, D>([&](auto nc) {
+                            constexpr int n = decltype(nc)::value;
+                            constexpr double db = ref_dphi(task_point(TK >= 0 ? TK : 0), b, n);
+                            if constexpr (db != 0.0) acc[j][b] += Bj[n] * db;
+                        });
+                    }
+                });
+            } else {
+#pragma unroll
+                for (int b = 0; b < NLOC; ++b) {
+                    double sacc = acc[j][b];
+                    if constexpr (h0 || h2) sacc += Aj * phi2[b];
+                    if constexpr (h1 || h3) {
+#pragma unroll
+                        for (int n = 0; n < D; ++n) sacc += Bj[n] * d2[b][n];
+                    }
+                    acc[j][b] = sacc;
+                }
+            }
+        }
+    });
+}
+
+template <class M, int TK>
+__device__ __forceinline__ void take_all2(const RecRef &R, int s, int off, double pa, const double (&da)[D],
+                                          const double (&phi2)[NLOC], const double (&d2)[NLOC][D],
+                                          double (&acc)[NF][NF][NLOC]) {
+    double Kd[D];      // Kd[n] = sum_m K[m][n] da[m]
+#pragma unroll
+    for (int n = 0; n < D; ++n) Kd[n] = 0.0;
+    if constexpr (L2Of<M>::get().klen > 0) {
+        if constexpr (D == 2) {
+            const double2 r0 = R.pair(s, off), r1 = R.pair(s, off + 2);
+            Kd[0] = r0.x * da[0] + r1.x * da[1];
+            Kd[1] = r0.y * da[0] + r1.y * da[1];
+        } else {
+#pragma unroll
+            for (int m = 0; m < D; ++m)
+#pragma unroll
+                for (int n = 0; n < D; ++n) Kd[n] += R(s, off + m * D + n) * da[m];
+        }
+    }
+    static_for<0, NF>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        take_rowj2<M, I, TK>(R, s, off, pa, da, Kd, phi2, d2, acc[I]);
+    });
+}
+
+// reference basis of the neighbour at the facet point (lf, qf) of my cell: its local facet and orientation are
+// run-time mesh data, the 1D factors come from constant memory (no shared-memory traffic)
+template <int TK>
+__device__ __forceinline__ void nb_basis(int code, double (&phi2)[NLOC], double (&d2)[NLOC][D]) {
+    constexpr int qf = task_point(TK).qf;
+    int tt[D > 1 ? D - 1 : 1];
+    tt[0] = 0;
+    if constexpr (D > 1) {
+#pragma unroll
+        for (int m = 0; m < D - 1; ++m) tt[m] = (qf / ipow(NQ, D - 2 - m)) % NQ;
+    }
+    int idx2[D];
+    neighbour_point(code, tt, idx2);
+    basis_ref(idx2, phi2, d2);
+}
+
+// reference values of the test function a of this lane at the compile-time task TK: products of 1D table
+// entries selected by the digits of a (selects of immediates: no registers are held across the kernel)
+template <int T>
+__device__ __forceinline__ double sel_L(int ak) {
+    double v = CT_L[T][0];
+    static_for<1, N1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        constexpr double c = CT_L[T][m];
+        v = (ak == m) ? c : v;
+    });
+    return v;
+}
+template <int T>
+__device__ __forceinline__ double sel_dL(int ak) {
+    double v = CT_DL[T][0];
+    static_for<1, N1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        constexpr double c = CT_DL[T][m];
+        v = (ak == m) ? c : v;
+    });
+    return v;
+}
+template <int TK>
+__device__ __forceinline__ void test_values(const int (&ad)[D], double &pa, double (&da)[D]) {
+    pa = 1.0;
+#pragma unroll
+    for (int m = 0; m < D; ++m) da[m] = 1.0;
+    static_for<0, D>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        constexpr int t = task_point(TK).idx[k];
+        const double l = sel_L<t>(ad[k]), dl = sel_dL<t>(ad[k]);
+        pa *= l;
+#pragma unroll
+        for (int m = 0; m < D; ++m) da[m] *= (m == k) ? dl : l;
+    });
+}
+
+// rounds in which the points of facet lf are consumed
+constexpr int facet_first_round(int lf) { return (NQC + lf * NQF) / G; }
+constexpr int facet_last_round(int lf) { return (NQC + lf * NQF + NQF - 1) / G; }
+constexpr bool any_straddle() {
+    for (int lf = 0; lf < NLF; ++lf)
+        if (facet_first_round(lf) != facet_last_round(lf)) return true;
+    return false;
+}
+constexpr bool STRADDLE = any_straddle();
+
+// ---------------------------------------------------------------- the kernel
+template <bool WITH_RES>
+__global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel(const ech_dg_args A) {
+    using RC = Rec<WITH_RES>;
+    constexpr int RECLEN = Rec<true>::LEN;       // one shared-memory geometry for both instantiations
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / G, a = lane - g * G;       // consumer role: test node a of cell g
+    const bool active_lane = g < CPW;
+    const int64_t c = ((int64_t)blockIdx.x * J2WARPS + warp) * CPW + g;
+    const bool active = active_lane && c < A.ncell;
+    const int64_t fstride = A.ncell_total * NLOC;
+    const int64_t rows_per_field = A.ncell_total * NLOC;
+    const WarpSmem W = warp_smem(smem, warp, RECLEN);
+    const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
+    const int gg = active_lane ? g : 0;
+    const int *meta = W.meta + gg * META_LEN;
+    // producer role: this lane evaluates slot ae of cell ge of the warp
+    const int ge = lane % CPW, ae = lane / CPW;
+    const int64_t ce = ((int64_t)blockIdx.x * J2WARPS + warp) * CPW + ge;
+    const bool active_e = ae < G && ce < A.ncell;
+    const RecRef RE{W.rec + 2 * ge};
+    const int *meta_e = W.meta + ge * META_LEN;
+    const double *own = W.nbd + (ge * NBD_SLOTS + NLF) * NBD_LEN;
+
+    int ncol = 0, pos_self = 0;
+    int64_t rp[NF];
+    if (active) {
+        ncol = A.ncol[c];
+        pos_self = A.slot_self[c];
+#pragma unroll
+        for (int i = 0; i < NF; ++i) rp[i] = A.rowptr[(int64_t)i * rows_per_field + c * NLOC + a];
+    }
+    stage_neighbours(A, W, g, a, c, active, fstride);
+
+    int ad[D];      // digits of my test node
+#pragma unroll
+    for (int k = 0; k < D; ++k) ad[k] = ((active_lane ? a : 0) / ipow(N1, D - 1 - k)) % N1;
+
+    double acc[NF][NF][NLOC];
+    zero_blocks<true>(acc);
+    // neighbour-block accumulators live inside one facet of one round, except for facets whose points
+    // straddle two rounds (then they persist across the producer phase)
+    double accn_persist[STRADDLE ? NF : 1][STRADDLE ? NF : 1][STRADDLE ? NLOC : 1];
+    if constexpr (STRADDLE) zero_blocks<false>(reinterpret_cast<double(&)[NF][NF][NLOC]>(accn_persist));
+    double res[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) res[i] = 0.0;
+
+    for (int round = 0; round < NROUND; ++round) {
+        // ---------------- produce: my task of this round
+        const int task = round * G + ae;
+        if (active_e && task < NTASK) {
+            Pt p;
+            p.K = A.consts;
+            Geo gm;
+            int idx[D];
+            double w;
+            double buf[RECLEN];
+#pragma unroll
+            for (int m = 0; m < RECLEN; ++m) buf[m] = 0.0;
+            if (task < NQC) {
+                cell_point(task, idx, w);
+                own_side2(own, idx, p, gm);
+                w *= fabs(gm.detJ);
+                if constexpr (WITH_RES) {
+                    Res o;
+                    cell_res(p, o);
+                    put_res2<MC>(buf, o, w, gm.invJ);
+                    flush_record(RE, ae, buf, 0, RC::RLEN);
+                }
+                { put_k<MC>(buf, RC::OFF_JP, gm.invJ, gm.invJ); constexpr int ke = RC::OFF_JP + L2Of<MC>::get().klen; flush_record(RE, ae, buf, RC::OFF_JP, ke); }
+                static_for<0, NF>([&](auto ic) {
+                    constexpr int I = decltype(ic)::value;
+                    RowJ rj;
+                    cell_jac<I>(p, rj);
+                    put_rowj2<MC, I>(buf, RC::OFF_JP, rj, w, gm.invJ, gm.invJ);
+                    { constexpr int fb = RC::OFF_JP + L2Of<MC>::get().rowbeg[I], fe = RC::OFF_JP + L2Of<MC>::get().rowbeg[I + 1]; flush_record(RE, ae, buf, fb, fe); }
+                });
+            } else {
+                const int ft = task - NQC;
+                const int lf = ft / NQF, qf = ft - lf * NQF;
+                const int nb = meta_e[lf];
+                int tt[D > 1 ? D - 1 : 1];
+                double ds;
+                facet_point(lf, qf, idx, tt, w);
+                double invJn[D][D];
+#pragma unroll
+                for (int m = 0; m < D; ++m)
+#pragma unroll
+                    for (int k = 0; k < D; ++k) invJn[m][k] = 0.0;
+                if (nb >= 0) {
+                    if constexpr (ECH_FAMILY_DG) {
+                        neighbour_side2(W.nbd + (ge * NBD_SLOTS + lf) * NBD_LEN, meta_e[NLF + lf], tt, p, invJn);
+                    }
+                }
+                own_side2(own, idx, p, gm);
+                p.fa = A.facet_area[ce * NLF + lf];
+                facet_normal(gm, lf, p.n, ds);
+                w *= ds;
+                if (nb < 0) {
+                    const int cls = -nb - 1;
+                    if constexpr (WITH_RES) {
+                        Res o;
+                        efacet_res(cls, p, o);
+                        put_res2<ME>(buf, o, w, gm.invJ);
+                        flush_record(RE, ae, buf, 0, RC::RLEN);
+                    }
+                    { put_k<ME>(buf, RC::OFF_JP, gm.invJ, gm.invJ); constexpr int ke = RC::OFF_JP + L2Of<ME>::get().klen; flush_record(RE, ae, buf, RC::OFF_JP, ke); }
+                    static_for<0, NF>([&](auto ic) {
+                        constexpr int I = decltype(ic)::value;
+                        RowJ rj;
+                        efacet_jac<I>(cls, p, rj);
+                        put_rowj2<ME, I>(buf, RC::OFF_JP, rj, w, gm.invJ, gm.invJ);
+                        { constexpr int fb = RC::OFF_JP + L2Of<ME>::get().rowbeg[I], fe = RC::OFF_JP + L2Of<ME>::get().rowbeg[I + 1]; flush_record(RE, ae, buf, fb, fe); }
+                    });
+                } else {
+                    if constexpr (ECH_FAMILY_DG) {
+                        if constexpr (WITH_RES) {
+                            Res o;
+                            ifacet_res(p, o);
+                            put_res2<MIP>(buf, o, w, gm.invJ);
+                            flush_record(RE, ae, buf, 0, RC::RLEN);
+                        }
+                        { put_k<MIP>(buf, RC::OFF_JP, gm.invJ, gm.invJ); constexpr int ke = RC::OFF_JP + L2Of<MIP>::get().klen; flush_record(RE, ae, buf, RC::OFF_JP, ke); }
+                        { put_k<MIM>(buf, RC::OFF_JM, gm.invJ, invJn); constexpr int ke = RC::OFF_JM + L2Of<MIM>::get().klen; flush_record(RE, ae, buf, RC::OFF_JM, ke); }
+                        static_for<0, NF>([&](auto ic) {
+                            constexpr int I = decltype(ic)::value;
+                            RowJ rj, rjm;
+                            ifacet_jac<I>(p, rj, rjm);
+                            put_rowj2<MIP, I>(buf, RC::OFF_JP, rj, w, gm.invJ, gm.invJ);
+                            { constexpr int fb = RC::OFF_JP + L2Of<MIP>::get().rowbeg[I], fe = RC::OFF_JP + L2Of<MIP>::get().rowbeg[I + 1]; flush_record(RE, ae, buf, fb, fe); }
+                            put_rowj2<MIM, I>(buf, RC::OFF_JM, rjm, w, gm.invJ, invJn);
+                            { constexpr int fb = RC::OFF_JM + L2Of<MIM>::get().rowbeg[I], fe = RC::OFF_JM + L2Of<MIM>::get().rowbeg[I + 1]; flush_record(RE, ae, buf, fb, fe); }
+                        });
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- consume: the records of my cell into my rows (slot = compile-time task)
+        if (active) {
+            static_for<0, NROUND>([&](auto rc) {
+                constexpr int RD = decltype(rc)::value;
+                if (round == RD) {
+                    // residual rows and own-block contributions of cell / exterior-facet points
+                    static_for<0, G>([&](auto sc) {
+                        constexpr int s = decltype(sc)::value;
+                        constexpr int TK = RD * G + s;
+                        if constexpr (TK < NTASK) {
+                            constexpr TaskPt tp = task_point(TK);
+                            double pa, da[D];
+                            test_values<TK>(ad, pa, da);
+                            if constexpr (WITH_RES) {
+#pragma unroll
+                                for (int i = 0; i < NF; ++i) {
+                                    double t = R(s, i) * pa;
+#pragma unroll
+                                    for (int m = 0; m < D; ++m) t += R(s, NF + i * D + m) * da[m];
+                                    res[i] += t;
+                                }
+                            }
+                            double phi2[NLOC], d2[NLOC][D];     // unused on the own side
+                            if constexpr (tp.kind == 0) {
+                                take_all2<MC, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, acc);
+                            } else {
+                                if (meta[tp.lf] < 0) take_all2<ME, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, acc);
+                            }
+                        }
+                    });
+                    // interior facets, facet by facet
+                    if constexpr (ECH_FAMILY_DG) {
+                        static_for<0, NLF>([&](auto lc) {
+                            constexpr int lf = decltype(lc)::value;
+                            constexpr int r0 = facet_first_round(lf), r1 = facet_last_round(lf);
+                            if constexpr (RD >= r0 && RD <= r1) {
+                                if (meta[lf] >= 0) {
+                                    double accn_local[r0 == r1 ? NF : 1][r0 == r1 ? NF : 1][r0 == r1 ? NLOC : 1];
+                                    double(&accn)[NF][NF][NLOC] = *reinterpret_cast<double(*)[NF][NF][NLOC]>(
+                                        r0 == r1 ? &accn_local[0][0][0] : &accn_persist[0][0][0]);
+                                    if constexpr (r0 == r1) zero_blocks<false>(accn);
+                                    static_for<0, NQF>([&](auto qc) {
+                                        constexpr int qf = decltype(qc)::value;
+                                        constexpr int TK = NQC + lf * NQF + qf;
+                                        if constexpr (TK / G == RD) {
+                                            constexpr int s = TK - RD * G;
+                                            double pa, da[D];
+                                            test_values<TK>(ad, pa, da);
+                                            double phi2[NLOC], d2[NLOC][D];
+                                            take_all2<MIP, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, acc);
+                                            nb_basis<TK>(meta[NLF + lf], phi2, d2);
+                                            take_all2<MIM, -1>(R, s, RC::OFF_JM, pa, da, phi2, d2, accn);
+                                        }
+                                    });
+                                    if constexpr (RD == r1) {
+                                        store_blocks<false>(A.out, rp, ncol, meta[2 * NLF + lf], accn);
+                                        if constexpr (r0 != r1) zero_blocks<false>(accn);
+                                    }
+                                }
+                            }
+                        });
+                    }
+                }
+            });
+        }
+        __syncwarp();
+    }
+    if (active) {
+        store_blocks<true>(A.out, rp, ncol, pos_self, acc);
+        if constexpr (WITH_RES) {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) A.out2[i * rows_per_field + c * NLOC + a] = res[i];
+        }
+    }
+}
+
+constexpr int J2SMEM = J2WARPS * warp_smem_doubles(Rec<true>::LEN) * 8;
+
+static int coop2_setup() {
+    static int done = 0;
+    if (done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(jacobian_coop2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, J2SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(jacobian_coop2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, J2SMEM);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "echem_b200: cudaFuncSetAttribute(jacobian_coop2_kernel, %d B) failed: %s\n", J2SMEM,
+                cudaGetErrorString(e));
+        return (int)e;
+    }
+    done = 1;
+    return 0;
+}
+
+static int launch_jacobian_coop2(const ech_dg_args *a, cudaStream_t s) {
+    if (a->ncell == 0) return 0;
+    int e = coop2_setup();
+    if (e) return e;
+    const int64_t cells_per_block = (int64_t)J2WARPS * CPW;
+    const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
+    if (a->out2)
+        jacobian_coop2_kernel<true><<<(unsigned)grid, J2WARPS * 32, J2SMEM, s>>>(*a);
+    else
+        jacobian_coop2_kernel<false><<<(unsigned)grid, J2WARPS * 32, J2SMEM, s>>>(*a);
+    e = (int)cudaGetLastError();
+    if (e) fprintf(stderr, "echem_b200: jacobian_coop2_kernel<<<%lld, %d, %d>>> failed: %s\n", (long long)grid,
+                   J2WARPS * 32, J2SMEM, cudaGetErrorString((cudaError_t)e));
+    return e;
+}
+
+}  // namespace v2
+}  // namespace echdg

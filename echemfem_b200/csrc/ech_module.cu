@@ -3,7 +3,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
 //        -include <generated header> ech_module.cu -o libech_phys_<key>.so
 #if ECH_FAMILY_DG
-#include "ech_dg_coop.cuh"
+#include "ech_dg_coop2.cuh"
 #else
 #include "ech_cg.cuh"
 #endif
@@ -30,14 +30,16 @@ int ech_mod_describe(int32_t *info, int capacity) {
     return need;
 }
 
-// variant 0 (default): cooperative kernels (one cell per NLOC lanes, shared quadrature work);
-// variant 1: row-per-thread kernels (kept for elements with more than 32 local nodes and as a cross-check)
+// variant 0 (default): cooperative kernels (one cell per NLOC lanes, shared quadrature work), Jacobian with
+//            reference-space records (ech_dg_coop2.cuh);
+// variant 1: row-per-thread kernels (kept for elements with more than 32 local nodes and as a cross-check);
+// variant 2: cooperative kernels, Jacobian with physical-space records (ech_dg_coop.cuh, first generation)
 static int g_variant = 0;
 
 void ech_mod_set_variant(int v) { g_variant = v; }
 
 #if ECH_FAMILY_DG
-static bool use_coop() { return echdg::COOP_OK && g_variant == 0; }
+static bool use_coop() { return echdg::COOP_OK && g_variant != 1; }
 
 int ech_mod_residual(const ech_dg_args *a, void *stream) {
     if (use_coop()) return echdg::launch_residual_coop(a, (cudaStream_t)stream);
@@ -45,7 +47,9 @@ int ech_mod_residual(const ech_dg_args *a, void *stream) {
 }
 
 int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
-    if (use_coop()) return echdg::launch_jacobian_coop(a, (cudaStream_t)stream);   // fused when a->out2 is set
+    // fused residual + Jacobian when a->out2 is set
+    if (use_coop() && g_variant == 0) return echdg::v2::launch_jacobian_coop2(a, (cudaStream_t)stream);
+    if (use_coop()) return echdg::launch_jacobian_coop(a, (cudaStream_t)stream);
     if (a->out2) {
         ech_dg_args r = *a;
         r.out = a->out2;

@@ -129,6 +129,15 @@ int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t rows_per_fiel
                            const int32_t *colidx, const double *lu, const int32_t *diag_pos, const double *r,
                            double *z, void *stream);
 
+/* Coarse space of the optional two-level preconditioner (not in the reference's "ilu" option set; it
+ * plays the role of the coarse levels of its gmg/amg sets, solver.py:1190-1213, for meshes on which
+ * block-Jacobi/ILU(0) alone stalls).  Piecewise-constant aggregation agg[dof] -> coarse dof:
+ * Ac[nc*nc] = P^T A P (dense, row-major);  rc = P^T v;  z += P yc. */
+int ech_coarse_galerkin(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                        const int32_t *agg, int32_t nc, double *Ac, void *stream);
+int ech_coarse_restrict(int64_t n, const int32_t *agg, int32_t nc, const double *v, double *rc, void *stream);
+int ech_coarse_prolong_add(int64_t n, const int32_t *agg, const double *yc, double *z, void *stream);
+
 typedef struct ech_gmres_opts {
     double rtol, atol;
     int32_t restart, max_it;
