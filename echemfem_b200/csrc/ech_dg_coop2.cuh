@@ -121,7 +121,208 @@ struct Rec {
     static constexpr int LEN = cmax(cmax(END_C, END_E), ECH_FAMILY_DG ? END_I : 2);
 };
 
-constexpr int J2WARPS = coop_warps(Rec<true>::LEN);
+
+// ---------------------------------------------------------------- staged cell data (asynchronous copies)
+// Per warp: [records | cell data | facet areas | runtime constants | facet metadata].
+// Cell data of (cell g, slot s) -- slot lf = neighbour across facet lf, slot NLF = the cell itself:
+//   X[NV*D] U[NF*NLOC] A[NAUX*NLOC] CV[2]   padded to an even length (16-byte units for cp.async / LDS.128),
+// cell stride = 10 mod 16 doubles, so that the 8 cells a quarter-warp reads at equal offsets fall into
+// distinct 16-byte bank groups.
+constexpr bool V16 = (NLOC % 2 == 0);          // 16-byte copies and 128-bit shared loads are possible
+constexpr int S_X = 0;
+constexpr int S_U = NV * D;
+constexpr int S_A = S_U + NF * NLOC;
+constexpr int S_CV = S_A + NAUX * NLOC;
+constexpr int SLOT_LEN = even(S_CV + 2);
+constexpr int cell_stride() {
+    const int base = NBD_SLOTS * SLOT_LEN;
+    return base + ((10 - base % 16) % 16 + 16) % 16;
+}
+constexpr int CELL_STRIDE = cell_stride();
+constexpr int NCONST_PAD = even(ECH_NCONST);
+
+struct Smem2 {
+    double *rec;       // RECLEN * 32
+    double *nbd;       // [CPW][CELL_STRIDE]
+    double *fa;        // [CPW][NLF] facet areas of my cells
+    double *kc;        // [NCONST_PAD] runtime constants
+    int *meta;         // [2][CPW][META_LEN]  (double-buffered: the next batch is staged while this one is consumed)
+};
+__host__ __device__ constexpr int warp_smem2_doubles(int reclen) {
+    return even(reclen * 32 + CPW * CELL_STRIDE + even(CPW * NLF) + NCONST_PAD + CPW * META_LEN);
+}
+__device__ __forceinline__ Smem2 warp_smem2(double *smem, int warp, int reclen) {
+    double *base = smem + (size_t)warp * warp_smem2_doubles(reclen);
+    Smem2 w;
+    w.rec = base;
+    w.nbd = base + reclen * 32;
+    w.fa = w.nbd + CPW * CELL_STRIDE;
+    w.kc = w.fa + even(CPW * NLF);
+    w.meta = reinterpret_cast<int *>(w.kc + NCONST_PAD);
+    return w;
+}
+constexpr int coop2_warps(int reclen) {
+#ifdef ECH_COOP_WARPS
+    return ECH_COOP_WARPS + 0 * reclen;
+#else
+    // one warp per CTA: warps never synchronise with each other, and single-warp CTAs retire and start
+    // independently (measured on cfg2: 2.64 ms against 2.72-2.76 ms for 2 or 4 warps per CTA)
+    return 1 + 0 * reclen;
+#endif
+}
+
+__device__ __forceinline__ void cp_async16(double *dst, const double *src) {
+#ifdef ECH_STAGE_SYNC
+    *reinterpret_cast<double2 *>(dst) = __ldg(reinterpret_cast<const double2 *>(src));
+    return;
+#endif
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
+#ifdef ECH_STAGE_SYNC
+    *dst = __ldg(src);
+    return;
+#endif
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_run(double *dst, const double *src, int k, int units) {
+    // unit k of a run of N doubles: 16-byte units when the run is pair-aligned, 8-byte units otherwise
+    (void)units;
+    if constexpr (V16 && N % 2 == 0)
+        cp_async16(dst + 2 * k, src + 2 * k);
+    else
+        cp_async8(dst + k, src + k);
+}
+template <int N>
+constexpr int run_units() { return (V16 && N % 2 == 0) ? N / 2 : N; }
+
+// copy the data of cell nb into one slot; with SPLIT, only the units k with k % NPART == part
+template <int SPLIT, int NPART>
+__device__ __forceinline__ void copy_slot(const ech_dg_args &A, double *d, int nb, int64_t fstride, int part) {
+    constexpr int UX = run_units<NV * D>(), UU = run_units<NLOC>();
+    const double *px = A.xcell + (int64_t)nb * (NV * D);
+    int k = 0;
+    static_for<0, UX>([&](auto uc) {
+        constexpr int u = decltype(uc)::value;
+        if (!SPLIT || (k % NPART) == part) cp_run<NV * D>(d + S_X, px, u, UX);
+        ++k;
+    });
+    static_for<0, NF>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const double *pu = A.u + j * fstride + (int64_t)nb * NLOC;
+        static_for<0, UU>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            if (!SPLIT || (k % NPART) == part) cp_run<NLOC>(d + S_U + j * NLOC, pu, u, UU);
+            ++k;
+        });
+    });
+    static_for<0, NAUX>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const double *pa = A.aux + j * fstride + (int64_t)nb * NLOC;
+        static_for<0, UU>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            if (!SPLIT || (k % NPART) == part) cp_run<NLOC>(d + S_A + j * NLOC, pa, u, UU);
+            ++k;
+        });
+    });
+    if (!SPLIT || (k % NPART) == part) cp_async8(d + S_CV, A.cell_volume + nb);
+    ++k;
+    if (!SPLIT || (k % NPART) == part) cp_async8(d + S_CV + 1, A.cell_diam + nb);
+}
+
+// Staging of one batch (my cell + its facet neighbours), split in two so that the two dependent round trips
+// of the NEXT batch overlap the work on the current one:
+//   load_ids   : neighbour ids of my cell (all lanes) + facet code / column slot (lane lf % G) -> registers
+//   issue_stage: facet metadata -> shared memory (buffer mb), then all copies as cp.async (no registers, no
+//                shared-memory store instructions); lane a copies neighbour slot lf = a (+ G ...) whole, the
+//                self slot is split over the lanes.
+// loads that must be ISSUED where they are written (the compiler otherwise sinks them to their first use, which
+// turns the latency they were meant to overlap into a stall there)
+__device__ __forceinline__ int ldg_s32(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_u8(const uint8_t *p) {
+    int v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int64_t ldg_s64(const int64_t *p) {
+    int64_t v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void load_ids(const ech_dg_args &A, int a, int64_t c, bool active, int (&ids)[NLF],
+                                         int (&cs)[2 * NLF]) {
+#pragma unroll
+    for (int lf = 0; lf < NLF; ++lf) {
+        ids[lf] = -1;
+        cs[lf] = cs[NLF + lf] = 0;
+    }
+    if (active) {
+#pragma unroll
+        for (int lf = 0; lf < NLF; ++lf) ids[lf] = ldg_s32(A.nbr + c * NLF + lf);
+#pragma unroll
+        for (int lf = 0; lf < NLF; ++lf)
+            if (lf % G == a) {
+                cs[lf] = ldg_u8(A.code + c * NLF + lf);
+                cs[NLF + lf] = ldg_u8(A.slot + c * NLF + lf);
+            }
+    }
+}
+
+__device__ __forceinline__ void issue_stage(const ech_dg_args &A, const Smem2 &W, int mb, int g, int a, int64_t c,
+                                            bool active, const int (&ids)[NLF], const int (&cs)[2 * NLF],
+                                            int64_t fstride) {
+    if (active) {
+        int *m = W.meta + (mb * CPW + g) * META_LEN;
+#pragma unroll
+        for (int lf = 0; lf < NLF; ++lf) {
+            if (lf % G == a) {
+                m[lf] = ids[lf];
+                m[NLF + lf] = cs[lf];
+                m[2 * NLF + lf] = cs[NLF + lf];
+                cp_async8(W.fa + g * NLF + lf, A.facet_area + c * NLF + lf);
+            }
+        }
+        for (int lf = a; lf < NLF; lf += G) {
+            int nb = ids[0];
+#pragma unroll
+            for (int t = 1; t < NLF; ++t) nb = (lf == t) ? ids[t] : nb;
+            if (nb >= 0) copy_slot<0, 1>(A, W.nbd + g * CELL_STRIDE + lf * SLOT_LEN, nb, fstride, 0);
+        }
+        copy_slot<1, G>(A, W.nbd + g * CELL_STRIDE + NLF * SLOT_LEN, (int)c, fstride, a);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// N consecutive doubles from shared memory (128-bit loads when the run is pair-aligned)
+template <int N>
+__device__ __forceinline__ void lds_run(const double *d, double *out) {
+#ifdef ECH_LDS64
+    constexpr bool wide = false;
+#else
+    constexpr bool wide = V16 && N % 2 == 0;
+#endif
+    if constexpr (wide) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(d + i);
+            out[i] = v.x;
+            out[i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = d[i];
+    }
+}
+
+constexpr int J2WARPS = coop2_warps(Rec<true>::LEN);
 
 // ---------------------------------------------------------------- producer helpers
 __device__ __forceinline__ void basis_ref(const int (&idx)[D], double (&phi)[NLOC], double (&dref)[NLOC][D]) {
@@ -160,9 +361,11 @@ __device__ __forceinline__ void interp_ref(const double *d, const double (&phi)[
         double s = 0.0, gr[D];
 #pragma unroll
         for (int m = 0; m < D; ++m) gr[m] = 0.0;
+        double U[NLOC];
+        lds_run<NLOC>(d + j * NLOC, U);
 #pragma unroll
         for (int b = 0; b < NLOC; ++b) {
-            const double ub = d[j * NLOC + b];
+            const double ub = U[b];
             s += ub * phi[b];
 #pragma unroll
             for (int m = 0; m < D; ++m) gr[m] += ub * dref[b][m];
@@ -179,23 +382,24 @@ __device__ __forceinline__ void interp_ref(const double *d, const double (&phi)[
 }
 
 __device__ __forceinline__ void read_coords(const double *d, double (&X)[NV][D]) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-        for (int k = 0; k < D; ++k) X[v][k] = d[NBD_X + v * D + k];
+    lds_run<NV * D>(d + S_X, &X[0][0]);
 }
 
 // own side of a point from the staged cell data
 __device__ __forceinline__ void own_side2(const double *d, const int (&idx)[D], Pt &p, Geo &gm) {
     double X[NV][D];
     read_coords(d, X);
-    p.cv = d[NBD_CV];
-    p.cd = d[NBD_CV + 1];
+    {
+        double cvd[2];
+        lds_run<2>(d + S_CV, cvd);
+        p.cv = cvd[0];
+        p.cd = cvd[1];
+    }
     geometry(X, idx, gm);
     double phi[NLOC], dref[NLOC][D];
     basis_ref(idx, phi, dref);
-    interp_ref<NF>(d + NBD_U, phi, dref, gm.invJ, p.u, p.gu);
-    if constexpr (NAUX > 0) interp_ref<ECH_NA1>(d + NBD_A, phi, dref, gm.invJ, p.a, p.ga);
+    interp_ref<NF>(d + S_U, phi, dref, gm.invJ, p.u, p.gu);
+    if constexpr (NAUX > 0) interp_ref<ECH_NA1>(d + S_A, phi, dref, gm.invJ, p.a, p.ga);
 #pragma unroll
     for (int k = 0; k < D; ++k) p.x[k] = gm.x[k];
 }
@@ -205,16 +409,20 @@ __device__ __forceinline__ void neighbour_side2(const double *d, int code, const
                                                 double (&invJn)[D][D]) {
     double X2[NV][D];
     read_coords(d, X2);
-    p.cvm = d[NBD_CV];
-    p.cdm = d[NBD_CV + 1];
+    {
+        double cvd[2];
+        lds_run<2>(d + S_CV, cvd);
+        p.cvm = cvd[0];
+        p.cdm = cvd[1];
+    }
     int idx2[D];
     neighbour_point(code, tt, idx2);
     Geo g2;
     geometry(X2, idx2, g2);
     double phi2[NLOC], dref2[NLOC][D];
     basis_ref(idx2, phi2, dref2);
-    interp_ref<NF>(d + NBD_U, phi2, dref2, g2.invJ, p.um, p.gum);
-    if constexpr (NAUX > 0) interp_ref<ECH_NA1>(d + NBD_A, phi2, dref2, g2.invJ, p.am, p.gam);
+    interp_ref<NF>(d + S_U, phi2, dref2, g2.invJ, p.um, p.gum);
+    if constexpr (NAUX > 0) interp_ref<ECH_NA1>(d + S_A, phi2, dref2, g2.invJ, p.am, p.gam);
 #pragma unroll
     for (int m = 0; m < D; ++m)
 #pragma unroll
@@ -483,42 +691,65 @@ constexpr bool STRADDLE = any_straddle();
 
 // ---------------------------------------------------------------- the kernel
 template <bool WITH_RES>
-__global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel(const ech_dg_args A) {
+__global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel(const ech_dg_args A, int64_t nbatch) {
     using RC = Rec<WITH_RES>;
     constexpr int RECLEN = Rec<true>::LEN;       // one shared-memory geometry for both instantiations
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / G, a = lane - g * G;       // consumer role: test node a of cell g
     const bool active_lane = g < CPW;
-    const int64_t c = ((int64_t)blockIdx.x * J2WARPS + warp) * CPW + g;
-    const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell_total * NLOC;
-    const WarpSmem W = warp_smem(smem, warp, RECLEN);
+    const Smem2 W = warp_smem2(smem, warp, RECLEN);
     const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int gg = active_lane ? g : 0;
-    const int *meta = W.meta + gg * META_LEN;
     // producer role: this lane evaluates slot ae of cell ge of the warp
     const int ge = lane % CPW, ae = lane / CPW;
-    const int64_t ce = ((int64_t)blockIdx.x * J2WARPS + warp) * CPW + ge;
-    const bool active_e = ae < G && ce < A.ncell;
     const RecRef RE{W.rec + 2 * ge};
-    const int *meta_e = W.meta + ge * META_LEN;
-    const double *own = W.nbd + (ge * NBD_SLOTS + NLF) * NBD_LEN;
-
-    int ncol = 0, pos_self = 0;
-    int64_t rp[NF];
-    if (active) {
-        ncol = A.ncol[c];
-        pos_self = A.slot_self[c];
-#pragma unroll
-        for (int i = 0; i < NF; ++i) rp[i] = A.rowptr[(int64_t)i * rows_per_field + c * NLOC + a];
-    }
-    stage_neighbours(A, W, g, a, c, active, fstride);
+    const double *own = W.nbd + ge * CELL_STRIDE + NLF * SLOT_LEN;
 
     int ad[D];      // digits of my test node
 #pragma unroll
     for (int k = 0; k < D; ++k) ad[k] = ((active_lane ? a : 0) / ipow(N1, D - 1 - k)) % N1;
+
+    // PERSISTENT warps: a warp walks over batches of CPW cells; the staging of the next batch (two dependent
+    // global round trips: neighbour ids, then their data) is issued while the current one is being consumed
+    const int64_t wstride = (int64_t)gridDim.x * J2WARPS;
+    int64_t batch = (int64_t)blockIdx.x * J2WARPS + warp;
+    for (int k = lane; k < ECH_NCONST; k += 32) cp_async8(W.kc + k, A.consts + k);
+    int ids[NLF], cs[2 * NLF];
+    int mb = 0;
+    if (batch < nbatch) {
+        const int64_t c0 = batch * CPW + g;
+        const bool act0 = active_lane && c0 < A.ncell;
+        load_ids(A, a, c0, act0, ids, cs);
+        issue_stage(A, W, mb, g, a, c0, act0, ids, cs, fstride);
+    }
+
+    for (; batch < nbatch; batch += wstride) {
+    const int64_t c = batch * CPW + g;
+    const bool active = active_lane && c < A.ncell;
+    const int64_t ce = batch * CPW + ge;
+    const bool active_e = ae < G && ce < A.ncell;
+    const int *meta = W.meta + (mb * CPW + gg) * META_LEN;
+    const int *meta_e = W.meta + (mb * CPW + ge) * META_LEN;
+    const bool has_next = batch + wstride < nbatch;
+    const int64_t cn = (batch + wstride) * CPW + g;
+    const bool active_n = has_next && active_lane && cn < A.ncell;
+    load_ids(A, a, cn, active_n, ids, cs);          // first round trip of the next batch (registers)
+
+    int ncol = 0, pos_self = 0;
+    int64_t rp[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) rp[i] = 0;
+    if (active) {
+        ncol = ldg_u8(A.ncol + c);
+        pos_self = ldg_u8(A.slot_self + c);
+#pragma unroll
+        for (int i = 0; i < NF; ++i) rp[i] = ldg_s64(A.rowptr + (int64_t)i * rows_per_field + c * NLOC + a);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
 
     double acc[NF][NF][NLOC];
     zero_blocks<true>(acc);
@@ -535,7 +766,11 @@ __global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel
         const int task = round * G + ae;
         if (active_e && task < NTASK) {
             Pt p;
+#ifdef ECH_KC_GLOBAL
             p.K = A.consts;
+#else
+            p.K = W.kc;
+#endif
             Geo gm;
             int idx[D];
             double w;
@@ -574,11 +809,15 @@ __global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel
                     for (int k = 0; k < D; ++k) invJn[m][k] = 0.0;
                 if (nb >= 0) {
                     if constexpr (ECH_FAMILY_DG) {
-                        neighbour_side2(W.nbd + (ge * NBD_SLOTS + lf) * NBD_LEN, meta_e[NLF + lf], tt, p, invJn);
+                        neighbour_side2(W.nbd + ge * CELL_STRIDE + lf * SLOT_LEN, meta_e[NLF + lf], tt, p, invJn);
                     }
                 }
                 own_side2(own, idx, p, gm);
+#ifdef ECH_KC_GLOBAL
                 p.fa = A.facet_area[ce * NLF + lf];
+#else
+                p.fa = W.fa[ge * NLF + lf];
+#endif
                 facet_normal(gm, lf, p.n, ds);
                 w *= ds;
                 if (nb < 0) {
@@ -621,6 +860,8 @@ __global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel
             }
         }
         __syncwarp();
+        // every producer is done with the staged cell data: second round trip of the next batch
+        if (round == NROUND - 1 && has_next) issue_stage(A, W, mb ^ 1, g, a, cn, active_n, ids, cs, fstride);
         // ---------------- consume: the records of my cell into my rows (slot = compile-time task)
         if (active) {
             static_for<0, NROUND>([&](auto rc) {
@@ -695,9 +936,15 @@ __global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel
             for (int i = 0; i < NF; ++i) A.out2[i * rows_per_field + c * NLOC + a] = res[i];
         }
     }
+    mb ^= 1;
+    }   // batches
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr int J2SMEM = J2WARPS * warp_smem_doubles(Rec<true>::LEN) * 8;
+constexpr int J2SMEM = J2WARPS * warp_smem2_doubles(Rec<true>::LEN) * 8;
+
+static int g_coop2_ctas_per_sm[2] = {0, 0};
+static int g_coop2_sms = 0;
 
 static int coop2_setup() {
     static int done = 0;
@@ -705,10 +952,19 @@ static int coop2_setup() {
     cudaError_t e = cudaFuncSetAttribute(jacobian_coop2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, J2SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(jacobian_coop2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, J2SMEM);
-    if (e != cudaSuccess) {
-        fprintf(stderr, "echem_b200: cudaFuncSetAttribute(jacobian_coop2_kernel, %d B) failed: %s\n", J2SMEM,
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_coop2_ctas_per_sm[1], jacobian_coop2_kernel<true>,
+                                                          J2WARPS * 32, J2SMEM);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_coop2_ctas_per_sm[0], jacobian_coop2_kernel<false>,
+                                                          J2WARPS * 32, J2SMEM);
+    int dev = 0;
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_coop2_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || g_coop2_ctas_per_sm[0] < 1 || g_coop2_ctas_per_sm[1] < 1) {
+        fprintf(stderr, "echem_b200: jacobian_coop2_kernel setup (%d B shared) failed: %s\n", J2SMEM,
                 cudaGetErrorString(e));
-        return (int)e;
+        return e != cudaSuccess ? (int)e : (int)cudaErrorLaunchOutOfResources;
     }
     done = 1;
     return 0;
@@ -718,12 +974,22 @@ static int launch_jacobian_coop2(const ech_dg_args *a, cudaStream_t s) {
     if (a->ncell == 0) return 0;
     int e = coop2_setup();
     if (e) return e;
-    const int64_t cells_per_block = (int64_t)J2WARPS * CPW;
-    const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
-    if (a->out2)
-        jacobian_coop2_kernel<true><<<(unsigned)grid, J2WARPS * 32, J2SMEM, s>>>(*a);
+    const int64_t nbatch = (a->ncell + CPW - 1) / CPW;
+    const int64_t need = (nbatch + J2WARPS - 1) / J2WARPS;
+    const int fused = a->out2 ? 1 : 0;
+    // ECH_COOP2_WAVES = w > 0: persistent grid of w waves of resident CTAs (SMs x CTAs per SM), each warp strides
+    // over the batches and stages batch i+1 while it consumes batch i.  Measured on cfg2 (profiles/): 2.78 ms
+    // against 2.64 ms for one batch per warp (the default, w = 0) -- with 2 warps per scheduler the start-up
+    // stagger of short-lived CTAs de-phases the warps better than the software pipeline hides the staging.
+#ifndef ECH_COOP2_WAVES
+#define ECH_COOP2_WAVES 0
+#endif
+    const int64_t resident = (int64_t)g_coop2_sms * g_coop2_ctas_per_sm[fused] * ECH_COOP2_WAVES;
+    const int64_t grid = (ECH_COOP2_WAVES == 0 || need < resident) ? need : resident;
+    if (fused)
+        jacobian_coop2_kernel<true><<<(unsigned)grid, J2WARPS * 32, J2SMEM, s>>>(*a, nbatch);
     else
-        jacobian_coop2_kernel<false><<<(unsigned)grid, J2WARPS * 32, J2SMEM, s>>>(*a);
+        jacobian_coop2_kernel<false><<<(unsigned)grid, J2WARPS * 32, J2SMEM, s>>>(*a, nbatch);
     e = (int)cudaGetLastError();
     if (e) fprintf(stderr, "echem_b200: jacobian_coop2_kernel<<<%lld, %d, %d>>> failed: %s\n", (long long)grid,
                    J2WARPS * 32, J2SMEM, cudaGetErrorString((cudaError_t)e));
