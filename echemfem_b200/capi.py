@@ -27,7 +27,8 @@ class GmresOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("restart", c_i32), ("max_it", c_i32),
                 ("precond", c_i32), ("monitor", c_i32), ("nfields", c_i32), ("nloc", c_i32),
                 ("rows_per_field", c_i64), ("nblocks", c_i64), ("block_cell_ptr", c_p), ("lu", c_p),
-                ("diag_pos", c_p)]
+                ("diag_pos", c_p), ("agg", c_p), ("nc", c_i32), ("reserved", c_i32), ("coarse_inv", c_p),
+                ("coarse_work", c_p)]
 
 
 EXPORTS = {
@@ -53,6 +54,7 @@ EXPORTS = {
     "ech_coarse_galerkin": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_i32, c_p, c_p]),
     "ech_coarse_restrict": (C.c_int, [c_i64, c_p, c_i32, c_p, c_p, c_p]),
     "ech_coarse_prolong_add": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),
+    "ech_dense_gemv": (C.c_int, [c_i32, c_i32, c_p, c_p, c_p, c_p]),
     "ech_gmres": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_p, C.POINTER(GmresOpts), c_p, c_p,
                             C.POINTER(c_i32), C.POINTER(C.c_double), c_p]),
     "ech_assemble_host": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -896,6 +896,28 @@ extern "C" int ech_coarse_prolong_add(int64_t n, const int32_t *agg, const doubl
     return ECH_OK;
 }
 
+__global__ void __launch_bounds__(256) dense_gemv_kernel(int nr, int nc, const double *__restrict__ M,
+                                                         const double *__restrict__ x, double *__restrict__ y) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= nr) return;
+    const double *row = M + (int64_t)r * nc;
+    double s = 0.0;
+    for (int k = lane; k < nc; k += 32) s += row[k] * x[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[r] = s;
+}
+
+extern "C" int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const double *x, double *y, void *stream) {
+    if (!M || !x || !y) return fail(nullptr, ECH_ERR_ARG, "ech_dense_gemv: null argument");
+    if (nr == 0) return ECH_OK;
+    dense_gemv_kernel<<<(unsigned)(((int64_t)nr * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nr, nc, M, x, y);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== GMRES
 extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx, const double *vals,
                          const double *b, double *x, const ech_gmres_opts *o, double *basis, double *work,
@@ -911,8 +933,29 @@ extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx
     double *partial = work + 3 * n + 4096;
     if (m + 2 > 4096) return fail(nullptr, ECH_ERR_ARG, "ech_gmres: restart too large");
     BlockPlan B{o->nfields, o->nloc, o->rows_per_field, o->nblocks, o->block_cell_ptr};
+    if (o->precond >= 2 && (!o->agg || !o->coarse_inv || !o->coarse_work || o->nc <= 0))
+        return fail(nullptr, ECH_ERR_ARG, "ech_gmres: coarse space not set");
+    // two-level preconditioner: out = M_ilu^-1 in (+) P Ac^-1 P^T (in  or  in - A out)
+    auto coarse_add = [&](const double *resid, double *out) -> int {
+        double *rc_ = o->coarse_work, *yc_ = o->coarse_work + o->nc;
+        int e;
+        if ((e = ech_coarse_restrict(n, o->agg, o->nc, resid, rc_, stream))) return e;
+        if ((e = ech_dense_gemv(o->nc, o->nc, o->coarse_inv, rc_, yc_, stream))) return e;
+        return ech_coarse_prolong_add(n, o->agg, yc_, out, stream);
+    };
     auto precond = [&](const double *in, double *out) -> int {
-        if (o->precond == 1) return ilu0_apply(B, rowptr, colidx, o->lu, o->diag_pos, in, out, s);
+        int e;
+        if (o->precond >= 1) {
+            if ((e = ilu0_apply(B, rowptr, colidx, o->lu, o->diag_pos, in, out, s))) return e;
+            if (o->precond == 2) return coarse_add(in, out);
+            if (o->precond == 3) {
+                double *res_ = o->coarse_work + 2 * (int64_t)o->nc;
+                if ((e = ech_spmv(n, rowptr, colidx, vals, out, res_, s))) return e;
+                if ((e = ech_axpby(n, 1.0, in, -1.0, res_, s))) return e;       // res = in - A out
+                return coarse_add(res_, out);
+            }
+            return ECH_OK;
+        }
         return ech_axpby(n, 1.0, in, 0.0, out, s);
     };
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hcol(m + 2), y(m);

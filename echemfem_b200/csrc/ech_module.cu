@@ -48,7 +48,10 @@ int ech_mod_residual(const ech_dg_args *a, void *stream) {
 
 int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
     // fused residual + Jacobian when a->out2 is set
-    if (use_coop() && g_variant == 0) return echdg::v2::launch_jacobian_coop2(a, (cudaStream_t)stream);
+    // reference-space records pay up to 9 local nodes (Q1 2D/3D, Q2 2D: cfg2 Q2 12.9 ms against 16.5 ms); beyond
+    // that the fully unrolled compile-time bases outgrow the register file (cfg2 Q3: 52 ms against 34 ms)
+    if (use_coop() && g_variant == 0 && echdg::NLOC <= 9)
+        return echdg::v2::launch_jacobian_coop2(a, (cudaStream_t)stream);
     if (use_coop()) return echdg::launch_jacobian_coop(a, (cudaStream_t)stream);
     if (a->out2) {
         ech_dg_args r = *a;

@@ -308,13 +308,53 @@ class NewtonEngine:
         }
         return self._lin
 
-    def linear_solve(self, rhs, rtol, atol, restart, max_it, monitor=False):
+    def _coarse_plan(self, target):
+        """Aggregation map of the optional coarse level: dofs are binned by their coordinates into boxes, one
+        coarse dof per (field, non-empty box), piecewise-constant prolongation (the nodal bases are partitions of
+        unity).  Not an option set of the reference: it stands in for the coarse levels of its gmg / amg sets
+        (solver.py:1190-1213) where block-Jacobi/ILU(0) alone needs O(N) Krylov iterations."""
+        C_ = getattr(self, "_coarse", None)
+        if C_ is not None and C_["target"] == target:
+            return C_
+        x = np.asarray(self.solver.W.scalar.node_coords(), dtype=float)
+        dim = x.shape[1]
+        nb = max(1, int(round((target / float(self.nf)) ** (1.0 / dim))))
+        lo, hi = x.min(axis=0), x.max(axis=0)
+        span = np.where(hi > lo, hi - lo, 1.0)
+        # equal numbers of boxes per direction scaled by the aspect ratio of the bounding box
+        aspect = span / span.prod() ** (1.0 / dim)
+        nbs = np.maximum(1, np.round(nb * aspect).astype(np.int64))
+        idx = np.minimum((nbs * (x - lo) / span).astype(np.int64), nbs - 1)
+        lin = idx[:, 0]
+        for k in range(1, dim):
+            lin = lin * nbs[k] + idx[:, k]
+        _, box = np.unique(lin, return_inverse=True)
+        nagg = int(box.max()) + 1
+        agg = np.concatenate([box + f * nagg for f in range(self.nf)]).astype(np.int32)
+        nc = nagg * self.nf
+        dev = self.dev
+        self._coarse = {
+            "target": target, "nc": nc, "agg": torch.from_numpy(agg).to(dev),
+            "Ac": torch.empty((nc, nc), dtype=torch.float64, device=dev),
+            "inv": None,
+            "work": torch.empty(2 * nc + self.ndof, dtype=torch.float64, device=dev),
+        }
+        return self._coarse
+
+    def linear_solve(self, rhs, rtol, atol, restart, max_it, monitor=False, coarse=0, coarse_mode=3):
         """Solve J dx = rhs with right-preconditioned GMRES; returns (dx, iterations)."""
         L = self._linear_plan(restart)
         t0 = time.time()
         capi.check(self.lib.ech_bjacobi_ilu0_factor(self.ndof, self.nf, self.N, self._unit, L["nblocks"],
                                                     ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
                                                     ptr(self.vals), ptr(L["lu"]), ptr(L["diag"]), self._stream()))
+        Cz = None
+        if coarse and self.halo is None:
+            Cz = self._coarse_plan(int(coarse))
+            capi.check(self.lib.ech_coarse_galerkin(self.ndof, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals),
+                                                    ptr(Cz["agg"]), Cz["nc"], ptr(Cz["Ac"]), self._stream()))
+            # the dense coarse solve is a library call (cuSOLVER through torch), once per Newton iteration
+            Cz["inv"] = torch.linalg.inv(Cz["Ac"]).contiguous()
         torch.cuda.synchronize()
         self.timers["PCSetUp"] += time.time() - t0
         if self.halo is not None:
@@ -324,7 +364,12 @@ class NewtonEngine:
             self.timers["KSPSolve"] += time.time() - t0
             return out
         opts = capi.GmresOpts(rtol, atol, L["restart"], max_it, 1, 1 if monitor else 0, self.nf, self._unit,
-                              self.N, L["nblocks"], ptr(L["block_ptr"]), ptr(L["lu"]), ptr(L["diag"]))
+                              self.N, L["nblocks"], ptr(L["block_ptr"]), ptr(L["lu"]), ptr(L["diag"]),
+                              None, 0, 0, None, None)
+        if Cz is not None:
+            opts.precond = int(coarse_mode)
+            opts.agg, opts.nc = ptr(Cz["agg"]), Cz["nc"]
+            opts.coarse_inv, opts.coarse_work = ptr(Cz["inv"]), ptr(Cz["work"])
         L["dx"].zero_()
         its = C.c_int32()
         rn = C.c_double()
@@ -475,6 +520,9 @@ class NewtonEngine:
         restart = P.get("ksp_gmres_restart", 30) if not direct else 200
         ksp_max_it = P.get("ksp_max_it", 10000)
         linesearch = P.get("snes_linesearch_type", "bt")
+        # coarse level: on by default where the reference would factor directly ("lu") and the system is large
+        coarse = P.get("pc_coarse_dofs", 4096 if (direct and self.ndof >= 100000) else 0)
+        coarse_mode = 2 if P.get("pc_coarse_type", "multiplicative") == "additive" else 3
 
         u = self.solver.u.tensor
         aux = self._aux_tensor()
@@ -528,7 +576,8 @@ class NewtonEngine:
                                                        ptr(self.vals), None, st))
             torch.cuda.synchronize()
             self.timers["JacobianEval"] += time.time() - t0
-            y, kits, ok = self.linear_solve(F, ksp_rtol, ksp_atol, restart, ksp_max_it)
+            y, kits, ok = self.linear_solve(F, ksp_rtol, ksp_atol, restart, ksp_max_it, coarse=coarse,
+                                            coarse_mode=coarse_mode)
             ksp_hist.append(kits)
             if not ok:
                 print("*** WARNING: linear solve did not reach ksp_rtol in %d iterations" % kits)

@@ -137,11 +137,14 @@ int ech_coarse_galerkin(int64_t nrows, const int64_t *rowptr, const int32_t *col
                         const int32_t *agg, int32_t nc, double *Ac, void *stream);
 int ech_coarse_restrict(int64_t n, const int32_t *agg, int32_t nc, const double *v, double *rc, void *stream);
 int ech_coarse_prolong_add(int64_t n, const int32_t *agg, const double *yc, double *z, void *stream);
+/* y[nr] = M[nr x nc] x (dense, row-major; one warp per row) */
+int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const double *x, double *y, void *stream);
 
 typedef struct ech_gmres_opts {
     double rtol, atol;
     int32_t restart, max_it;
-    int32_t precond;          /* 0 none, 1 block-Jacobi/ILU(0) (factor must be current) */
+    int32_t precond;          /* 0 none, 1 block-Jacobi/ILU(0) (factor must be current),
+                                 2 = 1 + additive coarse correction, 3 = 1 + multiplicative coarse correction */
     int32_t monitor;          /* print residual norms */
     /* preconditioner plan (precond == 1) */
     int32_t nfields, nloc;
@@ -149,6 +152,11 @@ typedef struct ech_gmres_opts {
     const int64_t *block_cell_ptr;
     const double *lu;
     const int32_t *diag_pos;
+    /* coarse space (precond >= 2): aggregation map, size, dense inverse of P^T A P (row-major), scratch */
+    const int32_t *agg;
+    int32_t nc, reserved;
+    const double *coarse_inv;
+    double *coarse_work;      /* 2 * nc (+ nrows for precond == 3) doubles */
 } ech_gmres_opts;
 
 /* Right-preconditioned restarted GMRES (classical Gram-Schmidt with one refinement, unpreconditioned

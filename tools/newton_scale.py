@@ -7,10 +7,20 @@ import product_cases
 from echemfem_b200.fd import errornorm
 
 sizes = [int(a) for a in sys.argv[1:]] or [64, 256]
+PC = os.environ.get("PC", "ilu")
+CUSTOM = {}
+if os.environ.get("COARSE"):
+    CUSTOM["pc_coarse_dofs"] = int(os.environ["COARSE"])
+if os.environ.get("COARSE_TYPE"):
+    CUSTOM["pc_coarse_type"] = os.environ["COARSE_TYPE"]
+if os.environ.get("KSP_RTOL"):
+    CUSTOM["ksp_rtol"] = float(os.environ["KSP_RTOL"])
 for N in sizes:
     t0 = time.time()
     s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5)
-    s.init_solver_parameters(pc_type="ilu")
+    s.init_solver_parameters(pc_type=PC)
+    s.solver_parameters.update(CUSTOM)
+    s.potential_solver_parameters.update(CUSTOM)
     s.solver_parameters.pop("snes_monitor", None)
     t1 = time.time()
     s.setup_solver()
