@@ -96,6 +96,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
+def ncu_traffic(deg, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json); None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get("cfg2_Q%d_N%d_fused" % (deg, n), {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(mesh, nf, nloc, nnz):
     ndof = nf * getattr(mesh, "num_owned", mesh.num_cells) * nloc
     nvert = mesh.coords.shape[0]
@@ -124,6 +135,32 @@ def cpu_baseline(sample_n, reps=1):
         disc.jacobian(u)
         best = min(best, time.perf_counter() - t0)
     return disc.ndof / best / 1e6, best, disc.ndof
+
+
+def newton_step(n, deg, tile):
+    """Newton-step wall time (BASELINE metric, second half): setup_solver() + solve() of the same MMS problem on an
+    n x n mesh with the reference's default option set ('lu': served by GMRES + block-Jacobi/ILU(0) + coarse
+    level run to 1e-12); per-step time = solve time / Newton iterations."""
+    import torch
+    import product_cases
+    from echemfem_b200.mesh import UnitSquareMesh
+    s = product_cases.AdvectionDiffusionMigrationSolver(n, 1.0, D1=0.5e-5, D2=1.0e-5, p=deg,
+                                                        mesh=UnitSquareMesh(n, n, tile=tile if n % tile == 0 else None))
+    s.init_solver_parameters(pc_type="lu")
+    s.solver_parameters.pop("snes_monitor", None)
+    s.setup_solver()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s.solve()
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    e = s._engine
+    its = max(e.last["snes_its"], 1)
+    return {"mesh": "UnitSquareMesh(%d,%d) DG Q%d" % (n, n, deg), "dofs": e.ndof, "snes_its": e.last["snes_its"],
+            "ksp_its_per_step": e.last["ksp_its_per_step"], "solve_s": t, "newton_step_s": t / its,
+            "timers_s": {k: round(v, 4) for k, v in e.timers.items()},
+            "linear_solver": "GMRES(200) + block-Jacobi/ILU(0) on %dx%d-cell tiles + aggregation coarse level, "
+                             "ksp_rtol 1e-12" % (tile, tile)}
 
 
 def run_reference(args):
@@ -163,7 +200,10 @@ def main():
     ap.add_argument("--degree", type=int, default=1, help="polynomial degree (the headline number is Q1)")
     ap.add_argument("--sample-n", dest="sample_n", type=int, default=96, help="CPU baseline sample mesh")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time SpMV")
+    ap.add_argument("--tile", type=int, default=0, help="number the cells tile by tile (T x T cells) instead of "
+                                                        "lexicographically")
+    ap.add_argument("--extras", action="store_true", help="also time SpMV and one full Newton solve")
+    ap.add_argument("--newton-n", dest="newton_n", type=int, default=256, help="mesh of the --extras Newton solve")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -200,7 +240,11 @@ def main():
                                       rank, world)
         s = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, D1=0.5e-5, D2=1.0e-5, mesh=lmesh, p=deg)
     else:
-        s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5, p=deg)
+        tmesh = None
+        if args.tile:
+            from echemfem_b200.mesh import UnitSquareMesh
+            tmesh = UnitSquareMesh(N, N, tile=args.tile)
+        s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5, p=deg, mesh=tmesh)
     eng = NewtonEngine(s)
     mesh = s.mesh
     x = s.V.node_coords()
@@ -294,6 +338,8 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         extras["spmv_ms"] = a0.elapsed_time(a1) / args.steps
+        if world == 1:
+            extras["newton"] = newton_step(args.newton_n, deg, args.tile or 16)
 
     times = torch.tensor([t_step, tF, tJ, t_e2e], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -308,7 +354,8 @@ def main():
             "metric": METRIC, "value": world * ndof / (t_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 MMS 2D DG Q%d electroneutral Nernst-Planck, UnitSquareMesh(%d,%d) quads" % (deg, N, N),
+            "config": {"workload": "cfg2 MMS 2D DG Q%d electroneutral Nernst-Planck, UnitSquareMesh(%d,%d) quads%s" % (
+                           deg, N, N, ", cells numbered in %dx%d tiles" % (args.tile, args.tile) if args.tile else ""),
                        "cells_per_gpu": getattr(mesh, "num_owned", mesh.num_cells), "dofs_per_gpu": ndof, "nnz_per_gpu": eng.nnz,
                        "l2_policy": "outputs (%.1f GB CSR values) exceed the 126 MB L2 every step" % (8 * eng.nnz / 1e9),
                        "parallelism": "cells partitioned in strips, one per GPU; ghost-cell state exchanged by NCCL "
@@ -319,7 +366,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "echdg::v2::jacobian_coop2_kernel<true> (fused F + J, 1 launch per step)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "algorithmic_bytes": BJ + 8 * ndof, "traffic": None,
+                         "algorithmic_bytes": BJ + 8 * ndof, "traffic": ncu_traffic(deg, N),
                          "jacobian_only_achieved_GBs": BJ / (tJ * 1e-3) / 1e9,
                          "residual_achieved_GBs": BF / (tF * 1e-3) / 1e9},
             "e2e": {"value": world * ndof / (t_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": t_e2e,

@@ -155,8 +155,24 @@ def _box_markers(lo, hi):
     return fn
 
 
-def TensorMesh(axes, name="tensor", marker_of_facet=None, layers=None):
-    """Tensor-product mesh from one vertex-coordinate array per direction (graded meshes)."""
+def tile_order(shape, tile):
+    """Permutation of the lexicographic cell numbers of a tensor mesh that makes the cells of one tile
+    (a box of `tile` cells per direction) contiguous: tiles in lexicographic order, cells inside a tile
+    lexicographic.  Contiguous cell ranges are what the block-Jacobi/ILU(0) preconditioner and the
+    one-warp-per-batch assembly kernels work on, so compact tiles give compact blocks (the reference's
+    DMPlex numbering is reordered for locality as well; SURVEY.md 8c Q7 -- numbering is not part of parity)."""
+    shape = tuple(int(n) for n in shape)
+    d = len(shape)
+    tile = tuple(int(t) for t in (tile if np.ndim(tile) else (tile,) * d))
+    idx = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+    keys = [i.reshape(-1) % t for i, t in zip(idx, tile)][::-1] + [i.reshape(-1) // t for i, t in zip(idx, tile)][::-1]
+    return np.lexsort(keys)          # last key (tile index of direction 0) is the primary one
+
+
+def TensorMesh(axes, name="tensor", marker_of_facet=None, layers=None, tile=None):
+    """Tensor-product mesh from one vertex-coordinate array per direction (graded meshes).
+
+    tile: cells are numbered tile by tile (see `tile_order`) instead of lexicographically."""
     axes = [np.asarray(a, dtype=float) for a in axes]
     d = len(axes)
     nv = [len(a) for a in axes]
@@ -170,16 +186,26 @@ def TensorMesh(axes, name="tensor", marker_of_facet=None, layers=None):
     cells = np.stack(corner, axis=1)
     if marker_of_facet is None:
         marker_of_facet = _box_markers([a[0] for a in axes], [a[-1] for a in axes])
+    shape = tuple(n - 1 for n in nv)
+    perm = None
+    if tile is not None:
+        perm = tile_order(shape, tile)
+        cells = cells[perm]
     m = Mesh(coords, cells, marker_of_facet, name=name, layers=layers)
-    m.shape = tuple(n - 1 for n in nv)
+    m.shape = shape
     m.axes = axes
+    m.cell_perm = perm               # new cell i is lexicographic cell perm[i]
+    if tile is not None:
+        t = tuple(int(v) for v in (tile if np.ndim(tile) else (tile,) * d))
+        if all(n % k == 0 for n, k in zip(shape, t)):
+            m.block_hint = int(np.prod(t))      # cells per preconditioner block = one tile
     return m
 
 
-def UnitSquareMesh(nx, ny, quadrilateral=True, **kw):
+def UnitSquareMesh(nx, ny, quadrilateral=True, tile=None, **kw):
     if not quadrilateral:
         raise NotImplementedError("only quadrilateral/hexahedral cells are supported")
-    return TensorMesh([np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1)], name="unit_square")
+    return TensorMesh([np.linspace(0.0, 1.0, nx + 1), np.linspace(0.0, 1.0, ny + 1)], name="unit_square", tile=tile)
 
 
 def RectangleMesh(nx, ny, Lx, Ly, quadrilateral=True, **kw):

@@ -286,6 +286,9 @@ class NewtonEngine:
         nunits = self.ncell if self.cg is None else self.N
         per = 64 if self.cg is None else 256
         nblocks = self.nblocks
+        hint = getattr(self.solver.mesh, "block_hint", None)
+        if nblocks is None and hint and self.cg is None and self.halo is None:
+            nblocks = max(1, nunits // int(hint))          # tile-numbered mesh: one block per tile
         if nblocks is None:
             # one warp factors / solves one block: enough blocks to fill the machine, >= ~256 rows per field each
             nblocks = int(max(1, min(nunits // per, 148 * 32)))
@@ -316,22 +319,8 @@ class NewtonEngine:
         C_ = getattr(self, "_coarse", None)
         if C_ is not None and C_["target"] == target:
             return C_
-        x = np.asarray(self.solver.W.scalar.node_coords(), dtype=float)
-        dim = x.shape[1]
-        nb = max(1, int(round((target / float(self.nf)) ** (1.0 / dim))))
-        lo, hi = x.min(axis=0), x.max(axis=0)
-        span = np.where(hi > lo, hi - lo, 1.0)
-        # equal numbers of boxes per direction scaled by the aspect ratio of the bounding box
-        aspect = span / span.prod() ** (1.0 / dim)
-        nbs = np.maximum(1, np.round(nb * aspect).astype(np.int64))
-        idx = np.minimum((nbs * (x - lo) / span).astype(np.int64), nbs - 1)
-        lin = idx[:, 0]
-        for k in range(1, dim):
-            lin = lin * nbs[k] + idx[:, k]
-        _, box = np.unique(lin, return_inverse=True)
-        nagg = int(box.max()) + 1
-        agg = np.concatenate([box + f * nagg for f in range(self.nf)]).astype(np.int32)
-        nc = nagg * self.nf
+        from .coarse import box_aggregates
+        agg, nc = box_aggregates(self.solver.W.scalar.node_coords(), self.nf, target)
         dev = self.dev
         self._coarse = {
             "target": target, "nc": nc, "agg": torch.from_numpy(agg).to(dev),

@@ -105,3 +105,25 @@ def test_contract_attributes():
     with pytest.raises(NotImplementedError):
         s.init_solver_parameters(pc_type="gmg")
     assert s.W.dim() == 2 * 16 and len(s.u.subfunctions) == 2
+
+
+def test_box_aggregates_cover_every_dof_and_field():
+    from echemfem_b200.coarse import box_aggregates
+    g = (np.arange(20) + 0.5) / 20.0
+    X, Y = np.meshgrid(g, 2.0 * g, indexing="ij")
+    coords = np.stack([X.ravel(), Y.ravel()], axis=1)
+    agg, nc = box_aggregates(coords, 3, 48)
+    n = coords.shape[0]
+    assert agg.shape == (3 * n,) and agg.dtype == np.int32
+    nagg = nc // 3
+    assert nc == 3 * nagg and 8 <= nagg <= 32
+    # fields use disjoint coarse dofs with the same box structure
+    assert np.array_equal(agg[n:2 * n], agg[:n] + nagg) and np.array_equal(agg[2 * n:], agg[:n] + 2 * nagg)
+    assert set(agg[:n]) == set(range(nagg))
+    # boxes are spatially compact: every aggregate spans less than half of the domain in each direction
+    for a in range(nagg):
+        pts = coords[agg[:n] == a]
+        assert (pts.max(axis=0) - pts.min(axis=0) < np.array([0.5, 1.0])).all()
+    # degenerate inputs
+    agg1, nc1 = box_aggregates(np.zeros((5, 2)), 2, 100)
+    assert nc1 == 2 and set(agg1) == {0, 1}

@@ -17,7 +17,11 @@ if os.environ.get("KSP_RTOL"):
     CUSTOM["ksp_rtol"] = float(os.environ["KSP_RTOL"])
 for N in sizes:
     t0 = time.time()
-    s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5)
+    mesh = None
+    if os.environ.get("TILE"):
+        from echemfem_b200.mesh import UnitSquareMesh
+        mesh = UnitSquareMesh(N, N, tile=int(os.environ["TILE"]))
+    s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5, mesh=mesh)
     s.init_solver_parameters(pc_type=PC)
     s.solver_parameters.update(CUSTOM)
     s.potential_solver_parameters.update(CUSTOM)
