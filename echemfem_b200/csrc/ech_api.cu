@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "echem_b200.h"
@@ -636,10 +637,13 @@ struct BlockPlan {
     const int64_t *cell_ptr;
 };
 
+// column col belongs to the block of cells [c0, c1) if it falls into the cell range of one of the fields.
+// Columns are int32, so the arithmetic is 32-bit (a 64-bit modulo per matrix entry used to dominate the
+// triangular solves).
 __device__ __forceinline__ bool in_block(const BlockPlan &B, int32_t col, int64_t c0, int64_t c1) {
-    const int64_t idx = col % B.rows_per_field;
-    const int64_t cell = idx / B.nloc;
-    return cell >= c0 && cell < c1;
+    const uint32_t rpf = (uint32_t)B.rows_per_field;
+    const uint32_t idx = (uint32_t)col % rpf;
+    return idx >= (uint32_t)(c0 * B.nloc) && idx < (uint32_t)(c1 * B.nloc);
 }
 
 __global__ void diag_pos_kernel(int64_t nrows, const int64_t *__restrict__ rowptr,
@@ -709,46 +713,143 @@ __global__ void __launch_bounds__(128) ilu0_factor_kernel(BlockPlan B, const int
     }
 }
 
-__global__ void __launch_bounds__(128) ilu0_apply_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
-                                                         const int32_t *__restrict__ colidx,
-                                                         const double *__restrict__ lu,
-                                                         const int32_t *__restrict__ diag_pos,
-                                                         const double *__restrict__ rhs, double *z) {
-    const int64_t blk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+// Triangular solves, one warp (= one CTA) per block, rows in sequence.
+//  * the block's part of z lives in SHARED memory during both sweeps (a global z costs a store -> load round
+//    trip through L2 per row: measured 1.3 us per row), and is written back coalesced at the end;
+//  * everything a row needs except z (row pointer, diagonal position, column indices -> local indices, factor
+//    values) is independent of the solve, so the entries of the NEXT row are loaded into registers (two chunks
+//    of 32) while the current row waits: the dependent chain per row is one shared-memory gather + one shuffle
+//    reduction.
+// SMEM = false: z stays in global memory (blocks too large for shared memory).
+struct RowChunk {
+    int32_t k0, k1;        // local index of the column inside the block (or global column when !SMEM); -1: none
+    double v0, v1;
+    int64_t beg, end;      // entry range of this half-row (L part or U part)
+    double piv;
+};
+
+template <bool SMEM>
+__device__ __forceinline__ int32_t block_local(const BlockPlan &B, int32_t col, uint32_t first, uint32_t nrow_f) {
+    // -1 if the column is outside the block
+    const uint32_t rpf = (uint32_t)B.rows_per_field;
+    const uint32_t f = (uint32_t)col / rpf;
+    const uint32_t idx = (uint32_t)col - f * rpf;
+    if (idx < first || idx >= first + nrow_f) return -1;
+    return SMEM ? (int32_t)(f * nrow_f + (idx - first)) : col;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void load_half_row(const BlockPlan &B, const int64_t *__restrict__ rowptr,
+                                              const int32_t *__restrict__ colidx, const double *__restrict__ lu,
+                                              const int32_t *__restrict__ diag_pos, int64_t r, bool upper, int lane,
+                                              uint32_t first, uint32_t nrow_f, RowChunk &R) {
+    const int64_t rs = rowptr[r], re = rowptr[r + 1];
+    const int64_t rd = rs + diag_pos[r];
+    R.beg = upper ? rd + 1 : rs;
+    R.end = upper ? re : rd;
+    R.piv = upper ? lu[rd] : 1.0;
+    const int64_t p0 = R.beg + lane, p1 = p0 + 32;
+    R.k0 = R.k1 = -1;
+    R.v0 = R.v1 = 0.0;
+    if (p0 < R.end) {
+        R.k0 = block_local<SMEM>(B, colidx[p0], first, nrow_f);
+        R.v0 = lu[p0];
+    }
+    if (p1 < R.end) {
+        R.k1 = block_local<SMEM>(B, colidx[p1], first, nrow_f);
+        R.v1 = lu[p1];
+    }
+}
+
+template <bool SMEM>
+__device__ __forceinline__ double half_row_dot(const BlockPlan &B, const int32_t *__restrict__ colidx,
+                                               const double *__restrict__ lu, const RowChunk &R, const double *z,
+                                               int lane, uint32_t first, uint32_t nrow_f) {
+    double s = 0.0;
+    if (R.k0 >= 0) s += R.v0 * z[R.k0];
+    if (R.k1 >= 0) s += R.v1 * z[R.k1];
+    for (int64_t p = R.beg + 64 + lane; p < R.end; p += 32) {       // rows longer than 64 entries per half
+        const int32_t k = block_local<SMEM>(B, colidx[p], first, nrow_f);
+        if (k >= 0) s += lu[p] * z[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(32) ilu0_apply_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
+                                                        const int32_t *__restrict__ colidx,
+                                                        const double *__restrict__ lu,
+                                                        const int32_t *__restrict__ diag_pos,
+                                                        const double *__restrict__ rhs, double *zg) {
+    extern __shared__ double zs[];
+    const int64_t blk = blockIdx.x;
+    const int lane = threadIdx.x;
     if (blk >= B.nblocks) return;
     const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
-    // forward: L y = rhs (unit diagonal)
-    for (int f = 0; f < B.nf; ++f) {
-        for (int64_t r = f * B.rows_per_field + c0 * B.nloc; r < f * B.rows_per_field + c1 * B.nloc; ++r) {
-            const int64_t rs = rowptr[r];
-            const int64_t rd = rs + diag_pos[r];
-            double s = 0.0;
-            for (int64_t p = rs + lane; p < rd; p += 32) {
-                const int32_t k = colidx[p];
-                if (in_block(B, k, c0, c1)) s += lu[p] * z[k];
+    const int64_t nrow_f = (c1 - c0) * B.nloc;           // rows of this block per field
+    const int64_t ntot = nrow_f * B.nf;
+    if (ntot == 0) return;
+    const int64_t first = c0 * B.nloc, last = c1 * B.nloc - 1;
+    const uint32_t first32 = (uint32_t)first, nrow32 = (uint32_t)nrow_f;
+    double *z = SMEM ? zs : zg;
+    // rows of the block in ascending global order: field-major, consecutive inside a field;
+    // li = index of the row inside the block (its slot in shared memory)
+    RowChunk cur, nxt;
+    {   // forward: L y = rhs (unit diagonal)
+        int f = 0;
+        int64_t j = 0, r = first;
+        load_half_row<SMEM>(B, rowptr, colidx, lu, diag_pos, r, false, lane, first32, nrow32, cur);
+        double rr = rhs[r];
+        for (int64_t i = 0; i < ntot; ++i) {
+            int fn = f;
+            int64_t jn = j + 1, rnext = r + 1;
+            if (jn == nrow_f) {
+                jn = 0;
+                fn = f + 1;
+                rnext = (int64_t)fn * B.rows_per_field + first;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) z[r] = rhs[r] - s;
+            double rn = 0.0;
+            if (i + 1 < ntot) {
+                load_half_row<SMEM>(B, rowptr, colidx, lu, diag_pos, rnext, false, lane, first32, nrow32, nxt);
+                rn = rhs[rnext];
+            }
+            const double s = half_row_dot<SMEM>(B, colidx, lu, cur, z, lane, first32, nrow32);
+            if (lane == 0) z[SMEM ? i : r] = rr - s;
             __syncwarp();
+            cur = nxt;
+            rr = rn;
+            f = fn;
+            j = jn;
+            r = rnext;
         }
     }
-    // backward: U z = y
-    for (int f = B.nf - 1; f >= 0; --f) {
-        for (int64_t r = f * B.rows_per_field + c1 * B.nloc - 1; r >= f * B.rows_per_field + c0 * B.nloc; --r) {
-            const int64_t rs = rowptr[r], re = rowptr[r + 1];
-            const int64_t rd = rs + diag_pos[r];
-            double s = 0.0;
-            for (int64_t p = rd + 1 + lane; p < re; p += 32) {
-                const int32_t k = colidx[p];
-                if (in_block(B, k, c0, c1)) s += lu[p] * z[k];
+    {   // backward: U z = y
+        int f = B.nf - 1;
+        int64_t j = nrow_f - 1, r = (int64_t)f * B.rows_per_field + last;
+        load_half_row<SMEM>(B, rowptr, colidx, lu, diag_pos, r, true, lane, first32, nrow32, cur);
+        for (int64_t i = ntot - 1; i >= 0; --i) {
+            int fn = f;
+            int64_t jn = j - 1, rprev = r - 1;
+            if (jn < 0) {
+                jn = nrow_f - 1;
+                fn = f - 1;
+                rprev = (int64_t)fn * B.rows_per_field + last;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) z[r] = (z[r] - s) / lu[rd];
+            if (i > 0) load_half_row<SMEM>(B, rowptr, colidx, lu, diag_pos, rprev, true, lane, first32, nrow32, nxt);
+            const double s = half_row_dot<SMEM>(B, colidx, lu, cur, z, lane, first32, nrow32);
+            if (lane == 0) z[SMEM ? i : r] = (z[SMEM ? i : r] - s) / cur.piv;
             __syncwarp();
+            cur = nxt;
+            f = fn;
+            j = jn;
+            r = rprev;
         }
+    }
+    if constexpr (SMEM) {
+        for (int f = 0; f < B.nf; ++f)
+            for (int64_t j = lane; j < nrow_f; j += 32) zg[(int64_t)f * B.rows_per_field + first + j] = zs[f * nrow_f + j];
     }
 }
 
@@ -782,12 +883,40 @@ extern "C" int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t r
     return ECH_OK;
 }
 
+// largest number of cells in a block of the plan (read back once per plan and cached)
+static int64_t max_block_cells(const BlockPlan &B, cudaStream_t s) {
+    static const int64_t *cached_ptr = nullptr;
+    static int64_t cached_n = -1, cached_max = 0;
+    if (cached_ptr == B.cell_ptr && cached_n == B.nblocks) return cached_max;
+    std::vector<int64_t> h((size_t)B.nblocks + 1);
+    if (cudaMemcpyAsync(h.data(), B.cell_ptr, sizeof(int64_t) * h.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return -1;
+    int64_t m = 0;
+    for (int64_t i = 0; i < B.nblocks; ++i) m = std::max(m, h[i + 1] - h[i]);
+    cached_ptr = B.cell_ptr;
+    cached_n = B.nblocks;
+    cached_max = m;
+    return m;
+}
+
 static int ilu0_apply(const BlockPlan &B, const int64_t *rowptr, const int32_t *colidx, const double *lu,
                       const int32_t *diag_pos, const double *r, double *z, cudaStream_t s) {
-    const int block = 128;
-    const int64_t nthreads = B.nblocks * 32;
-    ilu0_apply_kernel<<<(unsigned)((nthreads + block - 1) / block), block, 0, s>>>(B, rowptr, colidx, lu, diag_pos, r,
-                                                                                 z);
+    if (B.nblocks == 0) return ECH_OK;
+    const int64_t mc = max_block_cells(B, s);
+    if (mc < 0) return cuda_fail(nullptr, cudaGetLastError(), "ilu0_apply: read of the block plan");
+    const int64_t bytes = mc * B.nloc * B.nf * (int64_t)sizeof(double);
+    if (bytes <= 200 * 1024) {
+        static int64_t attr_bytes = 0;
+        if (bytes > attr_bytes) {
+            CK(nullptr, cudaFuncSetAttribute(ilu0_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)bytes));
+            attr_bytes = bytes;
+        }
+        ilu0_apply_kernel<true><<<(unsigned)B.nblocks, 32, (size_t)bytes, s>>>(B, rowptr, colidx, lu, diag_pos, r, z);
+    } else {
+        ilu0_apply_kernel<false><<<(unsigned)B.nblocks, 32, 0, s>>>(B, rowptr, colidx, lu, diag_pos, r, z);
+    }
     ++g_launches;
     CK(nullptr, cudaGetLastError());
     return ECH_OK;
