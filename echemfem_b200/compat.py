@@ -27,7 +27,7 @@ def install(force=False):
     shim.__all__ = names
     sys.modules["firedrake"] = shim
     pkg = types.ModuleType("echemfem")
-    for n in ("EchemSolver", "TransientEchemSolver"):
+    for n in ("EchemSolver", "TransientEchemSolver", "IntervalBoundaryLayerMesh", "RectangleBoundaryLayerMesh"):
         setattr(pkg, n, getattr(echemfem_b200, n))
     sys.modules["echemfem"] = pkg
     sys.modules["echemflow"] = pkg

@@ -71,3 +71,68 @@ def BortelsMesh(n_in=100, n_el=100, n_out=100, n_y=50):
     """297 x 49 = 14 553 cells with the default node counts."""
     x, y = bortels_axes(n_in, n_el, n_out, n_y)
     return TensorMesh([x, y], name="bortels_structuredquad_nondim", marker_of_facet=bortels_markers())
+
+
+# ---------------------------------------------------------------------------------------------------
+# Boundary-layer meshes (echemfem/utility_meshes.py:9-195): a uniform core plus uniformly refined layers
+# next to the marked boundaries.  The node abscissae follow the reference's arithmetic (same linspace /
+# arange end points), so node positions are bit-identical; the cells are numbered by TensorMesh.
+
+def _layered_axis(n, length, n_layer, l_layer, lo_layer, hi_layer):
+    """n uniform cells between the layers, n_layer cells of total width l_layer in each requested layer."""
+    a0, a1 = 0.0, float(length)
+    if lo_layer:
+        a0 += l_layer
+    if hi_layer:
+        a1 -= l_layer
+    ax = np.linspace(a0, a1, n + 1, dtype=np.double)
+    if lo_layer:
+        ax = np.append(np.linspace(0.0, l_layer - l_layer / n_layer, n_layer, dtype=np.double), ax)
+    if hi_layer:
+        ax = np.append(ax, np.linspace(a1 + l_layer / n_layer, length, n_layer, dtype=np.double))
+    return ax
+
+
+def RectangleBoundaryLayerMesh(nx, ny, Lx, Ly, n_bdlayer, L_bdlayer, Ly_bdlayer=None, ny_bdlayer=None,
+                               boundary=(1,), reorder=None, distribution_parameters=None, comm=None, tile=None):
+    """Quadrilateral mesh of [0, Lx] x [0, Ly] with boundary layers next to the sides listed in `boundary`
+    (1: x = 0, 2: x = Lx, 3: y = 0, 4: y = Ly); same signature as echemfem/utility_meshes.py:75-78."""
+    from .mesh import TensorMesh
+    for n in (nx, ny):
+        if n <= 0 or n % 1:
+            raise ValueError("Number of cells must be a postive integer")
+    lx_layer = L_bdlayer
+    ly_layer = L_bdlayer if Ly_bdlayer is None else Ly_bdlayer
+    nx_layer = n_bdlayer
+    ny_layer = n_bdlayer if ny_bdlayer is None else ny_bdlayer
+    xs = _layered_axis(nx, Lx, nx_layer, lx_layer, 1 in boundary, 2 in boundary)
+    ys = _layered_axis(ny, Ly, ny_layer, ly_layer, 3 in boundary, 4 in boundary)
+    return TensorMesh([xs, ys], name="rectangle_boundary_layer", tile=tile)
+
+
+def IntervalBoundaryLayerMesh(ncells, length_or_left, ncells_bdlayer, length_bdlayer, boundary=(2,), right=None,
+                              distribution_parameters=None, comm=None):
+    """Interval mesh with boundary layers at the ends listed in `boundary` (1: left, 2: right);
+    same signature as echemfem/utility_meshes.py:9-10."""
+    from .mesh import TensorMesh
+    if right is None:
+        left, right = 0.0, float(length_or_left)
+    else:
+        left = float(length_or_left)
+    if ncells <= 0 or ncells % 1:
+        raise ValueError("Number of cells must be a postive integer")
+    a0, a1 = left, right
+    if 1 in boundary:
+        a0 += length_bdlayer
+    if 2 in boundary:
+        a1 -= length_bdlayer
+    if a1 - a0 < 0:
+        raise ValueError("Requested mesh has negative length")
+    h = (a1 - a0) / ncells
+    h1 = length_bdlayer / ncells_bdlayer
+    ax = np.arange(a0, a1 + 0.01 * h, h, dtype=np.double)
+    if 1 in boundary:
+        ax = np.append(np.arange(left, length_bdlayer - 0.99 * h1, h1, dtype=np.double), ax)
+    if 2 in boundary:
+        ax = np.append(ax, np.arange(right - length_bdlayer + h1, right + 0.01 * h1, h1, dtype=np.double))
+    return TensorMesh([ax], name="interval_boundary_layer")

@@ -127,3 +127,26 @@ def test_box_aggregates_cover_every_dof_and_field():
     # degenerate inputs
     agg1, nc1 = box_aggregates(np.zeros((5, 2)), 2, 100)
     assert nc1 == 2 and set(agg1) == {0, 1}
+
+
+def test_boundary_layer_meshes_follow_reference_node_positions():
+    """echemfem/utility_meshes.py:9-195: uniform core + uniform layers; markers 1..4 as on box meshes."""
+    from echemfem_b200 import RectangleBoundaryLayerMesh, IntervalBoundaryLayerMesh
+    # examples/gupta_advection_migration.py-style: layers at y = 0 and y = Ly
+    m = RectangleBoundaryLayerMesh(10, 6, 2.0, 1.0, 4, 0.1, boundary=(3, 4))
+    assert m.shape == (10, 14) and m.num_cells == 140
+    ys = m.axes[1]
+    assert np.allclose(ys[:5], [0.0, 0.025, 0.05, 0.075, 0.1]) and np.allclose(ys[-5:], [0.9, 0.925, 0.95, 0.975, 1.0])
+    assert np.allclose(np.diff(ys[4:11]), 0.8 / 6) and np.allclose(np.diff(m.axes[0]), 0.2)
+    assert set(np.unique(m.ext_marker)) == {0, 1, 2, 3, 4}
+    # different layer in x and y
+    m2 = RectangleBoundaryLayerMesh(4, 4, 1.0, 1.0, 2, 0.2, Ly_bdlayer=0.1, ny_bdlayer=5, boundary=(1, 4))
+    assert m2.shape == (6, 9)
+    assert np.allclose(m2.axes[0][:3], [0.0, 0.1, 0.2]) and np.allclose(m2.axes[1][-6:], 0.9 + 0.02 * np.arange(6))
+    # interval: default layer on the right only (boundary=(2,))
+    mi = IntervalBoundaryLayerMesh(10, 1.0, 5, 0.1)
+    x = mi.axes[0]
+    assert mi.shape == (15,) and np.allclose(np.diff(x[:11]), 0.09) and np.allclose(np.diff(x[10:]), 0.02)
+    assert mi.num_exterior_facets == 2 and set(np.unique(mi.ext_marker)) == {0, 1, 2}
+    with pytest.raises(ValueError):
+        IntervalBoundaryLayerMesh(10, 0.1, 5, 0.2, boundary=(1, 2))
