@@ -29,8 +29,10 @@ class _Printer(C99CodePrinter):
     def _print_Pow(self, expr):
         b, e = expr.base, expr.exp
         if e.is_Integer and 1 < abs(int(e)) <= 4:
-            s = "*".join(["(%s)" % self._print(b)] * abs(int(e)))
-            return s if e > 0 else "(1.0/(%s))" % s
+            # always parenthesised: sympy's Mul printer places a positive power in a denominator as is
+            # (x * y**-4 prints as x/<y**4>), and an open product there would bind as ((x/y)*y)*y*y
+            s = "(%s)" % "*".join(["(%s)" % self._print(b)] * abs(int(e)))
+            return s if e > 0 else "(1.0/%s)" % s
         if e == sp.Rational(1, 2):
             return "sqrt(%s)" % self._print(b)
         if e == -sp.Rational(1, 2):

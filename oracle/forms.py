@@ -51,6 +51,55 @@ def _evalf(f, x):
     return f * np.ones(x.shape[:-1])
 
 
+class _GV:
+    """Value + spatial gradient of a pointwise function of the fields (forward mode): what UFL's
+    `grad(f(u))` expands to, restated so that the oracle needs no symbolic algebra.  `v`: (...,),
+    `g`: (..., d); dtype-generic (the outer complex step of the Jacobian passes through)."""
+
+    def __init__(self, v, g):
+        self.v, self.g = v, g
+
+    @staticmethod
+    def lift(a):
+        return a if isinstance(a, _GV) else _GV(a, 0.0)
+
+    def __add__(self, o):
+        o = _GV.lift(o)
+        return _GV(self.v + o.v, self.g + o.g)
+    __radd__ = __add__
+
+    def __neg__(self):
+        return _GV(-self.v, -self.g)
+
+    def __sub__(self, o):
+        return self + (-_GV.lift(o))
+
+    def __rsub__(self, o):
+        return _GV.lift(o) + (-self)
+
+    def __mul__(self, o):
+        o = _GV.lift(o)
+        return _GV(self.v * o.v, _col(self.v) * o.g + _col(o.v) * self.g)
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        o = _GV.lift(o)
+        return _GV(self.v / o.v, (_col(o.v) * self.g - _col(self.v) * o.g) / _col(o.v * o.v))
+
+    def __rtruediv__(self, o):
+        return _GV.lift(o) / self
+
+    def __pow__(self, n):                       # integer powers only
+        return _GV(self.v ** n, _col(n * self.v ** (n - 1)) * self.g)
+
+    def log(self):
+        return _GV(np.log(self.v), self.g / _col(self.v))
+
+
+def _col(a):
+    return a[..., None] if isinstance(a, np.ndarray) and a.ndim else a
+
+
 class Problem:
     """Physics description consumed by the oracle.
 
@@ -60,7 +109,7 @@ class Problem:
 
     def __init__(self, conc_params, physical_params, boundary_markers,
                  echem_params=(), p=1, family="DG", vel=None, SUPG=False,
-                 neumann=None, variant="spectral", C_IP=10.0, p_penalty=None):
+                 neumann=None, variant="spectral", C_IP=10.0, p_penalty=None, homog_params=()):
         self.conc_params = [dict(c) for c in conc_params]
         self.physical_params = dict(physical_params)
         self.boundary_markers = {}
@@ -75,8 +124,12 @@ class Problem:
         self.neumann = neumann
         self.C_IP = C_IP
         self.penalty_degree = p if p_penalty is None else p_penalty
+        self.homog_params = list(homog_params)
         flow = {k: False for k in ("advection", "diffusion", "migration",
-                                   "electroneutrality", "poisson", "porous")}
+                                   "electroneutrality", "poisson", "porous", "finite size",
+                                   "diffusion finite size_BK", "diffusion finite size_CS",
+                                   "diffusion finite size_SP", "diffusion finite size_SMPNP",
+                                   "diffusion finite size_BMCSL")}
         for f in physical_params["flow"]:
             if f not in flow:
                 raise NotImplementedError("oracle: flow option %r" % f)
@@ -88,6 +141,8 @@ class Problem:
             raise NotImplementedError('Migration requires Electroneutrality or Poisson')
         if flow["poisson"] and flow["electroneutrality"]:
             raise NotImplementedError('Electroneutrality not compatible with Poisson')
+        if family == "DG" and any(v for k, v in flow.items() if "finite size" in k):       # solver.py:139-142
+            raise NotImplementedError('finite size effects only implemented with CG')
         self.flow = flow
         self.num_c = len(conc_params)
         self.idx_c = list(range(self.num_c))
@@ -204,6 +259,73 @@ class Problem:
             fl = fl - self.K_mig(k) * gU
         return fl
 
+    def mass_action(self, u):
+        """Homogeneous bulk reactions by the law of mass action (`setup_bulk_reactions`, solver.py:1222-1274)."""
+        name_to_field = {self.conc_params[k]["name"]: i for i, k in enumerate(self.idx_c)}
+        rates = []
+        for rxn in self.homog_params:
+            kf = rxn["forward rate constant"]
+            kb = 0.0
+            if rxn.get("backward rate constant"):
+                kb = rxn["backward rate constant"]
+            elif rxn.get("equilibrium constant"):
+                kb = rxn["forward rate constant"] / rxn["equilibrium constant"]
+            c_ref = rxn["reference concentration"] if rxn.get("reference concentration") else 1.0
+            for name, st in rxn["stoichiometry"].items():
+                order = abs(st)
+                if rxn.get("reaction order") and rxn["reaction order"].get(name):
+                    order = rxn["reaction order"][name]
+                act = u[name_to_field[name]] / c_ref
+                if st < 0:
+                    kf = kf * act ** order
+                if st > 0:
+                    kb = kb * act ** order
+            rates.append(kf - kb)
+        out = [0.0] * self.num_c
+        for k in self.idx_c:
+            name = self.conc_params[k]["name"]
+            for rxn, r in zip(self.homog_params, rates):
+                if name in rxn["stoichiometry"]:
+                    c_ref = rxn["reference concentration"] if rxn.get("reference concentration") else 1.0
+                    out[k] = out[k] + rxn["stoichiometry"][name] * c_ref * r
+        if self.flow["porous"]:
+            out = [self.physical_params["porosity"] * r for r in out]       # saturation 1
+        return out
+
+    def excess_potential(self, cp, u, gu):
+        """mu_ex of the 'diffusion finite size_*' options with its gradient (solver.py:1554-1633).
+        The sums run over u[i], i < num_c, as in the reference."""
+        f = self.flow
+        if not any(f["diffusion finite size_" + t] for t in ("BK", "CS", "SP", "SMPNP", "BMCSL")):
+            return None
+        NA = self.physical_params["Avogadro constant"]
+
+        def packing(power, scale=1.0):
+            tot = _GV(0.0, 0.0)
+            for j in range(self.num_c):
+                aj = self.conc_params[j].get("solvated diameter")
+                if aj is not None and aj != 0.0:
+                    tot = tot + _GV(u[j], gu[j]) * (scale * NA * aj ** power)
+            return tot
+        if f["diffusion finite size_BK"]:
+            return -((1.0 - packing(3)).log())
+        if f["diffusion finite size_CS"]:
+            phi = packing(3)
+            return phi * (8.0 - 9.0 * phi + 3.0 * phi ** 2) / (1.0 - phi) ** 3
+        if f["diffusion finite size_SP"]:
+            return -((1.0 - 8.0 * packing(3)).log())
+        if f["diffusion finite size_SMPNP"]:
+            betaj = (cp.get("solvated diameter") / 2.3e-10) ** 3
+            return -betaj * ((1.0 - packing(3)).log())
+        p0, p1, p2, p3 = [packing(m, np.pi / 6.0) for m in range(4)]
+        ai = cp.get("solvated diameter")
+        return (-(1.0 + (2.0 * p2 ** 3 * ai ** 3 / (p3 ** 3)) - (3.0 * p2 ** 2 * ai ** 2 / (p3 ** 2))) * (1.0 - p3).log()
+                + (3.0 * p2 * ai + 3.0 * p1 * ai ** 2 + p0 * ai ** 3) / (1.0 - p3)
+                + (6.0 * p1 * p2 * ai ** 3 + 9.0 * p2 ** 2 * ai ** 2) / (2.0 * (1.0 - p3) ** 2)
+                + (3.0 * p2 ** 3 * ai ** 3) / (1.0 - p3) ** 3
+                + ((3.0 * p2 ** 2 * ai ** 2) / p3) * ((1.0 - 3.0 * p3 * 0.5) / (1.0 - p3) ** 2)
+                - (p2 ** 3 * ai ** 3) * (4.0 * p3 ** 2 - 5.0 * p3 + 2.0) / (p3 ** 2 * (1.0 - p3) ** 3))
+
     # -- cell integrals ---------------------------------------------------
     def cell(self, x, u, gu, geo):
         nf = self.num_fields
@@ -214,7 +336,9 @@ class Problem:
         pp = self.physical_params
         C, gC = self.concentrations(u, gu)
         reactions = None
-        if pp.get("bulk reaction") is not None:
+        if self.homog_params:
+            reactions = self.mass_action(self.reaction_u(u))                # overrides "bulk reaction", :1271-1274
+        elif pp.get("bulk reaction") is not None:
             reactions = pp["bulk reaction"](self.reaction_u(u), x)
         if self.has_potential:
             U, gU = u[self.i_Ul], gu[self.i_Ul]
@@ -223,6 +347,18 @@ class Problem:
         for i, k in enumerate(self.idx_c):
             cp = self.conc_params[k]
             D = self.Dk(k)
+            if self.flow["diffusion"] and self.flow["finite size"]:         # :1543-1552
+                NA = pp["Avogadro constant"]
+                den, num = 1.0, 0.0
+                for j in range(self.num_c):
+                    aj = self.conc_params[j].get("solvated diameter")
+                    if aj is not None and aj != 0.0:
+                        den = den - NA * aj ** 3 * u[j]
+                        num = num + NA * aj ** 3 * gu[j]
+                f1[i] = f1[i] + (D * C[k] / den)[..., None] * num
+            mu_ex = self.excess_potential(cp, u, gu)
+            if mu_ex is not None:                                           # :1554-1636  D C grad(ln C + mu_ex)
+                f1[i] = f1[i] + D * gC[k] + (D * C[k])[..., None] * mu_ex.g
             rterm = None
             if reactions is not None and not _is_zero(reactions[i]):
                 # solver.py:1497-1500  (note: indexed by i_c)
@@ -512,6 +648,9 @@ class Problem:
                     out.append((i, bm["bulk dirichlet"], ("bulk", k)))
                 if bm.get("gas") is not None and cp.get("gas") is not None:
                     out.append((i, bm["gas"], ("gas", k)))
+            if any(self.flow["diffusion finite size_" + t] for t in ("BK", "CS", "SP", "SMPNP", "BMCSL")):
+                if bm.get("bulk dirichlet") is not None:                       # solver.py:1563, 1575, 1587, 1607, 1635
+                    out.append((i, bm["bulk dirichlet"], ("bulk", k)))
         if self.flow["electroneutrality"]:
             if bm.get("bulk") is not None:
                 out.append((self.i_Ul, bm["bulk"], ("zero",)))

@@ -198,3 +198,23 @@ def porous_problem(vavg):
                        "solid conductivity": 1.0, "specific surface area": 1.0}
     markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4), "liquid applied": (1, 2, 3, 4)}
     return Problem(conc_params, physical_params, markers, vel=make_vel(vavg))
+
+
+def finite_size_problem(kind="BMCSL", p=1, homog=True):
+    """Oracle twin of product_cases.FiniteSizeSolver."""
+    from oracle.forms import Problem
+    import product_cases as pc
+
+    def bulk(n):
+        return {"A": lambda x: np.cos(x[..., 0]) + np.sin(x[..., 1]) + 3.0,
+                "B": lambda x: np.cos(x[..., 0]) - np.sin(x[..., 1]) + 3.0,
+                "N": lambda x: np.sin(x[..., 0]) * np.cos(x[..., 1]) + 2.0}[n]
+    conc_params = [{"name": n, "diffusion coefficient": D, "z": z, "solvated diameter": a, "bulk": bulk(n)}
+                   for n, D, z, a in pc.FS_SPECIES]
+    flow = ["migration", "poisson"]
+    flow += ["diffusion", "finite size"] if kind == "finite size" else ["diffusion finite size_" + kind]
+    physical_params = {"flow": flow, "F": 1.0, "R": 1.0, "T": 1.0, "vacuum permittivity": 2.0,
+                       "relative permittivity": 1e-1, "U_app": Uex, "Avogadro constant": 0.1}
+    markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4)}
+    return Problem(conc_params, physical_params, markers, family="CG", p=p,
+                   homog_params=[dict(r) for r in pc.FS_HOMOG] if homog else [])

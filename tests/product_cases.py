@@ -228,3 +228,32 @@ class PorousSolver(EchemSolver):
         y = SpatialCoordinate(self.mesh)[1]
         h = 1.0
         self.vel = as_vector((6. * self.physical_params["v_avg"] / h**2 * y * (h - y), Constant(0.)))
+
+
+FS_SPECIES = [("A", 1.0, 1.0, 0.5), ("B", 0.5, -1.0, 0.4), ("N", 0.8, 0.0, 0.3)]      # name, D, z, solvated diameter
+FS_HOMOG = [{"stoichiometry": {"A": -1, "B": -1, "N": 1}, "forward rate constant": 0.7,
+             "backward rate constant": 0.3, "reference concentration": 2.0},
+            {"stoichiometry": {"N": -2, "A": 1}, "forward rate constant": 0.05, "equilibrium constant": 4.0,
+             "reaction order": {"N": 1}}]
+
+
+class FiniteSizeSolver(EchemSolver):
+    """Poisson-Nernst-Planck with a finite-size correction of the chemical potential (examples/BMCSL.py:33-84 in
+    2D, dimensionless numbers) and homogeneous reactions by the law of mass action (homog_params,
+    examples/carbonate_homog_params.py).  CG only (solver.py:139-142)."""
+
+    def __init__(self, N, kind="BMCSL", p=1, homog=True):
+        mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        bulk = {"A": cos(x) + sin(y) + 3, "B": cos(x) - sin(y) + 3, "N": sin(x) * cos(y) + 2}
+        conc_params = [{"name": n, "diffusion coefficient": D, "z": z, "solvated diameter": a, "bulk": bulk[n]}
+                       for n, D, z, a in FS_SPECIES]
+        flow = ["migration", "poisson"]
+        flow += ["diffusion", "finite size"] if kind == "finite size" else ["diffusion finite size_" + kind]
+        physical_params = {"flow": flow, "F": 1.0, "R": 1.0, "T": 1.0, "vacuum permittivity": 2.0,
+                           "relative permittivity": 1e-1, "U_app": sin(x) + cos(y) + 3, "Avogadro constant": 0.1}
+        super().__init__(conc_params, physical_params, mesh, family="CG", p=p,
+                         homog_params=[dict(r) for r in FS_HOMOG] if homog else [])
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,), "applied": (1, 2, 3, 4,)}

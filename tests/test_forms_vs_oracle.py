@@ -103,3 +103,29 @@ def test_porous_pointwise():
             assert _close(evaluate(cf.cell["f1"][i][k], dat, cf), f1[i][0, :, k])
             assert _close(evaluate(cf.int["f1"][i][k], dat, cf), f1p[i][0, :, k])
             assert _close(evaluate(cf.ext[cls]["f1"][i][k], dat, cf), g1[i][0, :, k])
+
+
+@pytest.mark.parametrize("kind", ["BMCSL", "BK", "CS", "SP", "SMPNP", "finite size"])
+def test_finite_size_and_mass_action_pointwise(kind):
+    """Finite-size chemical potentials (solver.py:1543-1636) and law-of-mass-action reactions
+    (solver.py:1222-1274): product (sympy chain rule) vs oracle (forward-mode AD) at random points."""
+    s = product_cases.FiniteSizeSolver(2, kind)
+    cf = CompiledForm(s.Form, 4, len(s._aux), 2, 1, "CG")
+    prob = mms_cases.finite_size_problem(kind)
+    rng = np.random.default_rng(5)
+    dat = random_point_data(4, 1, 2, 32, rng)
+    x = dat["x"][None]
+    u = [dat["u"][j][None] for j in range(4)]
+    gu = [dat["gu"][j][None] for j in range(4)]
+    f0, f1 = prob.cell(x, u, gu, {"cell_volume": dat["cv"][None], "cell_diameter": dat["cd"][None]})
+    for i in range(4):
+        assert _close(evaluate(cf.cell["f0"][i], dat, cf), f0[i][0]), (kind, i)
+        for k in range(2):
+            assert _close(evaluate(cf.cell["f1"][i][k], dat, cf), f1[i][0, :, k]), (kind, i, k)
+
+
+def test_finite_size_rejected_on_dg():
+    from oracle.forms import Problem
+    with pytest.raises(NotImplementedError):
+        Problem([{"name": "A", "diffusion coefficient": 1.0, "z": 0.0}],
+                {"flow": ["diffusion", "finite size"], "Avogadro constant": 1.0}, {}, family="DG")

@@ -129,3 +129,30 @@ def test_porous_two_potentials_matches_oracle():
     for f in range(3):
         a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
         assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("kind", ["BMCSL", "finite size"])
+def test_finite_size_mass_action_matches_oracle(kind):
+    """cfg5 ingredients on the device: finite-size chemical potential (solver.py:1543-1636), homogeneous
+    reactions from homog_params (solver.py:1222-1274), Poisson coupling; CG Q1, four fields."""
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    from oracle.newton import solve_problem
+    N = 4
+    disc = Discretization(unit_square_mesh(N), mms_cases.finite_size_problem(kind))
+    s = product_cases.FiniteSizeSolver(N, kind)
+    x = disc.node_coords
+    pert = 1e-2 * np.sin(7 * x[:, 0] + 3 * x[:, 1])
+    u = np.concatenate([np.cos(x[:, 0]) + np.sin(x[:, 1]) + 3 + pert, np.cos(x[:, 0]) - np.sin(x[:, 1]) + 3 - pert,
+                        np.sin(x[:, 0]) * np.cos(x[:, 1]) + 2 + 0.5 * pert, mms_cases.Uex(x) + 0.5 * pert])
+    _compare_raw(disc, s, u, "finite size " + kind)
+    if kind == "BMCSL":
+        u_ref, info = solve_problem(disc)
+        s2 = product_cases.FiniteSizeSolver(N, kind)
+        s2.setup_solver()
+        s2.solve()
+        un = s2.u.numpy()
+        Ns = disc.ndof_scalar
+        for f in range(4):
+            a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
+            assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)

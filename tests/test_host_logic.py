@@ -150,3 +150,14 @@ def test_boundary_layer_meshes_follow_reference_node_positions():
     assert mi.num_exterior_facets == 2 and set(np.unique(mi.ext_marker)) == {0, 1, 2}
     with pytest.raises(ValueError):
         IntervalBoundaryLayerMesh(10, 0.1, 5, 0.2, boundary=(1, 2))
+
+
+def test_code_printer_keeps_integer_powers_together():
+    """x / y**4 must not print as x/(y)*(y)*(y)*(y) (found by the BMCSL parity test)."""
+    import sympy as sp
+    from echemfem_b200.compiler import _Printer
+    x, y = sp.symbols("x y")
+    for expr in (x / y ** 4, x * y ** 3 / (1 - y) ** 2, y ** -3, (x + 1) ** 2 / y ** 2):
+        code = _Printer().doprint(expr)
+        val = eval(code.replace("pow(", "np.power("), {"x": 1.7, "y": 0.6, "np": np})
+        assert abs(val - float(expr.subs({x: 1.7, y: 0.6}))) < 1e-12 * abs(val), code
