@@ -40,3 +40,60 @@ def FacetArea(mesh):
 def Mesh(path, **kw):
     from .meshio import read_msh
     return read_msh(path, **kw)
+
+
+def IntervalMesh(ncells, length_or_left, right=None, **kw):
+    """Uniform interval mesh; boundary ids 1 (left) and 2 (right), as Firedrake's."""
+    import numpy as np
+    left, right = (0.0, float(length_or_left)) if right is None else (float(length_or_left), float(right))
+    return TensorMesh([np.linspace(left, right, int(ncells) + 1)], name="interval")
+
+
+def UnitIntervalMesh(ncells, **kw):
+    return IntervalMesh(ncells, 1.0)
+
+
+def MeshHierarchy(mesh, refinement_levels, **kw):
+    """Uniform refinements of a tensor-product mesh (every cell split in two per direction and level);
+    `hierarchy[-1]` is what the reference's scripts take (examples/mms_scaling.py:72-76)."""
+    import numpy as np
+    if not hasattr(mesh, "axes"):
+        raise NotImplementedError("MeshHierarchy needs a tensor-product mesh")
+    out = [mesh]
+    axes = [np.asarray(a, dtype=float) for a in mesh.axes]
+    for _ in range(int(refinement_levels)):
+        axes = [np.sort(np.concatenate([a, 0.5 * (a[1:] + a[:-1])])) for a in axes]
+        out.append(TensorMesh(axes, name=mesh.name, layers=mesh.layers))
+    return out
+
+
+def ExtrudedMeshHierarchy(base_hierarchy, height, base_layer=1, refinement_ratio=2, **kw):
+    """Extrusion of every level of a hierarchy: `base_layer` layers on the coarsest level, `refinement_ratio`
+    times more per level, total height `height`."""
+    out = []
+    for lvl, m in enumerate(base_hierarchy):
+        layers = int(base_layer) * int(refinement_ratio) ** lvl
+        out.append(ExtrudedMesh(m, layers, float(height) / layers))
+    return out
+
+
+# logging knobs of `from firedrake import *` scripts (no-ops here)
+DEBUG, INFO, WARNING = 10, 20, 30
+
+
+def set_log_level(level):
+    pass
+
+
+class AssembledPC:
+    """Base class of the reference's custom PETSc preconditioners (examples/mms_scaling.py:24-62).  Python-level
+    PETSc preconditioners have no counterpart on the device path: the classes can be defined, but selecting them
+    (`pc_type: python`) falls back to the option sets of `init_solver_parameters`."""
+
+
+class PMGPC(AssembledPC):
+    pass
+
+
+class PCBase(AssembledPC):
+    pass

@@ -39,6 +39,21 @@ class Mesh:
         symbolic.set_geometric_dimension(self.dim)
         self._connect()
 
+    @property
+    def coordinates(self):
+        """`mesh.coordinates.dat.data[:] = ...` (examples/catalyst_layer_Cu_full.py:187-188): a writable view of
+        the vertex coordinates, shape (nv,) in 1D and (nv, d) otherwise.  Vertices of tensor meshes are numbered
+        lexicographically (left to right in 1D).  Move vertices before the solver is set up."""
+        view = self.coords[:, 0] if self.dim == 1 else self.coords
+
+        class _Dat:
+            data = view
+            data_ro = view
+
+        class _Coords:
+            dat = _Dat
+        return _Coords
+
     # Firedrake-compatible queries used by the reference (solver.py:202, 221, 752)
     def topological_dimension(self):
         return self.dim

@@ -161,3 +161,100 @@ def test_code_printer_keeps_integer_powers_together():
         code = _Printer().doprint(expr)
         val = eval(code.replace("pow(", "np.power("), {"x": 1.7, "y": 0.6, "np": np})
         assert abs(val - float(expr.subs({x: 1.7, y: 0.6}))) < 1e-12 * abs(val), code
+
+
+MSH2 = """$MeshFormat
+2.2 0 8
+$EndMeshFormat
+$Nodes
+6
+1 0 0 0
+2 1 0 0
+3 2 0 0
+4 0 1 0
+5 1 1 0
+6 2 1 0
+$EndNodes
+$Elements
+5
+1 1 2 10 1 1 4
+2 1 2 11 2 3 6
+3 1 2 13 3 1 2
+4 3 2 2 1 1 2 5 4
+5 3 2 2 1 3 2 5 6
+$EndElements
+"""
+
+MSH4 = """$MeshFormat
+4.1 0 8
+$EndMeshFormat
+$Entities
+0 2 1 0
+1 0 0 0 0 1 0 1 10 0
+2 2 0 0 2 1 0 1 11 0
+1 0 0 0 2 1 0 1 2 0
+$EndEntities
+$Nodes
+1 6 1 6
+2 1 0 6
+1
+2
+3
+4
+5
+6
+0 0 0
+1 0 0
+2 0 0
+0 1 0
+1 1 0
+2 1 0
+$EndNodes
+$Elements
+3 4 1 4
+1 1 1 1
+1 1 4
+1 2 1 1
+2 3 6
+2 1 3 2
+3 1 2 5 4
+4 2 3 6 5
+$EndElements
+"""
+
+GEO = """L = 2.; h = 1.;
+Point(1) = {0, 0, 0, 1}; Point(2) = {L, 0, 0, 1}; Point(3) = {L, h, 0, 1}; Point(4) = {0, h, 0, 1};
+Line(1) = {1, 2}; Line(2) = {2, 3}; Line(3) = {3, 4}; Line(4) = {4, 1};
+Curve Loop(5) = {1, 2, 3, 4}; Plane Surface(1) = {5};
+Physical Curve("in", 7) = {4}; Physical Curve("out", 8) = {2}; Physical Curve("wall", 9) = {1, 3};
+Transfinite Curve{1, -3} = 5 Using Progression 2; Transfinite Curve{4, -2} = 4 Using Bump 0.1;
+Transfinite Surface{1} = {1, 2, 3, 4}; Recombine Surface{1};
+"""
+
+
+def test_msh_reader_and_transfinite_geo(tmp_path):
+    """`Mesh('x.msh')` (examples/bortels_threeion_nondim.py:111): gmsh 2.2 / 4.1 ASCII quads with physical boundary
+    tags; a clockwise cell is re-oriented; without the .msh the structured mesh is built from the .geo."""
+    from echemfem_b200.fd import Mesh
+    from echemfem_b200.meshio import progression_nodes
+    for name, text in (("a.msh", MSH2), ("b.msh", MSH4)):
+        p = tmp_path / name
+        p.write_text(text)
+        m = Mesh(str(p))
+        assert m.num_cells == 2 and m.dim == 2 and m.num_interior_facets == 1
+        X = m.cell_coords()
+        e1, e2 = X[:, 2] - X[:, 0], X[:, 1] - X[:, 0]
+        assert np.all(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0] > 0)          # positively oriented local frames
+        tags = sorted(int(t) for t in m.ext_marker.ravel() if t)
+        assert tags == ([10, 11, 13] if name == "a.msh" else [10, 11])
+    (tmp_path / "c.geo").write_text(GEO)
+    m = Mesh(str(tmp_path / "c.msh"))
+    assert m.shape == (4, 3)
+    assert np.allclose(np.diff(m.axes[0]), 2.0 * np.array([1, 2, 4, 8]) / 15.0)
+    assert np.allclose(m.axes[0], progression_nodes(2.0, 5, 2.0))
+    assert np.isclose(m.axes[1][-1], 1.0) and np.allclose(m.axes[1], 1.0 - m.axes[1][::-1])   # Bump is symmetric
+    assert set(np.unique(m.ext_marker)) == {0, 7, 8, 9}
+    c0 = m.cell_coords()[0]
+    assert np.allclose(c0[0], [0.0, 0.0])
+    with pytest.raises(FileNotFoundError):
+        Mesh(str(tmp_path / "missing.msh"))
