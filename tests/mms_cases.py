@@ -218,3 +218,37 @@ def finite_size_problem(kind="BMCSL", p=1, homog=True):
     markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4)}
     return Problem(conc_params, physical_params, markers, family="CG", p=p,
                    homog_params=[dict(r) for r in pc.FS_HOMOG] if homog else [])
+
+
+def gupta_problem(SUPG=False):
+    """Oracle twin of product_cases.GuptaSolver (examples/gupta_advection_migration.py)."""
+    from oracle.forms import Problem
+    import product_cases as pc
+    Lx = pc.GUPTA_LX
+    conc_params = [{"name": n, "diffusion coefficient": D, "bulk": b, "z": z} for n, D, b, z in pc.GUPTA_SPECIES]
+    physical_params = {"flow": ["diffusion", "electroneutrality", "migration", "advection"],
+                       "F": 96485.3329, "R": 8.3144598, "T": 273.15 + 25.}
+
+    def current(cef):
+        def curr(u, x):
+            X = x[..., 0]
+            return cef * 50. * ((X >= 1e-3) & (X < Lx - 1e-3)).astype(float)
+        return curr
+    echem_params = [{"reaction": current(c), "stoichiometry": dict(st), "electrons": ne, "boundary": "electrode"}
+                    for c, st, ne in pc.GUPTA_CURRENTS]
+    markers = {"inlet": (1,), "outlet": (2,), "bulk": (4,), "electrode": (3,)}
+
+    def vel(x):
+        v = np.zeros(x.shape, dtype=x.dtype)
+        v[..., 0] = 1.91 * x[..., 1]
+        return v
+    return Problem(conc_params, physical_params, markers, echem_params=echem_params, family="CG", vel=vel, SUPG=SUPG,
+                   homog_params=[dict(r) for r in pc.GUPTA_HOMOG])
+
+
+def gupta_oracle_mesh(nx=6, ny=4, n_layer=3):
+    from oracle.mesh import tensor_mesh
+    from echemfem_b200.meshes import RectangleBoundaryLayerMesh
+    import product_cases as pc
+    m = RectangleBoundaryLayerMesh(nx, ny, pc.GUPTA_LX, pc.GUPTA_LY, n_layer, 1e-6, boundary=(3,))
+    return tensor_mesh([m.axes[0], m.axes[1]])

@@ -257,3 +257,46 @@ class FiniteSizeSolver(EchemSolver):
 
     def set_boundary_markers(self):
         self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,), "applied": (1, 2, 3, 4,)}
+
+
+GUPTA_SPECIES = [("CO2", 19.1e-10, 34.2, 0), ("HCO3", 9.23e-10, 499., -1), ("CO3", 11.9e-10, 7.6e-1, -2),
+                 ("OH", 52.7e-10, 3.3e-4, -1), ("K", 19.6e-10, 499. + 7.6e-1 + 3.3e-4, 1)]
+GUPTA_HOMOG = [{"stoichiometry": {"CO2": -1, "OH": -1, "HCO3": 1}, "forward rate constant": 5.93,
+                "backward rate constant": 1.34e-4},
+               {"stoichiometry": {"HCO3": -1, "OH": -1, "CO3": 1}, "forward rate constant": 1e5,
+                "backward rate constant": 2.15e4}]
+GUPTA_CURRENTS = [(0.1, {"CO2": -1, "OH": 1}, 2), (0.05, {"CO2": -1, "OH": 2}, 2), (0.25, {"CO2": -1, "OH": 8}, 8),
+                  (0.2, {"CO2": -2, "OH": 12}, 12), (0.4, {"OH": 2}, 2)]
+GUPTA_LX, GUPTA_LY = 1e-2, 1e-3
+
+
+class GuptaSolver(EchemSolver):
+    """examples/gupta_advection_migration.py:17-140 of the reference (BASELINE.json configs[2]) on a small mesh:
+    CG electroneutral Nernst-Planck, 5 species (K eliminated), two homogeneous reactions, constant-current
+    electrode fluxes on the active part of the wall, shear flow, inlet / outlet / bulk boundaries."""
+
+    def __init__(self, nx=6, ny=4, n_layer=3, SUPG=False):
+        from echemfem_b200 import RectangleBoundaryLayerMesh
+        Lx, Ly = GUPTA_LX, GUPTA_LY
+        mesh = RectangleBoundaryLayerMesh(nx, ny, Lx, Ly, n_layer, 1e-6, boundary=(3,))
+        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        active = conditional(And(x >= 1e-3, x < Lx - 1e-3), 1., 0.)
+        conc_params = [{"name": n, "diffusion coefficient": D, "bulk": b, "z": z} for n, D, b, z in GUPTA_SPECIES]
+        physical_params = {"flow": ["diffusion", "electroneutrality", "migration", "advection"],
+                           "F": 96485.3329, "R": 8.3144598, "T": 273.15 + 25.}
+
+        def current(cef):
+            def curr(u):
+                return cef * 50. * active
+            return curr
+        echem_params = [{"reaction": current(c), "stoichiometry": dict(st), "electrons": ne, "boundary": "electrode"}
+                        for c, st, ne in GUPTA_CURRENTS]
+        super().__init__(conc_params, physical_params, mesh, family="CG", echem_params=echem_params,
+                         homog_params=[dict(r) for r in GUPTA_HOMOG], SUPG=SUPG)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"inlet": (1,), "outlet": (2,), "bulk": (4,), "electrode": (3,)}
+
+    def set_velocity(self):
+        y = SpatialCoordinate(self.mesh)[1]
+        self.vel = as_vector([1.91 * y, Constant(0)])

@@ -156,3 +156,25 @@ def test_finite_size_mass_action_matches_oracle(kind):
         for f in range(4):
             a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
             assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("SUPG", [False, True])
+def test_gupta_cg_five_species_matches_oracle(SUPG):
+    """BASELINE configs[2] physics (examples/gupta_advection_migration.py) on a small boundary-layer mesh: CG,
+    K eliminated, two mass-action reactions, constant-current electrode fluxes, shear flow; with and without
+    SUPG (the north star's variant)."""
+    from oracle.assemble import Discretization
+    from echemfem_b200.newton import NewtonEngine
+    disc = Discretization(mms_cases.gupta_oracle_mesh(), mms_cases.gupta_problem(SUPG=SUPG))
+    s = product_cases.GuptaSolver(SUPG=SUPG)
+    x = disc.node_coords
+    ph = np.sin(7e2 * x[:, 0] + 3e3 * x[:, 1])
+    bulk = [b for _, _, b, _ in product_cases.GUPTA_SPECIES[:4]]
+    u = np.concatenate([b * (1.0 + 0.05 * ph * (1 + 0.1 * k)) for k, b in enumerate(bulk)] + [1e-3 * ph])
+    eng = _compare_raw(disc, s, u, "gupta SUPG=%s" % SUPG)
+    # per-field residual check (the global scale is set by the fast carbonate reaction)
+    F = eng.residual(s.u.tensor).cpu().numpy()
+    Fo = disc.residual(u)
+    Ns = disc.ndof_scalar
+    for f in range(5):
+        _assert_close(F[f * Ns:(f + 1) * Ns], Fo[f * Ns:(f + 1) * Ns], "gupta residual field %d" % f)
