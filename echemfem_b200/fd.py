@@ -63,7 +63,7 @@ def MeshHierarchy(mesh, refinement_levels, **kw):
     axes = [np.asarray(a, dtype=float) for a in mesh.axes]
     for _ in range(int(refinement_levels)):
         axes = [np.sort(np.concatenate([a, 0.5 * (a[1:] + a[:-1])])) for a in axes]
-        out.append(TensorMesh(axes, name=mesh.name, layers=mesh.layers))
+        out.append(TensorMesh(axes, name=mesh.name, layers=mesh.layers, marker_of_facet=mesh._marker_of_facet))
     return out
 
 

@@ -252,7 +252,30 @@ def ExtrudedMesh(base, layers, layer_height=None, **kw):
     else:
         axes = base.axes
     z = np.arange(layers + 1) * float(layer_height)
-    return TensorMesh(list(axes) + [z], name=base.name + "_extruded", layers=layers)
+    return TensorMesh(list(axes) + [z], name=base.name + "_extruded", layers=layers,
+                      marker_of_facet=_extruded_markers(base, float(z[0]), float(z[-1])))
+
+
+def _extruded_markers(base, z0, z1):
+    """Side facets of the extrusion carry the id of the base-mesh edge below them; bottom / top get 5 / 6."""
+    base_fn = base._marker_of_facet
+    if base_fn is None or base.dim != 2:
+        return None                                     # TensorMesh falls back to box ids
+    tol = 1e-12 * max(1.0, abs(z1 - z0))
+
+    def fn(fcoords, fverts):
+        out = np.zeros(fcoords.shape[0], dtype=np.int64)
+        zc = fcoords[:, :, 2]
+        flat = np.abs(zc - zc[:, :1]).max(axis=1) < tol
+        out[flat & (np.abs(zc[:, 0] - z0) < tol)] = 5
+        out[flat & (np.abs(zc[:, 0] - z1) < tol)] = 6
+        side = ~flat
+        if side.any():
+            # local facet vertices are lexicographic with z fastest: vertices 0 and 2 are the two base points
+            edge = fcoords[side][:, [0, 2], :2]
+            out[side] = base_fn(edge, None)
+        return out
+    return fn
 
 
 def _shape_derivs(d, xi):

@@ -59,7 +59,7 @@ def adm_problem(vavg, family="DG", p=1, D1=0.5, D2=1.0, variant="spectral", mark
                    vel=make_vel(vavg), variant=variant)
 
 
-def bortels_problem(U_app_factor=1.0):
+def bortels_problem(U_app_factor=1.0, hz=None):
     """examples/bortels_threeion_nondim.py for the oracle: Butler-Volmer electrodes as numpy closures."""
     from oracle.forms import Problem
     import product_cases
@@ -76,7 +76,10 @@ def bortels_problem(U_app_factor=1.0):
     def reaction(V):
         def r(u, x):
             eta = V - u[2]
-            return P["J0_hat"] * (np.exp(eta) - u[0] * np.exp(-eta))
+            shape = 1.0
+            if hz is not None:            # examples/bortels_threeion_extruded_3D_nondim.py: parabolic in z
+                shape = 3.0 / 5.0 * (2.0 - (x[..., 2] - 0.5 * hz) ** 2 / (0.5 * hz) ** 2)
+            return shape * P["J0_hat"] * (np.exp(eta) - u[0] * np.exp(-eta))
         return r
     echem_params = [
         {"reaction": reaction(0.0), "electrons": 2, "stoichiometry": {"Cu": 1}, "boundary": "cathode"},
@@ -86,7 +89,7 @@ def bortels_problem(U_app_factor=1.0):
     return Problem(conc_params, physical_params, markers, echem_params=echem_params, vel=make_vel(1.0))
 
 
-def bortels_oracle_mesh(n_in, n_el, n_out, n_y):
+def bortels_oracle_mesh(n_in, n_el, n_out, n_y, layers=None, hz=None):
     from oracle.mesh import tensor_mesh
     from echemfem_b200.meshes import bortels_axes, bortels_markers
     x, y = bortels_axes(n_in, n_el, n_out, n_y)
@@ -94,7 +97,18 @@ def bortels_oracle_mesh(n_in, n_el, n_out, n_y):
 
     def marker(xv):
         return int(fn(xv[None], None)[0])
-    return tensor_mesh([x, y], boundary_id_fn=marker)
+    if layers is None:
+        return tensor_mesh([x, y], boundary_id_fn=marker)
+    z = np.linspace(0.0, hz, layers + 1)
+
+    def marker3(xv):
+        """side facets: id of the plane edge below; bottom / top: 5 / 6 (never integrated)."""
+        zc = xv[:, 2]
+        if np.ptp(zc) < 1e-12:
+            return 5 if abs(zc[0]) < 1e-12 else 6
+        pts = np.unique(np.round(xv[:, :2], 14), axis=0)
+        return int(fn(pts[None], None)[0])
+    return tensor_mesh([x, y, z], boundary_id_fn=marker3)
 
 
 def supg_C1ex(x):

@@ -60,7 +60,7 @@ def bortels_parameters():
 class BortelsSolver(EchemSolver):
     """examples/bortels_threeion_nondim.py:24-135 of the reference (BASELINE.json configs[0])."""
 
-    def __init__(self, mesh, U_app_factor=1.0):
+    def __init__(self, mesh, U_app_factor=1.0, current_shape=1.0):
         P = bortels_parameters()
         conc_params = [
             {"name": "Cu", "diffusion coefficient": P["D_Cu_hat"], "z": 2., "bulk": 1., "C_ND": 1.},
@@ -76,7 +76,7 @@ class BortelsSolver(EchemSolver):
             C_b = conc_params[0]["bulk"]
             F, R, T = physical_params["F"], physical_params["R"], physical_params["T"]
             eta = V - U
-            return P["J0_hat"] * (exp(F / R / T * (eta)) - (C / C_b) * exp(-F / R / T * (eta)))
+            return current_shape * P["J0_hat"] * (exp(F / R / T * (eta)) - (C / C_b) * exp(-F / R / T * (eta)))
 
         def reaction_cathode(u):
             return reaction(u, Constant(0))
@@ -300,3 +300,18 @@ class GuptaSolver(EchemSolver):
     def set_velocity(self):
         y = SpatialCoordinate(self.mesh)[1]
         self.vel = as_vector([1.91 * y, Constant(0)])
+
+
+class Bortels3DSolver(BortelsSolver):
+    """examples/bortels_threeion_extruded_3D_nondim.py:74-222 of the reference (BASELINE.json configs[3]): the plane
+    channel extruded in z (DQ1 x DG1 hexes), exchange current density parabolic in z, side walls keep the ids of
+    the plane mesh, top and bottom are never integrated (solver.py:221-228)."""
+
+    def __init__(self, mesh, hz):
+        z = SpatialCoordinate(mesh)[2]
+        shape = 3.0 / 5.0 * (2 - (z - 0.5 * hz) ** 2 / (0.5 * hz) ** 2)
+        super().__init__(mesh, current_shape=shape)
+
+    def set_velocity(self):
+        y = SpatialCoordinate(self.mesh)[1]
+        self.vel = as_vector((6. * self.physical_params["v_avg"] * y * (1.0 - y), Constant(0.), Constant(0.)))

@@ -184,3 +184,36 @@ def test_bortels_newton_solution_matches_oracle():
     for f in range(3):
         a, b = u[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
         assert np.linalg.norm(a - b) <= 1e-8 * max(np.linalg.norm(b), 1e-3), "field %d" % f
+
+
+def test_bortels_3d_extruded_matches_oracle():
+    """BASELINE configs[3] physics (examples/bortels_threeion_extruded_3D_nondim.py): the graded plane channel
+    extruded into hexes, Butler-Volmer electrodes with a current density parabolic in z, ids of the plane mesh on
+    the side walls, top / bottom natural."""
+    from oracle.assemble import Discretization
+    from echemfem_b200.mesh import ExtrudedMesh
+    from echemfem_b200.meshes import BortelsMesh
+    from echemfem_b200.newton import NewtonEngine
+    n, layers, hz = (3, 4, 3, 3), 2, 6.0
+    disc = Discretization(mms_cases.bortels_oracle_mesh(*n, layers=layers, hz=hz), mms_cases.bortels_problem(hz=hz))
+    s = product_cases.Bortels3DSolver(ExtrudedMesh(BortelsMesh(*n), layers, hz / layers), hz)
+    eng = NewtonEngine(s)
+    assert eng.form.own_mask.sum() == 7
+    x = disc.node_coords
+    pert = 1e-2 * np.sin(3 * x[:, 0] + 5 * x[:, 1] + 0.7 * x[:, 2])
+    u = np.concatenate([1.0 + pert, 1.0 - 0.5 * pert, 0.1 + pert])
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+    indptr, indices = disc.pattern()
+    rp, ci, _ = eng.csr_host()
+    assert np.array_equal(rp, indptr) and np.array_equal(ci, indices)
+    for variant in (0, 1):
+        eng.set_variant(variant)
+        _assert_close(eng.residual(s.u.tensor).cpu().numpy(), disc.residual(u), "bortels 3D residual")
+        eng.jacobian(s.u.tensor)
+        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "bortels 3D jacobian")
+    eng.set_variant(0)
+    Ff = torch.zeros_like(s.u.tensor)
+    eng.vals.zero_()
+    eng.residual_jacobian(s.u.tensor, out=Ff)
+    _assert_close(Ff.cpu().numpy(), disc.residual(u), "bortels 3D fused residual")
+    _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "bortels 3D fused jacobian")
