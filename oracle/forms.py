@@ -126,7 +126,8 @@ class Problem:
         self.penalty_degree = p if p_penalty is None else p_penalty
         self.homog_params = list(homog_params)
         flow = {k: False for k in ("advection", "diffusion", "migration",
-                                   "electroneutrality", "poisson", "porous", "finite size",
+                                   "electroneutrality", "electroneutrality full", "poisson", "porous",
+                                   "finite size",
                                    "diffusion finite size_BK", "diffusion finite size_CS",
                                    "diffusion finite size_SP", "diffusion finite size_SMPNP",
                                    "diffusion finite size_BMCSL")}
@@ -137,10 +138,13 @@ class Problem:
         # solver.py:115-126
         if (not flow["migration"]) and flow["electroneutrality"]:
             raise NotImplementedError('Electroneutrality constraint requires Migration')
-        if flow["migration"] and not (flow["electroneutrality"] or flow["poisson"]):
+        if flow["migration"] and not (flow["electroneutrality"] or flow["poisson"] or flow["electroneutrality full"]):
             raise NotImplementedError('Migration requires Electroneutrality or Poisson')
-        if flow["poisson"] and flow["electroneutrality"]:
+        if flow["poisson"] and (flow["electroneutrality"] or flow["electroneutrality full"]):
             raise NotImplementedError('Electroneutrality not compatible with Poisson')
+        if flow["electroneutrality full"] and family == "DG":
+            raise NotImplementedError("oracle: 'electroneutrality full' is a CG-only option (solver.py:2018)")
+        self.Sw = self.physical_params.get("saturation", 1.0)             # solver.py:365-367 (no two-phase flow here)
         if family == "DG" and any(v for k, v in flow.items() if "finite size" in k):       # solver.py:139-142
             raise NotImplementedError('finite size effects only implemented with CG')
         self.flow = flow
@@ -156,7 +160,7 @@ class Problem:
             self.idx_c.remove(self.i_el)
         self.num_liquid = len(self.idx_c)
         self.num_mass = self.num_liquid
-        self.has_potential = flow["electroneutrality"] or flow["poisson"]
+        self.has_potential = flow["electroneutrality"] or flow["poisson"] or flow["electroneutrality full"]
         self.num_fields = self.num_mass + (1 if self.has_potential else 0)
         self.i_Ul = self.num_mass if self.has_potential else None
         self.i_Us = None
@@ -165,6 +169,14 @@ class Problem:
             self.num_fields += 1
         for i, k in enumerate(self.idx_c):
             self.conc_params[k]["i_c"] = i
+        # equation (test function) that receives the mass balance of kept species i: with the explicit
+        # electroneutrality constraint the LAST species is tested with the potential's test function and the
+        # constraint with the last species' one, so that no diagonal block is zero (solver.py:411-414, 455-457)
+        self.row = list(range(self.num_liquid))
+        self.row_constraint = None
+        if flow["electroneutrality full"]:
+            self.row[self.num_liquid - 1] = self.num_liquid
+            self.row_constraint = self.num_liquid - 1
 
     # -- helpers ----------------------------------------------------------
     def penalty(self, geo):
@@ -199,11 +211,11 @@ class Problem:
         return list(u)
 
     def effective(self, D, phase="liquid"):
-        """Bruggeman correlation (solver.py:1276-1286); saturation 1 (no gas phase in the oracle)."""
+        """Bruggeman correlation (solver.py:1276-1286)."""
         if not self.flow["porous"]:
             return D
         eps = self.physical_params["porosity"]
-        frac = {"solid": 1.0 - eps, "liquid": eps}[phase]
+        frac = {"solid": 1.0 - eps, "liquid": eps * self.Sw}[phase]
         return D * frac ** 1.5
 
     def Dk(self, k):
@@ -289,7 +301,7 @@ class Problem:
                     c_ref = rxn["reference concentration"] if rxn.get("reference concentration") else 1.0
                     out[k] = out[k] + rxn["stoichiometry"][name] * c_ref * r
         if self.flow["porous"]:
-            out = [self.physical_params["porosity"] * r for r in out]       # saturation 1
+            out = [self.physical_params["porosity"] * self.Sw * r for r in out]
         return out
 
     def excess_potential(self, cp, u, gu):
@@ -347,6 +359,7 @@ class Problem:
         for i, k in enumerate(self.idx_c):
             cp = self.conc_params[k]
             D = self.Dk(k)
+            r = self.row[i]
             if self.flow["diffusion"] and self.flow["finite size"]:         # :1543-1552
                 NA = pp["Avogadro constant"]
                 den, num = 1.0, 0.0
@@ -355,29 +368,47 @@ class Problem:
                     if aj is not None and aj != 0.0:
                         den = den - NA * aj ** 3 * u[j]
                         num = num + NA * aj ** 3 * gu[j]
-                f1[i] = f1[i] + (D * C[k] / den)[..., None] * num
+                f1[r] = f1[r] + (D * C[k] / den)[..., None] * num
             mu_ex = self.excess_potential(cp, u, gu)
             if mu_ex is not None:                                           # :1554-1636  D C grad(ln C + mu_ex)
-                f1[i] = f1[i] + D * gC[k] + (D * C[k])[..., None] * mu_ex.g
+                f1[r] = f1[r] + D * gC[k] + (D * C[k])[..., None] * mu_ex.g
             rterm = None
             if reactions is not None and not _is_zero(reactions[i]):
                 # solver.py:1497-1500  (note: indexed by i_c)
                 rterm = reactions[i]
-                f0[i] = f0[i] - rterm
+                f0[r] = f0[r] - rterm
             if self.flow["diffusion"]:
-                f1[i] = f1[i] + D * gC[k]                                   # :1515
+                f1[r] = f1[r] + D * gC[k]                                   # :1515
             fl = self.flow_vector(k, x, gU)
             if fl is not None:
-                f1[i] = f1[i] - C[k][..., None] * fl                        # :1649
+                f1[r] = f1[r] - C[k][..., None] * fl                        # :1649
                 if self.family != "DG" and self.SUPG:                       # :1655-1668
                     hk = np.sqrt(2.0) * geo["cell_volume"] / geo["cell_diameter"]
                     u_norm = _dot(fl, fl) ** 0.5
                     Pe = hk / 2.0 * u_norm / D
                     Pe_f = np.where(np.real(Pe) > 1, 1.0 - 1.0 / Pe, 0.0)
                     delta_k = hk / 2.0 / u_norm * Pe_f
-                    f1[i] = f1[i] + (delta_k * _dot(fl, gC[k]))[..., None] * fl
+                    f1[r] = f1[r] + (delta_k * _dot(fl, gC[k]))[..., None] * fl
                     if rterm is not None:
-                        f1[i] = f1[i] - (rterm * delta_k)[..., None] * fl
+                        f1[r] = f1[r] - (rterm * delta_k)[..., None] * fl
+            if self.flow["porous"]:                                         # volumetric Butler-Volmer, :1719-1726
+                av = pp["specific surface area"] * self.Sw
+                for echem in self.echem_params:
+                    if cp["name"] in echem["stoichiometry"]:
+                        nu = echem["stoichiometry"][cp["name"]]
+                        f0[r] = f0[r] - av * nu / echem["electrons"] / pp["F"] * echem["reaction"](self.reaction_u(u), x)
+        if self.flow["electroneutrality full"]:                             # :2015-2031, tested with v[num_liquid-1]
+            rc = self.row_constraint
+            for k in range(self.num_c):
+                z = self.conc_params[k].get("z")
+                if z != 0:
+                    f0[rc] = f0[rc] + z * u[k]
+        if self.i_Us is not None and self.echem_params:                     # solid Poisson source, :2162-2163
+            av = pp["specific surface area"] * self.Sw
+            for echem in self.echem_params:
+                f0[self.i_Us] = f0[self.i_Us] + av * echem["reaction"](self.reaction_u(u), x)
+        if self.flow["electroneutrality full"] and self.i_Us is not None:   # solid conduction, :2171
+            f1[self.i_Us] = f1[self.i_Us] + self.solid_KU() * gu[self.i_Us]
         if self.flow["electroneutrality"]:
             iU = self.i_Ul
             for k in self.idx_c + [self.i_el]:
@@ -391,6 +422,12 @@ class Problem:
                     f1[iU] = f1[iU] + zDF * gC[k]                           # :1924
                 if reactions is not None and not _is_zero(reactions[k]):
                     f0[iU] = f0[iU] - nd * z * pp["F"] * reactions[k]       # :1946
+                if self.flow["porous"]:                                     # :1963-1969
+                    av = pp["specific surface area"] * self.Sw
+                    for echem in self.echem_params:
+                        if cp["name"] in echem["stoichiometry"]:
+                            nu = echem["stoichiometry"][cp["name"]]
+                            f0[iU] = f0[iU] - nd * av * z * nu / echem["electrons"] * echem["reaction"](self.reaction_u(u), x)
             K_U = self.conductivity(C)
             f1[iU] = f1[iU] + _bc(K_U)[..., None] * gU                      # :1978
             if self.i_Us is not None:                                       # solid Poisson, :2162-2186
@@ -540,35 +577,36 @@ class Problem:
         for i, k in enumerate(self.idx_c):
             cp = self.conc_params[k]
             D = self.Dk(k)
+            r = self.row[i]
             C_0 = _evalf(cp.get("bulk"), x) if cp.get("bulk") is not None else None
             if self.flow["diffusion"]:
                 if on("bulk dirichlet") and DG:
-                    nitsche(i, D, C[k], gC[k], C_0, D_IP)                   # :1523-1529
+                    nitsche(r, D, C[k], gC[k], C_0, D_IP)                   # :1523-1529
                 if on("gas") and cp.get("gas") is not None and DG:
-                    nitsche(i, D, C[k], gC[k], _evalf(cp["gas"], x), D_IP)  # :1533-1538
+                    nitsche(r, D, C[k], gC[k], _evalf(cp["gas"], x), D_IP)  # :1533-1538
             fl = self.flow_vector(k, x, gU)
             if fl is not None:
                 if applied_ids is not None and marker in applied_ids:       # :1681-1685
                     fn = _dot(fl, n)
-                    f0[i] = f0[i] + _neg(fn) * fn * C_0 + _pos(fn) * fn * C[k]
+                    f0[r] = f0[r] + _neg(fn) * fn * C_0 + _pos(fn) * fn * C[k]
                 if bm.get("inlet") is not None:                             # :1687-1693
                     ids = set(bm["inlet"]) - set(applied_ids or ())
                     if marker in ids and not _is_zero(cp.get("bulk")):
                         vn = _dot(self.vel(x), n)
-                        f0[i] = f0[i] + _neg(vn) * vn * C_0
+                        f0[r] = f0[r] + _neg(vn) * vn * C_0
                 if bm.get("outlet") is not None:                            # :1695-1700
                     ids = set(bm["outlet"]) - set(applied_ids or ())
                     if marker in ids:
                         vn = _dot(self.vel(x), n)
-                        f0[i] = f0[i] + _pos(vn) * vn * C[k]
+                        f0[r] = f0[r] + _pos(vn) * vn * C[k]
             if on("bulk") and cp.get("mass transfer coefficient") is not None:
-                f0[i] = f0[i] - cp["mass transfer coefficient"] * (C_0 - C[k])  # :1703-1706
-            for echem in self.echem_params:                                 # :1710-1717
+                f0[r] = f0[r] - cp["mass transfer coefficient"] * (C_0 - C[k])  # :1703-1706
+            for echem in ([] if self.flow["porous"] else self.echem_params):   # :1710-1717 (surface reactions)
                 if marker in bm.get(echem["boundary"], ()) and cp["name"] in echem["stoichiometry"]:
                     nu = echem["stoichiometry"][cp["name"]]
-                    f0[i] = f0[i] - nu / echem["electrons"] / pp["F"] * echem["reaction"](ru, x)
+                    f0[r] = f0[r] - nu / echem["electrons"] / pp["F"] * echem["reaction"](ru, x)
             if on("neumann"):                                               # :1729-1731
-                f0[i] = f0[i] - self.neumann(C[k], cp, ru, x)
+                f0[r] = f0[r] - self.neumann(C[k], cp, ru, x)
 
         if self.flow["electroneutrality"]:
             iU = self.i_Ul
@@ -587,7 +625,7 @@ class Problem:
                         nitsche(iU, zDF, C[k], gC[k], _evalf(cp["gas"], x), None)
                 if on("bulk") and cp.get("mass transfer coefficient") is not None:
                     f0[iU] = f0[iU] - nd * z * pp["F"] * cp["mass transfer coefficient"] * (C_0 - C[k])
-                for echem in self.echem_params:                             # :1955-1962
+                for echem in ([] if self.flow["porous"] else self.echem_params):   # :1955-1962
                     if marker in bm.get(echem["boundary"], ()) and cp["name"] in echem["stoichiometry"]:
                         nu = echem["stoichiometry"][cp["name"]]
                         f0[iU] = f0[iU] - nd * z * nu / echem["electrons"] * echem["reaction"](ru, x)
@@ -668,6 +706,18 @@ class Problem:
                 out.append((self.i_Ul, bm["applied"], ("U_app",)))
             elif bm.get("bulk") is not None:
                 out.append((self.i_Ul, bm["bulk"], ("zero",)))
+        elif self.flow["electroneutrality full"]:                           # :2033-2044
+            is_applied = (bm.get("applied") is not None and not self.flow["porous"]) or \
+                bm.get("liquid applied") is not None
+            if is_applied:
+                out.append((self.i_Ul, bm["applied"], ("U_app",)))
+            elif bm.get("bulk") is not None:
+                out.append((self.i_Ul, bm["bulk"], ("zero",)))
+            if self.i_Us is not None:                                       # :2188-2212, solid
+                if bm.get("applied") is not None:
+                    out.append((self.i_Us, bm["applied"], ("U_app",)))
+                elif bm.get("inlet") is not None:
+                    out.append((self.i_Us, bm["inlet"], ("U_app",)))
         return out
 
 

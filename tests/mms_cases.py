@@ -266,3 +266,36 @@ def gupta_oracle_mesh(nx=6, ny=4, n_layer=3):
     import product_cases as pc
     m = RectangleBoundaryLayerMesh(nx, ny, pc.GUPTA_LX, pc.GUPTA_LY, n_layer, 1e-6, boundary=(3,))
     return tensor_mesh([m.axes[0], m.axes[1]])
+
+
+def catalyst_layer_problem(p=1):
+    """Oracle twin of product_cases.CatalystLayerSolver."""
+    from oracle.forms import Problem
+    import product_cases as pc
+    P, K = pc.CL_PARAMS, pc.CL_RATES
+    epsS = P["porosity"] * P["saturation"]
+
+    def bulk_reaction(y, x):
+        CO2, OH, H, CO3, HCO3 = y[0], y[1], y[2], y[3], y[4]
+        r1 = K["k1f"] * CO2 * OH - K["k1b"] * HCO3
+        r2 = K["k2f"] * HCO3 * OH - K["k2b"] * CO3
+        rw = K["kwf"] - K["kwb"] * H * OH
+        return [epsS * (-r1), epsS * (-r1 - r2 + rw), epsS * rw, epsS * r2, epsS * (r1 - r2), 0.0]
+
+    def tafel(i0, alpha, U0):
+        def r(u, x):
+            eta = u[7] - u[6] - (U0 + np.log(u[2] / 0.2))
+            return -i0 * np.exp(-alpha * eta)
+        return r
+    conc_params = []
+    for n, D, z, b, kmt, gas in pc.CL_SPECIES:
+        cp = {"name": n, "diffusion coefficient": D, "z": z, "bulk": b, "mass transfer coefficient": kmt}
+        if gas is not None:
+            cp["gas"] = gas
+        conc_params.append(cp)
+    physical_params = dict(P, flow=["diffusion", "migration", "electroneutrality full", "porous"], U_app=-0.3)
+    physical_params["bulk reaction"] = bulk_reaction
+    echem_params = [{"reaction": tafel(i0, al, U0), "electrons": ne, "stoichiometry": dict(nu)}
+                    for i0, al, U0, nu, ne in pc.CL_ECHEM]
+    markers = {"applied": (2,), "gas": (2,), "bulk": (1,)}
+    return Problem(conc_params, physical_params, markers, echem_params=echem_params, family="CG", p=p)

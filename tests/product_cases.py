@@ -315,3 +315,52 @@ class Bortels3DSolver(BortelsSolver):
     def set_velocity(self):
         y = SpatialCoordinate(self.mesh)[1]
         self.vel = as_vector((6. * self.physical_params["v_avg"] * y * (1.0 - y), Constant(0.), Constant(0.)))
+
+
+CL_SPECIES = [("CO2", 1.9, 0.0, 0.9, 1.3, 1.1), ("OH", 5.3, -1.0, 0.4, 0.8, None), ("H", 9.3, 1.0, 0.2, 1.7, None),
+              ("CO3", 0.9, -2.0, 0.3, 0.6, None), ("HCO3", 1.2, -1.0, 0.8, 0.9, None),
+              ("K", 2.0, 1.0, 1.6, 1.1, None)]          # name, D, z, bulk, mass transfer coefficient, gas value
+CL_PARAMS = {"F": 1.0, "R": 1.0, "T": 1.0, "porosity": 0.6, "saturation": 0.64, "specific surface area": 1.5,
+             "solid conductivity": 2.2}
+CL_RATES = {"k1f": 0.7, "k1b": 0.2, "k2f": 1.1, "k2b": 0.4, "kwf": 0.05, "kwb": 0.9}
+CL_ECHEM = [(0.02, 0.5, 0.11, {"CO2": 1, "OH": -6}, 6), (0.03, 0.4, -0.05, {"OH": -2}, 2)]   # i0, alpha, U0, nu, n
+
+
+class CatalystLayerSolver(EchemSolver):
+    """examples/catalyst_layer_Cu_full.py:20-256 of the reference (BASELINE.json configs[4]) with O(1) numbers on
+    a 2D strip: porous electrode, six species with the explicit electroneutrality constraint ("electroneutrality
+    full": shifted test functions, solver.py:411-414, 455-461), liquid + solid potential, homogeneous carbonate
+    reactions, volumetric Tafel kinetics depending on c_H and both potentials, gas-side Dirichlet value of CO2,
+    Robin exchange with the bulk electrolyte."""
+
+    def __init__(self, N, p=1):
+        mesh = RectangleMesh(N, max(N // 2, 1), 1.0, 0.5, quadrilateral=True)
+        P, K = CL_PARAMS, CL_RATES
+        epsS = P["porosity"] * P["saturation"]
+
+        def bulk_reaction(y):
+            CO2, OH, H, CO3, HCO3 = y[0], y[1], y[2], y[3], y[4]
+            r1 = K["k1f"] * CO2 * OH - K["k1b"] * HCO3
+            r2 = K["k2f"] * HCO3 * OH - K["k2b"] * CO3
+            rw = K["kwf"] - K["kwb"] * H * OH
+            return [epsS * (-r1), epsS * (-r1 - r2 + rw), epsS * rw, epsS * r2, epsS * (r1 - r2), 0.]
+
+        def tafel(i0, alpha, U0):
+            def r(u):
+                eta = u[7] - u[6] - (U0 + P["R"] * P["T"] / P["F"] * ln(u[2] / 0.2))
+                return -i0 * exp(-alpha * P["F"] / (P["R"] * P["T"]) * eta)
+            return r
+        conc_params = []
+        for n, D, z, b, kmt, gas in CL_SPECIES:
+            cp = {"name": n, "diffusion coefficient": D, "z": z, "bulk": b, "mass transfer coefficient": kmt}
+            if gas is not None:
+                cp["gas"] = gas
+            conc_params.append(cp)
+        physical_params = dict(P, flow=["diffusion", "migration", "electroneutrality full", "porous"], U_app=-0.3)
+        physical_params["bulk reaction"] = bulk_reaction
+        echem_params = [{"reaction": tafel(i0, al, U0), "electrons": ne, "stoichiometry": dict(nu)}
+                        for i0, al, U0, nu, ne in CL_ECHEM]
+        super().__init__(conc_params, physical_params, mesh, echem_params=echem_params, family="CG", p=p)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"applied": (2,), "gas": (2,), "bulk": (1,)}

@@ -178,3 +178,33 @@ def test_gupta_cg_five_species_matches_oracle(SUPG):
     Ns = disc.ndof_scalar
     for f in range(5):
         _assert_close(F[f * Ns:(f + 1) * Ns], Fo[f * Ns:(f + 1) * Ns], "gupta residual field %d" % f)
+
+
+@pytest.mark.parametrize("p", [1, 2])
+def test_catalyst_layer_full_electroneutrality_matches_oracle(p):
+    """BASELINE configs[4] physics (examples/catalyst_layer_Cu_full.py): porous electrode, six species + explicit
+    electroneutrality constraint with shifted test functions, liquid + solid potential, volumetric Tafel kinetics,
+    gas-side Dirichlet value, Robin exchange with the bulk; CG Q1 and Q2 (the example uses p = 2)."""
+    from oracle.mesh import tensor_mesh
+    from oracle.assemble import Discretization
+    from oracle.newton import solve_problem
+    N = 4
+    mesh = tensor_mesh([np.linspace(0.0, 1.0, N + 1), np.linspace(0.0, 0.5, N // 2 + 1)])
+    disc = Discretization(mesh, mms_cases.catalyst_layer_problem(p))
+    s = product_cases.CatalystLayerSolver(N, p=p)
+    x = disc.node_coords
+    ph = np.sin(5 * x[:, 0] + 3 * x[:, 1])
+    bulk = [b for _, _, _, b, _, _ in product_cases.CL_SPECIES]
+    u = np.concatenate([b * (1.0 + 0.05 * ph * (1 + 0.1 * k)) for k, b in enumerate(bulk)] +
+                       [-0.02 * (1 + ph), -0.3 + 0.02 * ph])
+    _compare_raw(disc, s, u, "catalyst layer p=%d" % p)
+    if p == 1:
+        u_ref, info = solve_problem(disc)
+        s2 = product_cases.CatalystLayerSolver(N, p=p)
+        s2.setup_solver(initial_solve=False)
+        s2.solve()
+        un = s2.u.numpy()
+        Ns = disc.ndof_scalar
+        for f in range(8):
+            a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
+            assert np.linalg.norm(a - b) <= 1e-8 * max(np.linalg.norm(b), 1e-2), "field %d" % f
