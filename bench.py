@@ -137,6 +137,38 @@ def cpu_baseline(sample_n, reps=1):
     return disc.ndof / best / 1e6, best, disc.ndof
 
 
+def _cpu_worker(sample_n):
+    v, t, nd = cpu_baseline(sample_n)
+    return t, nd
+
+
+def cpu_baseline_parallel(sample_n, procs, pool=None):
+    """The oracle on `procs` host cores at once, one process per core, each assembling its own sample mesh (the
+    path shards by cells with no exchange during assembly, as `mpiexec -n procs` would run the reference).
+    Returns (aggregate MDOF/s, wall seconds of the slowest worker, dofs per worker)."""
+    import multiprocessing as mp
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(procs)
+    try:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [sample_n] * procs)
+        wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    nd = res[0][1]
+    return procs * nd / wall / 1e6, wall, nd
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def newton_step(n, deg, tile):
     """Newton-step wall time (BASELINE metric, second half): setup_solver() + solve() of the same MMS problem on an
     n x n mesh with the reference's default option set ('lu': served by GMRES + block-Jacobi/ILU(0) + coarse
@@ -167,24 +199,33 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.sample_n
+    # bounded sample per step: K steps of `procs` concurrent 48 x 48 meshes end within a few minutes
+    n = args.sample_n if args.sample_n != 96 else 48
+    procs = args.cpu_procs or host_cores()
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    pool = mp.get_context("fork").Pool(procs)
     vals = []
     for _ in range(args.warmup):
-        cpu_baseline(n)
+        cpu_baseline_parallel(n, procs, pool)
     t0 = time.perf_counter()
     ndof = 0
     for _ in range(args.steps):
-        v, t, ndof = cpu_baseline(n)
+        v, t, nd = cpu_baseline_parallel(n, procs, pool)
+        ndof = nd * procs
         vals.append(t)
     total = time.perf_counter() - t0
+    pool.close()
+    pool.join()
     value = ndof * args.steps / sum(vals) / 1e6
-    sample = "UnitSquareMesh(%d,%d) DG Q1, %d dofs per step (numpy oracle, complex-step Jacobian)" % (n, n, ndof)
+    sample = ("%d processes x UnitSquareMesh(%d,%d) DG Q1 = %d dofs per step (numpy oracle, complex-step Jacobian)"
+              % (procs, n, n, ndof))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(vals) / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg2 MMS 2D DG Q1 electroneutral Nernst-Planck (bounded CPU sample)",
                        "sample_N": n},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": total}
     print(json.dumps(line))
@@ -200,6 +241,8 @@ def main():
     ap.add_argument("--degree", type=int, default=1, help="polynomial degree (the headline number is Q1)")
     ap.add_argument("--sample-n", dest="sample_n", type=int, default=96, help="CPU baseline sample mesh")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-procs", dest="cpu_procs", type=int, default=0, help="processes of the CPU baseline "
+                                                                               "(default: every core of the host)")
     ap.add_argument("--tile", type=int, default=0, help="number the cells tile by tile (T x T cells) instead of "
                                                         "lexicographically")
     ap.add_argument("--extras", action="store_true", help="also time SpMV and one full Newton solve")
@@ -378,10 +421,12 @@ def main():
         if extras.get("spmv_ms"):
             line["spmv_GBs"] = BS / (extras["spmv_ms"] * 1e-3) / 1e9
         if not args.no_cpu:
-            v, t, nd = cpu_baseline(args.sample_n)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "UnitSquareMesh(%d,%d) DG Q1, %d dofs, one residual + one Jacobian "
-                                              "(numpy oracle, complex-step Jacobian), %.1f s" % (args.sample_n, args.sample_n, nd, t)}
+            procs = args.cpu_procs or host_cores()
+            v, t, nd = cpu_baseline_parallel(args.sample_n, procs)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                                    "sample": "%d processes x UnitSquareMesh(%d,%d) DG Q1 (%d dofs each), one residual + "
+                                              "one Jacobian (numpy oracle, complex-step Jacobian), %.1f s"
+                                              % (procs, args.sample_n, args.sample_n, nd, t)}
         print(json.dumps(line), file=real_stdout, flush=True)
     if dist is not None:
         dist.destroy_process_group()
