@@ -249,6 +249,18 @@ extern "C" int ech_pattern_colidx(ech_handle *h, const int64_t *rowptr, int32_t 
 }
 
 // =============================================================== cell geometry
+// intervals: length, unit "area" of the two end points, diameter = length
+__global__ void cell_geometry_1d_kernel(int64_t ncell, const double *__restrict__ xcell, double *__restrict__ vol,
+                                        double *__restrict__ area, double *__restrict__ diam) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const double h = fabs(xcell[2 * c + 1] - xcell[2 * c]);
+    vol[c] = h;
+    diam[c] = h;
+    area[2 * c] = 1.0;
+    area[2 * c + 1] = 1.0;
+}
+
 // CellVolume / FacetArea / CellDiameter of multilinear cells: 3-point Gauss per
 // direction (exact for multilinear maps with planar facets), largest vertex distance.
 template <int D>
@@ -348,12 +360,14 @@ extern "C" int ech_cell_geometry(int32_t dim, int64_t ncell, const double *xcell
     if (ncell == 0) return ECH_OK;
     const int block = 128;
     const unsigned grid = (unsigned)((ncell + block - 1) / block);
-    if (dim == 2)
+    if (dim == 1)
+        cell_geometry_1d_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(ncell, xcell, vol, area, diam);
+    else if (dim == 2)
         cell_geometry_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(ncell, xcell, vol, area, diam);
     else if (dim == 3)
         cell_geometry_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(ncell, xcell, vol, area, diam);
     else
-        return fail(nullptr, ECH_ERR_ARG, "ech_cell_geometry: dim must be 2 or 3");
+        return fail(nullptr, ECH_ERR_ARG, "ech_cell_geometry: dim must be 1, 2 or 3");
     ++g_launches;
     CK(nullptr, cudaGetLastError());
     return ECH_OK;

@@ -96,7 +96,10 @@ __device__ __forceinline__ void geometry(const double (&X)[NV][D], const int (&i
             for (int m = 0; m < D; ++m) J[a][m] += dN[m] * X[v][a];
         }
     }
-    if constexpr (D == 2) {
+    if constexpr (D == 1) {
+        g.detJ = J[0][0];
+        g.invJ[0][0] = 1.0 / J[0][0];
+    } else if constexpr (D == 2) {
         const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
         const double r = 1.0 / det;
         g.detJ = det;

@@ -299,3 +299,22 @@ def catalyst_layer_problem(p=1):
                     for i0, al, U0, nu, ne in pc.CL_ECHEM]
     markers = {"applied": (2,), "gas": (2,), "bulk": (1,)}
     return Problem(conc_params, physical_params, markers, echem_params=echem_params, family="CG", p=p)
+
+
+def bmcsl_1d_problem(p=2, sigma=-0.3):
+    """Oracle twin of product_cases.BMCSL1DSolver."""
+    from oracle.forms import Problem
+    conc_params = [{"name": "Cl", "diffusion coefficient": 2.0, "bulk": 1.0, "z": -1, "solvated diameter": 0.0},
+                   {"name": "Li", "diffusion coefficient": 1.0, "bulk": 0.9, "z": 1, "solvated diameter": 0.76},
+                   {"name": "Cs", "diffusion coefficient": 2.0, "bulk": 0.1, "z": 1, "solvated diameter": 0.66}]
+    physical_params = {"flow": ["migration", "poisson", "diffusion finite size_BMCSL"], "F": 1.0, "R": 1.0, "T": 1.0,
+                       "U_app": 0.0, "vacuum permittivity": 0.05, "relative permittivity": 1.0,
+                       "Avogadro constant": 0.2, "surface charge density": sigma}
+    markers = {"bulk dirichlet": (1,), "applied": (1,), "poisson neumann": (2,)}
+    return Problem(conc_params, physical_params, markers, family="CG", p=p)
+
+
+def bmcsl_1d_oracle_mesh():
+    from oracle.mesh import tensor_mesh
+    from echemfem_b200.meshes import IntervalBoundaryLayerMesh
+    return tensor_mesh([IntervalBoundaryLayerMesh(6, 1.0, 4, 0.1, boundary=(2,)).axes[0]])

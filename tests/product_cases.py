@@ -364,3 +364,23 @@ class CatalystLayerSolver(EchemSolver):
 
     def set_boundary_markers(self):
         self.boundary_markers = {"applied": (2,), "gas": (2,), "bulk": (1,)}
+
+
+class BMCSL1DSolver(EchemSolver):
+    """examples/BMCSL.py:33-84 of the reference with O(1) numbers: 1D Poisson-Nernst-Planck with the BMCSL
+    finite-size correction on an interval with a boundary layer at the charged wall (CG P2): Dirichlet bulk /
+    zero potential on the left, surface charge density (Poisson Neumann) on the right."""
+
+    def __init__(self, p=2, sigma=-0.3):
+        from echemfem_b200 import IntervalBoundaryLayerMesh
+        mesh = IntervalBoundaryLayerMesh(6, 1.0, 4, 0.1, boundary=(2,))
+        conc_params = [{"name": "Cl", "diffusion coefficient": 2.0, "bulk": 1.0, "z": -1, "solvated diameter": 0.0},
+                       {"name": "Li", "diffusion coefficient": 1.0, "bulk": 0.9, "z": 1, "solvated diameter": 0.76},
+                       {"name": "Cs", "diffusion coefficient": 2.0, "bulk": 0.1, "z": 1, "solvated diameter": 0.66}]
+        physical_params = {"flow": ["migration", "poisson", "diffusion finite size_BMCSL"], "F": 1.0, "R": 1.0,
+                           "T": 1.0, "U_app": Constant(0.0), "vacuum permittivity": 0.05, "relative permittivity": 1.0,
+                           "Avogadro constant": 0.2, "surface charge density": Constant(sigma)}
+        super().__init__(conc_params, physical_params, mesh, family="CG", p=p)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk dirichlet": (1,), "applied": (1,), "poisson neumann": (2,)}

@@ -208,3 +208,24 @@ def test_catalyst_layer_full_electroneutrality_matches_oracle(p):
         for f in range(8):
             a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
             assert np.linalg.norm(a - b) <= 1e-8 * max(np.linalg.norm(b), 1e-2), "field %d" % f
+
+
+def test_bmcsl_1d_interval_matches_oracle():
+    """examples/BMCSL.py physics in 1D (d = 1 kernels): CG P2 on an interval with a boundary layer at the charged
+    wall; assembly entries and the converged Newton solution."""
+    from oracle.assemble import Discretization
+    from oracle.newton import solve_problem
+    disc = Discretization(mms_cases.bmcsl_1d_oracle_mesh(), mms_cases.bmcsl_1d_problem())
+    s = product_cases.BMCSL1DSolver()
+    x = disc.node_coords[:, 0]
+    u = np.concatenate([1.0 + 0.05 * np.sin(3 * x), 0.9 - 0.04 * np.sin(2 * x), 0.1 + 0.01 * np.cos(4 * x), 0.2 * x * x + 0.1 * x])        # U'(0) != 0: off the kink of conditional(flow.n)
+    _compare_raw(disc, s, u, "BMCSL 1D")
+    u_ref, info = solve_problem(disc)
+    s2 = product_cases.BMCSL1DSolver()
+    s2.setup_solver()
+    s2.solve()
+    un = s2.u.numpy()
+    Ns = disc.ndof_scalar
+    for f in range(4):
+        a, b = un[f * Ns:(f + 1) * Ns], u_ref[f * Ns:(f + 1) * Ns]
+        assert np.linalg.norm(a - b) <= 1e-8 * max(np.linalg.norm(b), 1e-2), "field %d" % f
