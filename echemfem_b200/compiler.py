@@ -116,7 +116,24 @@ class PointFunction:
         tmp = {s for s, _ in repl}
         for s in sorted(used - tmp, key=str):
             lines.append("%sconst double %s = %s;" % (indent, s, _bind(str(s), const_index)))
+        # sin and cos of the same argument (manufactured solutions, rotating fields) share one sincos() call
+        by_arg = {}
         for s, e in repl:
+            if isinstance(e, (sp.sin, sp.cos)):
+                by_arg.setdefault(e.args[0], {})[type(e)] = s
+        paired = {}
+        for arg, d in by_arg.items():
+            if sp.sin in d and sp.cos in d:
+                first = d[sp.sin] if [x for x, _ in repl].index(d[sp.sin]) < [x for x, _ in repl].index(d[sp.cos]) \
+                    else d[sp.cos]
+                paired[d[sp.sin]] = paired[d[sp.cos]] = (first, d[sp.sin], d[sp.cos], arg)
+        for s, e in repl:
+            if s in paired:
+                first, ss, sc, arg = paired[s]
+                if s == first:
+                    lines.append("%sdouble %s, %s;" % (indent, ss, sc))
+                    lines.append("%ssincos(%s, &%s, &%s);" % (indent, _ccode(arg), ss, sc))
+                continue
             lines.append("%sconst double %s = %s;" % (indent, s, _ccode(e)))
         for (t, _), e in zip(self.outputs, red):
             lines.append("%s%s = %s;" % (indent, t, _ccode(e)))
