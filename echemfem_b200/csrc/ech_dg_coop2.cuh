@@ -690,8 +690,13 @@ constexpr bool any_straddle() {
 constexpr bool STRADDLE = any_straddle();
 
 // ---------------------------------------------------------------- the kernel
+#ifdef ECH_MAXNREG
+#define ECH_COOP2_BOUNDS __maxnreg__(ECH_MAXNREG)
+#else
+#define ECH_COOP2_BOUNDS __launch_bounds__(J2WARPS * 32, ECH_JMINB)
+#endif
 template <bool WITH_RES>
-__global__ void __launch_bounds__(J2WARPS * 32, ECH_JMINB) jacobian_coop2_kernel(const ech_dg_args A, int64_t nbatch) {
+__global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int64_t nbatch) {
     using RC = Rec<WITH_RES>;
     constexpr int RECLEN = Rec<true>::LEN;       // one shared-memory geometry for both instantiations
     extern __shared__ double smem[];
