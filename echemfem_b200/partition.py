@@ -110,16 +110,64 @@ def _halo_plan(local, owner_of_ext_nbr, rank, size):
     return HaloPlan(rank, size, send, recv)
 
 
-def partition_mesh(mesh, rank, size, edges=None):
-    """Contiguous-range partition of an existing (global) mesh; returns (LocalMesh, HaloPlan)."""
+def graph_partition(mesh, nparts):
+    """Part id of every cell from the CELL GRAPH (cells = vertices, interior facets = edges), by recursive
+    graph bisection: cells are ordered by the difference of their graph distances to two mutually far cells and
+    cut where half of them (scaled to the number of parts on each side) lie on one side; both halves are split
+    again.  Stands in for the graph partitioner behind the reference's DMPlex distribution; it
+    uses nothing but connectivity, so it applies to gmsh-read unstructured meshes as well as to tensor meshes."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import shortest_path
     nc = mesh.num_cells
-    if edges is None:
-        edges = np.linspace(0, nc, size + 1).astype(np.int64)
-    c0, c1 = int(edges[rank]), int(edges[rank + 1])
-    owned = np.arange(c0, c1)
+    nb = mesh.nbr_cell
+    rows = np.repeat(np.arange(nc), nb.shape[1])
+    cols = nb.reshape(-1)
+    keep = cols >= 0
+    G = sp.csr_matrix((np.ones(int(keep.sum()), dtype=np.int8), (rows[keep], cols[keep])), shape=(nc, nc))
+    parts = np.zeros(nc, dtype=np.int64)
+
+    def dist(sub, start):
+        d = shortest_path(sub, method="D", directed=False, unweighted=True, indices=[start])[0]
+        d[~np.isfinite(d)] = d[np.isfinite(d)].max() + 1.0            # other components: farthest
+        return d
+
+    def split(cells, first, count):
+        if count == 1 or len(cells) == 0:
+            parts[cells] = first
+            return
+        sub = G[cells][:, cells]
+        # two mutually far cells a, b (pseudo-peripheral pair); cells are ordered by d(a, .) - d(b, .), so that
+        # BOTH sides of the cut are "half spaces" of the graph metric (a plain BFS ball leaves a remainder that
+        # may fall apart)
+        a = int(np.argmax(dist(sub, 0)))
+        da = dist(sub, a)
+        bb = int(np.argmax(da))
+        db = dist(sub, bb)
+        order = np.lexsort((np.arange(len(cells)), da, da - db))
+        left = count // 2
+        cut = int(round(len(cells) * left / float(count)))
+        split(cells[order[:cut]], first, left)
+        split(cells[order[cut:]], first + left, count - left)
+    split(np.arange(nc), 0, int(nparts))
+    return parts
+
+
+def partition_mesh(mesh, rank, size, edges=None, parts=None):
+    """Rank `rank`'s part of an existing (global) mesh; returns (LocalMesh, HaloPlan).
+
+    parts: part id per cell (e.g. from `graph_partition`); default: contiguous ranges of cell numbers (`edges`),
+    which on a tile-numbered mesh are unions of tiles."""
+    nc = mesh.num_cells
+    if parts is None:
+        if edges is None:
+            edges = np.linspace(0, nc, size + 1).astype(np.int64)
+        parts = np.searchsorted(edges, np.arange(nc), side="right") - 1
+    parts = np.asarray(parts, dtype=np.int64)
+    owned = np.nonzero(parts == rank)[0]
     nb = mesh.nbr_cell[owned]
-    ghosts = np.unique(nb[(nb >= 0) & ((nb < c0) | (nb >= c1))])
-    owner = np.searchsorted(edges, ghosts, side="right") - 1
+    cand = nb[nb >= 0]
+    ghosts = np.unique(cand[parts[cand] != rank])
+    owner = parts[ghosts]
     o = np.lexsort((ghosts, owner))
     ghosts, owner = ghosts[o], owner[o]
     order = np.concatenate([owned, ghosts])

@@ -20,9 +20,10 @@ def _global_csr(eng):
     return sp.csr_matrix((v, ci, rp), shape=(eng.ndof, eng.ndof))
 
 
-@pytest.mark.parametrize("size", [2, 3])
-def test_local_assembly_equals_global_rows(size):
+@pytest.mark.parametrize("size,how", [(2, "ranges"), (3, "ranges"), (4, "graph")])
+def test_local_assembly_equals_global_rows(size, how):
     from echemfem_b200.newton import NewtonEngine
+    from echemfem_b200.partition import graph_partition
     N, n, nf = 6, 4, 2
     mesh = UnitSquareMesh(N, N)
     sg = product_cases.AdvectionDiffusionMigrationSolver(0, 3.0, mesh=mesh)
@@ -35,8 +36,9 @@ def test_local_assembly_equals_global_rows(size):
     eg.jacobian(sg.u.tensor)
     Jg = _global_csr(eg)
     Ng = mesh.num_cells * n
+    parts = graph_partition(mesh, size) if how == "graph" else None
     for rank in range(size):
-        local, plan = partition_mesh(mesh, rank, size)
+        local, plan = partition_mesh(mesh, rank, size, parts=parts)
         s = product_cases.AdvectionDiffusionMigrationSolver(0, 3.0, mesh=local)
         e = NewtonEngine(s)
         e.halo = None                                        # ghosts are filled by hand below

@@ -106,3 +106,40 @@ def test_halo_exchange_gloo_world2():
     for p in procs:
         p.join(120)
     assert list(ok) == [1] * size
+
+
+@pytest.mark.parametrize("size", [2, 3, 8])
+def test_graph_partition_is_balanced_connected_and_consistent(size):
+    """Graph partitioner on a graded (Bortels) mesh: every cell owned once, parts balanced to one cell, each
+    part connected, cut small compared with a random assignment; local meshes built from it are consistent."""
+    from scipy.sparse.csgraph import connected_components
+    import scipy.sparse as sp
+    from echemfem_b200.meshes import BortelsMesh
+    from echemfem_b200.partition import graph_partition
+    mesh = BortelsMesh(9, 7, 9, 8)
+    parts = graph_partition(mesh, size)
+    counts = np.bincount(parts, minlength=size)
+    assert counts.sum() == mesh.num_cells and counts.max() - counts.min() <= 1
+    nb = mesh.nbr_cell
+    rows = np.repeat(np.arange(mesh.num_cells), nb.shape[1])
+    cols = nb.reshape(-1)
+    keep = cols >= 0
+    cut = int((parts[rows[keep]] != parts[cols[keep]]).sum()) // 2
+    rnd = np.random.default_rng(0).permutation(parts)
+    cut_rnd = int((rnd[rows[keep]] != rnd[cols[keep]]).sum()) // 2
+    assert cut < 0.35 * cut_rnd
+    G = sp.csr_matrix((np.ones(int(keep.sum())), (rows[keep], cols[keep])), shape=(mesh.num_cells,) * 2)
+    for r in range(size):
+        idx = np.nonzero(parts == r)[0]
+        ncomp, _ = connected_components(G[idx][:, idx], directed=False)
+        assert ncomp == 1
+    owned = []
+    for r in range(size):
+        local, plan = partition_mesh(mesh, r, size, parts=parts)
+        _check_local(mesh, local)
+        owned += list(local.global_ids[:local.num_owned])
+        # what I receive from a peer is exactly what that peer sends to me (matched by global id)
+        for peer, cells in plan.recv.items():
+            other, oplan = partition_mesh(mesh, peer, size, parts=parts)
+            assert np.array_equal(local.global_ids[cells], other.global_ids[oplan.send[r]])
+    assert sorted(owned) == list(range(mesh.num_cells))
