@@ -899,18 +899,18 @@ extern "C" int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t r
 
 // largest number of cells in a block of the plan (read back once per plan and cached)
 static int64_t max_block_cells(const BlockPlan &B, cudaStream_t s) {
-    static const int64_t *cached_ptr = nullptr;
-    static int64_t cached_n = -1, cached_max = 0;
-    if (cached_ptr == B.cell_ptr && cached_n == B.nblocks) return cached_max;
+    // one entry per plan (the multigrid levels alternate between several plans)
+    static std::vector<std::pair<std::pair<const int64_t *, int64_t>, int64_t>> cache;
+    for (const auto &c : cache)
+        if (c.first.first == B.cell_ptr && c.first.second == B.nblocks) return c.second;
     std::vector<int64_t> h((size_t)B.nblocks + 1);
     if (cudaMemcpyAsync(h.data(), B.cell_ptr, sizeof(int64_t) * h.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess)
         return -1;
     int64_t m = 0;
     for (int64_t i = 0; i < B.nblocks; ++i) m = std::max(m, h[i + 1] - h[i]);
-    cached_ptr = B.cell_ptr;
-    cached_n = B.nblocks;
-    cached_max = m;
+    if (cache.size() >= 64) cache.clear();
+    cache.push_back({{B.cell_ptr, B.nblocks}, m});
     return m;
 }
 

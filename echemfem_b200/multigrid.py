@@ -1,0 +1,247 @@
+"""Geometric multigrid preconditioner for DG systems on tensor-product meshes (the reference's `gmg` option set).
+
+Reference: `init_solver_parameters("gmg")` (echemfem/solver.py:1190-1201): FGMRES around a multigrid V-cycle with
+one Richardson iteration of block-Jacobi/ILU per level and a direct coarse solve, on a Firedrake `MeshHierarchy`
+(examples/mms_scaling.py:72-76).  Here:
+
+* the hierarchy comes from the tensor structure of the mesh: every other vertex is dropped per direction and
+  level (the inverse of `MeshHierarchy`'s uniform refinement), also for graded axes;
+* prolongation is the natural embedding of the coarse DG space into the fine one (the coarse polynomial of the
+  parent cell evaluated at the fine nodes), a tensor product of 1D matrices assembled on the host; restriction
+  is its transpose;
+* coarse operators are Galerkin products `P^T A P` of the assembled Jacobian (CSR x CSR products through
+  cuSPARSE/torch: a library call in the SETUP, once per Newton iteration) -- no re-assembly, so user physics and
+  boundary conditions need no coarse counterparts;
+* the smoother is the same block-Jacobi/ILU(0) as on the fine level (`ech_bjacobi_ilu0_*`, blocks = contiguous
+  ranges of tile-numbered cells), the transfer operators are applied with `ech_spmv`, the coarsest system is
+  solved with a dense inverse.
+
+Everything per level lives in HBM; a V-cycle is a fixed sequence of kernel launches.
+"""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import capi
+from .capi import ptr
+from .mesh import tile_order
+from .tables import element_nodes, basis_table
+
+
+def prolongation_1d(ax_f, ax_c, p):
+    """((n_f * n1) x (n_c * n1)) matrix of one direction: fine dof (cell i, node a) <- coarse dof (cell i // 2, node B)."""
+    nodes = element_nodes(p, "DG")
+    n1 = p + 1
+    nf, nc = len(ax_f) - 1, len(ax_c) - 1
+    i = np.arange(nf)
+    I = i // 2
+    x = ax_f[:-1][:, None] + nodes[None, :] * np.diff(ax_f)[:, None]               # (nf, n1) fine node positions
+    xi = (x - ax_c[I][:, None]) / (ax_c[I + 1] - ax_c[I])[:, None]
+    L, _ = basis_table(nodes, xi.reshape(-1))                                        # (nf * n1, n1)
+    rows = np.repeat(np.arange(nf * n1), n1)
+    cols = (np.repeat(I, n1)[:, None] * n1 + np.arange(n1)[None, :]).reshape(-1)
+    return sp.csr_matrix((L.reshape(-1), (rows, cols)), shape=(nf * n1, nc * n1))
+
+
+def _dof_map(shape, n1, inv_perm):
+    """kron index (d_0, d_1, ...) with d_k = i_k * n1 + a_k  ->  dof (cell number, lexicographic node)."""
+    d = len(shape)
+    sizes = [s * n1 for s in shape]
+    idx = np.arange(int(np.prod(sizes)))
+    cell = np.zeros_like(idx)
+    node = np.zeros_like(idx)
+    rem = idx
+    parts = []
+    for k in range(d - 1, -1, -1):
+        parts.append(rem % sizes[k])
+        rem = rem // sizes[k]
+    parts = parts[::-1]
+    for k in range(d):
+        cell = cell * shape[k] + parts[k] // n1
+        node = node * n1 + parts[k] % n1
+    if inv_perm is not None:
+        cell = inv_perm[cell]
+    return cell * (n1 ** d) + node
+
+
+class Level:
+    pass
+
+
+class Hierarchy:
+    """Levels of a tensor mesh and the scalar prolongations between them (host side)."""
+
+    def __init__(self, mesh, degree, tile=16, coarsest_cells=64, max_levels=12):
+        if not hasattr(mesh, "axes") or getattr(mesh, "halo_plan", None) is not None:
+            raise NotImplementedError("multigrid needs an undistributed tensor-product mesh")
+        self.p = degree
+        n1 = degree + 1
+        d = len(mesh.axes)
+        self.n = n1 ** d
+        axes = [np.asarray(a, dtype=float) for a in mesh.axes]
+        perm = getattr(mesh, "cell_perm", None)
+        self.levels = []
+        self.P = []                      # P[l]: level l (fine)  <-  level l + 1 (coarse), scalar dofs
+        while True:
+            shape = tuple(len(a) - 1 for a in axes)
+            L = Level()
+            L.axes, L.shape, L.perm = axes, shape, perm
+            L.ncell = int(np.prod(shape))
+            L.inv = None
+            if perm is not None:
+                L.inv = np.empty_like(perm)
+                L.inv[perm] = np.arange(len(perm))
+            self.levels.append(L)
+            if len(self.levels) >= max_levels or L.ncell <= coarsest_cells or any(s % 2 or s < 4 for s in shape):
+                break
+            cax = [a[::2] for a in axes]
+            cshape = tuple(len(a) - 1 for a in cax)
+            cperm = tile_order(cshape, tile) if all(s % tile == 0 and s > tile for s in cshape) else None
+            cinv = None
+            if cperm is not None:
+                cinv = np.empty_like(cperm)
+                cinv[cperm] = np.arange(len(cperm))
+            P = prolongation_1d(axes[0], cax[0], degree)
+            for k in range(1, d):
+                P = sp.kron(P, prolongation_1d(axes[k], cax[k], degree), format="csr")
+            P = P.tocoo()
+            rf = _dof_map(shape, n1, L.inv)
+            rc = _dof_map(cshape, n1, cinv)
+            self.P.append(sp.csr_matrix((P.data, (rf[P.row], rc[P.col])),
+                                        shape=(L.ncell * self.n, int(np.prod(cshape)) * self.n)))
+            axes, perm = cax, cperm
+
+    @property
+    def nlevels(self):
+        return len(self.levels)
+
+
+def _dev_csr(M, dev):
+    M = M.tocsr()
+    M.sort_indices()
+    return (torch.from_numpy(M.indptr.astype(np.int64)).to(dev), torch.from_numpy(M.indices.astype(np.int32)).to(dev),
+            torch.from_numpy(M.data.astype(np.float64)).to(dev))
+
+
+class Multigrid:
+    """Device side: Galerkin operators, smoothers and the V-cycle."""
+
+    def __init__(self, engine, tile=16, cells_per_block=256, coarsest_cells=64):
+        self.e = engine
+        self.lib = engine.lib
+        self.dev = engine.dev
+        self.nf = engine.nf
+        mesh = engine.solver.mesh
+        if engine.family != "DG":
+            raise NotImplementedError("multigrid is implemented for DG spaces")
+        self.h = Hierarchy(mesh, engine.solver.W.scalar.degree, tile=tile, coarsest_cells=coarsest_cells)
+        if self.h.nlevels < 2:
+            raise NotImplementedError("mesh cannot be coarsened")
+        n = self.h.n
+        self.lv = []
+        for l, L in enumerate(self.h.levels):
+            D = Level()
+            D.N = L.ncell * n                    # scalar dofs = field stride
+            D.ndof = D.N * self.nf
+            nb = max(1, L.ncell // cells_per_block)
+            if l == 0 and getattr(mesh, "block_hint", None):
+                nb = max(1, L.ncell // int(mesh.block_hint))
+            D.nblocks = nb
+            D.block_ptr = torch.from_numpy(np.linspace(0, L.ncell, nb + 1).astype(np.int64)).to(self.dev)
+            D.r = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
+            D.z = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
+            D.t = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
+            D.s = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
+            self.lv.append(D)
+        for l, P in enumerate(self.h.P):
+            D = self.lv[l]
+            D.P = _dev_csr(P, self.dev)
+            D.R = _dev_csr(P.T, self.dev)
+            # block-diagonal (all fields) transfer operators as torch CSR tensors for the Galerkin products
+            D.Pt = self._blockdiag(P)
+            D.Rt = self._blockdiag(P.T.tocsr())
+        self.nlevels = len(self.lv)
+
+    def _blockdiag(self, P):
+        P = P.tocsr()
+        P.sort_indices()
+        nr, nc = P.shape
+        nf = self.nf
+        crow = np.concatenate([P.indptr[:-1] + f * P.nnz for f in range(nf)] + [[nf * P.nnz]])
+        col = np.concatenate([P.indices + f * nc for f in range(nf)])
+        val = np.tile(P.data, nf)
+        it = np.int32 if max(nf * P.nnz, nf * nc) < 2 ** 31 - 1 else np.int64
+        return torch.sparse_csr_tensor(torch.from_numpy(crow.astype(it)).to(self.dev),
+                                       torch.from_numpy(col.astype(it)).to(self.dev),
+                                       torch.from_numpy(val).to(self.dev), size=(nf * nr, nf * nc))
+
+    # -- setup: Galerkin products + ILU factors, once per Newton iteration -------------------------------
+    def setup(self):
+        e, lib, st = self.e, self.lib, self.e._stream()
+        fine = self.lv[0]
+        fine.rowptr, fine.colidx, fine.vals = e.rowptr, e.colidx, e.vals
+        for l in range(self.nlevels - 1):
+            D, Dc = self.lv[l], self.lv[l + 1]
+            nnz = D.vals.numel()
+            it = torch.int32 if nnz < 2 ** 31 - 1 and D.Pt.crow_indices().dtype == torch.int32 else torch.int64
+            A = torch.sparse_csr_tensor(D.rowptr.to(it), D.colidx.to(it), D.vals, size=(D.ndof, D.ndof))
+            Pt, Rt = D.Pt, D.Rt
+            if Pt.crow_indices().dtype != it:
+                Pt = torch.sparse_csr_tensor(Pt.crow_indices().to(it), Pt.col_indices().to(it), Pt.values(), size=Pt.shape)
+                Rt = torch.sparse_csr_tensor(Rt.crow_indices().to(it), Rt.col_indices().to(it), Rt.values(), size=Rt.shape)
+            Ac = torch.sparse.mm(Rt, torch.sparse.mm(A, Pt))
+            Dc.rowptr = Ac.crow_indices().to(torch.int64).contiguous()
+            Dc.colidx = Ac.col_indices().to(torch.int32).contiguous()
+            Dc.vals = Ac.values().contiguous()
+            del A, Ac
+        for l, D in enumerate(self.lv[:-1]):
+            if not hasattr(D, "lu") or D.lu.numel() != D.vals.numel():
+                D.lu = torch.empty_like(D.vals)
+                D.diag = torch.empty(D.ndof, dtype=torch.int32, device=self.dev)
+            capi.check(lib.ech_bjacobi_ilu0_factor(D.ndof, self.nf, D.N, self.h.n, D.nblocks, ptr(D.block_ptr),
+                                                   ptr(D.rowptr), ptr(D.colidx), ptr(D.vals), ptr(D.lu), ptr(D.diag),
+                                                   st))
+        C = self.lv[-1]
+        dense = torch.sparse_csr_tensor(C.rowptr, C.colidx.to(torch.int64), C.vals, size=(C.ndof, C.ndof)).to_dense()
+        C.inv = torch.linalg.inv(dense).contiguous()
+
+    # -- apply ---------------------------------------------------------------------------------------------
+    def _smooth(self, D, r, z):
+        capi.check(self.lib.ech_bjacobi_ilu0_apply(D.ndof, self.nf, D.N, self.h.n, D.nblocks, ptr(D.block_ptr),
+                                                   ptr(D.rowptr), ptr(D.colidx), ptr(D.lu), ptr(D.diag), ptr(r), ptr(z),
+                                                   self.e._stream()))
+
+    def _spmv(self, D, x, y):
+        capi.check(self.lib.ech_spmv(D.ndof, ptr(D.rowptr), ptr(D.colidx), ptr(D.vals), ptr(x), ptr(y), self.e._stream()))
+
+    def _transfer(self, M, nrow, x, xstride, y, ystride):
+        """y_f = M x_f for every field f (scalar operator applied field by field)."""
+        rp, ci, v = M
+        es = x.element_size()
+        for f in range(self.nf):
+            capi.check(self.lib.ech_spmv(nrow, ptr(rp), ptr(ci), ptr(v),
+                                         capi.C.c_void_p(x.data_ptr() + f * xstride * es),
+                                         capi.C.c_void_p(y.data_ptr() + f * ystride * es), self.e._stream()))
+
+    def vcycle(self, l, r, z):
+        """z = V-cycle(r) on level l; r is not modified."""
+        lib, st = self.lib, self.e._stream()
+        D = self.lv[l]
+        if l == self.nlevels - 1:
+            capi.check(lib.ech_dense_gemv(D.ndof, D.ndof, ptr(D.inv), ptr(r), ptr(z), st))
+            return
+        Dc = self.lv[l + 1]
+        self._smooth(D, r, z)                                                  # pre-smoothing
+        self._spmv(D, z, D.t)
+        capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(r), -1.0, ptr(D.t), st))      # t = r - A z
+        self._transfer(D.R, Dc.N, D.t, D.N, Dc.r, Dc.N)                         # restrict
+        self.vcycle(l + 1, Dc.r, Dc.z)
+        self._transfer(D.P, D.N, Dc.z, Dc.N, D.t, D.N)                          # prolongate
+        capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(D.t), 1.0, ptr(z), st))       # z += P z_c
+        self._spmv(D, z, D.t)
+        capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(r), -1.0, ptr(D.t), st))      # t = r - A z
+        self._smooth(D, D.t, D.s)                                               # post-smoothing
+        capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(D.s), 1.0, ptr(z), st))
+
+    def apply(self, r, z):
+        self.vcycle(0, r, z)

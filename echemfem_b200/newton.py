@@ -330,9 +330,32 @@ class NewtonEngine:
         }
         return self._coarse
 
-    def linear_solve(self, rhs, rtol, atol, restart, max_it, monitor=False, coarse=0, coarse_mode=3):
+    def multigrid(self, **kw):
+        """The geometric multigrid hierarchy of this mesh (built once), or None if the mesh has none."""
+        if not hasattr(self, "_mg"):
+            self._mg = None
+            try:
+                from .multigrid import Multigrid
+                if self.halo is None and self.cg is None:
+                    self._mg = Multigrid(self, **kw)
+            except NotImplementedError:
+                self._mg = None
+        return self._mg
+
+    def linear_solve(self, rhs, rtol, atol, restart, max_it, monitor=False, coarse=0, coarse_mode=3, mg=False):
         """Solve J dx = rhs with right-preconditioned GMRES; returns (dx, iterations)."""
         L = self._linear_plan(restart)
+        M = self.multigrid() if mg else None
+        if M is not None:
+            t0 = time.time()
+            M.setup()
+            torch.cuda.synchronize()
+            self.timers["PCSetUp"] += time.time() - t0
+            t0 = time.time()
+            out = self._dist_gmres(rhs, rtol, atol, max_it, monitor, precond=M.apply)
+            torch.cuda.synchronize()
+            self.timers["KSPSolve"] += time.time() - t0
+            return out
         t0 = time.time()
         capi.check(self.lib.ech_bjacobi_ilu0_factor(self.ndof, self.nf, self.N, self._unit, L["nblocks"],
                                                     ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
@@ -372,11 +395,13 @@ class NewtonEngine:
             capi.check(rc)
         return L["dx"], its.value, rc == 0
 
-    def _dist_gmres(self, b, rtol, atol, max_it, monitor=False):
-        """Right-preconditioned restarted GMRES across ranks: the same algorithm as `ech_gmres`, with the
-        ghost-dof exchange in front of every SpMV and the Gram-Schmidt dot products all-reduced over NCCL
-        (PETSc: VecScatter + MPI_Allreduce inside KSPSolve).  Preconditioner blocks never cross ranks."""
+    def _dist_gmres(self, b, rtol, atol, max_it, monitor=False, precond=None):
+        """Right-preconditioned restarted GMRES driven from Python: the same algorithm as `ech_gmres`, with
+        (across ranks) the ghost-dof exchange in front of every SpMV and the Gram-Schmidt dot products
+        all-reduced over NCCL (PETSc: VecScatter + MPI_Allreduce inside KSPSolve), and with a pluggable
+        preconditioner (multigrid V-cycle).  Preconditioner blocks never cross ranks."""
         import torch.distributed as dist
+        distributed = self.halo is not None
         L = self._lin
         n, m = self.ndof, L["restart"]
         lib, st = self.lib, self._stream()
@@ -390,17 +415,20 @@ class NewtonEngine:
 
         def mdot(k, vec):
             capi.check(lib.ech_multidot(n, k, ptr(V), ptr(vec), ptr(partial), ptr(hdev), st))
-            dist.all_reduce(hdev[:k + 1])
+            if distributed:
+                dist.all_reduce(hdev[:k + 1])
             return hdev[:k + 1].cpu().numpy()
 
-        def precond(src, dst):
-            dst.zero_()
-            capi.check(lib.ech_bjacobi_ilu0_apply(n, self.nf, self.N, self._unit, L["nblocks"], ptr(L["block_ptr"]),
-                                                  ptr(self.rowptr), ptr(self.colidx), ptr(L["lu"]), ptr(L["diag"]),
-                                                  ptr(src), ptr(dst), st))
+        if precond is None:
+            def precond(src, dst):
+                dst.zero_()
+                capi.check(lib.ech_bjacobi_ilu0_apply(n, self.nf, self.N, self._unit, L["nblocks"],
+                                                      ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
+                                                      ptr(L["lu"]), ptr(L["diag"]), ptr(src), ptr(dst), st))
 
         def matvec(src, dst):
-            self.halo.exchange(src)
+            if distributed:
+                self.halo.exchange(src)
             capi.check(lib.ech_spmv(n, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(src), ptr(dst), st))
 
         bnorm = math.sqrt(max(mdot(0, b)[0], 0.0))
@@ -415,7 +443,7 @@ class NewtonEngine:
             torch.sub(b, w, out=V0)
             beta = math.sqrt(max(mdot(0, V0)[0], 0.0))
             rnorm = beta
-            if monitor and self.halo.plan.rank == 0:
+            if monitor and (not distributed or self.halo.plan.rank == 0):
                 print("  %3d KSP Residual norm %.12e" % (its, rnorm))
             if beta <= tol:
                 converged = True
@@ -450,7 +478,7 @@ class NewtonEngine:
                 g[j] = cs[j] * g[j]
                 its += 1
                 rnorm = abs(g[j + 1])
-                if monitor and self.halo.plan.rank == 0:
+                if monitor and (not distributed or self.halo.plan.rank == 0):
                     print("  %3d KSP Residual norm %.12e" % (its, rnorm))
                 j += 1
                 if rnorm <= tol or hn == 0.0:
@@ -465,7 +493,8 @@ class NewtonEngine:
             capi.check(lib.ech_multiaxpy(n, k, ptr(V), ptr(hdev), 1.0, ptr(t2), st))
             precond(t2, zt)
             x.add_(zt)
-        x.mul_(self._owned_mask())          # ghost entries of the update are refreshed by the next exchange
+        if distributed:
+            x.mul_(self._owned_mask())      # ghost entries of the update are refreshed by the next exchange
         return x, its, converged
 
     # -- Newton -----------------------------------------------------------------------------
@@ -512,6 +541,9 @@ class NewtonEngine:
         # coarse level: on by default where the reference would factor directly ("lu") and the system is large
         coarse = P.get("pc_coarse_dofs", 4096 if (direct and self.ndof >= 100000) else 0)
         coarse_mode = 2 if P.get("pc_coarse_type", "multiplicative") == "additive" else 3
+        # multigrid: the reference's "gmg" option set (pc_type mg), and where it would factor directly on a large
+        # tensor mesh; falls back to the one-level / aggregation preconditioners when the mesh has no hierarchy
+        mg = P.get("pc_type") == "mg" or (direct and self.ndof >= 100000 and P.get("pc_mg", True))
 
         u = self.solver.u.tensor
         aux = self._aux_tensor()
@@ -566,7 +598,7 @@ class NewtonEngine:
             torch.cuda.synchronize()
             self.timers["JacobianEval"] += time.time() - t0
             y, kits, ok = self.linear_solve(F, ksp_rtol, ksp_atol, restart, ksp_max_it, coarse=coarse,
-                                            coarse_mode=coarse_mode)
+                                            coarse_mode=coarse_mode, mg=mg)
             ksp_hist.append(kits)
             if not ok:
                 print("*** WARNING: linear solve did not reach ksp_rtol in %d iterations" % kits)

@@ -701,7 +701,13 @@ class EchemSolver:
             opts.update({"mat_type": "aij", "ksp_type": "fgmres", "ksp_rtol": 1e-10,
                          "ksp_converged_reason": None, "ksp_monitor": None, "ksp_gmres_restart": 1000,
                          "pc_type": "bjacobi", "sub_pc_type": "ilu", "sub_pc_factor_levels": 0})
-        elif pc_type in ("gmg", "amg") or pc_type.startswith(("block", "cpr")):
+        elif pc_type == "gmg":                                                   # solver.py:1190-1201
+            opts.update({"mat_type": "aij", "ksp_type": "fgmres", "ksp_gmres_restart": 200,
+                         "ksp_converged_reason": None, "ksp_monitor": None, "ksp_rtol": 1e-2, "pc_type": "mg",
+                         "mg_coarse_ksp_type": "preonly", "mg_coarse_pc_type": "lu",
+                         "mg_levels_ksp_type": "richardson", "mg_levels_ksp_max_it": 1,
+                         "mg_levels_pc_type": "bjacobi", "mg_levels_sub_pc_type": "ilu"})
+        elif pc_type == "amg" or pc_type.startswith(("block", "cpr")):
             raise NotImplementedError("pc_type %r (multigrid / fieldsplit) is outside the accelerated path; "
                                       "use 'lu' or 'ilu'" % pc_type)
         else:

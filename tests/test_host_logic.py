@@ -258,3 +258,47 @@ def test_msh_reader_and_transfinite_geo(tmp_path):
     assert np.allclose(c0[0], [0.0, 0.0])
     with pytest.raises(FileNotFoundError):
         Mesh(str(tmp_path / "missing.msh"))
+
+
+@pytest.mark.parametrize("p,tile", [(1, None), (1, 4), (2, None)])
+def test_multigrid_prolongation_embeds_the_coarse_dg_space(p, tile):
+    """multigrid.Hierarchy: P maps the nodal values of a coarse piecewise polynomial to its nodal values on the
+    fine mesh exactly (graded axes, tile-numbered cells, Q1 and Q2), so P^T A P is a Galerkin coarse operator."""
+    from echemfem_b200.mesh import TensorMesh
+    from echemfem_b200.multigrid import Hierarchy
+    from echemfem_b200.function import FunctionSpace
+    ax = [np.array([0.0, 0.1, 0.3, 0.35, 0.6, 0.7, 0.9, 0.95, 1.0]), np.linspace(0.0, 2.0, 9) ** 1.3]
+    mesh = TensorMesh(ax, tile=tile)
+    h = Hierarchy(mesh, p, tile=2, coarsest_cells=4)
+    assert h.nlevels == 3 and [L.shape for L in h.levels] == [(8, 8), (4, 4), (2, 2)]
+    Vf = FunctionSpace(mesh, "DG", p)
+    xf = Vf.node_coords()
+    # coarse level 1 as a mesh of its own, numbered as the hierarchy numbers it
+    L1 = h.levels[1]
+    mc = TensorMesh(L1.axes)
+    if L1.perm is not None:
+        from echemfem_b200.mesh import Mesh
+        mc = Mesh(mc.coords, mc.cells[L1.perm], None)
+    xc = FunctionSpace(mc, "DG", p).node_coords()
+    n = (p + 1) ** 2
+    # a different polynomial of degree p (per direction) in every coarse cell
+    rng = np.random.default_rng(0)
+    coef = rng.normal(size=(L1.ncell, 3))
+
+    def f(x, cell):
+        c = coef[cell]
+        if p == 1:
+            return c[:, 0] + c[:, 1] * x[:, 0] + c[:, 2] * x[:, 0] * x[:, 1]
+        return c[:, 0] + c[:, 1] * x[:, 0] ** 2 * x[:, 1] + c[:, 2] * x[:, 1] ** 2
+    cell_c = np.repeat(np.arange(L1.ncell), n)
+    uc = f(xc, cell_c)
+    # parent (in hierarchy numbering) of every fine dof: locate the fine node in the coarse axes
+    ix = np.searchsorted(L1.axes[0], xf[:, 0], side="right") - 1
+    iy = np.searchsorted(L1.axes[1], xf[:, 1], side="right") - 1
+    lex = ix * L1.shape[1] + iy
+    parent = lex if L1.inv is None else L1.inv[lex]
+    uf = f(xf, parent)
+    assert np.abs(h.P[0] @ uc - uf).max() < 1e-12 * np.abs(uf).max()
+    # partition of unity: constants are reproduced on every level
+    for P in h.P:
+        assert np.allclose(P @ np.ones(P.shape[1]), 1.0)
