@@ -172,18 +172,10 @@ constexpr int coop2_warps(int reclen) {
 }
 
 __device__ __forceinline__ void cp_async16(double *dst, const double *src) {
-#ifdef ECH_STAGE_SYNC
-    *reinterpret_cast<double2 *>(dst) = __ldg(reinterpret_cast<const double2 *>(src));
-    return;
-#endif
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async8(double *dst, const double *src) {
-#ifdef ECH_STAGE_SYNC
-    *dst = __ldg(src);
-    return;
-#endif
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
                  : "memory");
 }
@@ -304,11 +296,7 @@ __device__ __forceinline__ void issue_stage(const ech_dg_args &A, const Smem2 &W
 // N consecutive doubles from shared memory (128-bit loads when the run is pair-aligned)
 template <int N>
 __device__ __forceinline__ void lds_run(const double *d, double *out) {
-#ifdef ECH_LDS64
-    constexpr bool wide = false;
-#else
     constexpr bool wide = V16 && N % 2 == 0;
-#endif
     if constexpr (wide) {
 #pragma unroll
         for (int i = 0; i < N; i += 2) {
@@ -771,11 +759,7 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
         const int task = round * G + ae;
         if (active_e && task < NTASK) {
             Pt p;
-#ifdef ECH_KC_GLOBAL
-            p.K = A.consts;
-#else
             p.K = W.kc;
-#endif
             Geo gm;
             int idx[D];
             double w;
@@ -818,11 +802,7 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
                     }
                 }
                 own_side2(own, idx, p, gm);
-#ifdef ECH_KC_GLOBAL
-                p.fa = A.facet_area[ce * NLF + lf];
-#else
                 p.fa = W.fa[ge * NLF + lf];
-#endif
                 facet_normal(gm, lf, p.n, ds);
                 w *= ds;
                 if (nb < 0) {
