@@ -162,11 +162,13 @@ def cpu_baseline_parallel(sample_n, procs, pool=None):
     return procs * nd / wall / 1e6, wall, nd
 
 
-def host_cores():
+def host_cores(cap=64):
+    """Cores this process may run on, capped (one oracle worker holds ~0.5 GB)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return max(1, os.cpu_count() or 1)
+        n = os.cpu_count() or 1
+    return max(1, min(n, cap))
 
 
 def newton_step(n, deg, tile):
