@@ -722,7 +722,26 @@ __global__ void __launch_bounds__(128) ilu0_factor_kernel(BlockPlan B, const int
                 }
                 __syncwarp();
             }
-            if (lane == 0 && lu[rd] == 0.0) atomicExch(flag, 1);
+            // zero (or negligible) pivot: PETSc's `shift nonzero` -- replace it by a small multiple of the row's
+            // largest entry and carry on (flag 2 = shifted, reported as a warning by the caller)
+            {
+                double rmax = 0.0;
+                for (int64_t q = rs + lane; q < re; q += 32) rmax = fmax(rmax, fabs(lu[q]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+                if (lane == 0) {
+                    const double piv = lu[rd];
+                    if (!(fabs(piv) > 1e-13 * rmax)) {
+                        if (rmax == 0.0 || piv != piv) {
+                            atomicExch(flag, 1);
+                        } else {
+                            lu[rd] = (piv < 0.0 ? -1.0 : 1.0) * 1e-10 * rmax;
+                            atomicMax(flag, 2);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
 }
@@ -792,19 +811,12 @@ __device__ __forceinline__ double half_row_dot(const BlockPlan &B, const int32_t
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(32) ilu0_apply_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
-                                                        const int32_t *__restrict__ colidx,
-                                                        const double *__restrict__ lu,
-                                                        const int32_t *__restrict__ diag_pos,
-                                                        const double *__restrict__ rhs, double *zg) {
-    extern __shared__ double zs[];
-    const int64_t blk = blockIdx.x;
-    const int lane = threadIdx.x;
-    if (blk >= B.nblocks) return;
-    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+__device__ __forceinline__ void ilu0_solve_block(const BlockPlan &B, const int64_t *__restrict__ rowptr,
+                                                 const int32_t *__restrict__ colidx, const double *__restrict__ lu,
+                                                 const int32_t *__restrict__ diag_pos, const double *__restrict__ rhs,
+                                                 double *zg, double *zs, int64_t c0, int64_t c1, int lane) {
     const int64_t nrow_f = (c1 - c0) * B.nloc;           // rows of this block per field
     const int64_t ntot = nrow_f * B.nf;
-    if (ntot == 0) return;
     const int64_t first = c0 * B.nloc, last = c1 * B.nloc - 1;
     const uint32_t first32 = (uint32_t)first, nrow32 = (uint32_t)nrow_f;
     double *z = SMEM ? zs : zg;
@@ -867,6 +879,26 @@ __global__ void __launch_bounds__(32) ilu0_apply_kernel(BlockPlan B, const int64
     }
 }
 
+// cap_rows: rows the dynamic shared memory of this launch holds; a block with more rows (uneven plans) solves
+// in global memory instead
+__global__ void __launch_bounds__(32) ilu0_apply_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
+                                                        const int32_t *__restrict__ colidx,
+                                                        const double *__restrict__ lu,
+                                                        const int32_t *__restrict__ diag_pos,
+                                                        const double *__restrict__ rhs, double *zg, int64_t cap_rows) {
+    extern __shared__ double zs[];
+    const int64_t blk = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (blk >= B.nblocks) return;
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    const int64_t ntot = (c1 - c0) * B.nloc * B.nf;
+    if (ntot == 0) return;
+    if (ntot <= cap_rows)
+        ilu0_solve_block<true>(B, rowptr, colidx, lu, diag_pos, rhs, zg, zs, c0, c1, lane);
+    else
+        ilu0_solve_block<false>(B, rowptr, colidx, lu, diag_pos, rhs, zg, zs, c0, c1, lane);
+}
+
 extern "C" int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
                                        int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
                                        const int32_t *colidx, const double *vals, double *lu, int32_t *diag_pos,
@@ -893,44 +925,30 @@ extern "C" int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t r
     CK(nullptr, cudaStreamSynchronize(s));
     cudaFree(flag);
     CK(nullptr, cudaGetLastError());
-    if (hflag) return fail(nullptr, ECH_ERR_BREAKDOWN, "ech_bjacobi_ilu0_factor: zero pivot");
+    if (hflag == 1) return fail(nullptr, ECH_ERR_BREAKDOWN, "ech_bjacobi_ilu0_factor: zero pivot");
+    if (hflag == 2) {
+        static int warned = 0;
+        if (!warned++) fprintf(stderr, "echem_b200: ILU(0) met negligible pivots; shifted (PETSc shift_type nonzero)\n");
+    }
     return ECH_OK;
-}
-
-// largest number of cells in a block of the plan (read back once per plan and cached)
-static int64_t max_block_cells(const BlockPlan &B, cudaStream_t s) {
-    // one entry per plan (the multigrid levels alternate between several plans)
-    static std::vector<std::pair<std::pair<const int64_t *, int64_t>, int64_t>> cache;
-    for (const auto &c : cache)
-        if (c.first.first == B.cell_ptr && c.first.second == B.nblocks) return c.second;
-    std::vector<int64_t> h((size_t)B.nblocks + 1);
-    if (cudaMemcpyAsync(h.data(), B.cell_ptr, sizeof(int64_t) * h.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess)
-        return -1;
-    int64_t m = 0;
-    for (int64_t i = 0; i < B.nblocks; ++i) m = std::max(m, h[i + 1] - h[i]);
-    if (cache.size() >= 64) cache.clear();
-    cache.push_back({{B.cell_ptr, B.nblocks}, m});
-    return m;
 }
 
 static int ilu0_apply(const BlockPlan &B, const int64_t *rowptr, const int32_t *colidx, const double *lu,
                       const int32_t *diag_pos, const double *r, double *z, cudaStream_t s) {
     if (B.nblocks == 0) return ECH_OK;
-    const int64_t mc = max_block_cells(B, s);
-    if (mc < 0) return cuda_fail(nullptr, cudaGetLastError(), "ilu0_apply: read of the block plan");
-    const int64_t bytes = mc * B.nloc * B.nf * (int64_t)sizeof(double);
-    if (bytes <= 200 * 1024) {
-        static int64_t attr_bytes = 0;
-        if (bytes > attr_bytes) {
-            CK(nullptr, cudaFuncSetAttribute(ilu0_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)bytes));
-            attr_bytes = bytes;
-        }
-        ilu0_apply_kernel<true><<<(unsigned)B.nblocks, 32, (size_t)bytes, s>>>(B, rowptr, colidx, lu, diag_pos, r, z);
-    } else {
-        ilu0_apply_kernel<false><<<(unsigned)B.nblocks, 32, 0, s>>>(B, rowptr, colidx, lu, diag_pos, r, z);
+    // shared memory for the largest block of an even split of the cells (what every caller builds); blocks of
+    // an uneven plan that exceed it fall back to global memory inside the kernel
+    const int64_t ncell = B.rows_per_field / B.nloc;
+    const int64_t mc = (ncell + B.nblocks - 1) / B.nblocks + 1;
+    int64_t bytes = mc * B.nloc * B.nf * (int64_t)sizeof(double);
+    if (bytes > 200 * 1024) bytes = 0;
+    static int64_t attr_bytes = 0;
+    if (bytes > attr_bytes) {
+        CK(nullptr, cudaFuncSetAttribute(ilu0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        attr_bytes = bytes;
     }
+    ilu0_apply_kernel<<<(unsigned)B.nblocks, 32, (size_t)bytes, s>>>(B, rowptr, colidx, lu, diag_pos, r, z,
+                                                                     bytes / (int64_t)sizeof(double));
     ++g_launches;
     CK(nullptr, cudaGetLastError());
     return ECH_OK;

@@ -123,10 +123,36 @@ def _dev_csr(M, dev):
             torch.from_numpy(M.data.astype(np.float64)).to(dev))
 
 
+def spgemm_rows(rowptr, colidx, vals, ncols, B, bnnz_per_row, max_products=1.5e8):
+    """C = A B for a CSR matrix A given by (rowptr int64, colidx int32, vals) and a torch CSR tensor B, computed in
+    row chunks of A (cuSPARSE SpGEMM runs out of work space on products with billions of intermediate terms).
+    Returns (rowptr int64, colidx int32, vals) of C with sorted columns."""
+    nrows = rowptr.numel() - 1
+    nnz = int(vals.numel())
+    idt = B.crow_indices().dtype
+    per_row = max(1.0, nnz / max(nrows, 1)) * max(1.0, bnnz_per_row)
+    chunk = int(max(1024, min(nrows, max_products / per_row)))
+    crows, cols, vs = [], [], []
+    base = 0
+    for r0 in range(0, nrows, chunk):
+        r1 = min(nrows, r0 + chunk)
+        p0, p1 = int(rowptr[r0].item()), int(rowptr[r1].item())
+        A = torch.sparse_csr_tensor((rowptr[r0:r1 + 1] - p0).to(idt), colidx[p0:p1].to(idt), vals[p0:p1],
+                                    size=(r1 - r0, ncols))
+        C = torch.sparse.mm(A, B)
+        cr = C.crow_indices().to(torch.int64)
+        crows.append(cr[:-1] + base if r1 < nrows else cr + base)
+        cols.append(C.col_indices().to(torch.int32))
+        vs.append(C.values())
+        base += int(cr[-1].item())
+        del A, C
+    return torch.cat(crows).contiguous(), torch.cat(cols).contiguous(), torch.cat(vs).contiguous()
+
+
 class Multigrid:
     """Device side: Galerkin operators, smoothers and the V-cycle."""
 
-    def __init__(self, engine, tile=16, cells_per_block=256, coarsest_cells=64):
+    def __init__(self, engine, tile=8, cells_per_block=64, coarsest_cells=64):
         self.e = engine
         self.lib = engine.lib
         self.dev = engine.dev
@@ -143,6 +169,8 @@ class Multigrid:
             D = Level()
             D.N = L.ncell * n                    # scalar dofs = field stride
             D.ndof = D.N * self.nf
+            # one warp solves one block row by row: small blocks keep the smoother of the coarse levels (few
+            # cells, little parallelism) from dominating the cycle; the fine level follows the mesh tiles
             nb = max(1, L.ncell // cells_per_block)
             if l == 0 and getattr(mesh, "block_hint", None):
                 nb = max(1, L.ncell // int(mesh.block_hint))
@@ -182,18 +210,14 @@ class Multigrid:
         fine.rowptr, fine.colidx, fine.vals = e.rowptr, e.colidx, e.vals
         for l in range(self.nlevels - 1):
             D, Dc = self.lv[l], self.lv[l + 1]
-            nnz = D.vals.numel()
-            it = torch.int32 if nnz < 2 ** 31 - 1 and D.Pt.crow_indices().dtype == torch.int32 else torch.int64
-            A = torch.sparse_csr_tensor(D.rowptr.to(it), D.colidx.to(it), D.vals, size=(D.ndof, D.ndof))
-            Pt, Rt = D.Pt, D.Rt
-            if Pt.crow_indices().dtype != it:
-                Pt = torch.sparse_csr_tensor(Pt.crow_indices().to(it), Pt.col_indices().to(it), Pt.values(), size=Pt.shape)
-                Rt = torch.sparse_csr_tensor(Rt.crow_indices().to(it), Rt.col_indices().to(it), Rt.values(), size=Rt.shape)
-            Ac = torch.sparse.mm(Rt, torch.sparse.mm(A, Pt))
-            Dc.rowptr = Ac.crow_indices().to(torch.int64).contiguous()
-            Dc.colidx = Ac.col_indices().to(torch.int32).contiguous()
-            Dc.vals = Ac.values().contiguous()
-            del A, Ac
+            # A P, then P^T (A P), each in row chunks
+            ap = spgemm_rows(D.rowptr, D.colidx, D.vals, D.ndof, D.Pt, D.Pt.values().numel() / D.ndof)
+            AP = torch.sparse_csr_tensor(ap[0].to(D.Pt.crow_indices().dtype), ap[1].to(D.Pt.crow_indices().dtype), ap[2],
+                                         size=(D.ndof, Dc.ndof))
+            Rt = D.Rt
+            Dc.rowptr, Dc.colidx, Dc.vals = spgemm_rows(Rt.crow_indices().to(torch.int64), Rt.col_indices().to(torch.int32),
+                                                        Rt.values(), D.ndof, AP, ap[2].numel() / D.ndof)
+            del ap, AP
         for l, D in enumerate(self.lv[:-1]):
             if not hasattr(D, "lu") or D.lu.numel() != D.vals.numel():
                 D.lu = torch.empty_like(D.vals)

@@ -336,7 +336,9 @@ class NewtonEngine:
             self._mg = None
             try:
                 from .multigrid import Multigrid
-                if self.halo is None and self.cg is None:
+                # validated for Q1; higher degrees need a p-coarsening level first (the reference's PMGPC,
+                # examples/mms_scaling.py:211-238), until then they keep the one-level / aggregation path
+                if self.halo is None and self.cg is None and self.solver.W.scalar.degree == 1:
                     self._mg = Multigrid(self, **kw)
             except NotImplementedError:
                 self._mg = None
