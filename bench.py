@@ -193,8 +193,10 @@ def newton_step(n, deg, tile):
     return {"mesh": "UnitSquareMesh(%d,%d) DG Q%d" % (n, n, deg), "dofs": e.ndof, "snes_its": e.last["snes_its"],
             "ksp_its_per_step": e.last["ksp_its_per_step"], "solve_s": t, "newton_step_s": t / its,
             "timers_s": {k: round(v, 4) for k, v in e.timers.items()},
-            "linear_solver": "GMRES(200) + block-Jacobi/ILU(0) on %dx%d-cell tiles + aggregation coarse level, "
-                             "ksp_rtol 1e-12" % (tile, tile)}
+            "linear_solver": ("GMRES(200) + geometric multigrid V-cycle (block-Jacobi/ILU(0) smoothers, Galerkin coarse "
+                              "operators), ksp_rtol 1e-12" if getattr(e, "_mg", None) is not None else
+                              "GMRES(200) + block-Jacobi/ILU(0) on %dx%d-cell tiles + aggregation coarse level, "
+                              "ksp_rtol 1e-12" % (tile, tile))}
 
 
 def run_reference(args):
@@ -248,7 +250,8 @@ def main():
     ap.add_argument("--tile", type=int, default=0, help="number the cells tile by tile (T x T cells) instead of "
                                                         "lexicographically")
     ap.add_argument("--extras", action="store_true", help="also time SpMV and one full Newton solve")
-    ap.add_argument("--newton-n", dest="newton_n", type=int, default=256, help="mesh of the --extras Newton solve")
+    ap.add_argument("--newton-n", dest="newton_n", type=int, default=1408, help="mesh of the --extras Newton solve "
+                                                                               "(default: the cfg2 mesh itself)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -384,7 +387,9 @@ def main():
         torch.cuda.synchronize()
         extras["spmv_ms"] = a0.elapsed_time(a1) / args.steps
         if world == 1:
-            extras["newton"] = newton_step(args.newton_n, deg, args.tile or 16)
+            del xv, yv
+            torch.cuda.empty_cache()
+            extras["newton"] = newton_step(args.newton_n, deg, args.tile or 8)
 
     times = torch.tensor([t_step, tF, tJ, t_e2e], dtype=torch.float64, device="cuda")
     if dist is not None:
