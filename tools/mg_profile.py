@@ -1,0 +1,43 @@
+"""Where a multigrid-preconditioned Krylov iteration spends its time at cfg2 size (GPU box)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import product_cases
+from echemfem_b200.mesh import UnitSquareMesh
+from echemfem_b200.newton import NewtonEngine
+from echemfem_b200 import capi
+from echemfem_b200.capi import ptr
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1408
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5, mesh=UnitSquareMesh(N, N, tile=T))
+eng = NewtonEngine(s)
+x = s.V.node_coords()
+u = np.concatenate([np.cos(x[:, 0]) + np.sin(x[:, 1]) + 3, np.sin(x[:, 0]) + np.cos(x[:, 1]) + 3])
+s.u.tensor.copy_(torch.from_numpy(u).cuda())
+F = eng.residual(s.u.tensor).clone()
+eng.jacobian(s.u.tensor)
+M = eng.multigrid()
+t0 = time.time(); M.setup(); torch.cuda.synchronize(); print("setup %.2f s, levels %d" % (time.time() - t0, M.nlevels))
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+r = F.clone(); z = torch.zeros_like(r)
+print("V-cycle total      %.2f ms" % timed(lambda: M.apply(r, z)))
+for l, D in enumerate(M.lv[:-1]):
+    print("level %d: ndof %9d nblocks %6d  smooth %.3f ms  spmv %.3f ms  restrict %.3f ms  prolong %.3f ms" % (
+        l, D.ndof, D.nblocks, timed(lambda: M._smooth(D, D.r if l else r, D.z)), timed(lambda: M._spmv(D, D.z, D.t)),
+        timed(lambda: M._transfer(D.R, M.lv[l + 1].N, D.t, D.N, M.lv[l + 1].r, M.lv[l + 1].N)),
+        timed(lambda: M._transfer(D.P, D.N, M.lv[l + 1].z, M.lv[l + 1].N, D.t, D.N))))
+L = eng._linear_plan(200)
+V = L["basis"]; n = eng.ndof; work = L["work"]; hdev = work[3 * n:3 * n + 202]; partial = work[3 * n + 4096:]
+for k in (10, 50, 100):
+    print("multidot k=%d %.2f ms   multiaxpy %.2f ms" % (k, timed(lambda: capi.check(eng.lib.ech_multidot(n, k, ptr(V), ptr(r), ptr(partial), ptr(hdev), eng._stream()))),
+          timed(lambda: capi.check(eng.lib.ech_multiaxpy(n, k, ptr(V), ptr(hdev), -1.0, ptr(z), eng._stream())))))
