@@ -102,8 +102,10 @@ def test_contract_attributes():
     assert s.solver_parameters["pc_type"] == "lu" and s.solver_parameters["snes_max_it"] == 50
     s.init_solver_parameters(pc_type="ilu")
     assert s.solver_parameters["ksp_type"] == "fgmres" and s.solver_parameters["ksp_gmres_restart"] == 1000
+    s.init_solver_parameters(pc_type="gmg")                                  # solver.py:1190-1201
+    assert s.solver_parameters["pc_type"] == "mg" and s.solver_parameters["ksp_rtol"] == 1e-2
     with pytest.raises(NotImplementedError):
-        s.init_solver_parameters(pc_type="gmg")
+        s.init_solver_parameters(pc_type="amg")
     assert s.W.dim() == 2 * 16 and len(s.u.subfunctions) == 2
 
 
