@@ -122,6 +122,31 @@ struct Rec {
 };
 
 
+// rounds in which the points of facet lf are consumed
+constexpr int facet_first_round(int lf) { return (NQC + lf * NQF) / G; }
+constexpr int facet_last_round(int lf) { return (NQC + lf * NQF + NQF - 1) / G; }
+constexpr bool any_straddle() {
+    for (int lf = 0; lf < NLF; ++lf)
+        if (facet_first_round(lf) != facet_last_round(lf)) return true;
+    return false;
+}
+constexpr bool STRADDLE = any_straddle();
+
+// Large elements (3D, many fields): NF*NF*NLOC own-block accumulators per lane do not fit the register file
+// next to the point evaluation (ptxas: 7 KB of spills per thread for three fields on hexes).  They then live in
+// shared memory, [equation][field][node][lane] (conflict-free), and the consumer walks the records of a round
+// once per equation with only that equation's NF*NLOC accumulators in registers.
+// Measured on configs[3] (hexes, 3 fields, 12.6 M dofs): spills drop from 7 KB to 0.6 KB per thread, but the fused
+// step is SLOWER (27.7 ms against 24.4 ms): the per-equation passes recompute the test / neighbour bases and the
+// extra 18 KB per warp cost occupancy.  Opt-in (-DECH_SMEM_ACC) until the producer side of 3D is leaner.
+#ifdef ECH_SMEM_ACC
+constexpr bool SMEM_ACC = !STRADDLE && (NF * NF * NLOC > 48);
+#else
+constexpr bool SMEM_ACC = false;
+#endif
+constexpr int ACC_DOUBLES = SMEM_ACC ? NF * NF * NLOC * 32 : 0;
+
+
 // ---------------------------------------------------------------- staged cell data (asynchronous copies)
 // Per warp: [records | cell data | facet areas | runtime constants | facet metadata].
 // Cell data of (cell g, slot s) -- slot lf = neighbour across facet lf, slot NLF = the cell itself:
@@ -146,10 +171,11 @@ struct Smem2 {
     double *nbd;       // [CPW][CELL_STRIDE]
     double *fa;        // [CPW][NLF] facet areas of my cells
     double *kc;        // [NCONST_PAD] runtime constants
+    double *acc;       // [NF][NF][NLOC][32] own-block accumulators (SMEM_ACC only)
     int *meta;         // [2][CPW][META_LEN]  (double-buffered: the next batch is staged while this one is consumed)
 };
 __host__ __device__ constexpr int warp_smem2_doubles(int reclen) {
-    return even(reclen * 32 + CPW * CELL_STRIDE + even(CPW * NLF) + NCONST_PAD + CPW * META_LEN);
+    return even(reclen * 32 + CPW * CELL_STRIDE + even(CPW * NLF) + NCONST_PAD + ACC_DOUBLES + CPW * META_LEN);
 }
 __device__ __forceinline__ Smem2 warp_smem2(double *smem, int warp, int reclen) {
     double *base = smem + (size_t)warp * warp_smem2_doubles(reclen);
@@ -158,7 +184,8 @@ __device__ __forceinline__ Smem2 warp_smem2(double *smem, int warp, int reclen) 
     w.nbd = base + reclen * 32;
     w.fa = w.nbd + CPW * CELL_STRIDE;
     w.kc = w.fa + even(CPW * NLF);
-    w.meta = reinterpret_cast<int *>(w.kc + NCONST_PAD);
+    w.acc = w.kc + NCONST_PAD;
+    w.meta = reinterpret_cast<int *>(w.acc + ACC_DOUBLES);
     return w;
 }
 constexpr int coop2_warps(int reclen) {
@@ -614,6 +641,55 @@ __device__ __forceinline__ void take_all2(const RecRef &R, int s, int off, doubl
     });
 }
 
+// one equation of take_all2 (used by the shared-memory-accumulator path, which walks the records once per equation)
+template <class M, int I, int TK>
+__device__ __forceinline__ void take_row2(const RecRef &R, int s, int off, double pa, const double (&da)[D],
+                                          const double (&phi2)[NLOC], const double (&d2)[NLOC][D],
+                                          double (&acc)[NF][NLOC]) {
+    double Kd[D];
+#pragma unroll
+    for (int n = 0; n < D; ++n) Kd[n] = 0.0;
+    if constexpr (L2Of<M>::get().klen > 0) {
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int n = 0; n < D; ++n) Kd[n] += R(s, off + m * D + n) * da[m];
+    }
+    take_rowj2<M, I, TK>(R, s, off, pa, da, Kd, phi2, d2, acc);
+}
+
+template <bool OWN, int I>
+__device__ __forceinline__ void store_row_blocks(double *__restrict__ out, int64_t rpI, int ncol, int pos,
+                                                 const double (&acc)[NF][NLOC]) {
+    double *__restrict__ vals = out + rpI;
+    static_for<0, NF>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr bool on = OWN ? OWN_BLOCK[I][j] : NBR_BLOCK[I][j];
+        if constexpr (on) store_block(vals + block_offset<I, j>(ncol, pos), acc[j]);
+    });
+}
+
+template <int I>
+__device__ __forceinline__ void acc_load(const double *sacc, int lane, double (&acc)[NF][NLOC]) {
+    static_for<0, NF>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if constexpr (OWN_BLOCK[I][j]) {
+#pragma unroll
+            for (int b = 0; b < NLOC; ++b) acc[j][b] = sacc[((I * NF + j) * NLOC + b) * 32 + lane];
+        }
+    });
+}
+template <int I>
+__device__ __forceinline__ void acc_store(double *sacc, int lane, const double (&acc)[NF][NLOC]) {
+    static_for<0, NF>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if constexpr (OWN_BLOCK[I][j]) {
+#pragma unroll
+            for (int b = 0; b < NLOC; ++b) sacc[((I * NF + j) * NLOC + b) * 32 + lane] = acc[j][b];
+        }
+    });
+}
+
 // reference basis of the neighbour at the facet point (lf, qf) of my cell: its local facet and orientation are
 // run-time mesh data, the 1D factors come from constant memory (no shared-memory traffic)
 template <int TK>
@@ -667,15 +743,6 @@ __device__ __forceinline__ void test_values(const int (&ad)[D], double &pa, doub
     });
 }
 
-// rounds in which the points of facet lf are consumed
-constexpr int facet_first_round(int lf) { return (NQC + lf * NQF) / G; }
-constexpr int facet_last_round(int lf) { return (NQC + lf * NQF + NQF - 1) / G; }
-constexpr bool any_straddle() {
-    for (int lf = 0; lf < NLF; ++lf)
-        if (facet_first_round(lf) != facet_last_round(lf)) return true;
-    return false;
-}
-constexpr bool STRADDLE = any_straddle();
 
 // ---------------------------------------------------------------- the kernel
 #ifdef ECH_MAXNREG
@@ -744,8 +811,12 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
-    double acc[NF][NF][NLOC];
-    zero_blocks<true>(acc);
+    double acc[SMEM_ACC ? 1 : NF][SMEM_ACC ? 1 : NF][SMEM_ACC ? 1 : NLOC];
+    if constexpr (SMEM_ACC) {
+        for (int k = 0; k < NF * NF * NLOC; ++k) W.acc[k * 32 + lane] = 0.0;      // my own column of the warp's array
+    } else {
+        zero_blocks<true>(reinterpret_cast<double(&)[NF][NF][NLOC]>(acc));
+    }
     // neighbour-block accumulators live inside one facet of one round, except for facets whose points
     // straddle two rounds (then they persist across the producer phase)
     double accn_persist[STRADDLE ? NF : 1][STRADDLE ? NF : 1][STRADDLE ? NLOC : 1];
@@ -852,6 +923,8 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
             static_for<0, NROUND>([&](auto rc) {
                 constexpr int RD = decltype(rc)::value;
                 if (round == RD) {
+                    if constexpr (!SMEM_ACC) {
+                    double(&accR)[NF][NF][NLOC] = reinterpret_cast<double(&)[NF][NF][NLOC]>(acc);
                     // residual rows and own-block contributions of cell / exterior-facet points
                     static_for<0, G>([&](auto sc) {
                         constexpr int s = decltype(sc)::value;
@@ -871,9 +944,9 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
                             }
                             double phi2[NLOC], d2[NLOC][D];     // unused on the own side
                             if constexpr (tp.kind == 0) {
-                                take_all2<MC, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, acc);
+                                take_all2<MC, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, accR);
                             } else {
-                                if (meta[tp.lf] < 0) take_all2<ME, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, acc);
+                                if (meta[tp.lf] < 0) take_all2<ME, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, accR);
                             }
                         }
                     });
@@ -896,7 +969,7 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
                                             double pa, da[D];
                                             test_values<TK>(ad, pa, da);
                                             double phi2[NLOC], d2[NLOC][D];
-                                            take_all2<MIP, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, acc);
+                                            take_all2<MIP, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, accR);
                                             nb_basis<TK>(meta[NLF + lf], phi2, d2);
                                             take_all2<MIM, -1>(R, s, RC::OFF_JM, pa, da, phi2, d2, accn);
                                         }
@@ -909,13 +982,92 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
                             }
                         });
                     }
+                    } else {
+                    // ---- shared-memory accumulators: residual first, then one pass over the records per equation
+                    if constexpr (WITH_RES) {
+                        static_for<0, G>([&](auto sc) {
+                            constexpr int s = decltype(sc)::value;
+                            constexpr int TK = RD * G + s;
+                            if constexpr (TK < NTASK) {
+                                double pa, da[D];
+                                test_values<TK>(ad, pa, da);
+#pragma unroll
+                                for (int i = 0; i < NF; ++i) {
+                                    double t = R(s, i) * pa;
+#pragma unroll
+                                    for (int m = 0; m < D; ++m) t += R(s, NF + i * D + m) * da[m];
+                                    res[i] += t;
+                                }
+                            }
+                        });
+                    }
+                    static_for<0, NF>([&](auto ic) {
+                        constexpr int I = decltype(ic)::value;
+                        double accI[NF][NLOC];
+                        acc_load<I>(W.acc, lane, accI);
+                        double phi2[NLOC], d2[NLOC][D];
+                        static_for<0, G>([&](auto sc) {
+                            constexpr int s = decltype(sc)::value;
+                            constexpr int TK = RD * G + s;
+                            if constexpr (TK < NTASK) {
+                                constexpr TaskPt tp = task_point(TK);
+                                double pa, da[D];
+                                test_values<TK>(ad, pa, da);
+                                if constexpr (tp.kind == 0) {
+                                    take_row2<MC, I, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, accI);
+                                } else {
+                                    if (meta[tp.lf] < 0) take_row2<ME, I, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, accI);
+                                }
+                            }
+                        });
+                        if constexpr (ECH_FAMILY_DG) {
+                            static_for<0, NLF>([&](auto lc) {
+                                constexpr int lf = decltype(lc)::value;
+                                constexpr int r0 = facet_first_round(lf);        // == last round (no straddling here)
+                                if constexpr (RD == r0) {
+                                    if (meta[lf] >= 0) {
+                                        double accnI[NF][NLOC];
+                                        static_for<0, NF>([&](auto jc) {
+                                            constexpr int j = decltype(jc)::value;
+                                            if constexpr (NBR_BLOCK[I][j]) {
+#pragma unroll
+                                                for (int b = 0; b < NLOC; ++b) accnI[j][b] = 0.0;
+                                            }
+                                        });
+                                        static_for<0, NQF>([&](auto qc) {
+                                            constexpr int qf = decltype(qc)::value;
+                                            constexpr int TK = NQC + lf * NQF + qf;
+                                            constexpr int s = TK - RD * G;
+                                            double pa, da[D];
+                                            test_values<TK>(ad, pa, da);
+                                            take_row2<MIP, I, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, accI);
+                                            nb_basis<TK>(meta[NLF + lf], phi2, d2);
+                                            take_row2<MIM, I, -1>(R, s, RC::OFF_JM, pa, da, phi2, d2, accnI);
+                                        });
+                                        store_row_blocks<false, I>(A.out, rp[I], ncol, meta[2 * NLF + lf], accnI);
+                                    }
+                                }
+                            });
+                        }
+                        acc_store<I>(W.acc, lane, accI);
+                    });
+                    }
                 }
             });
         }
         __syncwarp();
     }
     if (active) {
-        store_blocks<true>(A.out, rp, ncol, pos_self, acc);
+        if constexpr (SMEM_ACC) {
+            static_for<0, NF>([&](auto ic) {
+                constexpr int I = decltype(ic)::value;
+                double accI[NF][NLOC];
+                acc_load<I>(W.acc, lane, accI);
+                store_row_blocks<true, I>(A.out, rp[I], ncol, pos_self, accI);
+            });
+        } else {
+            store_blocks<true>(A.out, rp, ncol, pos_self, reinterpret_cast<double(&)[NF][NF][NLOC]>(acc));
+        }
         if constexpr (WITH_RES) {
 #pragma unroll
             for (int i = 0; i < NF; ++i) A.out2[i * rows_per_field + c * NLOC + a] = res[i];

@@ -68,3 +68,28 @@ def test_gmg_option_set_newton_solution():
     assert errornorm(s.C1ex, c1) < 2e-4 and errornorm(s.Uex, U) < 2e-4
     e = s._engine
     assert e.multigrid() is not None and max(e.last["ksp_its_per_step"]) <= 30
+
+
+def test_multigrid_on_extruded_hexes():
+    """3D (DQ1 x DG1 hexes, the configs[3] element): the tensor hierarchy, prolongation and V-cycle in three dimensions."""
+    from echemfem_b200.mesh import ExtrudedMesh
+    from echemfem_b200.newton import NewtonEngine
+    from echemfem_b200.multigrid import Multigrid
+    mesh = ExtrudedMesh(UnitSquareMesh(8, 8), 8, 1.0 / 8)
+    s = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, mesh=mesh)
+    eng = NewtonEngine(s, nblocks=64)
+    x = s.V.node_coords()
+    u = np.concatenate([mms_cases.C1ex(x), mms_cases.Uex(x) + 1e-3 * np.sin(7 * x[:, 0] + 3 * x[:, 1] + x[:, 2])])
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+    F = eng.residual(s.u.tensor).clone()
+    eng.jacobian(s.u.tensor)
+    eng._mg = Multigrid(eng, tile=4, cells_per_block=8, coarsest_cells=64)
+    assert eng._mg.nlevels == 2 and eng._mg.h.levels[1].shape == (4, 4, 4)
+    rp, ci, v = eng.csr_host()
+    A = sp.csr_matrix((v, ci, rp), shape=(eng.ndof, eng.ndof))
+    dx1, its1, ok1 = eng.linear_solve(F, 1e-10, 1e-50, 200, 2000)
+    dx1 = dx1.clone()
+    dx2, its2, ok2 = eng.linear_solve(F, 1e-10, 1e-50, 200, 2000, mg=True)
+    assert ok1 and ok2 and its2 < its1
+    b = F.cpu().numpy()
+    assert np.linalg.norm(A @ dx2.cpu().numpy() - b) <= 1e-8 * np.linalg.norm(b)
