@@ -354,7 +354,7 @@ class NewtonEngine:
             torch.cuda.synchronize()
             self.timers["PCSetUp"] += time.time() - t0
             t0 = time.time()
-            out = self._dist_gmres(rhs, rtol, atol, max_it, monitor, precond=M.apply)
+            out = self._gmres(rhs, rtol, atol, max_it, monitor, precond=M.apply)
             torch.cuda.synchronize()
             self.timers["KSPSolve"] += time.time() - t0
             return out
@@ -373,7 +373,7 @@ class NewtonEngine:
         self.timers["PCSetUp"] += time.time() - t0
         if self.halo is not None:
             t0 = time.time()
-            out = self._dist_gmres(rhs, rtol, atol, max_it, monitor)
+            out = self._gmres(rhs, rtol, atol, max_it, monitor)
             torch.cuda.synchronize()
             self.timers["KSPSolve"] += time.time() - t0
             return out
@@ -397,7 +397,7 @@ class NewtonEngine:
             capi.check(rc)
         return L["dx"], its.value, rc == 0
 
-    def _dist_gmres(self, b, rtol, atol, max_it, monitor=False, precond=None):
+    def _gmres(self, b, rtol, atol, max_it, monitor=False, precond=None):
         """Right-preconditioned restarted GMRES driven from Python: the same algorithm as `ech_gmres`, with
         (across ranks) the ghost-dof exchange in front of every SpMV and the Gram-Schmidt dot products
         all-reduced over NCCL (PETSc: VecScatter + MPI_Allreduce inside KSPSolve), and with a pluggable
