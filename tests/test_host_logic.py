@@ -304,3 +304,30 @@ def test_multigrid_prolongation_embeds_the_coarse_dg_space(p, tile):
     # partition of unity: constants are reproduced on every level
     for P in h.P:
         assert np.allclose(P @ np.ones(P.shape[1]), 1.0)
+
+
+def test_multigrid_hierarchy_3d_and_1d():
+    """Hierarchy in one and three dimensions: level shapes, partition of unity, exact transfer of a coarse polynomial."""
+    from echemfem_b200.mesh import TensorMesh
+    from echemfem_b200.multigrid import Hierarchy
+    from echemfem_b200.function import FunctionSpace
+    m3 = TensorMesh([np.linspace(0, 1, 5), np.linspace(0, 2, 5) ** 1.2, np.linspace(0, 1, 9)], tile=(2, 2, 4))
+    h = Hierarchy(m3, 1, tile=2, coarsest_cells=8)
+    assert [L.shape for L in h.levels] == [(4, 4, 8), (2, 2, 4)]
+    P = h.P[0]
+    assert P.shape == (128 * 8, 16 * 8) and np.allclose(P @ np.ones(P.shape[1]), 1.0)
+    # a globally trilinear function is in every level's space: nodal values map to nodal values
+    xf = FunctionSpace(m3, "DG", 1).node_coords()
+    L1 = h.levels[1]
+    from echemfem_b200.mesh import Mesh
+    mc = TensorMesh(L1.axes)
+    if L1.perm is not None:
+        mc = Mesh(mc.coords, mc.cells[L1.perm], None)
+    xc = FunctionSpace(mc, "DG", 1).node_coords()
+    f = lambda x: 1.0 + x[:, 0] - 2.0 * x[:, 1] * x[:, 2] + 0.5 * x[:, 0] * x[:, 1] * x[:, 2]
+    assert np.abs(P @ f(xc) - f(xf)).max() < 1e-12
+    m1 = TensorMesh([np.linspace(0, 1, 17) ** 2])
+    h1 = Hierarchy(m1, 2, coarsest_cells=2)
+    assert [L.shape for L in h1.levels] == [(16,), (8,), (4,), (2,)]
+    for P in h1.P:
+        assert np.allclose(P @ np.ones(P.shape[1]), 1.0)
