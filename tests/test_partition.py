@@ -68,13 +68,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, size, port, ok):
+def _worker(rank, size, port, ok, graph=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=size)
     try:
         mesh = UnitSquareMesh(6, 4)
-        local, plan = partition_mesh(mesh, rank, size)
+        parts = None
+        if graph:
+            from echemfem_b200.partition import graph_partition
+            parts = graph_partition(mesh, size)
+        local, plan = partition_mesh(mesh, rank, size, parts=parts)
         nf, nloc = 2, 4
         ntot = local.num_cells
         hx = HaloExchange(plan, nf, nloc, ntot, torch.device("cpu"))
@@ -95,12 +99,13 @@ def _worker(rank, size, port, ok):
         dist.destroy_process_group()
 
 
-def test_halo_exchange_gloo_world2():
+@pytest.mark.parametrize("graph", [False, True])
+def test_halo_exchange_gloo_world2(graph):
     size = 2
     ctx = mp.get_context("spawn")
     ok = ctx.Array("i", [0] * size)
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, size, port, ok)) for r in range(size)]
+    procs = [ctx.Process(target=_worker, args=(r, size, port, ok, graph)) for r in range(size)]
     for p in procs:
         p.start()
     for p in procs:
