@@ -18,6 +18,8 @@ one Richardson iteration of block-Jacobi/ILU per level and a direct coarse solve
 
 Everything per level lives in HBM; a V-cycle is a fixed sequence of kernel launches.
 """
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -174,6 +176,8 @@ class Multigrid:
             nb = max(1, L.ncell // cells_per_block)
             if l == 0 and getattr(mesh, "block_hint", None):
                 nb = max(1, L.ncell // int(mesh.block_hint))
+            if os.environ.get("ECH_MG_CELLS_PER_BLOCK"):             # tuning hook (tools/newton_scale.py)
+                nb = max(1, L.ncell // int(os.environ["ECH_MG_CELLS_PER_BLOCK"]))
             D.nblocks = nb
             D.block_ptr = torch.from_numpy(np.linspace(0, L.ncell, nb + 1).astype(np.int64)).to(self.dev)
             D.r = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
