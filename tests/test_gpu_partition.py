@@ -64,3 +64,31 @@ def test_local_assembly_equals_global_rows(size, how):
         D = Jl_glob - Jg[gmap[owned_rows]]
         assert abs(D).max() <= 1e-12 * abs(Jg).max()
         assert Jl[owned_rows].nnz == Jg[gmap[owned_rows]].nnz
+
+
+def test_tile_numbered_mesh_gives_the_same_operator():
+    """Cells numbered tile by tile (mesh.tile_order): residual and Jacobian equal those of the lexicographic mesh
+    after permuting the dofs -- numbering is not part of parity but must not change the operator."""
+    from echemfem_b200.newton import NewtonEngine
+    N, n, nf = 8, 4, 2
+    out = {}
+    for tile in (None, 4):
+        mesh = UnitSquareMesh(N, N, tile=tile)
+        s = product_cases.AdvectionDiffusionMigrationSolver(0, 3.0, mesh=mesh)
+        e = NewtonEngine(s)
+        x = s.V.node_coords()
+        u = np.concatenate([np.cos(x[:, 0]) + np.sin(x[:, 1]) + 3 + 1e-2 * np.sin(9 * x[:, 0] * x[:, 1]),
+                            np.sin(x[:, 0]) + np.cos(x[:, 1]) + 3])
+        s.u.tensor.copy_(torch.from_numpy(u).cuda())
+        F = e.residual(s.u.tensor).cpu().numpy()
+        e.jacobian(s.u.tensor)
+        out[tile] = (mesh, F, _global_csr(e))
+    mesh_t, Ft, Jt = out[4]
+    _, Fl, Jl = out[None]
+    perm = mesh_t.cell_perm                                   # tile cell i is lexicographic cell perm[i]
+    Ns = N * N * n
+    dof = (perm[:, None] * n + np.arange(n)[None, :]).reshape(-1)
+    gmap = np.concatenate([f * Ns + dof for f in range(nf)])    # tile dof -> lexicographic dof
+    assert np.abs(Ft - Fl[gmap]).max() <= 1e-12 * np.abs(Fl).max()
+    D = Jt - Jl[gmap][:, gmap]
+    assert abs(D).max() <= 1e-12 * abs(Jl).max() and Jt.nnz == Jl.nnz
