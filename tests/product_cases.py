@@ -384,3 +384,52 @@ class BMCSL1DSolver(EchemSolver):
 
     def set_boundary_markers(self):
         self.boundary_markers = {"bulk dirichlet": (1,), "applied": (1,), "poisson neumann": (2,)}
+
+
+class DiffusionFiniteSizeSolver(EchemSolver):
+    """tests/test_diffusion_finite_size.py:6-46 of the reference: diffusion with the steric ("finite size") flux."""
+
+    def __init__(self, N, family="DG"):
+        mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        C1ex = sin(x) + cos(y)
+        C2ex = cos(x) + sin(y)
+        self.C1ex, self.C2ex = C1ex, C2ex
+
+        def f(C):
+            num = grad(C1ex) + grad(C2ex)
+            den = 1.0 - C1ex - C2ex
+            f1 = - div(grad(C1ex) + C1ex * num / den)
+            f2 = - div(grad(C2ex) + C2ex * num / den)
+            return [f1, f2]
+        conc_params = [{"name": "C1", "diffusion coefficient": 1.0, "bulk": C1ex, "solvated diameter": 1.0},
+                       {"name": "C2", "diffusion coefficient": 1.0, "bulk": C2ex, "solvated diameter": 1.0}]
+        physical_params = {"flow": ["diffusion", "finite size"], "vacuum permittivity": 1.0,
+                           "relative permittivity": 1.0, "Avogadro constant": 1.0, "bulk reaction": f}
+        super().__init__(conc_params, physical_params, mesh, family=family)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4)}
+
+
+class DiffusionCylindricalSolver(EchemSolver):
+    """tests/test_diffusion_cylindrical.py:6-41 of the reference: axisymmetric diffusion (r weight in every measure)."""
+
+    def __init__(self, N, family="DG"):
+        mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        r, z = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
+        C1ex = sin(z) + cos(r)
+        C2ex = cos(z) * cos(r) + sin(z) * cos(r)
+        self.C1ex, self.C2ex = C1ex, C2ex
+
+        def f(C):
+            f1 = sin(r) / r + cos(r) + sin(z)
+            f2 = (r * cos(r) + sin(r)) * (cos(z) + sin(z)) / r + cos(r) * (cos(z) + sin(z))
+            return [f1, f2]
+        conc_params = [{"name": "C1", "diffusion coefficient": 1.0, "bulk": C1ex},
+                       {"name": "C2", "diffusion coefficient": 1.0, "bulk": C2ex}]
+        physical_params = {"flow": ["diffusion"], "bulk reaction": f}
+        super().__init__(conc_params, physical_params, mesh, family=family, cylindrical=True)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"bulk dirichlet": (2, 3, 4)}

@@ -83,3 +83,26 @@ def test_convergence_SUPG(D, first):
         err = errornorm(s.C1ex, c1) + errornorm(s.C2ex, c2)
         assert err < 0.26 * err_old
         err_old = err
+
+
+def test_convergence_finite_size_CG():
+    """tests/test_diffusion_finite_size.py:54-63."""
+    err_old = 1e6
+    for i in range(4):
+        s = _solve(product_cases.DiffusionFiniteSizeSolver(2 ** (i + 1), family="CG"))
+        c1, c2 = s.u.subfunctions
+        err = errornorm(s.C1ex, c1) + errornorm(s.C2ex, c2)
+        assert err < 0.26 * err_old
+        err_old = err
+
+
+@pytest.mark.parametrize("family,thr", [("DG", 0.29), ("CG", 0.26)])
+def test_convergence_cylindrical(family, thr):
+    """tests/test_diffusion_cylindrical.py:44-65."""
+    err_old = 1e6
+    for i in range(4):
+        s = _solve(product_cases.DiffusionCylindricalSolver(2 ** (i + 1), family=family))
+        c1, c2 = s.u.subfunctions
+        err = errornorm(s.C1ex, c1) + errornorm(s.C2ex, c2)
+        assert err < thr * err_old
+        err_old = err

@@ -331,3 +331,23 @@ def test_multigrid_hierarchy_3d_and_1d():
     assert [L.shape for L in h1.levels] == [(16,), (8,), (4,), (2,)]
     for P in h1.P:
         assert np.allclose(P @ np.ones(P.shape[1]), 1.0)
+
+
+def test_invalid_physics_is_rejected_at_construction():
+    """tests/test_diffusion_finite_size.py:49-51 and tests/test_notimplemented.py of the reference (solver.py:115-142)."""
+    import product_cases
+    from echemfem_b200 import EchemSolver
+    from echemfem_b200.fd import UnitIntervalMesh
+    with pytest.raises(NotImplementedError):
+        product_cases.DiffusionFiniteSizeSolver(2, family="DG")
+
+    class Solver(EchemSolver):
+        def __init__(self, flow):
+            super().__init__([], {"flow": flow}, UnitIntervalMesh(2), family="CG")
+
+        def set_boundary_markers(self):
+            self.boundary_markers = {}
+    for flow in (["electroneutrality"], ["poisson", "migration", "electroneutrality"],
+                 ["poisson", "migration", "electroneutrality full"], ["migration"]):
+        with pytest.raises(NotImplementedError):
+            Solver(flow)
