@@ -433,3 +433,39 @@ class DiffusionCylindricalSolver(EchemSolver):
 
     def set_boundary_markers(self):
         self.boundary_markers = {"bulk dirichlet": (2, 3, 4)}
+
+
+class ScalarAdvectionDiffusionSolver(EchemSolver):
+    """tests/test_advection_diffusion.py:6-65 of the reference: two passive species, DG (upwind) or CG (no SUPG),
+    on quadrilaterals or on hexes extruded from them."""
+
+    def __init__(self, N, D, extruded=False, family="DG"):
+        if extruded:
+            mesh = ExtrudedMesh(UnitSquareMesh(N, N, quadrilateral=True), N, layer_height=1.0 / N)
+        else:
+            mesh = UnitSquareMesh(N, N, quadrilateral=True)
+        xs = SpatialCoordinate(mesh)
+        x, y = xs[0], xs[1]
+        C1ex = sin(x) + cos(y)
+        C2ex = cos(x) + sin(y)
+        self.C1ex, self.C2ex = C1ex, C2ex
+
+        def f(C):
+            f1 = div(self.vel * C1ex - D * grad(C1ex))
+            f2 = div(self.vel * C2ex - D * grad(C2ex))
+            return [f1, f2]
+        conc_params = [{"name": "C1", "diffusion coefficient": D, "bulk": C1ex},
+                       {"name": "C2", "diffusion coefficient": D, "bulk": C2ex}]
+        physical_params = {"flow": ["diffusion", "advection"], "bulk reaction": f, "v_avg": 1.0}
+        super().__init__(conc_params, physical_params, mesh, family=family)
+
+    def set_boundary_markers(self):
+        self.boundary_markers = {"inlet": (1, 2, 3, 4), "outlet": (1, 2, 3, 4), "bulk dirichlet": (1, 2, 3, 4)}
+
+    def set_velocity(self):
+        y = SpatialCoordinate(self.mesh)[1]
+        x_vel = 6. * self.physical_params["v_avg"] * y * (1.0 - y)
+        if self.mesh.layers is not None:
+            self.vel = as_vector((x_vel, Constant(0.), Constant(0.)))
+        else:
+            self.vel = as_vector((x_vel, Constant(0.)))

@@ -106,3 +106,18 @@ def test_convergence_cylindrical(family, thr):
         err = errornorm(s.C1ex, c1) + errornorm(s.C2ex, c2)
         assert err < thr * err_old
         err_old = err
+
+
+@pytest.mark.parametrize("family,D,first,thr,extruded", [
+    ("DG", 1.0, 1, 0.29, False), ("DG", 1e-3, 1, 0.29, False), ("CG", 1.0, 1, 0.29, False), ("CG", 1.0 / 20.0, 2, 0.62, False),
+    ("DG", 1.0, 1, 0.29, True), ("CG", 1.0, 1, 0.29, True)])
+def test_convergence_advection_diffusion(family, D, first, thr, extruded):
+    """tests/test_advection_diffusion.py:68-145: passive transport, DG upwind / CG, quadrilaterals and extruded hexes
+    (three levels on hexes, as in the reference)."""
+    err_old = 1e6
+    for i in range(3 if extruded else 4):
+        s = _solve(product_cases.ScalarAdvectionDiffusionSolver(2 ** (i + first), D, extruded=extruded, family=family))
+        c1, c2 = s.u.subfunctions
+        err = errornorm(s.C1ex, c1) + errornorm(s.C2ex, c2)
+        assert err < thr * err_old
+        err_old = err
