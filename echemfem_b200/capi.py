@@ -58,6 +58,7 @@ EXPORTS = {
     "ech_gmres": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_p, C.POINTER(GmresOpts), c_p, c_p,
                             C.POINTER(c_i32), C.POINTER(C.c_double), c_p]),
     "ech_assemble_host": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ech_set_host_chunks": (C.c_int, [c_p, C.c_int]),
     "ech_launch_count": (c_i64, [c_p]),
 }
 

@@ -28,6 +28,18 @@ struct Module {
     int (*residual)(const ech_dg_args *, void *) = nullptr;
     int (*jacobian)(const ech_dg_args *, void *) = nullptr;
     int (*launches)(int) = nullptr;
+    int (*range_align)(void) = nullptr;     // optional (modules whose kernels take a cell range)
+};
+
+// chunked host-buffer pipeline of ech_assemble_host (built on first use)
+struct HostPipe {
+    int nchunks = 0, npieces = 0;
+    std::vector<int64_t> chunk_begin;       // [nchunks+1] kernel chunks over the owned cells
+    std::vector<int64_t> piece_begin;       // [npieces+1] H2D pieces over owned + ghost cells
+    std::vector<int> need_piece;            // [nchunks]   last H2D piece a chunk's kernel reads
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    std::vector<cudaEvent_t> ev_piece, ev_chunk;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
 };
 
 }  // namespace
@@ -40,6 +52,8 @@ struct ech_handle {
     int nf = 0, nloc = 0;
     unsigned long long own_bits[16], nbr_bits[16];   // per equation: bit j
     std::string err;
+    int host_chunks = 8;                    // ech_set_host_chunks
+    HostPipe pipe;
 };
 
 static std::string g_err;
@@ -77,6 +91,7 @@ extern "C" int ech_create(const char *module_path, const ech_mesh_desc *mesh, ec
     h->mod.residual = (int (*)(const ech_dg_args *, void *))dlsym(h->mod.dl, "ech_mod_residual");
     h->mod.jacobian = (int (*)(const ech_dg_args *, void *))dlsym(h->mod.dl, "ech_mod_jacobian");
     h->mod.launches = (int (*)(int))dlsym(h->mod.dl, "ech_mod_launches");
+    h->mod.range_align = (int (*)(void))dlsym(h->mod.dl, "ech_mod_range_align");
     if (!h->mod.describe || !h->mod.residual || !h->mod.jacobian || !h->mod.launches) {
         int rc = fail(nullptr, ECH_ERR_MODULE, "ech_create: physics module lacks ech_mod_* symbols");
         dlclose(h->mod.dl);
@@ -114,8 +129,19 @@ extern "C" int ech_create(const char *module_path, const ech_mesh_desc *mesh, ec
     return ECH_OK;
 }
 
+static void pipe_release(HostPipe &p) {
+    for (cudaEvent_t e : p.ev_piece) cudaEventDestroy(e);
+    for (cudaEvent_t e : p.ev_chunk) cudaEventDestroy(e);
+    if (p.ev_start) cudaEventDestroy(p.ev_start);
+    if (p.ev_done) cudaEventDestroy(p.ev_done);
+    if (p.h2d) cudaStreamDestroy(p.h2d);
+    if (p.d2h) cudaStreamDestroy(p.d2h);
+    p = HostPipe();
+}
+
 extern "C" void ech_destroy(ech_handle *h) {
     if (!h) return;
+    pipe_release(h->pipe);
     if (h->mod.dl) dlclose(h->mod.dl);
     delete h;
 }
@@ -394,6 +420,7 @@ static void fill_args(const ech_handle *h, ech_dg_args &a) {
     a.inc_loc = m.inc_loc;
     a.colslot = m.colslot;
     a.adj_count = m.adj_count;
+    a.cell_begin = 0;
 }
 
 extern "C" int ech_residual(ech_handle *h, const double *u, const double *aux, const double *consts, double *F,
@@ -1219,6 +1246,129 @@ extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx
 }
 
 // =============================================================== host-buffer boundary
+extern "C" int ech_set_host_chunks(ech_handle *h, int nchunks) {
+    if (!h || nchunks < 0 || nchunks > 4096) return fail(h, ECH_ERR_ARG, "ech_set_host_chunks: bad argument");
+    h->host_chunks = nchunks;
+    pipe_release(h->pipe);
+    return ECH_OK;
+}
+
+// H2D pieces per kernel chunk: a chunk's kernel waits for the piece that holds the largest cell number it
+// reads (its own cells and their facet neighbours), not for the whole next chunk
+static const int PIECES_PER_CHUNK = 4;
+
+static int pipe_build(ech_handle *h, int align, cudaStream_t s) {
+    HostPipe &p = h->pipe;
+    const ech_mesh_desc &m = h->mesh;
+    const int nlf = 2 * m.dim;
+    int nchunks = h->host_chunks;
+    const int64_t per = ((m.ncell + nchunks - 1) / nchunks + align - 1) / align * align;
+    nchunks = (int)((m.ncell + per - 1) / per);
+    p.chunk_begin.resize(nchunks + 1);
+    for (int k = 0; k <= nchunks; ++k) p.chunk_begin[k] = std::min<int64_t>((int64_t)k * per, m.ncell);
+    // pieces: each chunk in PIECES_PER_CHUNK parts (ghost cells travel ahead of the first piece)
+    p.piece_begin.clear();
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t b = p.chunk_begin[k], len = p.chunk_begin[k + 1] - b;
+        for (int q = 0; q < PIECES_PER_CHUNK; ++q) {
+            const int64_t pb = b + len * q / PIECES_PER_CHUNK;
+            if (p.piece_begin.empty() || pb > p.piece_begin.back()) p.piece_begin.push_back(pb);
+        }
+    }
+    p.piece_begin.push_back(m.ncell);
+    p.npieces = (int)p.piece_begin.size() - 1;
+    // largest cell number each chunk reads
+    std::vector<int32_t> nbr((size_t)m.ncell * nlf);
+    CK(h, cudaMemcpyAsync(nbr.data(), m.nbr, sizeof(int32_t) * nbr.size(), cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    p.need_piece.resize(nchunks);
+    for (int k = 0; k < nchunks; ++k) {
+        int64_t hi = p.chunk_begin[k + 1] - 1;
+        for (int64_t c = p.chunk_begin[k]; c < p.chunk_begin[k + 1]; ++c)
+            for (int f = 0; f < nlf; ++f) {
+                const int64_t o = nbr[(size_t)c * nlf + f];
+                if (o < m.ncell) hi = std::max(hi, o);      // ghost cells are on the device before any piece
+            }
+        const int q = (int)(std::upper_bound(p.piece_begin.begin(), p.piece_begin.end(), hi) - p.piece_begin.begin()) - 1;
+        p.need_piece[k] = std::min(std::max(q, 0), p.npieces - 1);
+    }
+    CK(h, cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
+    p.ev_piece.assign(p.npieces, nullptr);
+    p.ev_chunk.assign(nchunks, nullptr);
+    for (auto &e : p.ev_piece) CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : p.ev_chunk) CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&p.ev_start, cudaEventDisableTiming));
+    CK(h, cudaEventCreateWithFlags(&p.ev_done, cudaEventDisableTiming));
+    p.nchunks = nchunks;
+    return ECH_OK;
+}
+
+// Chunked pipeline (discontinuous spaces, fused kernel): the state of cell range k+1 travels to the device while
+// the kernel assembles range k and the residual of range k-1 travels back; both PCIe directions are busy at once.
+// The same kernel runs on the same data as in the one-launch path: results are bit-identical.
+static int assemble_host_pipelined(ech_handle *h, int align, const double *u_host, double *u_dev, const double *aux,
+                                   const double *consts, const int64_t *rowptr, double *vals, double *F_dev,
+                                   double *F_host, cudaStream_t s) {
+    HostPipe &p = h->pipe;
+    if (p.nchunks == 0) {
+        int rc = pipe_build(h, align, s);
+        if (rc) return rc;
+    }
+    const int nf = h->nf;
+    const int64_t n = h->nloc, fstride = h->mesh.ncell_total * n;
+    // the copy streams start after everything already queued on the caller's stream
+    CK(h, cudaEventRecord(p.ev_start, s));
+    CK(h, cudaStreamWaitEvent(p.h2d, p.ev_start, 0));
+    CK(h, cudaStreamWaitEvent(p.d2h, p.ev_start, 0));
+    if (h->mesh.ncell_total > h->mesh.ncell) {
+        const int64_t b = h->mesh.ncell * n, len = (h->mesh.ncell_total - h->mesh.ncell) * n;
+        for (int i = 0; i < nf; ++i)
+            CK(h, cudaMemcpyAsync(u_dev + i * fstride + b, u_host + i * fstride + b, sizeof(double) * len,
+                                  cudaMemcpyHostToDevice, p.h2d));
+    }
+    for (int q = 0; q < p.npieces; ++q) {
+        const int64_t b = p.piece_begin[q] * n, len = (p.piece_begin[q + 1] - p.piece_begin[q]) * n;
+        for (int i = 0; i < nf; ++i)
+            CK(h, cudaMemcpyAsync(u_dev + i * fstride + b, u_host + i * fstride + b, sizeof(double) * len,
+                                  cudaMemcpyHostToDevice, p.h2d));
+        CK(h, cudaEventRecord(p.ev_piece[q], p.h2d));
+    }
+    ech_dg_args a;
+    fill_args(h, a);
+    a.u = u_dev;
+    a.aux = aux;
+    a.consts = consts;
+    a.rowptr = rowptr;
+    a.out = vals;
+    a.out2 = F_dev;
+    int waited = -1;
+    for (int k = 0; k < p.nchunks; ++k) {
+        if (p.need_piece[k] > waited) {
+            waited = p.need_piece[k];
+            CK(h, cudaStreamWaitEvent(s, p.ev_piece[waited], 0));
+        }
+        a.cell_begin = p.chunk_begin[k];
+        a.ncell = p.chunk_begin[k + 1];
+        int rc = h->mod.jacobian(&a, (void *)s);
+        g_launches += h->mod.launches(2);
+        if (rc) return cuda_fail(h, (cudaError_t)rc, "ech_assemble_host launch");
+        CK(h, cudaEventRecord(p.ev_chunk[k], s));
+        CK(h, cudaStreamWaitEvent(p.d2h, p.ev_chunk[k], 0));
+        // ghost rows (never written by the kernels) ride with the last chunk, as in the one-copy path
+        const int64_t b = p.chunk_begin[k] * n;
+        const int64_t e = (k + 1 == p.nchunks ? h->mesh.ncell_total : p.chunk_begin[k + 1]) * n;
+        for (int i = 0; i < nf; ++i)
+            CK(h, cudaMemcpyAsync(F_host + i * fstride + b, F_dev + i * fstride + b, sizeof(double) * (e - b),
+                                  cudaMemcpyDeviceToHost, p.d2h));
+    }
+    CK(h, cudaEventRecord(p.ev_done, p.d2h));
+    CK(h, cudaStreamWaitEvent(s, p.ev_done, 0));
+    CK(h, cudaStreamWaitEvent(s, p.ev_piece[p.npieces - 1], 0));
+    CK(h, cudaStreamSynchronize(s));
+    return ECH_OK;
+}
+
 extern "C" int ech_assemble_host(ech_handle *h, const double *u_host, double *u_dev, const double *aux,
                                  const double *consts, const int64_t *rowptr, double *vals, double *F_dev,
                                  double *F_host, void *stream) {
@@ -1226,6 +1376,9 @@ extern "C" int ech_assemble_host(ech_handle *h, const double *u_host, double *u_
     cudaStream_t s = (cudaStream_t)stream;
     int64_t nrows;
     ech_num_rows(h, &nrows);
+    const int align = (vals && rowptr && h->info[7] != 0 && h->mod.range_align) ? h->mod.range_align() : 0;
+    if (align > 0 && h->host_chunks > 1 && h->mesh.ncell >= (int64_t)h->host_chunks * align)
+        return assemble_host_pipelined(h, align, u_host, u_dev, aux, consts, rowptr, vals, F_dev, F_host, s);
     const int64_t nstate = nrows;
     CK(h, cudaMemcpyAsync(u_dev, u_host, sizeof(double) * nstate, cudaMemcpyHostToDevice, s));
     int rc = vals ? ech_residual_jacobian(h, u_dev, aux, consts, rowptr, vals, F_dev, stream)

@@ -775,7 +775,8 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
     // PERSISTENT warps: a warp walks over batches of CPW cells; the staging of the next batch (two dependent
     // global round trips: neighbour ids, then their data) is issued while the current one is being consumed
     const int64_t wstride = (int64_t)gridDim.x * J2WARPS;
-    int64_t batch = (int64_t)blockIdx.x * J2WARPS + warp;
+    // a launch covers the batches of cells [A.cell_begin, A.ncell) (cell_begin is a multiple of CPW)
+    int64_t batch = A.cell_begin / CPW + (int64_t)blockIdx.x * J2WARPS + warp;
     for (int k = lane; k < ECH_NCONST; k += 32) cp_async8(W.kc + k, A.consts + k);
     int ids[NLF], cs[2 * NLF];
     int mb = 0;
@@ -1111,8 +1112,10 @@ static int launch_jacobian_coop2(const ech_dg_args *a, cudaStream_t s) {
     if (a->ncell == 0) return 0;
     int e = coop2_setup();
     if (e) return e;
-    const int64_t nbatch = (a->ncell + CPW - 1) / CPW;
-    const int64_t need = (nbatch + J2WARPS - 1) / J2WARPS;
+    if (a->cell_begin < 0 || a->cell_begin % CPW) return (int)cudaErrorInvalidValue;
+    if (a->cell_begin >= a->ncell) return 0;
+    const int64_t nbatch = (a->ncell + CPW - 1) / CPW;       // end batch (exclusive)
+    const int64_t need = (nbatch - a->cell_begin / CPW + J2WARPS - 1) / J2WARPS;
     const int fused = a->out2 ? 1 : 0;
     // ECH_COOP2_WAVES = w > 0: persistent grid of w waves of resident CTAs (SMs x CTAs per SM), each warp strides
     // over the batches and stages batch i+1 while it consumes batch i.  Measured on cfg2 (profiles/): 2.78 ms

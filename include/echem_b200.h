@@ -169,10 +169,17 @@ int ech_gmres(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const
 
 /* -- host-buffer boundary: what a binding inside the reference's SNES callbacks would call ------- */
 /* u_host -> device, residual (and Jacobian values into the device-resident matrix), F -> F_host.
- * vals stays on the device (the linear solve consumes it there). Synchronises. */
+ * vals stays on the device (the linear solve consumes it there). Synchronises.  u_host / F_host should be
+ * page-locked (cudaHostAlloc / cudaHostRegister) for the copies to overlap the kernels. */
 int ech_assemble_host(ech_handle *h, const double *u_host, double *u_dev, const double *aux,
                       const double *consts, const int64_t *rowptr, double *vals, double *F_dev,
                       double *F_host, void *stream);
+
+/* Chunking of ech_assemble_host for discontinuous spaces (default 8): the owned cells are cut into nchunks
+ * contiguous ranges; the state of range k+1 is copied in while range k is assembled and the residual of
+ * range k-1 is copied out (three streams).  0 or 1: one copy in, one launch, one copy out.  Results are
+ * bit-identical either way. */
+int ech_set_host_chunks(ech_handle *h, int nchunks);
 
 /* number of kernels launched by this library (and the bound module) since ech_create */
 int64_t ech_launch_count(const ech_handle *h);

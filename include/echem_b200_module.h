@@ -43,6 +43,10 @@ typedef struct ech_dg_args {
     const uint8_t *inc_loc;   /* [ninc]      local index of the node in that cell              */
     const uint8_t *colslot;   /* [ninc][n]   position of the cell's b-th node in the row's sorted column nodes */
     const int32_t *adj_count; /* [nnodes]    number of column nodes of a row                   */
+    /* cell range of a launch: rows are assembled for cells [cell_begin, ncell).  0 for a whole-mesh launch;
+     * non-zero only in the chunked host-buffer pipeline (ech_assemble_host), a multiple of
+     * ech_mod_range_align() */
+    int64_t cell_begin;
 } ech_dg_args;
 
 /* info[0..7] = d, p, nf, naux, nconst, nq, nclasses, family(1=DG); then nf*nf own-block flags,
@@ -53,6 +57,9 @@ ECH_MOD_EXPORT int ech_mod_residual(const ech_dg_args *a, void *stream);
 ECH_MOD_EXPORT int ech_mod_jacobian(const ech_dg_args *a, void *stream);
 /* 0: cooperative kernels (default), 1: row-per-thread kernels */
 ECH_MOD_EXPORT void ech_mod_set_variant(int variant);
+/* granularity (in cells) of ech_dg_args.cell_begin for the fused residual + Jacobian launch; 0 if this
+ * module's kernels only do whole-mesh launches */
+ECH_MOD_EXPORT int ech_mod_range_align(void);
 /* number of kernel launches one residual / Jacobian call makes */
 ECH_MOD_EXPORT int ech_mod_launches(int which);
 
