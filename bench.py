@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--degree", type=int, default=1, help="polynomial degree (the headline number is Q1)")
     ap.add_argument("--sample-n", dest="sample_n", type=int, default=96, help="CPU baseline sample mesh")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--host-chunks", dest="host_chunks", type=int, default=8, help="cell ranges of the e2e "
+    ap.add_argument("--host-chunks", dest="host_chunks", type=int, default=16, help="cell ranges of the e2e "
                     "host-buffer pipeline (ech_set_host_chunks)")
     ap.add_argument("--cpu-procs", dest="cpu_procs", type=int, default=0, help="processes of the CPU baseline "
                                                                                "(default: every core of the host)")

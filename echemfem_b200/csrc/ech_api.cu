@@ -52,7 +52,7 @@ struct ech_handle {
     int nf = 0, nloc = 0;
     unsigned long long own_bits[16], nbr_bits[16];   // per equation: bit j
     std::string err;
-    int host_chunks = 8;                    // ech_set_host_chunks
+    int host_chunks = 16;                   // ech_set_host_chunks
     HostPipe pipe;
 };
 
@@ -1253,9 +1253,13 @@ extern "C" int ech_set_host_chunks(ech_handle *h, int nchunks) {
     return ECH_OK;
 }
 
-// H2D pieces per kernel chunk: a chunk's kernel waits for the piece that holds the largest cell number it
-// reads (its own cells and their facet neighbours), not for the whole next chunk
-static const int PIECES_PER_CHUNK = 4;
+// all fields of a cell range in one strided copy (rows = fields, pitch = field stride)
+static cudaError_t copy_fields(double *dst, const double *src, int64_t fstride, int64_t begin, int64_t len, int nf,
+                               cudaMemcpyKind kind, cudaStream_t s) {
+    if (len <= 0) return cudaSuccess;
+    return cudaMemcpy2DAsync(dst + begin, sizeof(double) * fstride, src + begin, sizeof(double) * fstride,
+                             sizeof(double) * len, (size_t)nf, kind, s);
+}
 
 static int pipe_build(ech_handle *h, int align, cudaStream_t s) {
     HostPipe &p = h->pipe;
@@ -1266,32 +1270,26 @@ static int pipe_build(ech_handle *h, int align, cudaStream_t s) {
     nchunks = (int)((m.ncell + per - 1) / per);
     p.chunk_begin.resize(nchunks + 1);
     for (int k = 0; k <= nchunks; ++k) p.chunk_begin[k] = std::min<int64_t>((int64_t)k * per, m.ncell);
-    // pieces: each chunk in PIECES_PER_CHUNK parts (ghost cells travel ahead of the first piece)
-    p.piece_begin.clear();
-    for (int k = 0; k < nchunks; ++k) {
-        const int64_t b = p.chunk_begin[k], len = p.chunk_begin[k + 1] - b;
-        for (int q = 0; q < PIECES_PER_CHUNK; ++q) {
-            const int64_t pb = b + len * q / PIECES_PER_CHUNK;
-            if (p.piece_begin.empty() || pb > p.piece_begin.back()) p.piece_begin.push_back(pb);
-        }
-    }
-    p.piece_begin.push_back(m.ncell);
-    p.npieces = (int)p.piece_begin.size() - 1;
-    // largest cell number each chunk reads
+    // One copy piece per chunk, ending just behind the largest cell number the chunk's kernel reads (its own
+    // cells and their facet neighbours), so that kernel k waits for piece k only.  Ghost cells travel ahead of
+    // the first piece.  Copies cost tens of microseconds each: fewer, larger pieces win (profiles/r1k_*).
     std::vector<int32_t> nbr((size_t)m.ncell * nlf);
     CK(h, cudaMemcpyAsync(nbr.data(), m.nbr, sizeof(int32_t) * nbr.size(), cudaMemcpyDeviceToHost, s));
     CK(h, cudaStreamSynchronize(s));
+    p.piece_begin.assign(1, 0);
     p.need_piece.resize(nchunks);
     for (int k = 0; k < nchunks; ++k) {
         int64_t hi = p.chunk_begin[k + 1] - 1;
         for (int64_t c = p.chunk_begin[k]; c < p.chunk_begin[k + 1]; ++c)
             for (int f = 0; f < nlf; ++f) {
                 const int64_t o = nbr[(size_t)c * nlf + f];
-                if (o < m.ncell) hi = std::max(hi, o);      // ghost cells are on the device before any piece
+                if (o < m.ncell) hi = std::max(hi, o);
             }
-        const int q = (int)(std::upper_bound(p.piece_begin.begin(), p.piece_begin.end(), hi) - p.piece_begin.begin()) - 1;
-        p.need_piece[k] = std::min(std::max(q, 0), p.npieces - 1);
+        const int64_t end = k + 1 == nchunks ? m.ncell : std::min<int64_t>(hi + 1, m.ncell);
+        if (end > p.piece_begin.back()) p.piece_begin.push_back(end);
+        p.need_piece[k] = (int)p.piece_begin.size() - 2;      // the piece that ends at or behind `end`
     }
+    p.npieces = (int)p.piece_begin.size() - 1;
     CK(h, cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
     CK(h, cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
     p.ev_piece.assign(p.npieces, nullptr);
@@ -1323,15 +1321,11 @@ static int assemble_host_pipelined(ech_handle *h, int align, const double *u_hos
     CK(h, cudaStreamWaitEvent(p.d2h, p.ev_start, 0));
     if (h->mesh.ncell_total > h->mesh.ncell) {
         const int64_t b = h->mesh.ncell * n, len = (h->mesh.ncell_total - h->mesh.ncell) * n;
-        for (int i = 0; i < nf; ++i)
-            CK(h, cudaMemcpyAsync(u_dev + i * fstride + b, u_host + i * fstride + b, sizeof(double) * len,
-                                  cudaMemcpyHostToDevice, p.h2d));
+        CK(h, copy_fields(u_dev, u_host, fstride, b, len, nf, cudaMemcpyHostToDevice, p.h2d));
     }
     for (int q = 0; q < p.npieces; ++q) {
         const int64_t b = p.piece_begin[q] * n, len = (p.piece_begin[q + 1] - p.piece_begin[q]) * n;
-        for (int i = 0; i < nf; ++i)
-            CK(h, cudaMemcpyAsync(u_dev + i * fstride + b, u_host + i * fstride + b, sizeof(double) * len,
-                                  cudaMemcpyHostToDevice, p.h2d));
+        CK(h, copy_fields(u_dev, u_host, fstride, b, len, nf, cudaMemcpyHostToDevice, p.h2d));
         CK(h, cudaEventRecord(p.ev_piece[q], p.h2d));
     }
     ech_dg_args a;
@@ -1358,9 +1352,7 @@ static int assemble_host_pipelined(ech_handle *h, int align, const double *u_hos
         // ghost rows (never written by the kernels) ride with the last chunk, as in the one-copy path
         const int64_t b = p.chunk_begin[k] * n;
         const int64_t e = (k + 1 == p.nchunks ? h->mesh.ncell_total : p.chunk_begin[k + 1]) * n;
-        for (int i = 0; i < nf; ++i)
-            CK(h, cudaMemcpyAsync(F_host + i * fstride + b, F_dev + i * fstride + b, sizeof(double) * (e - b),
-                                  cudaMemcpyDeviceToHost, p.d2h));
+        CK(h, copy_fields(F_host, F_dev, fstride, b, e - b, nf, cudaMemcpyDeviceToHost, p.d2h));
     }
     CK(h, cudaEventRecord(p.ev_done, p.d2h));
     CK(h, cudaStreamWaitEvent(s, p.ev_done, 0));

@@ -175,7 +175,7 @@ int ech_assemble_host(ech_handle *h, const double *u_host, double *u_dev, const 
                       const double *consts, const int64_t *rowptr, double *vals, double *F_dev,
                       double *F_host, void *stream);
 
-/* Chunking of ech_assemble_host for discontinuous spaces (default 8): the owned cells are cut into nchunks
+/* Chunking of ech_assemble_host for discontinuous spaces (default 16): the owned cells are cut into nchunks
  * contiguous ranges; the state of range k+1 is copied in while range k is assembled and the residual of
  * range k-1 is copied out (three streams).  0 or 1: one copy in, one launch, one copy out.  Results are
  * bit-identical either way. */
