@@ -1334,8 +1334,8 @@ static int assemble_host_pipelined(ech_handle *h, int align, const double *u_hos
     a.aux = aux;
     a.consts = consts;
     a.rowptr = rowptr;
-    a.out = vals;
-    a.out2 = F_dev;
+    a.out = vals ? vals : F_dev;            // residual only when there is no matrix to fill
+    a.out2 = vals ? F_dev : nullptr;
     int waited = -1;
     for (int k = 0; k < p.nchunks; ++k) {
         if (p.need_piece[k] > waited) {
@@ -1344,8 +1344,8 @@ static int assemble_host_pipelined(ech_handle *h, int align, const double *u_hos
         }
         a.cell_begin = p.chunk_begin[k];
         a.ncell = p.chunk_begin[k + 1];
-        int rc = h->mod.jacobian(&a, (void *)s);
-        g_launches += h->mod.launches(2);
+        int rc = vals ? h->mod.jacobian(&a, (void *)s) : h->mod.residual(&a, (void *)s);
+        g_launches += h->mod.launches(vals ? 2 : 0);
         if (rc) return cuda_fail(h, (cudaError_t)rc, "ech_assemble_host launch");
         CK(h, cudaEventRecord(p.ev_chunk[k], s));
         CK(h, cudaStreamWaitEvent(p.d2h, p.ev_chunk[k], 0));
@@ -1368,7 +1368,8 @@ extern "C" int ech_assemble_host(ech_handle *h, const double *u_host, double *u_
     cudaStream_t s = (cudaStream_t)stream;
     int64_t nrows;
     ech_num_rows(h, &nrows);
-    const int align = (vals && rowptr && h->info[7] != 0 && h->mod.range_align) ? h->mod.range_align() : 0;
+    if (vals && !rowptr) return fail(h, ECH_ERR_ARG, "ech_assemble_host: vals without rowptr");
+    const int align = (h->info[7] != 0 && h->mod.range_align) ? h->mod.range_align() : 0;
     if (align > 0 && h->host_chunks > 1 && h->mesh.ncell >= (int64_t)h->host_chunks * align)
         return assemble_host_pipelined(h, align, u_host, u_dev, aux, consts, rowptr, vals, F_dev, F_host, s);
     const int64_t nstate = nrows;

@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / G, a = lane - g * G;       // cell-major lane numbering
     const bool active_lane = g < CPW;
-    const int64_t c = ((int64_t)blockIdx.x * JWARPS + warp) * CPW + g;
+    const int64_t c = A.cell_begin + ((int64_t)blockIdx.x * JWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const int64_t rows_per_field = A.ncell_total * NLOC;
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(JWARPS * 32, ECH_JMINB) jacobian_coop_kernel(c
     const int *meta = W.meta + gg * META_LEN;
     // producer role: this lane evaluates slot ae of cell ge of the warp
     const int ge = lane % CPW, ae = lane / CPW;
-    const int64_t ce = ((int64_t)blockIdx.x * JWARPS + warp) * CPW + ge;
+    const int64_t ce = A.cell_begin + ((int64_t)blockIdx.x * JWARPS + warp) * CPW + ge;
     const bool active_e = ae < G && ce < A.ncell;
     const RecRef RE{W.rec + 2 * ge};
     const int *meta_e = W.meta + ge * META_LEN;
@@ -741,13 +741,13 @@ __global__ void __launch_bounds__(RWARPS * 32) residual_coop_kernel(const ech_dg
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / G, a = lane - g * G;       // cell-major lane numbering
     const bool active_lane = g < CPW;
-    const int64_t c = ((int64_t)blockIdx.x * RWARPS + warp) * CPW + g;
+    const int64_t c = A.cell_begin + ((int64_t)blockIdx.x * RWARPS + warp) * CPW + g;
     const bool active = active_lane && c < A.ncell;
     const int64_t fstride = A.ncell_total * NLOC;
     const WarpSmem W = warp_smem(smem, warp, RREC_LEN);
     const RecRef R{W.rec + 2 * (active_lane ? g : 0)};
     const int ge = lane % CPW, ae = lane / CPW;     // producer role (see RecRef)
-    const int64_t ce = ((int64_t)blockIdx.x * RWARPS + warp) * CPW + ge;
+    const int64_t ce = A.cell_begin + ((int64_t)blockIdx.x * RWARPS + warp) * CPW + ge;
     const bool active_e = ae < G && ce < A.ncell;
     const RecRef RE{W.rec + 2 * ge};
     const int *meta_e = W.meta + ge * META_LEN;
@@ -858,7 +858,9 @@ static int launch_jacobian_coop(const ech_dg_args *a, cudaStream_t s) {
     int e = coop_setup();
     if (e) return e;
     const int64_t cells_per_block = (int64_t)JWARPS * CPW;
-    const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
+    if (a->cell_begin < 0) return (int)cudaErrorInvalidValue;
+    if (a->cell_begin >= a->ncell) return 0;
+    const int64_t grid = (a->ncell - a->cell_begin + cells_per_block - 1) / cells_per_block;   // cells [cell_begin, ncell)
     if (a->out2)
         jacobian_coop_kernel<true><<<(unsigned)grid, JWARPS * 32, JFSMEM, s>>>(*a);
     else
@@ -874,7 +876,9 @@ static int launch_residual_coop(const ech_dg_args *a, cudaStream_t s) {
     int e = coop_setup();
     if (e) return e;
     const int64_t cells_per_block = (int64_t)RWARPS * CPW;
-    const int64_t grid = (a->ncell + cells_per_block - 1) / cells_per_block;
+    if (a->cell_begin < 0) return (int)cudaErrorInvalidValue;
+    if (a->cell_begin >= a->ncell) return 0;
+    const int64_t grid = (a->ncell - a->cell_begin + cells_per_block - 1) / cells_per_block;   // cells [cell_begin, ncell)
     residual_coop_kernel<<<(unsigned)grid, RWARPS * 32, RSMEM, s>>>(*a);
     e = (int)cudaGetLastError();
     if (e) fprintf(stderr, "echem_b200: residual_coop_kernel<<<%lld, %d, %d>>> failed: %s\n", (long long)grid,

@@ -43,12 +43,12 @@ static bool use_coop() { return echdg::COOP_OK && g_variant != 1; }
 
 static bool use_coop2() { return use_coop() && g_variant == 0 && echdg::NLOC <= 9; }
 
-// only the reference-record kernel takes a cell range
-int ech_mod_range_align() { return use_coop2() ? echdg::CPW : 0; }
+// the cooperative kernels (both generations, residual and Jacobian) take a cell range
+int ech_mod_range_align() { return use_coop() ? echdg::CPW : 0; }
 
 int ech_mod_residual(const ech_dg_args *a, void *stream) {
-    if (a->cell_begin) return (int)cudaErrorInvalidValue;
     if (use_coop()) return echdg::launch_residual_coop(a, (cudaStream_t)stream);
+    if (a->cell_begin) return (int)cudaErrorInvalidValue;
     return echdg::launch_residual(a, (cudaStream_t)stream);
 }
 
@@ -57,8 +57,8 @@ int ech_mod_jacobian(const ech_dg_args *a, void *stream) {
     // reference-space records pay up to 9 local nodes (Q1 2D/3D, Q2 2D: cfg2 Q2 12.9 ms against 16.5 ms); beyond
     // that the fully unrolled compile-time bases outgrow the register file (cfg2 Q3: 52 ms against 34 ms)
     if (use_coop2()) return echdg::v2::launch_jacobian_coop2(a, (cudaStream_t)stream);
-    if (a->cell_begin) return (int)cudaErrorInvalidValue;
     if (use_coop()) return echdg::launch_jacobian_coop(a, (cudaStream_t)stream);
+    if (a->cell_begin) return (int)cudaErrorInvalidValue;
     if (a->out2) {
         ech_dg_args r = *a;
         r.out = a->out2;

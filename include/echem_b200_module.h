@@ -57,8 +57,8 @@ ECH_MOD_EXPORT int ech_mod_residual(const ech_dg_args *a, void *stream);
 ECH_MOD_EXPORT int ech_mod_jacobian(const ech_dg_args *a, void *stream);
 /* 0: cooperative kernels (default), 1: row-per-thread kernels */
 ECH_MOD_EXPORT void ech_mod_set_variant(int variant);
-/* granularity (in cells) of ech_dg_args.cell_begin for the fused residual + Jacobian launch; 0 if this
- * module's kernels only do whole-mesh launches */
+/* granularity (in cells) of ech_dg_args.cell_begin for residual and Jacobian launches; 0 if this module's
+ * kernels only do whole-mesh launches */
 ECH_MOD_EXPORT int ech_mod_range_align(void);
 /* number of kernel launches one residual / Jacobian call makes */
 ECH_MOD_EXPORT int ech_mod_launches(int which);

@@ -25,7 +25,7 @@ def _setup(mesh, **kw):
     return s, e, u
 
 
-def _host_call(e, s, u_host, chunks):
+def _host_call(e, s, u_host, chunks, with_matrix=True):
     lib = e.lib
     capi.check(lib.ech_set_host_chunks(e.h, chunks), e.h)
     uh = torch.from_numpy(u_host.copy()).pin_memory()
@@ -36,7 +36,7 @@ def _host_call(e, s, u_host, chunks):
     aux, consts = e._aux_tensor(), e._consts()      # held: the call takes raw pointers
     n0 = lib.ech_launch_count(e.h)
     capi.check(lib.ech_assemble_host(e.h, ptr(uh), ptr(u_dev), ptr(aux), ptr(consts), ptr(e.rowptr),
-                                     ptr(e.vals), ptr(e.F), ptr(Fh), e._stream()), e.h)
+                                     ptr(e.vals) if with_matrix else None, ptr(e.F), ptr(Fh), e._stream()), e.h)
     launches = lib.ech_launch_count(e.h) - n0
     assert torch.equal(u_dev.cpu(), uh)
     return Fh.numpy().copy(), e.vals.cpu().numpy().copy(), launches
@@ -75,11 +75,68 @@ def test_pipelined_host_assembly_3d():
         assert np.array_equal(Fk, F_dev) and np.array_equal(Jk, J_dev), chunks
 
 
-def test_host_assembly_falls_back_to_one_launch_where_ranges_are_not_supported():
-    """Q3 (first-generation kernel) and CG modules have no cell-range launch: one copy, one call, one copy."""
+def test_pipelined_host_assembly_q3_first_generation_kernel():
+    """Q3 runs the first-generation cooperative Jacobian kernel; it takes cell ranges too."""
     s, e, u = _setup(UnitSquareMesh(12, 12), p=3)
     s.u.tensor.copy_(torch.from_numpy(u).cuda())
     F_dev = e.residual_jacobian(s.u.tensor)[0].cpu().numpy().copy()
     J_dev = e.vals.cpu().numpy().copy()
-    Fk, Jk, lk = _host_call(e, s, u, 8)
+    for chunks in (0, 5, 8):
+        Fk, Jk, lk = _host_call(e, s, u, chunks)
+        assert (lk == 1) if chunks < 2 else (2 <= lk <= chunks)
+        assert np.array_equal(Fk, F_dev) and np.array_equal(Jk, J_dev), chunks
+
+
+@pytest.mark.parametrize("p", [1, 2])
+def test_pipelined_host_residual_only(p):
+    """The SNES function callback alone (line search): vals = NULL, residual kernel per cell range."""
+    s, e, u = _setup(UnitSquareMesh(20, 17), p=p)
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+    F_dev = e.residual(s.u.tensor).cpu().numpy().copy()
+    for chunks in (0, 2, 7, 16):
+        Fk, Jk, lk = _host_call(e, s, u, chunks, with_matrix=False)
+        assert (lk == 1) if chunks < 2 else (2 <= lk <= chunks)
+        assert np.isnan(Jk).all()                   # the matrix was not touched
+        assert np.array_equal(Fk, F_dev), chunks
+
+
+def test_host_assembly_of_a_continuous_space_is_one_launch_set():
+    """CG modules have no cell-range launch (rows are shared between cells): one copy, one call, one copy."""
+    from echemfem_b200.newton import NewtonEngine
+    s = product_cases.AdvectionDiffusionMigrationSolver(12, 1.0, family="CG")
+    e = NewtonEngine(s)
+    rng = np.random.default_rng(3)
+    u = 3.0 + 0.1 * rng.standard_normal(s.u.tensor.numel())
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+    F_dev = e.residual_jacobian(s.u.tensor)[0].cpu().numpy().copy()
+    J_dev = e.vals.cpu().numpy().copy()
+    Fk, Jk, _ = _host_call(e, s, u, 8)
     assert np.array_equal(Fk, F_dev) and np.array_equal(Jk, J_dev)
+
+
+@pytest.mark.parametrize("size,how", [(2, "ranges"), (3, "graph")])
+def test_pipelined_host_assembly_with_ghost_cells(size, how):
+    """A rank's local mesh (owned + ghost cells): ghost state travels ahead of the first range, ghost
+    rows ride with the last one; results equal the one-launch path bit for bit."""
+    from echemfem_b200.newton import NewtonEngine
+    from echemfem_b200.partition import partition_mesh, graph_partition
+    mesh = UnitSquareMesh(20, 20)
+    parts = graph_partition(mesh, size) if how == "graph" else None
+    rng = np.random.default_rng(11)
+    for rank in range(size):
+        local, plan = partition_mesh(mesh, rank, size, parts=parts)
+        assert local.num_cells > local.num_owned
+        s = product_cases.AdvectionDiffusionMigrationSolver(0, 3.0, mesh=local)
+        e = NewtonEngine(s)
+        e.halo = None                                        # ghost values are part of the host state here
+        u = 3.0 + 0.1 * rng.standard_normal(s.u.tensor.numel())
+        s.u.tensor.copy_(torch.from_numpy(u).cuda())
+        e.F.zero_()
+        F_dev = e.residual_jacobian(s.u.tensor)[0].cpu().numpy().copy()
+        J_dev = e.vals.cpu().numpy().copy()
+        n = 4
+        owned = np.concatenate([f * local.num_cells * n + np.arange(local.num_owned * n) for f in range(2)])
+        for chunks in (0, 4, 9):
+            Fk, Jk, _ = _host_call(e, s, u, chunks)
+            assert np.array_equal(Fk[owned], F_dev[owned]), (rank, chunks)
+            assert np.array_equal(Jk, J_dev), (rank, chunks)
