@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -906,13 +907,147 @@ __device__ __forceinline__ void ilu0_solve_block(const BlockPlan &B, const int64
     }
 }
 
-// cap_rows: rows the dynamic shared memory of this launch holds; a block with more rows (uneven plans) solves
-// in global memory instead
+// Ring variant of the shared-memory solve (the one that runs; ilu0_solve_block<true> is its two-round-trips-per-row
+// predecessor, <false> the global-memory fallback).  What a row needs besides z never depends on the solve, so it
+// is fetched far ahead of the dependent chain:
+//  * row pointers and diagonal positions of 32 consecutive rows of the sweep come in one coalesced load per lane,
+//    one batch ahead, and are handed out with shuffles;
+//  * the (column, value) pairs of the row ILU_RING steps ahead are copied into a shared-memory ring with cp.async
+//    (lane l copies entries l and l + 32 of the half-row and later reads only what it copied itself);
+//  * the right-hand side of the whole block is loaded into z up front.
+// Left on the per-row chain: one shared-memory gather of z, a shuffle reduction, one store.  Arithmetic and
+// summation order are those of ilu0_solve_block<true>: results are bit-identical.
+constexpr int ILU_RING = 8;
+constexpr int ILU_SLOTS = ILU_RING + 1;      // the slot being filled is never the one being read
+constexpr int64_t ILU_RING_BYTES = (int64_t)ILU_SLOTS * (64 * (sizeof(double) + sizeof(int32_t)) + sizeof(double));
+
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <bool UPPER>
+__device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_t *__restrict__ rowptr,
+                                                const int32_t *__restrict__ colidx, const double *__restrict__ lu,
+                                                const int32_t *__restrict__ diag_pos, double *z, double *ring_v,
+                                                double *ring_p, int32_t *ring_k, uint32_t first, uint32_t nrow_f,
+                                                uint32_t ntot, int lane) {
+    const uint32_t FULL = 0xffffffffu;
+    // step s of the sweep handles block row i = s (forward) or ntot-1-s (backward)
+    auto batch_ptrs = [&](uint32_t b, int64_t &beg, int32_t &len) {
+        const uint32_t st = b * 32 + lane;
+        beg = 0;
+        len = 0;
+        if (st < ntot) {
+            const uint32_t i = UPPER ? ntot - 1 - st : st;
+            const uint32_t f = i / nrow_f, j = i - f * nrow_f;
+            const int64_t r = (int64_t)f * B.rows_per_field + first + j;
+            const int64_t rs = rowptr[r], re = rowptr[r + 1];
+            const int32_t dp = diag_pos[r];
+            beg = UPPER ? rs + dp : rs;                       // upper: the diagonal leads the half-row
+            len = UPPER ? (int32_t)(re - rs) - dp : dp;
+        }
+    };
+    int64_t begC, begN;
+    int32_t lenC, lenN;
+    batch_ptrs(0, begC, lenC);
+    batch_ptrs(1, begN, lenN);
+    uint32_t curb = 0;                                       // batch whose pointers are in begC / lenC
+    auto issue = [&](uint32_t st) {                          // st: step whose half-row is fetched (warp-uniform)
+        if (st < ntot) {
+            int64_t beg;
+            int32_t len;
+            if ((st >> 5) == curb) {                         // (a select would wait for the batch still in flight)
+                beg = __shfl_sync(FULL, begC, st & 31);
+                len = __shfl_sync(FULL, lenC, st & 31);
+            } else {
+                beg = __shfl_sync(FULL, begN, st & 31);
+                len = __shfl_sync(FULL, lenN, st & 31);
+            }
+            const int slot = st % ILU_SLOTS;
+            // off-diagonal entries: [beg, beg+len) for L, [beg+1, beg+len) for U
+            const int64_t e0 = beg + (UPPER ? 1 : 0);
+            const int32_t n = len - (UPPER ? 1 : 0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;
+                if (e < n) {
+                    cp_async4(ring_k + slot * 64 + e, colidx + e0 + e);
+                    cp_async8(ring_v + slot * 64 + e, lu + e0 + e);
+                }
+            }
+            if (UPPER && lane == 0) cp_async8(ring_p + slot, lu + beg);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (uint32_t st = 0; st < (uint32_t)ILU_RING; ++st) issue(st);
+    for (uint32_t st = 0; st < ntot; ++st) {
+        if ((st >> 5) != curb) {                             // first step of a batch: rotate, fetch the one after
+            curb = st >> 5;
+            begC = begN;
+            lenC = lenN;
+            batch_ptrs(curb + 1, begN, lenN);
+        }
+        issue(st + ILU_RING);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ILU_RING) : "memory");
+        const int64_t beg = __shfl_sync(FULL, begC, st & 31);
+        const int32_t len = __shfl_sync(FULL, lenC, st & 31);
+        const int slot = st % ILU_SLOTS;
+        const int64_t e0 = beg + (UPPER ? 1 : 0);
+        const int32_t n = len - (UPPER ? 1 : 0);
+        double s = 0.0;
+        if (lane < n) {
+            const int32_t k = block_local<true>(B, ring_k[slot * 64 + lane], first, nrow_f);
+            if (k >= 0) s += ring_v[slot * 64 + lane] * z[k];
+        }
+        if (lane + 32 < n) {
+            const int32_t k = block_local<true>(B, ring_k[slot * 64 + lane + 32], first, nrow_f);
+            if (k >= 0) s += ring_v[slot * 64 + lane + 32] * z[k];
+        }
+        for (int64_t p = e0 + 64 + lane; p < e0 + n; p += 32) {       // rows longer than 64 entries per half
+            const int32_t k = block_local<true>(B, colidx[p], first, nrow_f);
+            if (k >= 0) s += lu[p] * z[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) {
+            const uint32_t i = UPPER ? ntot - 1 - st : st;
+            z[i] = UPPER ? (z[i] - s) / ring_p[slot] : z[i] - s;
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void ilu0_solve_block_ring(const BlockPlan &B, const int64_t *__restrict__ rowptr,
+                                                      const int32_t *__restrict__ colidx,
+                                                      const double *__restrict__ lu,
+                                                      const int32_t *__restrict__ diag_pos,
+                                                      const double *__restrict__ rhs, double *zg, double *zs,
+                                                      double *ring, int64_t c0, int64_t c1, int lane) {
+    const uint32_t nrow_f = (uint32_t)((c1 - c0) * B.nloc), ntot = nrow_f * (uint32_t)B.nf;
+    const uint32_t first = (uint32_t)(c0 * B.nloc);
+    double *ring_v = ring, *ring_p = ring + ILU_SLOTS * 64;
+    int32_t *ring_k = reinterpret_cast<int32_t *>(ring_p + ILU_SLOTS);
+    for (int f = 0; f < B.nf; ++f)
+        for (uint32_t j = lane; j < nrow_f; j += 32) zs[f * nrow_f + j] = rhs[(int64_t)f * B.rows_per_field + first + j];
+    __syncwarp();
+    ilu0_ring_sweep<false>(B, rowptr, colidx, lu, diag_pos, zs, ring_v, ring_p, ring_k, first, nrow_f, ntot, lane);
+    ilu0_ring_sweep<true>(B, rowptr, colidx, lu, diag_pos, zs, ring_v, ring_p, ring_k, first, nrow_f, ntot, lane);
+    for (int f = 0; f < B.nf; ++f)
+        for (uint32_t j = lane; j < nrow_f; j += 32) zg[(int64_t)f * B.rows_per_field + first + j] = zs[f * nrow_f + j];
+}
+
+// cap_rows: rows the dynamic shared memory of this launch holds (followed by the prefetch ring when ring != 0);
+// a block with more rows (uneven plans) solves in global memory instead
 __global__ void __launch_bounds__(32) ilu0_apply_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
                                                         const int32_t *__restrict__ colidx,
                                                         const double *__restrict__ lu,
                                                         const int32_t *__restrict__ diag_pos,
-                                                        const double *__restrict__ rhs, double *zg, int64_t cap_rows) {
+                                                        const double *__restrict__ rhs, double *zg, int64_t cap_rows,
+                                                        int ring) {
     extern __shared__ double zs[];
     const int64_t blk = blockIdx.x;
     const int lane = threadIdx.x;
@@ -920,7 +1055,9 @@ __global__ void __launch_bounds__(32) ilu0_apply_kernel(BlockPlan B, const int64
     const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
     const int64_t ntot = (c1 - c0) * B.nloc * B.nf;
     if (ntot == 0) return;
-    if (ntot <= cap_rows)
+    if (ntot <= cap_rows && ring == 1)
+        ilu0_solve_block_ring(B, rowptr, colidx, lu, diag_pos, rhs, zg, zs, zs + cap_rows, c0, c1, lane);
+    else if (ntot <= cap_rows)
         ilu0_solve_block<true>(B, rowptr, colidx, lu, diag_pos, rhs, zg, zs, c0, c1, lane);
     else
         ilu0_solve_block<false>(B, rowptr, colidx, lu, diag_pos, rhs, zg, zs, c0, c1, lane);
@@ -969,13 +1106,18 @@ static int ilu0_apply(const BlockPlan &B, const int64_t *rowptr, const int32_t *
     const int64_t mc = (ncell + B.nblocks - 1) / B.nblocks + 1;
     int64_t bytes = mc * B.nloc * B.nf * (int64_t)sizeof(double);
     if (bytes > 200 * 1024) bytes = 0;
+    const int64_t cap_rows = bytes / (int64_t)sizeof(double);
+    // ECH_ILU_RING=0 selects the predecessor without the prefetch ring (cross-check, tools/mg_profile.py)
+    static const int ring_env = getenv("ECH_ILU_RING") ? atoi(getenv("ECH_ILU_RING")) : 1;
+    const int ring = (ring_env && bytes > 0) ? 1 : 0;
+    if (ring) bytes += ILU_RING_BYTES;
     static int64_t attr_bytes = 0;
     if (bytes > attr_bytes) {
         CK(nullptr, cudaFuncSetAttribute(ilu0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         attr_bytes = bytes;
     }
     ilu0_apply_kernel<<<(unsigned)B.nblocks, 32, (size_t)bytes, s>>>(B, rowptr, colidx, lu, diag_pos, r, z,
-                                                                     bytes / (int64_t)sizeof(double));
+                                                                     cap_rows, ring);
     ++g_launches;
     CK(nullptr, cudaGetLastError());
     return ECH_OK;
