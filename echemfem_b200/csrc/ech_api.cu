@@ -792,9 +792,14 @@ struct RowChunk {
 template <bool SMEM>
 __device__ __forceinline__ int32_t block_local(const BlockPlan &B, int32_t col, uint32_t first, uint32_t nrow_f) {
     // -1 if the column is outside the block
+    // field of the column by repeated subtraction: at most nf - 1 steps, off the divider (this sits on the
+    // dependent chain of every row of the triangular solves)
     const uint32_t rpf = (uint32_t)B.rows_per_field;
-    const uint32_t f = (uint32_t)col / rpf;
-    const uint32_t idx = (uint32_t)col - f * rpf;
+    uint32_t f = 0, idx = (uint32_t)col;
+    while (idx >= rpf) {
+        idx -= rpf;
+        ++f;
+    }
     if (idx < first || idx >= first + nrow_f) return -1;
     return SMEM ? (int32_t)(f * nrow_f + (idx - first)) : col;
 }
@@ -928,6 +933,18 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
+// column -> slot of z in shared memory, or -1 outside the block; a uniform loop over the fields, no divider and
+// no divergent branch (this sits on the per-row chain, and the kernel is issue-bound on the fine level)
+__device__ __forceinline__ int32_t ring_local(int32_t col, uint32_t first, uint32_t nrow_f, uint32_t rpf, int nf) {
+    const uint32_t d = (uint32_t)col - first;
+    int32_t k = -1;
+    for (int f = 0; f < nf; ++f) {
+        const uint32_t dd = d - (uint32_t)f * rpf;
+        if (dd < nrow_f) k = (int32_t)((uint32_t)f * nrow_f + dd);
+    }
+    return k;
+}
+
 template <bool UPPER>
 __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_t *__restrict__ rowptr,
                                                 const int32_t *__restrict__ colidx, const double *__restrict__ lu,
@@ -935,7 +952,10 @@ __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_
                                                 double *ring_p, int32_t *ring_k, uint32_t first, uint32_t nrow_f,
                                                 uint32_t ntot, int lane) {
     const uint32_t FULL = 0xffffffffu;
-    // step s of the sweep handles block row i = s (forward) or ntot-1-s (backward)
+    const uint32_t rpf = (uint32_t)B.rows_per_field;
+    const int nf = B.nf;
+    // step s of the sweep handles block row i = s (forward) or ntot-1-s (backward);
+    // beg / len of a half-row: off-diagonal entries only (the pivot of a U row sits at beg - 1)
     auto batch_ptrs = [&](uint32_t b, int64_t &beg, int32_t &len) {
         const uint32_t st = b * 32 + lane;
         beg = 0;
@@ -946,8 +966,8 @@ __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_
             const int64_t r = (int64_t)f * B.rows_per_field + first + j;
             const int64_t rs = rowptr[r], re = rowptr[r + 1];
             const int32_t dp = diag_pos[r];
-            beg = UPPER ? rs + dp : rs;                       // upper: the diagonal leads the half-row
-            len = UPPER ? (int32_t)(re - rs) - dp : dp;
+            beg = UPPER ? rs + dp + 1 : rs;
+            len = UPPER ? (int32_t)(re - rs) - dp - 1 : dp;
         }
     };
     int64_t begC, begN;
@@ -955,34 +975,37 @@ __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_
     batch_ptrs(0, begC, lenC);
     batch_ptrs(1, begN, lenN);
     uint32_t curb = 0;                                       // batch whose pointers are in begC / lenC
+    int slot_i = 0;                                          // ring slot the next issue fills
     auto issue = [&](uint32_t st) {                          // st: step whose half-row is fetched (warp-uniform)
         if (st < ntot) {
             int64_t beg;
-            int32_t len;
+            int32_t n;
             if ((st >> 5) == curb) {                         // (a select would wait for the batch still in flight)
                 beg = __shfl_sync(FULL, begC, st & 31);
-                len = __shfl_sync(FULL, lenC, st & 31);
+                n = __shfl_sync(FULL, lenC, st & 31);
             } else {
                 beg = __shfl_sync(FULL, begN, st & 31);
-                len = __shfl_sync(FULL, lenN, st & 31);
+                n = __shfl_sync(FULL, lenN, st & 31);
             }
-            const int slot = st % ILU_SLOTS;
-            // off-diagonal entries: [beg, beg+len) for L, [beg+1, beg+len) for U
-            const int64_t e0 = beg + (UPPER ? 1 : 0);
-            const int32_t n = len - (UPPER ? 1 : 0);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int e = lane + 32 * h;
-                if (e < n) {
-                    cp_async4(ring_k + slot * 64 + e, colidx + e0 + e);
-                    cp_async8(ring_v + slot * 64 + e, lu + e0 + e);
-                }
+            const int32_t *ck = colidx + beg + lane;
+            const double *cv = lu + beg + lane;
+            int32_t *dk = ring_k + slot_i * 64 + lane;
+            double *dv = ring_v + slot_i * 64 + lane;
+            if (lane < n) {
+                cp_async4(dk, ck);
+                cp_async8(dv, cv);
             }
-            if (UPPER && lane == 0) cp_async8(ring_p + slot, lu + beg);
+            if (n > 32 && lane + 32 < n) {
+                cp_async4(dk + 32, ck + 32);
+                cp_async8(dv + 32, cv + 32);
+            }
+            if (UPPER && lane == 0) cp_async8(ring_p + slot_i, lu + beg - 1);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        slot_i = slot_i + 1 == ILU_SLOTS ? 0 : slot_i + 1;
     };
     for (uint32_t st = 0; st < (uint32_t)ILU_RING; ++st) issue(st);
+    int slot = 0;                                            // ring slot of the row being solved
     for (uint32_t st = 0; st < ntot; ++st) {
         if ((st >> 5) != curb) {                             // first step of a batch: rotate, fetch the one after
             curb = st >> 5;
@@ -992,23 +1015,22 @@ __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_
         }
         issue(st + ILU_RING);
         asm volatile("cp.async.wait_group %0;" ::"n"(ILU_RING) : "memory");
-        const int64_t beg = __shfl_sync(FULL, begC, st & 31);
-        const int32_t len = __shfl_sync(FULL, lenC, st & 31);
-        const int slot = st % ILU_SLOTS;
-        const int64_t e0 = beg + (UPPER ? 1 : 0);
-        const int32_t n = len - (UPPER ? 1 : 0);
-        double s = 0.0;
-        if (lane < n) {
-            const int32_t k = block_local<true>(B, ring_k[slot * 64 + lane], first, nrow_f);
-            if (k >= 0) s += ring_v[slot * 64 + lane] * z[k];
-        }
-        if (lane + 32 < n) {
-            const int32_t k = block_local<true>(B, ring_k[slot * 64 + lane + 32], first, nrow_f);
-            if (k >= 0) s += ring_v[slot * 64 + lane + 32] * z[k];
-        }
-        for (int64_t p = e0 + 64 + lane; p < e0 + n; p += 32) {       // rows longer than 64 entries per half
-            const int32_t k = block_local<true>(B, colidx[p], first, nrow_f);
-            if (k >= 0) s += lu[p] * z[k];
+        const int32_t n = __shfl_sync(FULL, lenC, st & 31);
+        // lanes beyond the half-row read stale ring entries and contribute fma(0, z, s) = s
+        int32_t k = ring_local(ring_k[slot * 64 + lane], first, nrow_f, rpf, nf);
+        if (lane >= n) k = -1;
+        double s = fma(k >= 0 ? ring_v[slot * 64 + lane] : 0.0, z[k >= 0 ? k : 0], 0.0);
+        if (n > 32) {                                        // warp-uniform
+            int32_t k1 = ring_local(ring_k[slot * 64 + lane + 32], first, nrow_f, rpf, nf);
+            if (lane + 32 >= n) k1 = -1;
+            s = fma(k1 >= 0 ? ring_v[slot * 64 + lane + 32] : 0.0, z[k1 >= 0 ? k1 : 0], s);
+            if (n > 64) {                                    // rows longer than 64 entries per half
+                const int64_t e0 = __shfl_sync(FULL, begC, st & 31);
+                for (int64_t p = e0 + 64 + lane; p < e0 + n; p += 32) {
+                    const int32_t kt = ring_local(colidx[p], first, nrow_f, rpf, nf);
+                    if (kt >= 0) s += lu[p] * z[kt];
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
@@ -1016,6 +1038,7 @@ __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_
             const uint32_t i = UPPER ? ntot - 1 - st : st;
             z[i] = UPPER ? (z[i] - s) / ring_p[slot] : z[i] - s;
         }
+        slot = slot + 1 == ILU_SLOTS ? 0 : slot + 1;
         __syncwarp();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
