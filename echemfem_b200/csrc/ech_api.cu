@@ -935,17 +935,27 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 
 // column -> slot of z in shared memory, or -1 outside the block; a uniform loop over the fields, no divider and
 // no divergent branch (this sits on the per-row chain, and the kernel is issue-bound on the fine level)
+template <int NFT>      // number of fields at compile time (the loop unrolls), 0: run time
 __device__ __forceinline__ int32_t ring_local(int32_t col, uint32_t first, uint32_t nrow_f, uint32_t rpf, int nf) {
     const uint32_t d = (uint32_t)col - first;
     int32_t k = -1;
-    for (int f = 0; f < nf; ++f) {
-        const uint32_t dd = d - (uint32_t)f * rpf;
-        if (dd < nrow_f) k = (int32_t)((uint32_t)f * nrow_f + dd);
+    if constexpr (NFT > 0) {
+#pragma unroll
+        for (int f = 0; f < NFT; ++f) {
+            const uint32_t dd = d - (uint32_t)f * rpf;
+            if (dd < nrow_f) k = (int32_t)((uint32_t)f * nrow_f + dd);
+        }
+    } else {
+#pragma unroll 1
+        for (int f = 0; f < nf; ++f) {
+            const uint32_t dd = d - (uint32_t)f * rpf;
+            if (dd < nrow_f) k = (int32_t)((uint32_t)f * nrow_f + dd);
+        }
     }
     return k;
 }
 
-template <bool UPPER>
+template <bool UPPER, int NFT>
 __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_t *__restrict__ rowptr,
                                                 const int32_t *__restrict__ colidx, const double *__restrict__ lu,
                                                 const int32_t *__restrict__ diag_pos, double *z, double *ring_v,
@@ -1017,17 +1027,17 @@ __device__ __forceinline__ void ilu0_ring_sweep(const BlockPlan &B, const int64_
         asm volatile("cp.async.wait_group %0;" ::"n"(ILU_RING) : "memory");
         const int32_t n = __shfl_sync(FULL, lenC, st & 31);
         // lanes beyond the half-row read stale ring entries and contribute fma(0, z, s) = s
-        int32_t k = ring_local(ring_k[slot * 64 + lane], first, nrow_f, rpf, nf);
+        int32_t k = ring_local<NFT>(ring_k[slot * 64 + lane], first, nrow_f, rpf, nf);
         if (lane >= n) k = -1;
         double s = fma(k >= 0 ? ring_v[slot * 64 + lane] : 0.0, z[k >= 0 ? k : 0], 0.0);
         if (n > 32) {                                        // warp-uniform
-            int32_t k1 = ring_local(ring_k[slot * 64 + lane + 32], first, nrow_f, rpf, nf);
+            int32_t k1 = ring_local<NFT>(ring_k[slot * 64 + lane + 32], first, nrow_f, rpf, nf);
             if (lane + 32 >= n) k1 = -1;
             s = fma(k1 >= 0 ? ring_v[slot * 64 + lane + 32] : 0.0, z[k1 >= 0 ? k1 : 0], s);
             if (n > 64) {                                    // rows longer than 64 entries per half
                 const int64_t e0 = __shfl_sync(FULL, begC, st & 31);
                 for (int64_t p = e0 + 64 + lane; p < e0 + n; p += 32) {
-                    const int32_t kt = ring_local(colidx[p], first, nrow_f, rpf, nf);
+                    const int32_t kt = ring_local<NFT>(colidx[p], first, nrow_f, rpf, nf);
                     if (kt >= 0) s += lu[p] * z[kt];
                 }
             }
@@ -1057,8 +1067,19 @@ __device__ __forceinline__ void ilu0_solve_block_ring(const BlockPlan &B, const 
     for (int f = 0; f < B.nf; ++f)
         for (uint32_t j = lane; j < nrow_f; j += 32) zs[f * nrow_f + j] = rhs[(int64_t)f * B.rows_per_field + first + j];
     __syncwarp();
-    ilu0_ring_sweep<false>(B, rowptr, colidx, lu, diag_pos, zs, ring_v, ring_p, ring_k, first, nrow_f, ntot, lane);
-    ilu0_ring_sweep<true>(B, rowptr, colidx, lu, diag_pos, zs, ring_v, ring_p, ring_k, first, nrow_f, ntot, lane);
+#define ECH_RING_SWEEPS(NFT)                                                                                          \
+    ilu0_ring_sweep<false, NFT>(B, rowptr, colidx, lu, diag_pos, zs, ring_v, ring_p, ring_k, first, nrow_f, ntot, lane); \
+    ilu0_ring_sweep<true, NFT>(B, rowptr, colidx, lu, diag_pos, zs, ring_v, ring_p, ring_k, first, nrow_f, ntot, lane);
+    if (B.nf == 2) {
+        ECH_RING_SWEEPS(2)
+    } else if (B.nf == 3) {
+        ECH_RING_SWEEPS(3)
+    } else if (B.nf == 1) {
+        ECH_RING_SWEEPS(1)
+    } else {
+        ECH_RING_SWEEPS(0)
+    }
+#undef ECH_RING_SWEEPS
     for (int f = 0; f < B.nf; ++f)
         for (uint32_t j = lane; j < nrow_f; j += 32) zg[(int64_t)f * B.rows_per_field + first + j] = zs[f * nrow_f + j];
 }
