@@ -51,6 +51,10 @@ class _Printer(C99CodePrinter):
     def _print_Abs(self, expr):
         return "fabs(%s)" % self._print(expr.args[0])
 
+    def _print_PosPart(self, expr):
+        # (x + |x|) / 2 == fmax(x, 0) bit for bit, with x evaluated once (symbolic.PosPart)
+        return "fmax((double)(%s), 0.0)" % self._print(expr.args[0])
+
     def _print_Max(self, expr):
         args = [self._print(a) for a in expr.args]
         out = args[0]

@@ -299,6 +299,10 @@ __global__ void cell_geometry_kernel(int64_t ncell, const double *__restrict__ x
     double X[NV][D];
     for (int v = 0; v < NV; ++v)
         for (int a = 0; a < D; ++a) X[v][a] = xcell[(c * NV + v) * D + a];
+    // volumes, areas and diameters are translation invariant: work relative to vertex 0 (differences of nearby
+    // vertices are exact, so J keeps full relative accuracy however far the cell is from the origin)
+    for (int v = NV - 1; v >= 0; --v)
+        for (int a = 0; a < D; ++a) X[v][a] -= X[0][a];
     const double gp[3] = {0.5 - 0.5 * 0.7745966692414834, 0.5, 0.5 + 0.5 * 0.7745966692414834};
     const double gw[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
     auto jac = [&](const double (&xi)[D], double (&J)[D][D]) {

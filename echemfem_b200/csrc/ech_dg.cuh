@@ -69,14 +69,18 @@ __device__ __forceinline__ void geometry(const double (&X)[NV][D], const int (&i
 #pragma unroll
     for (int k = 0; k < D; ++k) xi[k] = TAB_X[idx[k]];
     double J[D][D];
+    // Edge form: x = X_0 + sum_v N_v (X_v - X_0), J = sum_v dN_v (X_v - X_0) (the shape functions sum to one, their
+    // derivatives to zero).  The differences of neighbouring vertices are exact in floating point, so a cell of
+    // size h at distance |X| from the origin keeps full relative accuracy in J instead of losing log10(|X| / h)
+    // digits to cancellation (graded Bortels meshes: |X| / h ~ 1e4).
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-        g.x[a] = 0.0;
+        g.x[a] = X[0][a];
 #pragma unroll
         for (int m = 0; m < D; ++m) J[a][m] = 0.0;
     }
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
+    for (int v = 1; v < NV; ++v) {
         double N = 1.0, dN[D];
 #pragma unroll
         for (int m = 0; m < D; ++m) dN[m] = 1.0;
@@ -91,9 +95,10 @@ __device__ __forceinline__ void geometry(const double (&X)[NV][D], const int (&i
         }
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-            g.x[a] += N * X[v][a];
+            const double e = X[v][a] - X[0][a];
+            g.x[a] += N * e;
 #pragma unroll
-            for (int m = 0; m < D; ++m) J[a][m] += dN[m] * X[v][a];
+            for (int m = 0; m < D; ++m) J[a][m] += dN[m] * e;
         }
     }
     if constexpr (D == 1) {

@@ -229,7 +229,7 @@ def evaluate_expression(expr, x):
             args.append(np.full(x.shape[0], sym.Constant.lookup(s)))
         else:
             raise ValueError("cannot interpolate an expression depending on %s" % s)
-    f = sp.lambdify(syms, e, [{"rpow": np.power}, "numpy"])
+    f = sp.lambdify(syms, e, [{"rpow": np.power, "PosPart": lambda v: np.maximum(v, 0.0)}, "numpy"])
     out = f(*args) if syms else float(e)
     return np.broadcast_to(np.asarray(out, dtype=float), (x.shape[0],)).copy()
 

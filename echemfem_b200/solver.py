@@ -267,7 +267,7 @@ class EchemSolver:
         """(v+ - v-)(flow_N+ C+ - flow_N- C-),  flow_N = (flow.n + |flow.n|)/2  (solver.py:1652-1654)."""
         n = S.facet_normal(self.mesh.dim)
         fn = dot(flow, n)
-        flow_N = 0.5 * (fn + abs(fn))
+        flow_N = S.positive_part(fn)         # 0.5 * (fn + abs(fn)), kept as one node (symbolic.PosPart)
         return (test('+') - test('-')) * (flow_N('+') * C('+') - flow_N('-') * C('-')) * self.dS
 
     def _packing(self, u, powers=(3,)):

@@ -436,6 +436,28 @@ sign = _fn(sp.sign)
 pi = sp.pi
 
 
+class PosPart(sp.Function):
+    """(x + |x|) / 2 kept as ONE node.  sympy distributes the 1/2 and expands x, after which x and |x| are evaluated
+    along different association orders and a negative x leaves eps * |x| instead of the exact 0 the reference's
+    `0.5*(fn + abs(fn))` gives -- enough to spoil the 1e-12 entry tolerance of blocks whose own scale is 1e5 times
+    smaller than the advective flux.  Printed as fmax(x, 0), which equals (x + |x|) / 2 bit for bit; differentiates
+    as UFL does (d|x| = sign(x) dx)."""
+    nargs = 1
+
+    @classmethod
+    def eval(cls, x):
+        if x.is_Number:
+            return sp.Max(x, 0)
+
+    def fdiff(self, argindex=1):
+        return (1 + sp.sign(self.args[0])) / 2
+
+
+def positive_part(e):
+    """(e + |e|) / 2 (upwind flux of echemfem/solver.py:1652-1654)."""
+    return as_expr(e)._map(PosPart)
+
+
 def max_value(a, b):
     return Expr(sp.Max(as_expr(a).v, as_expr(b).v))
 

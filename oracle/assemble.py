@@ -65,8 +65,11 @@ class Discretization:
         """
         N, dN = fem.tabulate(np.array([0.0, 1.0]), xi)          # (npts, 2^d), (npts, 2^d, d)
         X = self.Xc[cells]                                      # (ne, 2^d, d)
-        x = np.einsum("qv,eva->eqa", N, X)
-        J = np.einsum("qvb,eva->eqab", dN, X)
+        # edge form (sum N = 1, sum dN = 0): differences of neighbouring vertices are exact, so J keeps full
+        # relative accuracy for small cells far from the origin (graded meshes) instead of cancelling
+        E = X[:, 1:] - X[:, :1]
+        x = X[:, :1] + np.einsum("qv,eva->eqa", N[:, 1:], E)
+        J = np.einsum("qvb,eva->eqab", dN[:, 1:], E)
         return x, J
 
     def _geometry_constants(self):
@@ -256,6 +259,30 @@ class Discretization:
             np.add.at(F, self._rows(c).ravel(), R.ravel())
         return F
 
+    def residual_scale(self, u):
+        """Per-field max-abs of the ELEMENT vectors (cell, interior-facet halves, exterior facets) whose sum is the
+        assembled residual: the `tau_block` of residual entries.  Near a solution the assembled entries
+        cancel to far below the terms that were added, and rounding error scales with the terms."""
+        u = np.asarray(u, dtype=float)
+        tau = np.zeros(self.nf)
+
+        def see(R):
+            if R.shape[0]:
+                np.maximum(tau, np.abs(R).max(axis=(0, 2)), out=tau)
+        cells = np.arange(self.mesh.num_cells)
+        see(self._cell_local(self._local(u, cells), cells))
+        if self.prob.family == "DG":
+            for fl, l0, l1, xi0, xi1 in self._int_groups():
+                IF = self.mesh.int_facets[fl]
+                Rp, Rm = self._int_local(self._local(u, IF[:, 0]), self._local(u, IF[:, 1]), fl, l0, l1, xi0, xi1)
+                see(Rp)
+                see(Rm)
+        aux = self._aux()
+        for sel, lf, m in self._ext_groups():
+            c = self.mesh.ext_facets[sel, 0]
+            see(self._ext_local(self._local(u, c), sel, lf, m, aux))
+        return tau
+
     # -- local Jacobians by complex step ----------------------------------
     def _cs(self, fun, U, h=1e-30):
         """d fun / d U for U (ne, nf, n) -> (ne, nf, n, nf, n) [row eq, row node, col field, col node]."""
@@ -366,8 +393,13 @@ class Discretization:
         P.sort_indices()
         return P.indptr.astype(np.int64), P.indices.astype(np.int32)
 
-    def jacobian(self, u):
-        """CSR Jacobian on the fixed pattern (explicit zeros kept)."""
+    def jacobian(self, u, return_scale=False):
+        """CSR Jacobian on the fixed pattern (explicit zeros kept).
+
+        return_scale: also return, on the same pattern, the sum of the ABSOLUTE values of the element-level
+        contributions (cell matrix + facet macro-element blocks) to every entry.  Its block-wise maximum is the
+        `tau_block` of SURVEY 8c: assembled entries may cancel to far below the element blocks that were added
+        (advection cell term against upwind facet term), and rounding error scales with those."""
         own, nbr = self.block_mask()
         em = self.element_matrices(u)
         nf, n = self.nf, self.n
@@ -397,10 +429,15 @@ class Discretization:
             c = self.mesh.ext_facets[sel, 0]
             add(c, c, K, own)
         indptr, indices = self.pattern()
-        A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
-                          shape=(self.ndof, self.ndof))
+        rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+        A = sp.csr_matrix((vals, (rows, cols)), shape=(self.ndof, self.ndof))
         A.sum_duplicates()
-        return _on_pattern(A, indptr, indices, self.ndof)
+        J = _on_pattern(A, indptr, indices, self.ndof)
+        if not return_scale:
+            return J
+        S = sp.csr_matrix((np.abs(vals), (rows, cols)), shape=(self.ndof, self.ndof))
+        S.sum_duplicates()
+        return J, _on_pattern(S, indptr, indices, self.ndof).data
 
     # -- helpers ----------------------------------------------------------
     def interpolate(self, f):

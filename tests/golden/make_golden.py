@@ -55,10 +55,11 @@ def cases():
 
 def main():
     for name, (d, u) in cases().items():
-        J = d.jacobian(u)
+        # Fscale / Jscale: element-level scales of the entries (the tau_block of tests/parity.py)
+        J, Jscale = d.jacobian(u, return_scale=True)
         indptr, indices = d.pattern()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), u=u, F=d.residual(u), indptr=indptr.astype(np.int64),
-                            indices=indices.astype(np.int32), data=J.data)
+                            indices=indices.astype(np.int32), data=J.data, Fscale=d.residual_scale(u), Jscale=Jscale)
         print(name, "ndof", d.ndof, "nnz", J.nnz)
 
 

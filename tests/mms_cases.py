@@ -138,8 +138,12 @@ def poisson_C2ex(x):
     return np.cos(x[..., 0]) - np.sin(x[..., 1]) + 3.0
 
 
-def poisson_problem(family="DG"):
-    """tests/test_diffusion_migration_poisson.py:6-57 of the reference for the oracle."""
+def poisson_problem(family="DG", variant=None):
+    """tests/test_diffusion_migration_poisson.py:6-57 of the reference for the oracle.
+
+    `variant` switches on one of the Poisson branches the reference's own tests never reach
+    (echemfem/solver.py:2085-2093, 2219-2232): "robin" (gap capacitance on side 2), "applied liquid current"
+    (applied current density on side 2), "liquid conductivity" (K_U given instead of the permittivities)."""
     from oracle.forms import Problem
 
     def f(u, x):
@@ -162,6 +166,17 @@ def poisson_problem(family="DG"):
     physical_params = {"flow": ["diffusion", "migration", "poisson"], "F": 1.0, "R": 1.0, "T": 1.0,
                        "vacuum permittivity": 2.0, "relative permittivity": 1e-1, "U_app": Uex, "bulk reaction": f}
     markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4)}
+    if variant == "robin":
+        physical_params["gap capacitance"] = 0.7
+        markers.update({"applied": (1, 3, 4), "robin": (2,)})
+    elif variant == "applied liquid current":
+        physical_params["applied current density"] = 0.3
+        markers.update({"applied": (1, 3, 4), "applied liquid current": (2,)})
+    elif variant == "liquid conductivity":
+        del physical_params["vacuum permittivity"], physical_params["relative permittivity"]
+        physical_params["liquid conductivity"] = 0.4
+    elif variant is not None:
+        raise ValueError(variant)
     return Problem(conc_params, physical_params, markers, family=family)
 
 
@@ -185,8 +200,9 @@ def heat_problem(t, dt, u_old, family="DG"):
     return prob, c1, c2
 
 
-def porous_problem(vavg):
-    """tests/test_advection_diffusion_migration_porous.py:6-70 of the reference for the oracle (DG)."""
+def porous_problem(vavg, solid_current=False):
+    """tests/test_advection_diffusion_migration_porous.py:6-70 of the reference for the oracle (DG).
+    `solid_current`: side 2 carries "applied solid current" (solver.py:2219-2221) instead of the applied potential."""
     from oracle.forms import Problem
     eps = 0.5
     De = lambda D: D * eps ** 1.5
@@ -211,6 +227,9 @@ def porous_problem(vavg):
                        "F": 1.0, "R": 1.0, "T": 1.0, "U_app": Uex, "bulk reaction": f, "porosity": eps,
                        "solid conductivity": 1.0, "specific surface area": 1.0}
     markers = {"bulk dirichlet": (1, 2, 3, 4), "applied": (1, 2, 3, 4), "liquid applied": (1, 2, 3, 4)}
+    if solid_current:
+        physical_params["applied current density"] = 0.25
+        markers.update({"applied": (1, 3, 4), "applied solid current": (2,)})
     return Problem(conc_params, physical_params, markers, vel=make_vel(vavg))
 
 

@@ -44,5 +44,5 @@ def evaluate(expr, dat, form=None):
     npts = dat["x"].shape[0]
     if not syms:
         return np.full(npts, float(expr))
-    f = sp.lambdify(syms, expr, [{"rpow": np.power}, "numpy"])
+    f = sp.lambdify(syms, expr, [{"rpow": np.power, "PosPart": lambda v: np.maximum(v, 0.0)}, "numpy"])
     return np.broadcast_to(f(*[_value(str(s), dat) for s in syms]), (npts,)).astype(float)

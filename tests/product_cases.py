@@ -7,42 +7,9 @@ from echemfem_b200.fd import *  # noqa: F401,F403
 from echemfem_b200 import EchemSolver
 
 
-class AdvectionDiffusionMigrationSolver(EchemSolver):
-    def __init__(self, N, vavg, family="DG", p=1, D1=0.5, D2=1.0, mesh=None):
-        if mesh is None:
-            mesh = UnitSquareMesh(N, N, quadrilateral=True)
-        conc_params = []
-        x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
-        C1ex = cos(x) + sin(y) + 3
-        C2ex = C1ex
-        Uex = sin(x) + cos(y) + 3
-        self.C1ex = C1ex
-        self.C2ex = C2ex
-        self.Uex = Uex
-
-        def f(C):
-            z1 = 2.0
-            z2 = -2.0
-            f1 = div((self.vel - D1 * z1 * grad(Uex)) * C1ex) - div(D1 * grad(C1ex))
-            f2 = div((self.vel - D2 * z2 * grad(Uex)) * C2ex) - div(D2 * grad(C2ex))
-            return [f1, f2]
-
-        conc_params.append({"name": "C1", "diffusion coefficient": D1, "z": 2., "bulk": C1ex})
-        conc_params.append({"name": "C2", "diffusion coefficient": D2, "z": -2., "bulk": C2ex})
-        physical_params = {"flow": ["diffusion", "advection", "migration", "electroneutrality"],
-                           "F": 1.0, "R": 1.0, "T": 1.0, "U_app": Uex, "bulk reaction": f,
-                           "v_avg": Constant(vavg)}
-        super().__init__(conc_params, physical_params, mesh, family=family, p=p)
-
-    def set_boundary_markers(self):
-        self.boundary_markers = {"applied": (1, 2, 3, 4,), "bulk dirichlet": (1, 2, 3, 4,)}
-
-    def set_velocity(self):
-        xs = SpatialCoordinate(self.mesh)
-        y = xs[1]
-        h = 1.0
-        comps = [6. * self.physical_params["v_avg"] / h**2 * y * (h - y)] + [Constant(0.)] * (len(xs) - 1)
-        self.vel = as_vector(comps)
+from echemfem_b200.workloads import MMSSolver as AdvectionDiffusionMigrationSolver  # noqa: E402,F401
+# (tests/test_advection_diffusion_migration.py:11-63 of the reference; the class lives in the package because it
+# is also the benchmark workload of BASELINE.json configs[1])
 
 
 def bortels_parameters():
@@ -135,13 +102,14 @@ class AdvectionDiffusionSolver(EchemSolver):
 class DiffusionMigrationPoissonSolver(EchemSolver):
     """tests/test_diffusion_migration_poisson.py:6-57 of the reference: Nernst-Planck + true Poisson."""
 
-    def __init__(self, N, family="DG"):
+    def __init__(self, N, family="DG", variant=None):
         mesh = UnitSquareMesh(N, N, quadrilateral=True)
         x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
         C1ex = cos(x) + sin(y) + 3
         C2ex = cos(x) - sin(y) + 3
         Uex = sin(x) + cos(y) + 3
         self.C1ex, self.C2ex, self.Uex = C1ex, C2ex, Uex
+        self.variant = variant        # Poisson branches of solver.py:2085-2093, 2219-2232 (see mms_cases.poisson_problem)
 
         def f(C):
             D1, D2, z1, z2, K = 0.5, 1.0, 2.0, -2.0, 2e-1
@@ -155,10 +123,21 @@ class DiffusionMigrationPoissonSolver(EchemSolver):
         physical_params = {"flow": ["diffusion", "migration", "poisson"], "F": 1.0, "R": 1.0, "T": 1.0,
                            "vacuum permittivity": 2.0, "relative permittivity": 1e-1, "U_app": Uex,
                            "bulk reaction": f}
+        if variant == "robin":
+            physical_params["gap capacitance"] = 0.7
+        elif variant == "applied liquid current":
+            physical_params["applied current density"] = 0.3
+        elif variant == "liquid conductivity":
+            del physical_params["vacuum permittivity"], physical_params["relative permittivity"]
+            physical_params["liquid conductivity"] = 0.4
         super().__init__(conc_params, physical_params, mesh, family=family)
 
     def set_boundary_markers(self):
         self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,), "applied": (1, 2, 3, 4,)}
+        if self.variant == "robin":
+            self.boundary_markers.update({"applied": (1, 3, 4), "robin": (2,)})
+        elif self.variant == "applied liquid current":
+            self.boundary_markers.update({"applied": (1, 3, 4), "applied liquid current": (2,)})
 
 
 from echemfem_b200 import TransientEchemSolver  # noqa: E402
@@ -194,7 +173,7 @@ class PorousSolver(EchemSolver):
     """tests/test_advection_diffusion_migration_porous.py:6-70 of the reference: porous electrode model,
     liquid + solid potentials, Bruggeman effective coefficients."""
 
-    def __init__(self, N, vavg):
+    def __init__(self, N, vavg, solid_current=False):
         mesh = UnitSquareMesh(N, N, quadrilateral=True)
         x, y = SpatialCoordinate(mesh)[0], SpatialCoordinate(mesh)[1]
         C1ex = cos(x) + sin(y) + 3
@@ -202,6 +181,7 @@ class PorousSolver(EchemSolver):
         U1ex = sin(x) + cos(y) + 3
         U2ex = sin(x) + cos(y) + 3
         self.C1ex, self.C2ex, self.U1ex, self.U2ex = C1ex, C2ex, U1ex, U2ex
+        self.solid_current = solid_current       # "applied solid current" on side 2 (solver.py:2219-2221)
 
         def f(C):
             D1, D2, z1, z2, K = 0.5, 1.0, 2.0, -2.0, 1.0
@@ -218,11 +198,15 @@ class PorousSolver(EchemSolver):
                            "F": 1.0, "R": 1.0, "T": 1.0, "U_app": U1ex, "bulk reaction": f, "v_avg": vavg,
                            "porosity": 0.5, "solid conductivity": 1., "specific surface area": 1.,
                            "standard potential": 0.}
+        if solid_current:
+            physical_params["applied current density"] = 0.25
         super().__init__(conc_params, physical_params, mesh)
 
     def set_boundary_markers(self):
         self.boundary_markers = {"bulk dirichlet": (1, 2, 3, 4,), "applied": (1, 2, 3, 4,),
                                  "liquid applied": (1, 2, 3, 4)}
+        if self.solid_current:
+            self.boundary_markers.update({"applied": (1, 3, 4), "applied solid current": (2,)})
 
     def set_velocity(self):
         y = SpatialCoordinate(self.mesh)[1]

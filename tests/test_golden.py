@@ -17,10 +17,9 @@ def _load(name):
     return np.load(os.path.join(HERE, "golden", name + ".npz"))
 
 
-def _close(a, b, what, rtol=1e-12):
-    tau = max(np.abs(a).max(), np.abs(b).max())
-    err = np.abs(a - b).max()
-    assert err <= 10 * rtol * tau, "%s: max abs err %.3e vs scale %.3e" % (what, err, tau)
+import parity  # noqa: E402
+
+
 
 
 @pytest.fixture(scope="module")
@@ -35,8 +34,9 @@ def test_oracle_reproduces_golden(oracle_cases, name):
     assert np.array_equal(u, g["u"])
     indptr, indices = d.pattern()
     assert np.array_equal(indptr, g["indptr"]) and np.array_equal(indices, g["indices"])
-    _close(d.residual(u), g["F"], name + " residual", 1e-13)
-    _close(d.jacobian(u).data, g["data"], name + " jacobian", 1e-13)
+    parity.assert_vec_close(d.residual(u), g["F"], d.nf, name + " residual", 1e-13, scale=g["Fscale"])
+    parity.assert_csr_close(d.jacobian(u).data, g["data"], indptr, indices, d.nf, d.ndof_scalar, d.n,
+                            name + " jacobian", continuous=(d.prob.family != "DG"), rtol=1e-13, scale=g["Jscale"])
 
 
 def _product(name):
@@ -67,5 +67,6 @@ def test_cuda_path_reproduces_golden(name):
     assert np.array_equal(rp, g["indptr"]) and np.array_equal(ci, g["indices"])          # sparsity: bit-exact
     F = torch.zeros_like(s.u.tensor)
     eng.residual_jacobian(s.u.tensor, out=F)
-    _close(F.cpu().numpy(), g["F"], name + " residual")
-    _close(eng.vals.cpu().numpy(), g["data"], name + " jacobian")
+    parity.assert_vec_close(F.cpu().numpy(), g["F"], eng.nf, name + " residual", scale=g["Fscale"])
+    parity.assert_csr_close(eng.vals.cpu().numpy(), g["data"], g["indptr"], g["indices"], eng.nf, eng.N, eng.nloc,
+                            name + " jacobian", continuous=(eng.family == "CG"), scale=g["Jscale"])

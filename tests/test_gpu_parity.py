@@ -1,18 +1,17 @@
 """CUDA assembly vs oracle: sparsity bit-exact, residual and Jacobian entries to 1e-12 (north_star tolerance).
 
-Entry tolerance: |a - b| <= 1e-12 * max(|a|, |b|, tau) with tau the largest
-magnitude in the compared array block (pure relative error is meaningless for entries that
-cancel to ~0).
+Entry tolerance (tests/parity.py): |a - b| <= 1e-12 * max(|a|, |b|, tau_block), tau_block the
+max-abs of the (row cell, column cell, field pair) element block; one scale per field for residuals.
 """
 import numpy as np
 import pytest
 import torch
 
 import mms_cases
+import parity
 import product_cases
 
 pytestmark = pytest.mark.gpu
-RTOL = 1e-12
 
 
 def _state(disc, seed=0):
@@ -21,12 +20,6 @@ def _state(disc, seed=0):
     ph = 7 * x[:, 0] + 3 * x[:, 1] + (5 * x[:, 2] if x.shape[1] > 2 else 0.0)
     pert = 1e-3 * np.sin(ph)     # varies in every direction: no facet sees an exactly zero normal flux (|.| kink)
     return np.concatenate([mms_cases.C1ex(x) + pert, mms_cases.Uex(x) - pert])
-
-
-def _assert_close(a, b, what):
-    tau = max(np.abs(a).max(), np.abs(b).max())
-    err = np.abs(a - b).max()
-    assert err <= RTOL * tau * 10, "%s: max abs err %.3e vs scale %.3e" % (what, err, tau)
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -50,18 +43,18 @@ def test_adm_dg_q1_assembly_matches_oracle(N, vavg, variant):
     assert np.array_equal(ci, indices)
 
     F = eng.residual(s.u.tensor).cpu().numpy()
-    _assert_close(F, disc.residual(u), "residual")
+    parity.check_F(eng, F, disc.residual(u), "residual", scale=disc.residual_scale(u))
 
     eng.jacobian(s.u.tensor)
     vals = eng.vals.cpu().numpy()
-    J = disc.jacobian(u)
-    _assert_close(vals, J.data, "jacobian")
+    J, Jscale = disc.jacobian(u, return_scale=True)
+    parity.check_J(eng, vals, (J, Jscale), "jacobian")
 
     # SpMV against scipy on the same matrix
     x = np.cos(np.arange(disc.ndof) * 0.37)
     y = torch.empty(disc.ndof, dtype=torch.float64, device="cuda")
     eng.spmv(torch.from_numpy(x).cuda(), y)
-    _assert_close(y.cpu().numpy(), J @ x, "spmv")
+    parity.check_F(eng, y.cpu().numpy(), J @ x, "spmv")
     eng.set_variant(0)
 
 
@@ -95,16 +88,16 @@ def _compare(disc, s, tag):
     for variant in (0, 1):
         eng.set_variant(variant)
         F = eng.residual(s.u.tensor).cpu().numpy()
-        _assert_close(F, disc.residual(u), "%s residual v%d" % (tag, variant))
+        parity.check_F(eng, F, disc.residual(u), "%s residual v%d" % (tag, variant), scale=disc.residual_scale(u))
         eng.vals.zero_()
         eng.jacobian(s.u.tensor)
-        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "%s jacobian v%d" % (tag, variant))
+        parity.check_J(eng, eng.vals.cpu().numpy(), disc.jacobian(u, return_scale=True), "%s jacobian v%d" % (tag, variant))
         # fused evaluation of both at the same state
         eng.vals.zero_()
         Ff = torch.zeros_like(s.u.tensor)
         eng.residual_jacobian(s.u.tensor, out=Ff)
-        _assert_close(Ff.cpu().numpy(), disc.residual(u), "%s fused residual v%d" % (tag, variant))
-        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "%s fused jacobian v%d" % (tag, variant))
+        parity.check_F(eng, Ff.cpu().numpy(), disc.residual(u), "%s fused residual v%d" % (tag, variant), scale=disc.residual_scale(u))
+        parity.check_J(eng, eng.vals.cpu().numpy(), disc.jacobian(u, return_scale=True), "%s fused jacobian v%d" % (tag, variant))
     eng.set_variant(0)
 
 
@@ -116,6 +109,18 @@ def test_higher_order_dg_matches_oracle(p, N):
     disc = Discretization(unit_square_mesh(N), mms_cases.adm_problem(1.0, p=p))
     s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, p=p)
     _compare(disc, s, "Q%d" % p)
+
+
+@pytest.mark.parametrize("p,N", [(1, 11), (2, 4), (3, 3)])
+def test_bench_config_modules_match_oracle(p, N):
+    """The physics modules bench.py loads (cfg2: D = (0.5e-5, 1e-5) of examples/mms_scaling.py:90-93, floats baked
+    into the generated header, so these are different binaries from the D = (0.5, 1) ones above): Q1 / Q2 / Q3,
+    every kernel variant, separate and fused evaluation, entry by entry."""
+    from oracle.mesh import unit_square_mesh
+    from oracle.assemble import Discretization
+    disc = Discretization(unit_square_mesh(N), mms_cases.adm_problem(1.0, D1=0.5e-5, D2=1.0e-5, p=p))
+    s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5, p=p)
+    _compare(disc, s, "bench cfg2 Q%d" % p)
 
 
 def test_graded_mesh_matches_oracle():
@@ -162,9 +167,9 @@ def test_bortels_three_ion_matches_oracle():
     assert np.array_equal(rp, indptr) and np.array_equal(ci, indices)
     for variant in (0, 1):
         eng.set_variant(variant)
-        _assert_close(eng.residual(s.u.tensor).cpu().numpy(), disc.residual(u), "bortels residual")
+        parity.check_F(eng, eng.residual(s.u.tensor).cpu().numpy(), disc.residual(u), "bortels residual", scale=disc.residual_scale(u))
         eng.jacobian(s.u.tensor)
-        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "bortels jacobian")
+        parity.check_J(eng, eng.vals.cpu().numpy(), disc.jacobian(u, return_scale=True), "bortels jacobian")
     eng.set_variant(0)
 
 
@@ -208,12 +213,12 @@ def test_bortels_3d_extruded_matches_oracle():
     assert np.array_equal(rp, indptr) and np.array_equal(ci, indices)
     for variant in (0, 1):
         eng.set_variant(variant)
-        _assert_close(eng.residual(s.u.tensor).cpu().numpy(), disc.residual(u), "bortels 3D residual")
+        parity.check_F(eng, eng.residual(s.u.tensor).cpu().numpy(), disc.residual(u), "bortels 3D residual", scale=disc.residual_scale(u))
         eng.jacobian(s.u.tensor)
-        _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "bortels 3D jacobian")
+        parity.check_J(eng, eng.vals.cpu().numpy(), disc.jacobian(u, return_scale=True), "bortels 3D jacobian")
     eng.set_variant(0)
     Ff = torch.zeros_like(s.u.tensor)
     eng.vals.zero_()
     eng.residual_jacobian(s.u.tensor, out=Ff)
-    _assert_close(Ff.cpu().numpy(), disc.residual(u), "bortels 3D fused residual")
-    _assert_close(eng.vals.cpu().numpy(), disc.jacobian(u).data, "bortels 3D fused jacobian")
+    parity.check_F(eng, Ff.cpu().numpy(), disc.residual(u), "bortels 3D fused residual", scale=disc.residual_scale(u))
+    parity.check_J(eng, eng.vals.cpu().numpy(), disc.jacobian(u, return_scale=True), "bortels 3D fused jacobian")

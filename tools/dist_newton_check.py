@@ -20,6 +20,7 @@ from echemfem_b200.mesh import UnitSquareMesh
 from echemfem_b200.partition import partition_mesh
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+kind = sys.argv[2] if len(sys.argv) > 2 else "range"        # "range": contiguous cell ranges; "graph": graph_partition
 mesh = UnitSquareMesh(N, N)
 # serial reference on this rank's GPU
 ss = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, mesh=mesh)
@@ -28,7 +29,11 @@ ss.setup_solver()
 ss.solve()
 u_serial = ss.u.numpy()
 # distributed
-lmesh, plan = partition_mesh(mesh, rank, world)
+parts = None
+if kind == "graph":
+    from echemfem_b200.partition import graph_partition
+    parts = graph_partition(mesh, world)
+lmesh, plan = partition_mesh(mesh, rank, world, parts=parts)
 sd = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, mesh=lmesh)
 if rank != 0:
     sd.solver_parameters.pop("snes_monitor", None)
@@ -48,6 +53,6 @@ t = torch.tensor([err], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     e = sd._engine.last
-    print("DIST_NEWTON world=%d N=%d snes_its=%d ksp_its=%s max_rel_err=%.3e" % (world, N, e["snes_its"], e["ksp_its_per_step"], t.item()))
+    print("DIST_NEWTON kind=%s world=%d N=%d snes_its=%d ksp_its=%s max_rel_err=%.3e" % (kind, world, N, e["snes_its"], e["ksp_its_per_step"], t.item()))
     assert t.item() < 1e-8
 dist.destroy_process_group()
