@@ -144,6 +144,13 @@ class Discretization:
             Uold = self._local(tr["u_old"], cells)
             for i in range(self.prob.num_mass):
                 f0[i] = f0[i] + (u[i] - np.einsum("eb,qb->eq", Uold[:, i], phi)) / tr["dt"]
+        # element-level magnitude of analytically cancelling pointwise sums (Problem.cancel0), for the tolerance
+        c0 = getattr(self.prob, "cancel0", None)
+        self._cell_cancel = None
+        if c0 is not None and any(np.any(c) for c in c0):
+            aw, ap = np.abs(w), np.abs(phi)
+            self._cell_cancel = np.stack([np.einsum("eq,eq,qb->eb", aw, np.real(c), ap) +
+                                          1j * np.einsum("eq,eq,qb->eb", aw, np.imag(c), ap) for c in c0], axis=1)
         return self._test(f0, f1, w, phi, gphi)
 
     def _test(self, f0, f1, w, phi, gphi):
@@ -271,6 +278,8 @@ class Discretization:
                 np.maximum(tau, np.abs(R).max(axis=(0, 2)), out=tau)
         cells = np.arange(self.mesh.num_cells)
         see(self._cell_local(self._local(u, cells), cells))
+        if self._cell_cancel is not None:
+            see(np.real(self._cell_cancel))
         if self.prob.family == "DG":
             for fl, l0, l1, xi0, xi1 in self._int_groups():
                 IF = self.mesh.int_facets[fl]
@@ -284,16 +293,22 @@ class Discretization:
         return tau
 
     # -- local Jacobians by complex step ----------------------------------
-    def _cs(self, fun, U, h=1e-30):
-        """d fun / d U for U (ne, nf, n) -> (ne, nf, n, nf, n) [row eq, row node, col field, col node]."""
+    def _cs(self, fun, U, h=1e-30, cancel=None):
+        """d fun / d U for U (ne, nf, n) -> (ne, nf, n, nf, n) [row eq, row node, col field, col node].
+        cancel: list that receives the matching magnitudes of analytically cancelling sums (cell terms only)."""
         ne, nf, n = U.shape
         K = np.zeros((ne, nf, n, nf, n))
+        Kc = np.zeros((ne, nf, n, nf, n)) if cancel is not None else None
         Uc = U.astype(complex)
         for j in range(nf):
             for b in range(n):
                 Uc[:, j, b] += 1j * h
                 K[:, :, :, j, b] = np.imag(fun(Uc)) / h
+                if Kc is not None and self._cell_cancel is not None:
+                    Kc[:, :, :, j, b] = np.imag(self._cell_cancel) / h
                 Uc[:, j, b] = U[:, j, b]
+        if cancel is not None:
+            cancel.append(Kc)
         return K
 
     def element_matrices(self, u):
@@ -303,7 +318,9 @@ class Discretization:
         cells = np.arange(nc)
         out = {}
         U = self._local(u, cells)
-        out["cell"] = self._cs(lambda V: self._cell_local(V, cells), U)
+        canc = []
+        out["cell"] = self._cs(lambda V: self._cell_local(V, cells), U, cancel=canc)
+        out["cell_cancel"] = canc[0]
         out["int"] = []
         if self.prob.family == "DG":
             for fl, l0, l1, xi0, xi1 in self._int_groups():
@@ -429,13 +446,17 @@ class Discretization:
             c = self.mesh.ext_facets[sel, 0]
             add(c, c, K, own)
         indptr, indices = self.pattern()
-        rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
-        A = sp.csr_matrix((vals, (rows, cols)), shape=(self.ndof, self.ndof))
+        A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                          shape=(self.ndof, self.ndof))
         A.sum_duplicates()
         J = _on_pattern(A, indptr, indices, self.ndof)
         if not return_scale:
             return J
-        S = sp.csr_matrix((np.abs(vals), (rows, cols)), shape=(self.ndof, self.ndof))
+        if np.any(em["cell_cancel"]):
+            # magnitudes of analytically cancelling pointwise sums (Problem.cancel0): part of what was added
+            add(cells, cells, np.where(own[None, :, None, :, None], em["cell_cancel"], 0.0), own)
+        S = sp.csr_matrix((np.abs(np.concatenate(vals)), (np.concatenate(rows), np.concatenate(cols))),
+                          shape=(self.ndof, self.ndof))
         S.sum_duplicates()
         return J, _on_pattern(S, indptr, indices, self.ndof).data
 

@@ -345,6 +345,11 @@ class Problem:
         zero = np.zeros(x.shape[:-1], dtype=u[0].dtype)
         f0 = [zero.copy() for _ in range(nf)]
         f1 = [np.zeros(x.shape, dtype=u[0].dtype) for _ in range(nf)]
+        # magnitude of pointwise sums that cancel analytically (real part: of the terms themselves, imaginary part: of
+        # their complex-step derivatives).  The charge source sum_k z_k F R_k of charge-conserving reactions is zero
+        # in exact arithmetic; evaluated term by term, as the reference does (solver.py:1944-1946), it leaves
+        # eps * max|z_k F R_k| -- a rounding floor no assembled entry reveals.  Read by the tests' tolerance only.
+        self.cancel0 = [zero.real.copy().astype(complex) for _ in range(nf)]
         pp = self.physical_params
         C, gC = self.concentrations(u, gu)
         reactions = None
@@ -421,7 +426,9 @@ class Problem:
                 if self.flow["diffusion"]:
                     f1[iU] = f1[iU] + zDF * gC[k]                           # :1924
                 if reactions is not None and not _is_zero(reactions[k]):
-                    f0[iU] = f0[iU] - nd * z * pp["F"] * reactions[k]       # :1946
+                    term = nd * z * pp["F"] * reactions[k]
+                    f0[iU] = f0[iU] - term                                  # :1946
+                    self.cancel0[iU] = self.cancel0[iU] + np.abs(np.real(term)) + 1j * np.abs(np.imag(term))
                 if self.flow["porous"]:                                     # :1963-1969
                     av = pp["specific surface area"] * self.Sw
                     for echem in self.echem_params:
