@@ -88,7 +88,7 @@ class CpuPort:
         self.form = CompiledForm(solver.Form, self.nf, self.naux, mesh.dim, V.degree, V.family)
         self.lib = C.CDLL(build(self.form.header, self.form.key))
         self.lib.cpu_port_assemble.restype = C.c_int
-        self.lib.cpu_port_assemble.argtypes = [C.POINTER(_Mesh)] + [C.c_void_p] * 6 + [C.c_int64, C.c_int64, C.c_int]
+        self.lib.cpu_port_assemble.argtypes = [C.POINTER(_Mesh)] + [C.c_void_p] * 8 + [C.c_int64, C.c_int64, C.c_int]
         self.nthreads = int(nthreads)
         self.ncell_total = mesh.num_cells
         self.ncell = getattr(mesh, "num_owned", mesh.num_cells)
@@ -123,15 +123,22 @@ class CpuPort:
             lens.append(np.repeat(per_cell, self.n))
         return np.concatenate([[0], np.cumsum(np.concatenate(lens))]).astype(np.int64)
 
-    def assemble(self, u, jacobian=True, residual=True, cells=None):
-        """(F, vals) at state u (field-blocked, owned + ghost layout); either may be None if not requested."""
+    def assemble(self, u, jacobian=True, residual=True, cells=None, scales=False, out=None):
+        """(F, vals) at state u (field-blocked, owned + ghost layout); either may be None if not requested.
+        scales: also return (F_scale, vals_scale), the sums of absolute element-level contributions to every entry
+        (the tau_block of tests/parity.py).  out: (F, vals) arrays to write into (rows outside `cells` untouched)."""
         u = np.ascontiguousarray(u, dtype=np.float64)
         assert u.size == self.ndof
-        F = np.zeros(self.ndof) if residual else None
-        vals = np.zeros(self.nnz) if jacobian else None
+        if out is not None:
+            F, vals = out
+        else:
+            F = np.zeros(self.ndof) if residual else None
+            vals = np.zeros(self.nnz) if jacobian else None
+        Fs = np.zeros(self.ndof) if (scales and F is not None) else None
+        vs = np.zeros(self.nnz) if (scales and vals is not None) else None
         c0, c1 = (0, self.ncell) if cells is None else cells
         p = lambda a: None if a is None else a.ctypes.data
         rc = self.lib.cpu_port_assemble(C.byref(self._mesh), p(u), p(self.aux), p(self.consts), p(self.rowptr),
-                                        p(vals), p(F), c0, c1, self.nthreads)
+                                        p(vals), p(F), p(vs), p(Fs), c0, c1, self.nthreads)
         assert rc == 0
-        return F, vals
+        return (F, vals, Fs, vs) if scales else (F, vals)

@@ -273,18 +273,36 @@ static inline void load_fields(const double *base, int64_t stride, int64_t c, in
         for (int b = 0; b < NLOC; ++b) U[j * NLOC + b] = base[j * stride + c * NLOC + b];
 }
 
-// rows of cell c: residual (F != NULL) and / or Jacobian values (vals != NULL)
+// fold one element-level piece (cell integral, one facet) into the cell's totals; the sums of absolute pieces are the
+// element-level scales of the entries (tau_block of tests/parity.py)
+template <int N>
+static inline void fold(double *piece, double *total, double *total_abs) {
+    for (int k = 0; k < N; ++k) {
+        total[k] += piece[k];
+        total_abs[k] += fabs(piece[k]);
+        piece[k] = 0.0;
+    }
+}
+
+// rows of cell c: residual (F != NULL) and / or Jacobian values (vals != NULL); Fs / vs (optional): sums of the
+// absolute element-level contributions to the same entries
 static void assemble_cell(const Mesh &m, int64_t c, const double *u, const double *aux, const double *consts,
-                          const int64_t *rowptr, double *vals, double *F) {
+                          const int64_t *rowptr, double *vals, double *F, double *vs, double *Fs) {
     const int64_t fstride = m.ncell_total * NLOC;
     const double *X = m.xcell + c * (NV * D);
     double U[NF * NLOC], AX[NA1 * NLOC];
     load_fields(u, fstride, c, NF, U);
     if (NAUX > 0) load_fields(aux, fstride, c, NAUX, AX);
-    double R[NF][NLOC];
-    double Aown[NF][NLOC][NF][NLOC], Anb[NF][NLOC][NF][NLOC];       // [I][a][j][b]
+    constexpr int NR = NF * NLOC, NA = NF * NLOC * NF * NLOC;
+    double R[NF][NLOC], Rt[NF][NLOC], Rabs[NF][NLOC];                // piece, total, sum of |pieces|
+    double Aown[NF][NLOC][NF][NLOC], Anb[NF][NLOC][NF][NLOC];       // [I][a][j][b]; Aown: current piece
+    double At[NF][NLOC][NF][NLOC], Aabs[NF][NLOC][NF][NLOC];
     memset(R, 0, sizeof(R));
+    memset(Rt, 0, sizeof(Rt));
+    memset(Rabs, 0, sizeof(Rabs));
     memset(Aown, 0, sizeof(Aown));
+    memset(At, 0, sizeof(At));
+    memset(Aabs, 0, sizeof(Aabs));
     Pt p;
     p.K = consts;
     p.cv = m.cell_volume[c];
@@ -314,6 +332,8 @@ static void assemble_cell(const Mesh &m, int64_t c, const double *u, const doubl
                 add_row<MC, I>(rj, w, P, P, Aown[I]);
             });
     }
+    fold<NR>(&R[0][0], &Rt[0][0], &Rabs[0][0]);
+    fold<NA>(&Aown[0][0][0][0], &At[0][0][0][0], &Aabs[0][0][0][0]);
     for (int lf = 0; lf < NLF; ++lf) {
         const int nb = m.nbr[c * NLF + lf];
         p.fa = m.facet_area[c * NLF + lf];
@@ -381,12 +401,19 @@ static void assemble_cell(const Mesh &m, int64_t c, const double *u, const doubl
                     for (int a = 0; a < NLOC; ++a) {
                         double *row = vals + rowptr[(int64_t)I * fstride + c * NLOC + a];
                         for (int j = 0; j < NF; ++j)
-                            if (NBR_BLOCK[I][j]) memcpy(row + block_offset<I>(j, ncol, pos), Anb[I][a][j], sizeof(double) * NLOC);
+                            if (NBR_BLOCK[I][j]) {
+                                memcpy(row + block_offset<I>(j, ncol, pos), Anb[I][a][j], sizeof(double) * NLOC);
+                                if (vs)
+                                    for (int b = 0; b < NLOC; ++b)
+                                        (vs + (row - vals))[block_offset<I>(j, ncol, pos) + b] = fabs(Anb[I][a][j][b]);
+                            }
                     }
                 });
             }
 #endif
         }
+        fold<NR>(&R[0][0], &Rt[0][0], &Rabs[0][0]);
+        fold<NA>(&Aown[0][0][0][0], &At[0][0][0][0], &Aabs[0][0][0][0]);
     }
     if (doJ) {
         const int pos = m.slot_self[c];
@@ -395,13 +422,19 @@ static void assemble_cell(const Mesh &m, int64_t c, const double *u, const doubl
             for (int a = 0; a < NLOC; ++a) {
                 double *row = vals + rowptr[(int64_t)I * fstride + c * NLOC + a];
                 for (int j = 0; j < NF; ++j)
-                    if (OWN_BLOCK[I][j]) memcpy(row + block_offset<I>(j, ncol, pos), Aown[I][a][j], sizeof(double) * NLOC);
+                    if (OWN_BLOCK[I][j]) {
+                        memcpy(row + block_offset<I>(j, ncol, pos), At[I][a][j], sizeof(double) * NLOC);
+                        if (vs) memcpy(vs + (row - vals) + block_offset<I>(j, ncol, pos), Aabs[I][a][j], sizeof(double) * NLOC);
+                    }
             }
         });
     }
     if (doF)
         for (int i = 0; i < NF; ++i)
-            for (int a = 0; a < NLOC; ++a) F[i * fstride + c * NLOC + a] = R[i][a];
+            for (int a = 0; a < NLOC; ++a) {
+                F[i * fstride + c * NLOC + a] = Rt[i][a];
+                if (Fs) Fs[i * fstride + c * NLOC + a] = Rabs[i][a];
+            }
 }
 
 }  // namespace port
@@ -430,16 +463,17 @@ int cpu_port_describe(int32_t *info) {
 }
 
 // Residual into F (if non-NULL) and CSR Jacobian values into vals (if non-NULL) for the cells [cell_begin, cell_end);
+// vals_scale / F_scale (optional): element-level scales of the same entries (sums of absolute contributions);
 // nthreads <= 0: OpenMP default.  All pointers are host pointers; layouts are those of include/echem_b200_module.h.
 int cpu_port_assemble(const cpu_port_mesh *m, const double *u, const double *aux, const double *consts,
-                      const int64_t *rowptr, double *vals, double *F, int64_t cell_begin, int64_t cell_end,
-                      int nthreads) {
+                      const int64_t *rowptr, double *vals, double *F, double *vals_scale, double *F_scale,
+                      int64_t cell_begin, int64_t cell_end, int nthreads) {
     port::Mesh M{m->ncell, m->ncell_total, m->xcell, m->nbr, m->code, m->slot, m->slot_self, m->ncol,
                  m->cell_volume, m->cell_diam, m->facet_area};
     if (cell_end > m->ncell) cell_end = m->ncell;
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel for schedule(static)
-    for (int64_t c = cell_begin; c < cell_end; ++c) port::assemble_cell(M, c, u, aux, consts, rowptr, vals, F);
+    for (int64_t c = cell_begin; c < cell_end; ++c) port::assemble_cell(M, c, u, aux, consts, rowptr, vals, F, vals ? vals_scale : nullptr, F ? F_scale : nullptr);
     return 0;
 }
 

@@ -19,6 +19,13 @@ def _check(disc, s, u, what):
     parity.assert_vec_close(F, disc.residual(u), port.nf, what + " residual", scale=disc.residual_scale(u))
     J, Jscale = disc.jacobian(u, return_scale=True)
     parity.assert_csr_close(vals, J.data, indptr, indices, port.nf, port.N, port.n, what + " jacobian", scale=Jscale)
+    # the port's element-level scales are the oracle's (same pieces: cell integral + facet halves)
+    _, _, Fs, vs = port.assemble(u, scales=True)
+    assert np.abs(vs - Jscale).max() <= 1e-10 * Jscale.max(), what
+    tau = disc.residual_scale(u)          # also counts analytically cancelling pointwise sums, so it may be larger
+    for f in range(port.nf):
+        fs = Fs.reshape(port.nf, -1)[f]
+        assert np.all(fs >= np.abs(F.reshape(port.nf, -1)[f]) * (1 - 1e-12)) and fs.max() <= 8 * tau[f], what
     # cell ranges (threads / chunks) write disjoint rows
     F2, vals2 = port.assemble(u, cells=(0, port.ncell // 2))
     F3, vals3 = port.assemble(u, cells=(port.ncell // 2, port.ncell))
