@@ -28,7 +28,8 @@ class GmresOpts(C.Structure):
                 ("precond", c_i32), ("monitor", c_i32), ("nfields", c_i32), ("nloc", c_i32),
                 ("rows_per_field", c_i64), ("nblocks", c_i64), ("block_cell_ptr", c_p), ("lu", c_p),
                 ("diag_pos", c_p), ("agg", c_p), ("nc", c_i32), ("reserved", c_i32), ("coarse_inv", c_p),
-                ("coarse_work", c_p)]
+                ("coarse_work", c_p), ("lcol", c_p), ("passptr", c_p), ("slots", c_p), ("lanes_per_row", c_i32),
+                ("max_block_rows", c_i32)]
 
 
 EXPORTS = {
@@ -51,6 +52,12 @@ EXPORTS = {
     "ech_multiaxpy": (C.c_int, [c_i64, c_i32, c_p, c_p, C.c_double, c_p, c_p]),
     "ech_bjacobi_ilu0_factor": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_apply": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ech_bjacobi_ilu0_plan_count": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_i32, c_p, c_p,
+                                              c_p, C.POINTER(c_i64), c_p]),
+    "ech_bjacobi_ilu0_plan_fill": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_i32, c_p, c_p,
+                                             c_p, c_p]),
+    "ech_bjacobi_ilu0_apply_planned": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_p, c_p, c_p,
+                                                 c_i32, c_p, c_p, c_p]),
     "ech_coarse_galerkin": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_i32, c_p, c_p]),
     "ech_coarse_restrict": (C.c_int, [c_i64, c_p, c_i32, c_p, c_p, c_p]),
     "ech_coarse_prolong_add": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),

@@ -1180,6 +1180,385 @@ extern "C" int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t ro
     return ilu0_apply(B, rowptr, colidx, lu, diag_pos, r, z, (cudaStream_t)stream);
 }
 
+// =============================================================== level-scheduled triangular solves
+// The row-sequential solves above walk the rows of a block one by one (512 dependent steps for an 8 x 8 tile of
+// Q1 cells with two fields).  The dependency graph is much shallower: inside a field, a cell waits only for its
+// lower-numbered neighbours, so the rows of an anti-diagonal of cells are independent (wavefronts).  The PLAN
+// (pattern + blocks only, built once):
+//   lcol[nnz]   uint16: position of the entry's column inside the block's z (0xFFFF: outside the block) -- replaces
+//               the 4-byte column index in the solve (10 instead of 12 bytes per entry);
+//   slots       one 8-byte record per (pass, row group): rows of one dependency level, G = 32 / LPR at a time
+//               {entry offset relative to the field's first entry of the block, row inside the block, half-row
+//               length}; passes of a block are contiguous, lower sweep first;
+//   passptr     [2][nblocks + 1] first pass of each block per sweep.
+// The solve keeps z in shared memory; per pass each group of LPR lanes takes one row: the slot of pass t+2 and the
+// (lcol, value) pairs of pass t+1 are in flight while pass t is reduced, so no global latency is on the chain.
+// Arithmetic per row is that of ILU(0) in natural order; only the summation order inside a row differs.
+struct IluSlot {
+    uint32_t rel;      // first entry of the half-row, relative to the block's first entry of the row's field
+    uint16_t i;        // row inside the block (field-major); 0xFFFF: empty slot
+    uint16_t len;      // entries of the half-row (off-diagonal)
+};
+static_assert(sizeof(IluSlot) == 8, "IluSlot");
+
+constexpr int ILU_MAXROWS = 16384;     // rows per block the planned solve handles (levels + z in shared memory)
+
+// levels of one sweep for the block of this warp; lev[] in shared memory (uint16).  UPPER = false: L (forward).
+template <bool UPPER>
+__device__ void ilu0_plan_levels(const BlockPlan &B, const int64_t *__restrict__ rowptr,
+                                 const int32_t *__restrict__ colidx, uint16_t *lev, uint32_t first, uint32_t nrow_f,
+                                 uint32_t ntot, int lane, uint16_t *lcol) {
+    const uint32_t rpf = (uint32_t)B.rows_per_field;
+    for (uint32_t st = 0; st < ntot; ++st) {
+        const uint32_t i = UPPER ? ntot - 1 - st : st;
+        const uint32_t f = i / nrow_f, j = i - f * nrow_f;
+        const int64_t r = (int64_t)f * B.rows_per_field + first + j;
+        const int64_t rs = rowptr[r], re = rowptr[r + 1];
+        int m = 0;
+        for (int64_t p = rs + lane; p < re; p += 32) {
+            const int32_t c = colidx[p];
+            const int32_t k = ring_local<0>(c, first, nrow_f, rpf, B.nf);
+            if (!UPPER && lcol) lcol[p] = k >= 0 ? (uint16_t)k : (uint16_t)0xFFFF;
+            const bool dep = UPPER ? (c > r) : (c < r);
+            if (k >= 0 && dep) m = max(m, (int)lev[k]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) lev[i] = (uint16_t)(m + 1);
+        __syncwarp();
+    }
+}
+
+// pass 1: levels of both sweeps -> levels[2][nrows] (global, per global row), lcol, passes per block
+__global__ void __launch_bounds__(32) ilu0_plan_count_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
+                                                            const int32_t *__restrict__ colidx, int G,
+                                                            uint16_t *lcol, uint16_t *levels, int64_t nrows,
+                                                            int64_t *npass, uint32_t cap_rows) {
+    extern __shared__ uint16_t sh16[];
+    const int64_t blk = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    const uint32_t nrow_f = (uint32_t)((c1 - c0) * B.nloc), ntot = nrow_f * (uint32_t)B.nf;
+    const uint32_t first = (uint32_t)(c0 * B.nloc);
+    if (ntot == 0 || ntot > cap_rows) {
+        if (lane == 0) npass[blk] = npass[B.nblocks + 1 + blk] = 0;
+        return;
+    }
+    uint16_t *lev = sh16;
+    int *cnt = reinterpret_cast<int *>(sh16 + ((ntot + 1) & ~1u));      // [ntot + 1]
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        if (sweep == 0)
+            ilu0_plan_levels<false>(B, rowptr, colidx, lev, first, nrow_f, ntot, lane, lcol);
+        else
+            ilu0_plan_levels<true>(B, rowptr, colidx, lev, first, nrow_f, ntot, lane, nullptr);
+        for (uint32_t k = lane; k <= ntot; k += 32) cnt[k] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < ntot; i += 32) {
+            const uint32_t f = i / nrow_f, j = i - f * nrow_f;
+            levels[(int64_t)sweep * nrows + (int64_t)f * B.rows_per_field + first + j] = lev[i];
+            atomicAdd(&cnt[lev[i]], 1);
+        }
+        __syncwarp();
+        long long tot = 0;
+        for (uint32_t k = lane; k <= ntot; k += 32) tot += (cnt[k] + G - 1) / G;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) npass[(int64_t)sweep * (B.nblocks + 1) + blk] = tot;
+        __syncwarp();
+    }
+}
+
+// exclusive scan of the pass counts, per sweep, sweep 1 continuing after sweep 0 (one thread: plan time only)
+__global__ void ilu0_plan_scan_kernel(int64_t nblocks, int64_t *npass) {
+    int64_t run = 0;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        int64_t *p = npass + (int64_t)sweep * (nblocks + 1);
+        for (int64_t b = 0; b < nblocks; ++b) {
+            const int64_t c = p[b];
+            p[b] = run;
+            run += c;
+        }
+        p[nblocks] = run;
+    }
+}
+
+// pass 2: rows sorted by level into slots
+__global__ void __launch_bounds__(32) ilu0_plan_fill_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
+                                                           const int32_t *__restrict__ colidx, int G,
+                                                           const uint16_t *__restrict__ levels, int64_t nrows,
+                                                           const int64_t *__restrict__ passptr, IluSlot *slots,
+                                                           uint32_t cap_rows) {
+    extern __shared__ uint16_t sh16[];
+    const int64_t blk = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    const uint32_t nrow_f = (uint32_t)((c1 - c0) * B.nloc), ntot = nrow_f * (uint32_t)B.nf;
+    const uint32_t first = (uint32_t)(c0 * B.nloc);
+    if (ntot == 0 || ntot > cap_rows) return;
+    int *cnt = reinterpret_cast<int *>(sh16);           // [ntot + 2]: level -> rows, then -> first slot
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        const int64_t p0 = passptr[(int64_t)sweep * (B.nblocks + 1) + blk];
+        const int64_t p1 = passptr[(int64_t)sweep * (B.nblocks + 1) + blk + 1];
+        IluSlot *S = slots + p0 * G;
+        for (int64_t q = lane; q < (p1 - p0) * G; q += 32) S[q] = IluSlot{0u, (uint16_t)0xFFFF, (uint16_t)0};
+        for (uint32_t k = lane; k <= ntot + 1; k += 32) cnt[k] = 0;
+        __syncwarp();
+        const uint16_t *lv = levels + (int64_t)sweep * nrows;
+        for (uint32_t i = lane; i < ntot; i += 32) {
+            const uint32_t f = i / nrow_f, j = i - f * nrow_f;
+            atomicAdd(&cnt[lv[(int64_t)f * B.rows_per_field + first + j]], 1);
+        }
+        __syncwarp();
+        if (lane == 0) {                                  // levels -> first slot (serial: plan time only)
+            int run = 0;
+            for (uint32_t k = 0; k <= ntot; ++k) {
+                const int c = cnt[k];
+                cnt[k] = run;
+                run += ((c + G - 1) / G) * G;
+            }
+        }
+        __syncwarp();
+        // rows in natural order, one after the other, so that the slot order inside a level is reproducible
+        for (uint32_t base = 0; base < ntot; base += 32) {
+            const uint32_t i = base + lane;
+            int level = -1;
+            IluSlot sl{0u, (uint16_t)0xFFFF, (uint16_t)0};
+            if (i < ntot) {
+                const uint32_t f = i / nrow_f, j = i - f * nrow_f;
+                const int64_t r = (int64_t)f * B.rows_per_field + first + j;
+                level = lv[r];
+                const int64_t rs = rowptr[r], re = rowptr[r + 1];
+                int64_t lo = rs, hi = re - 1, dpos = rs;
+                while (lo <= hi) {                         // diagonal position (columns are sorted)
+                    const int64_t mid = (lo + hi) >> 1;
+                    const int32_t cj = colidx[mid];
+                    if (cj == r) {
+                        dpos = mid;
+                        break;
+                    }
+                    if (cj < r) lo = mid + 1; else hi = mid - 1;
+                }
+                const int64_t fbase = rowptr[(int64_t)f * B.rows_per_field + first];
+                const int64_t beg = sweep ? dpos + 1 : rs;
+                const int64_t len = sweep ? re - dpos - 1 : dpos - rs;
+                sl = IluSlot{(uint32_t)(beg - fbase), (uint16_t)i, (uint16_t)len};
+            }
+            for (int l = 0; l < 32; ++l) {                 // lane by lane: deterministic placement
+                if (lane == l && level >= 0) {
+                    const int pos = cnt[level]++;
+                    S[pos] = sl;
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// the solve: one warp per block, ILU_WPC blocks per CTA (a CTA of one warp would cap the SM at 32 resident blocks)
+constexpr int ILU_WPC = 4;
+constexpr int ILU_R = 10;              // entries per lane held in registers per stage (longer half-rows loop)
+constexpr int ILU_AHEAD = 1;           // passes whose entries are in flight while one is being reduced
+
+struct IluStage {
+    double v[ILU_R];
+    uint16_t k[ILU_R];
+    double piv;
+};
+
+template <int LPR, bool UPPER>
+__device__ __forceinline__ void ilu0_planned_sweep(const double *__restrict__ lu, const uint16_t *__restrict__ lcol,
+                                                   const IluSlot *__restrict__ S, int64_t npass,
+                                                   const int64_t *fbase, double *z, int lane, uint32_t nrow_f) {
+    constexpr int G = 32 / LPR;
+    constexpr int R = ILU_R;
+    const int g = lane / LPR, l = lane - g * LPR;
+    const IluSlot EMPTY{0u, (uint16_t)0xFFFF, (uint16_t)0};
+    auto field_base = [&](uint32_t i) -> int64_t {
+        uint32_t f = 0;                 // field of row i by repeated subtraction (nf is small)
+        while (i >= nrow_f) {
+            i -= nrow_f;
+            ++f;
+        }
+        return fbase[f];
+    };
+    auto slot_at = [&](int64_t t) -> IluSlot { return t < npass ? S[t * G + g] : EMPTY; };
+    auto fetch = [&](const IluSlot &sl, IluStage &st) {
+        const bool live = sl.i != 0xFFFF;
+        const int64_t b = live ? field_base(sl.i) + sl.rel : 0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int e = l + q * LPR;
+            const bool on = live && e < (int)sl.len;
+            st.v[q] = on ? __ldcs(lu + b + e) : 0.0;
+            st.k[q] = on ? __ldcs(lcol + b + e) : (uint16_t)0xFFFF;
+        }
+        st.piv = (UPPER && live) ? __ldcs(lu + b - 1) : 1.0;
+    };
+    // software pipeline (registers, stage index resolved by full unrolling): the entries of the next ILU_AHEAD
+    // passes and the slot of the pass after those are in flight while one pass is reduced
+    constexpr int NS = ILU_AHEAD + 1;
+    IluSlot sl[NS];
+    IluStage st[NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+        sl[a] = slot_at(a);
+        fetch(sl[a], st[a]);
+    }
+    IluSlot nxt = slot_at(NS);
+    for (int64_t t0 = 0; t0 < npass; t0 += NS) {
+#pragma unroll
+        for (int a = 0; a < NS; ++a) {
+            const int64_t t = t0 + a;
+            if (t < npass) {                                              // warp-uniform
+                const IluSlot cur = sl[a];
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < R; q += 2) {
+                    s0 = fma(st[a].v[q], st[a].k[q] != 0xFFFF ? z[st[a].k[q]] : 0.0, s0);
+                    s1 = fma(st[a].v[q + 1], st[a].k[q + 1] != 0xFFFF ? z[st[a].k[q + 1]] : 0.0, s1);
+                }
+                if (cur.i != 0xFFFF && (int)cur.len > R * LPR) {          // long half-rows: the rest from global memory
+                    const int64_t b = field_base(cur.i) + cur.rel;
+                    for (int e = l + R * LPR; e < (int)cur.len; e += LPR) {
+                        const uint16_t k = lcol[b + e];
+                        if (k != 0xFFFF) s0 = fma(lu[b + e], z[k], s0);
+                    }
+                }
+                double sum = s0 + s1;
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const double piv = st[a].piv;
+                sl[a] = nxt;                                              // pass t + NS takes over this stage
+                fetch(sl[a], st[a]);
+                nxt = slot_at(t + NS + 1);
+                if (l == 0 && cur.i != 0xFFFF) z[cur.i] = UPPER ? (z[cur.i] - sum) / piv : z[cur.i] - sum;
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(32 * ILU_WPC) ilu0_apply_planned_kernel(
+    BlockPlan B, const int64_t *__restrict__ rowptr, const double *__restrict__ lu, const uint16_t *__restrict__ lcol,
+    const int64_t *__restrict__ passptr, const IluSlot *__restrict__ slots, const double *__restrict__ rhs, double *zg,
+    int64_t cap_rows) {
+    extern __shared__ double zs_all[];
+    constexpr int G = 32 / LPR;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t)blockIdx.x * ILU_WPC + warp;
+    if (blk >= B.nblocks) return;
+    double *zs = zs_all + (size_t)warp * (cap_rows + 8);
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    const uint32_t nrow_f = (uint32_t)((c1 - c0) * B.nloc), ntot = nrow_f * (uint32_t)B.nf;
+    const uint32_t first = (uint32_t)(c0 * B.nloc);
+    if (ntot == 0) return;
+    int64_t *fbase = reinterpret_cast<int64_t *>(zs + cap_rows);      // [nf <= 8]
+    for (int f = lane; f < B.nf; f += 32) fbase[f] = rowptr[(int64_t)f * B.rows_per_field + first];
+    for (int f = 0; f < B.nf; ++f)
+        for (uint32_t j = lane; j < nrow_f; j += 32) zs[f * nrow_f + j] = rhs[(int64_t)f * B.rows_per_field + first + j];
+    __syncwarp();
+    const int64_t pl0 = passptr[blk], pl1 = passptr[blk + 1];
+    const int64_t pu0 = passptr[B.nblocks + 1 + blk], pu1 = passptr[B.nblocks + 1 + blk + 1];
+    ilu0_planned_sweep<LPR, false>(lu, lcol, slots + pl0 * G, pl1 - pl0, fbase, zs, lane, nrow_f);
+    ilu0_planned_sweep<LPR, true>(lu, lcol, slots + pu0 * G, pu1 - pu0, fbase, zs, lane, nrow_f);
+    for (int f = 0; f < B.nf; ++f)
+        for (uint32_t j = lane; j < nrow_f; j += 32) zg[(int64_t)f * B.rows_per_field + first + j] = zs[f * nrow_f + j];
+}
+
+static int plan_lpr_ok(int lpr) { return lpr == 2 || lpr == 4 || lpr == 8 || lpr == 16; }
+
+extern "C" int ech_bjacobi_ilu0_plan_count(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                           int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                           const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row,
+                                           uint16_t *lcol, uint16_t *levels, int64_t *passptr, int64_t *npass_host,
+                                           void *stream) {
+    if (!block_cell_ptr || !rowptr || !colidx || !lcol || !levels || !passptr || !npass_host ||
+        !plan_lpr_ok(lanes_per_row) || max_block_rows <= 0 || max_block_rows > ILU_MAXROWS)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_plan_count: bad argument (blocks of at most 16384 rows)");
+    cudaStream_t s = (cudaStream_t)stream;
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    const int64_t maxrows = max_block_rows;
+    const size_t smem = (size_t)((maxrows + 2) * 2 + (maxrows + 2) * 4 + 16);
+    CK(nullptr, cudaFuncSetAttribute(ilu0_plan_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ilu0_plan_count_kernel<<<(unsigned)nblocks, 32, smem, s>>>(B, rowptr, colidx, 32 / lanes_per_row, lcol, levels,
+                                                              nrows, passptr, (uint32_t)maxrows);
+    ilu0_plan_scan_kernel<<<1, 1, 0, s>>>(nblocks, passptr);
+    g_launches += 2;
+    int64_t tot[1];
+    CK(nullptr, cudaMemcpyAsync(tot, passptr + 2 * (nblocks + 1) - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(nullptr, cudaStreamSynchronize(s));
+    CK(nullptr, cudaGetLastError());
+    npass_host[0] = tot[0];
+    return ECH_OK;
+}
+
+extern "C" int ech_bjacobi_ilu0_plan_fill(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                          int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                          const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row,
+                                          const uint16_t *levels, const int64_t *passptr, uint64_t *slots,
+                                          void *stream) {
+    if (!block_cell_ptr || !rowptr || !colidx || !levels || !passptr || !slots || !plan_lpr_ok(lanes_per_row) ||
+        max_block_rows <= 0 || max_block_rows > ILU_MAXROWS)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_plan_fill: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    const int64_t maxrows = max_block_rows;
+    const size_t smem = (size_t)((maxrows + 4) * 4 + 16);
+    CK(nullptr, cudaFuncSetAttribute(ilu0_plan_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ilu0_plan_fill_kernel<<<(unsigned)nblocks, 32, smem, s>>>(B, rowptr, colidx, 32 / lanes_per_row, levels, nrows,
+                                                             passptr, reinterpret_cast<IluSlot *>(slots),
+                                                             (uint32_t)maxrows);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+static int ilu0_apply_planned(const BlockPlan &B, int64_t maxrows, const int64_t *rowptr, const double *lu,
+                              const uint16_t *lcol, const int64_t *passptr, const uint64_t *slots, int lpr,
+                              const double *r, double *z, cudaStream_t s) {
+    if (B.nblocks == 0) return ECH_OK;
+    if (maxrows <= 0 || maxrows > ILU_MAXROWS)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_apply_planned: block too large");
+    if (B.nf > 8) return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_apply_planned: more than 8 fields");
+    const size_t smem = (size_t)ILU_WPC * (size_t)(maxrows + 8) * 8;
+    const IluSlot *S = reinterpret_cast<const IluSlot *>(slots);
+    const unsigned grid = (unsigned)((B.nblocks + ILU_WPC - 1) / ILU_WPC);
+#define ECH_LAUNCH_PLANNED(L)                                                                                        \
+    {                                                                                                                \
+        static size_t attr = 0;                                                                                      \
+        if (smem > attr) {                                                                                           \
+            CK(nullptr, cudaFuncSetAttribute(ilu0_apply_planned_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                            \
+            attr = smem;                                                                                             \
+        }                                                                                                            \
+        ilu0_apply_planned_kernel<L><<<grid, 32 * ILU_WPC, smem, s>>>(B, rowptr, lu, lcol, passptr, S, r, z, maxrows); \
+    }
+    if (lpr == 2) ECH_LAUNCH_PLANNED(2)
+    else if (lpr == 4) ECH_LAUNCH_PLANNED(4)
+    else if (lpr == 8) ECH_LAUNCH_PLANNED(8)
+    else if (lpr == 16) ECH_LAUNCH_PLANNED(16)
+    else return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_apply_planned: lanes_per_row");
+#undef ECH_LAUNCH_PLANNED
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_bjacobi_ilu0_apply_planned(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                              int64_t nblocks, const int64_t *block_cell_ptr,
+                                              int32_t max_block_rows, const int64_t *rowptr, const double *lu,
+                                              const uint16_t *lcol, const int64_t *passptr, const uint64_t *slots,
+                                              int32_t lanes_per_row, const double *r, double *z, void *stream) {
+    (void)nrows;
+    if (!block_cell_ptr || !rowptr || !lu || !lcol || !passptr || !slots || !r || !z)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_apply_planned: null argument");
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    return ilu0_apply_planned(B, max_block_rows, rowptr, lu, lcol, passptr, slots, lanes_per_row, r, z,
+                              (cudaStream_t)stream);
+}
+
 // =============================================================== coarse space (two-level preconditioner)
 // Piecewise-constant aggregation: fine dof r belongs to coarse dof agg[r].  Ac = P^T A P is accumulated
 // with warp-level pre-reduction (entries of a row that hit the same coarse column are summed with
@@ -1324,7 +1703,12 @@ extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx
     auto precond = [&](const double *in, double *out) -> int {
         int e;
         if (o->precond >= 1) {
-            if ((e = ilu0_apply(B, rowptr, colidx, o->lu, o->diag_pos, in, out, s))) return e;
+            if (o->slots)
+                e = ilu0_apply_planned(B, o->max_block_rows, rowptr, o->lu, o->lcol, o->passptr, o->slots,
+                                       o->lanes_per_row, in, out, s);
+            else
+                e = ilu0_apply(B, rowptr, colidx, o->lu, o->diag_pos, in, out, s);
+            if (e) return e;
             if (o->precond == 2) return coarse_add(in, out);
             if (o->precond == 3) {
                 double *res_ = o->coarse_work + 2 * (int64_t)o->nc;

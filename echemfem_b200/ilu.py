@@ -1,0 +1,55 @@
+"""Plan of the level-scheduled block-Jacobi / ILU(0) solves (`ech_bjacobi_ilu0_plan_*`, include/echem_b200.h).
+
+PETSc's `bjacobi` + `sub_pc_type ilu` (echemfem/solver.py:1186-1188) applies L and U row by row; the plan sorts the
+rows of every block by dependency level once per sparsity pattern, so that the solve walks wavefronts instead of rows.
+Device buffers are torch tensors owned here; the library only fills them.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import ptr
+
+MAX_BLOCK_ROWS = 16384
+
+
+class IluPlan:
+    def __init__(self, lib, dev, stream, ndof, nf, rows_per_field, unit, block_edges, block_ptr, rowptr, colidx, nnz):
+        self.lib, self.ndof, self.nf, self.N, self.unit = lib, int(ndof), int(nf), int(rows_per_field), int(unit)
+        self.nblocks = len(block_edges) - 1
+        self.block_ptr = block_ptr
+        self.max_rows = int(np.diff(np.asarray(block_edges)).max()) * self.unit * self.nf if self.nblocks else 0
+        self.ok = 0 < self.max_rows <= MAX_BLOCK_ROWS and nnz > 0
+        if not self.ok:
+            return
+        # lanes sharing a row hold 10 entries each in registers; a half-row has at most (row length - 1) entries
+        row = nnz / max(self.ndof, 1)
+        self.lpr = 4 if row <= 41 else (8 if row <= 81 else 16)
+        G = 32 // self.lpr
+        self.lcol = torch.empty(nnz, dtype=torch.int16, device=dev)
+        levels = torch.empty(2 * self.ndof, dtype=torch.int16, device=dev)
+        self.passptr = torch.zeros(2 * (self.nblocks + 1), dtype=torch.int64, device=dev)
+        npass = C.c_int64()
+        capi.check(lib.ech_bjacobi_ilu0_plan_count(self.ndof, self.nf, self.N, self.unit, self.nblocks, ptr(block_ptr),
+                                                   self.max_rows, ptr(rowptr), ptr(colidx), self.lpr, ptr(self.lcol),
+                                                   ptr(levels), ptr(self.passptr), C.byref(npass), stream))
+        self.npass = int(npass.value)
+        self.slots = torch.empty(max(self.npass * G, 1), dtype=torch.int64, device=dev)
+        capi.check(lib.ech_bjacobi_ilu0_plan_fill(self.ndof, self.nf, self.N, self.unit, self.nblocks, ptr(block_ptr),
+                                                  self.max_rows, ptr(rowptr), ptr(colidx), self.lpr, ptr(levels),
+                                                  ptr(self.passptr), ptr(self.slots), stream))
+        self.rowptr = rowptr
+        del levels
+
+    def apply(self, lu, r, z, stream):
+        capi.check(self.lib.ech_bjacobi_ilu0_apply_planned(self.ndof, self.nf, self.N, self.unit, self.nblocks,
+                                                           ptr(self.block_ptr), self.max_rows, ptr(self.rowptr),
+                                                           ptr(lu), ptr(self.lcol), ptr(self.passptr), ptr(self.slots),
+                                                           self.lpr, ptr(r), ptr(z), stream))
+
+    def set_opts(self, opts):
+        """Fill the plan fields of an `ech_gmres_opts`."""
+        opts.lcol, opts.passptr, opts.slots = ptr(self.lcol), ptr(self.passptr), ptr(self.slots)
+        opts.lanes_per_row, opts.max_block_rows = self.lpr, self.max_rows

@@ -179,7 +179,9 @@ class Multigrid:
             if os.environ.get("ECH_MG_CELLS_PER_BLOCK"):             # tuning hook (tools/newton_scale.py)
                 nb = max(1, L.ncell // int(os.environ["ECH_MG_CELLS_PER_BLOCK"]))
             D.nblocks = nb
-            D.block_ptr = torch.from_numpy(np.linspace(0, L.ncell, nb + 1).astype(np.int64)).to(self.dev)
+            D.block_edges = np.linspace(0, L.ncell, nb + 1).astype(np.int64)
+            D.block_ptr = torch.from_numpy(D.block_edges).to(self.dev)
+            D.ilu_plan = None
             D.r = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
             D.z = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
             D.t = torch.zeros(D.ndof, dtype=torch.float64, device=self.dev)
@@ -193,6 +195,7 @@ class Multigrid:
             D.Pt = self._blockdiag(P)
             D.Rt = self._blockdiag(P.T.tocsr())
         self.nlevels = len(self.lv)
+        self.planned = os.environ.get("ECH_ILU_PLANNED", "1") != "0"
 
     def _blockdiag(self, P):
         P = P.tocsr()
@@ -229,12 +232,23 @@ class Multigrid:
             capi.check(lib.ech_bjacobi_ilu0_factor(D.ndof, self.nf, D.N, self.h.n, D.nblocks, ptr(D.block_ptr),
                                                    ptr(D.rowptr), ptr(D.colidx), ptr(D.vals), ptr(D.lu), ptr(D.diag),
                                                    st))
+            if self.planned and (D.ilu_plan is None or D.ilu_plan.lcol.numel() != D.vals.numel()):
+                # level-scheduled solves: the plan follows the pattern (fixed after the first Galerkin product)
+                from .ilu import IluPlan
+                D.ilu_plan = IluPlan(lib, self.dev, st, D.ndof, self.nf, D.N, self.h.n, D.block_edges, D.block_ptr,
+                                     D.rowptr, D.colidx, int(D.vals.numel()))
+                if not D.ilu_plan.ok:
+                    D.ilu_plan = None
+                    self.planned = False
         C = self.lv[-1]
         dense = torch.sparse_csr_tensor(C.rowptr, C.colidx.to(torch.int64), C.vals, size=(C.ndof, C.ndof)).to_dense()
         C.inv = torch.linalg.inv(dense).contiguous()
 
     # -- apply ---------------------------------------------------------------------------------------------
     def _smooth(self, D, r, z):
+        if D.ilu_plan is not None:
+            D.ilu_plan.apply(D.lu, r, z, self.e._stream())
+            return
         capi.check(self.lib.ech_bjacobi_ilu0_apply(D.ndof, self.nf, D.N, self.h.n, D.nblocks, ptr(D.block_ptr),
                                                    ptr(D.rowptr), ptr(D.colidx), ptr(D.lu), ptr(D.diag), ptr(r), ptr(z),
                                                    self.e._stream()))

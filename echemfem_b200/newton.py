@@ -300,9 +300,19 @@ class NewtonEngine:
         if m < restart:
             print("*** WARNING: ksp_gmres_restart %d capped to %d by device memory" % (restart, m))
         dev = self.dev
+        import os
+        from .ilu import IluPlan
+        block_ptr = torch.from_numpy(edges).to(dev)
+        plan = None
+        if os.environ.get("ECH_ILU_PLANNED", "1") != "0":
+            # level-scheduled triangular solves: the plan depends on the pattern and the blocks only
+            plan = IluPlan(self.lib, dev, self._stream(), self.ndof, self.nf, self.N, self._unit, edges, block_ptr,
+                           self.rowptr, self.colidx, self.nnz)
+            if not plan.ok:
+                plan = None
         self._lin = {
-            "restart": m, "nblocks": nblocks,
-            "block_ptr": torch.from_numpy(edges).to(dev),
+            "restart": m, "nblocks": nblocks, "ilu_plan": plan,
+            "block_ptr": block_ptr,
             "lu": torch.empty(self.nnz, dtype=torch.float64, device=dev),
             "diag": torch.empty(self.ndof, dtype=torch.int32, device=dev),
             "basis": torch.empty((m + 1) * self.ndof, dtype=torch.float64, device=dev),
@@ -379,7 +389,9 @@ class NewtonEngine:
             return out
         opts = capi.GmresOpts(rtol, atol, L["restart"], max_it, 1, 1 if monitor else 0, self.nf, self._unit,
                               self.N, L["nblocks"], ptr(L["block_ptr"]), ptr(L["lu"]), ptr(L["diag"]),
-                              None, 0, 0, None, None)
+                              None, 0, 0, None, None, None, None, None, 0, 0)
+        if L["ilu_plan"] is not None:
+            L["ilu_plan"].set_opts(opts)
         if Cz is not None:
             opts.precond = int(coarse_mode)
             opts.agg, opts.nc = ptr(Cz["agg"]), Cz["nc"]
@@ -424,6 +436,9 @@ class NewtonEngine:
         if precond is None:
             def precond(src, dst):
                 dst.zero_()
+                if L["ilu_plan"] is not None:
+                    L["ilu_plan"].apply(L["lu"], src, dst, st)
+                    return
                 capi.check(lib.ech_bjacobi_ilu0_apply(n, self.nf, self.N, self._unit, L["nblocks"],
                                                       ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
                                                       ptr(L["lu"]), ptr(L["diag"]), ptr(src), ptr(dst), st))

@@ -129,6 +129,27 @@ int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t rows_per_fiel
                            const int32_t *colidx, const double *lu, const int32_t *diag_pos, const double *r,
                            double *z, void *stream);
 
+/* Level-scheduled triangular solves (same factors, same result up to the summation order inside a row).  The PLAN
+ * depends on the pattern and the blocks only and is built once: plan_count computes the dependency levels of
+ * both sweeps, the block-local column table lcol[nnz] and the passes per block (passptr[2][nblocks+1], scanned);
+ * *npass_host receives the total, the caller allocates slots[npass * (32 / lanes_per_row)] (8 bytes each) and
+ * plan_fill sorts the rows into them.  levels: scratch of 2 * nrows uint16.  max_block_rows: rows (all fields)
+ * of the largest block, at most 16384.  lanes_per_row in {2, 4, 8, 16}: lanes that share one row.
+ * plan_count synchronises the stream. */
+int ech_bjacobi_ilu0_plan_count(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row, uint16_t *lcol,
+                                uint16_t *levels, int64_t *passptr, int64_t *npass_host, void *stream);
+int ech_bjacobi_ilu0_plan_fill(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                               int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                               const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row,
+                               const uint16_t *levels, const int64_t *passptr, uint64_t *slots, void *stream);
+int ech_bjacobi_ilu0_apply_planned(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                   int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                   const int64_t *rowptr, const double *lu, const uint16_t *lcol,
+                                   const int64_t *passptr, const uint64_t *slots, int32_t lanes_per_row,
+                                   const double *r, double *z, void *stream);
+
 /* Coarse space of the optional two-level preconditioner (not in the reference's "ilu" option set; it
  * plays the role of the coarse levels of its gmg/amg sets, solver.py:1190-1213, for meshes on which
  * block-Jacobi/ILU(0) alone stalls).  Piecewise-constant aggregation agg[dof] -> coarse dof:
@@ -157,6 +178,11 @@ typedef struct ech_gmres_opts {
     int32_t nc, reserved;
     const double *coarse_inv;
     double *coarse_work;      /* 2 * nc (+ nrows for precond == 3) doubles */
+    /* level-scheduled solves (ech_bjacobi_ilu0_plan_*): used when slots != NULL */
+    const uint16_t *lcol;
+    const int64_t *passptr;
+    const uint64_t *slots;
+    int32_t lanes_per_row, max_block_rows;
 } ech_gmres_opts;
 
 /* Right-preconditioned restarted GMRES (classical Gram-Schmidt with one refinement, unpreconditioned

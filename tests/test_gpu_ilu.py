@@ -85,8 +85,37 @@ def test_block_ilu0_apply_matches_host(case):
                                             ptr(e.colidx), ptr(lu), ptr(diag), ptr(rd), ptr(z), st))
     z = z.cpu().numpy()
     assert np.isfinite(z).all()
+    # level-scheduled solves (ech_bjacobi_ilu0_plan_* / _apply_planned) on the same factors, every lane grouping
+    from echemfem_b200.ilu import IluPlan
+    zp = {}
+    for lpr in (None, 2, 16):
+        plan = IluPlan(e.lib, e.dev, st, e.ndof, nf, ncell * n, n, np.array(bounds), block_ptr, e.rowptr, e.colidx,
+                       e.nnz)
+        assert plan.ok
+        if lpr is not None and lpr != plan.lpr:          # rebuild with another grouping: same result up to rounding
+            plan.lpr = lpr
+            G = 32 // lpr
+            levels = torch.empty(2 * e.ndof, dtype=torch.int16, device="cuda")
+            import ctypes as C
+            npass = C.c_int64()
+            capi.check(e.lib.ech_bjacobi_ilu0_plan_count(e.ndof, nf, ncell * n, n, nblocks, ptr(block_ptr), plan.max_rows,
+                                                         ptr(e.rowptr), ptr(e.colidx), lpr, ptr(plan.lcol), ptr(levels),
+                                                         ptr(plan.passptr), C.byref(npass), st))
+            plan.npass = int(npass.value)
+            plan.slots = torch.empty(max(npass.value * G, 1), dtype=torch.int64, device="cuda")
+            capi.check(e.lib.ech_bjacobi_ilu0_plan_fill(e.ndof, nf, ncell * n, n, nblocks, ptr(block_ptr), plan.max_rows,
+                                                        ptr(e.rowptr), ptr(e.colidx), lpr, ptr(levels),
+                                                        ptr(plan.passptr), ptr(plan.slots), st))
+        zz = torch.full_like(rd, float("nan"))
+        plan.apply(lu, rd, zz, st)
+        zp[plan.lpr] = zz.cpu().numpy()
+        assert np.isfinite(zp[plan.lpr]).all(), (case, plan.lpr)
+        # every row has a slot in each sweep; a pass holds up to 32 / lpr rows of one dependency level
+        assert plan.npass * (32 // plan.lpr) >= 2 * e.ndof and plan.npass <= 2 * e.ndof
     for b in range(nblocks):
         c0, c1 = bounds[b], bounds[b + 1]
         rows = np.concatenate([f * ncell * n + np.arange(c0 * n, c1 * n) for f in range(nf)])
         zh = _host_block_ilu0_solve(A, rows, r)
         assert np.abs(z[rows] - zh).max() <= 1e-10 * max(np.abs(zh).max(), 1.0), (case, b)
+        for lpr, zz in zp.items():
+            assert np.abs(zz[rows] - zh).max() <= 1e-10 * max(np.abs(zh).max(), 1.0), (case, b, lpr)
