@@ -1,17 +1,24 @@
 #!/usr/bin/env python
-"""Headline benchmark: residual + Jacobian assembly throughput (MDOF/s) of the DG Nernst-Planck MMS case.
+"""Headline benchmark of BASELINE.json: "Jacobian+residual assembly MDOF/s and Newton-step time at 1/2/4/8 B200".
 
 Workload (BASELINE.json configs[1]; SURVEY.md 8d "cfg2"): 2D electroneutral Nernst-Planck MMS,
 UnitSquareMesh(N, N) quadrilaterals, DG Q1, fields (C1, Phi), D = (0.5e-5, 1e-5) as in
-examples/mms_scaling.py:90-93, N = 1408 -> 15.86 M dofs, 634 M non-zeros.
+examples/mms_scaling.py:90-93, N = 1408 -> 15.86 M dofs, 634 M non-zeros (`echemfem_b200.workloads`).
 State: nodal interpolant of the exact fields + 1e-3 sin(7x + 3y).
 
-One "step" = one residual evaluation + one Jacobian evaluation (what SNES does once per Newton
-iteration, echemfem/solver.py:725).  Prints ONE JSON line (see the task contract).
+One "step" = one residual evaluation + one Jacobian evaluation at the same state (what SNES does once per Newton
+iteration, echemfem/solver.py:725), one fused kernel launch.  The ONE JSON line also carries, measured in the same
+run: the SpMV of the assembled Jacobian (`spmv`), one full Newton solve -- setup_solver() + solve() with the
+reference's default option set -- (`newton`: seconds per Newton step), the host-buffer path (`e2e`), the roofline
+of the fused kernel and the CPU baseline (the C++/OpenMP port of the same assembly on every host core, same mesh).
+
+  python bench.py                       1 GPU
+  torchrun ... bench.py --gpus N        N GPUs: weak scaling, one 1408 x 1408 strip per GPU (default), or
+               --scaling strong         the fixed 1408 x 1408 mesh cut into N strips
+  python bench.py --impl reference      the CPU arm alone (rank 0 only), same workload, all host cores
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -20,10 +27,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "assembly_throughput_residual_plus_jacobian"
 UNIT = "MDOF/s"
+TILE = 8                # cells are numbered in 8 x 8 tiles: compact preconditioner blocks (assembly does not care)
 
 
 def measured_peak():
@@ -108,6 +115,7 @@ def ncu_traffic(deg, n):
 
 
 def algorithmic_bytes(mesh, nf, nloc, nnz):
+    """B_J, B_F, B_SpMV from the counts of the mesh one rank owns."""
     ndof = nf * getattr(mesh, "num_owned", mesh.num_cells) * nloc
     nvert = mesh.coords.shape[0]
     d = mesh.dim
@@ -117,122 +125,104 @@ def algorithmic_bytes(mesh, nf, nloc, nnz):
     return BJ, BF, BS
 
 
-def cpu_baseline(sample_n, reps=1):
-    """The oracle (numpy port of the reference algorithm) on this host: residual + Jacobian, one core."""
-    import mms_cases
-    from oracle.mesh import unit_square_mesh
-    from oracle.assemble import Discretization
-    import numpy as np
-    disc = Discretization(unit_square_mesh(sample_n), mms_cases.adm_problem(1.0, D1=0.5e-5, D2=1.0e-5))
-    x = disc.node_coords
-    u = np.concatenate([mms_cases.C1ex(x), mms_cases.Uex(x)]) + 1e-3 * np.tile(np.sin(7 * x[:, 0] + 3 * x[:, 1]), 2)
-    disc.block_mask()
-    disc.pattern()
-    best = float("inf")
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        disc.residual(u)
-        disc.jacobian(u)
-        best = min(best, time.perf_counter() - t0)
-    return disc.ndof / best / 1e6, best, disc.ndof
-
-
-def _cpu_worker(sample_n):
-    v, t, nd = cpu_baseline(sample_n)
-    return t, nd
-
-
-def cpu_baseline_parallel(sample_n, procs, pool=None):
-    """The oracle on `procs` host cores at once, one process per core, each assembling its own sample mesh (the
-    path shards by cells with no exchange during assembly, as `mpiexec -n procs` would run the reference).
-    Returns (aggregate MDOF/s, wall seconds of the slowest worker, dofs per worker)."""
-    import multiprocessing as mp
-    own = pool is None
-    if own:
-        pool = mp.get_context("fork").Pool(procs)
+def host_cores():
     try:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [sample_n] * procs)
-        wall = time.perf_counter() - t0
-    finally:
-        if own:
-            pool.close()
-            pool.join()
-    nd = res[0][1]
-    return procs * nd / wall / 1e6, wall, nd
-
-
-def host_cores(cap=64):
-    """Cores this process may run on, capped (one oracle worker holds ~0.5 GB)."""
-    try:
-        n = len(os.sched_getaffinity(0))
+        return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        n = os.cpu_count() or 1
-    return max(1, min(n, cap))
+        return os.cpu_count() or 1
 
 
-def newton_step(n, deg, tile):
-    """Newton-step wall time (BASELINE metric, second half): setup_solver() + solve() of the same MMS problem on an
-    n x n mesh with the reference's default option set ('lu': served by GMRES + block-Jacobi/ILU(0) + coarse
-    level run to 1e-12); per-step time = solve time / Newton iterations."""
-    import torch
-    import product_cases
-    from echemfem_b200.mesh import UnitSquareMesh
-    s = product_cases.AdvectionDiffusionMigrationSolver(n, 1.0, D1=0.5e-5, D2=1.0e-5, p=deg,
-                                                        mesh=UnitSquareMesh(n, n, tile=tile if n % tile == 0 else None))
-    s.init_solver_parameters(pc_type="lu")
-    s.solver_parameters.pop("snes_monitor", None)
-    s.setup_solver()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    s.solve()
-    torch.cuda.synchronize()
-    t = time.perf_counter() - t0
-    e = s._engine
-    its = max(e.last["snes_its"], 1)
-    return {"mesh": "UnitSquareMesh(%d,%d) DG Q%d" % (n, n, deg), "dofs": e.ndof, "snes_its": e.last["snes_its"],
-            "ksp_its_per_step": e.last["ksp_its_per_step"], "solve_s": t, "newton_step_s": t / its,
-            "timers_s": {k: round(v, 4) for k, v in e.timers.items()},
-            "linear_solver": ("GMRES(200) + geometric multigrid V-cycle (block-Jacobi/ILU(0) smoothers, Galerkin coarse "
-                              "operators), ksp_rtol 1e-12" if getattr(e, "_mg", None) is not None else
-                              "GMRES(200) + block-Jacobi/ILU(0) on %dx%d-cell tiles + aggregation coarse level, "
-                              "ksp_rtol 1e-12" % (tile, tile))}
+# ---------------------------------------------------------------------------------------------------------------
+# the workload, shared by both arms
+def build_problem(args, rank, world):
+    """The solver of this rank: (solver, description).  world == 1: the N x N mesh.  Weak scaling: the global mesh
+    is (world * N) x N cells on [0, world] x [0, 1], rank r owns the r-th strip of N x N cells plus one ghost
+    column per cut.  Strong scaling: the N x N mesh itself is cut into `world` strips."""
+    import numpy as np
+    from echemfem_b200.workloads import cfg2_solver, CFG2_N
+    from echemfem_b200.mesh import TensorMesh
+    deg = args.degree
+    N = args.N or CFG2_N[deg]
+    tile = TILE if N % TILE == 0 else None
+    if world == 1:
+        mesh = TensorMesh([np.linspace(0.0, 1.0, N + 1), np.linspace(0.0, 1.0, N + 1)], name="unit_square", tile=tile)
+        desc = "UnitSquareMesh(%d,%d) quads" % (N, N)
+    else:
+        from echemfem_b200.partition import strip_partition
+        nx, Lx = (world * N, float(world)) if args.scaling == "weak" else (N, 1.0)
+        if tile is not None and (nx // world) % TILE:
+            tile = None
+        mesh, _ = strip_partition([np.linspace(0.0, Lx, nx + 1), np.linspace(0.0, 1.0, N + 1)], rank, world, tile=tile)
+        desc = "%d x %d quads on [0,%g] x [0,1], one strip of %d x %d cells per GPU (%s scaling)" % (
+            nx, N, Lx, nx // world, N, args.scaling)
+    return cfg2_solver(N, p=deg, mesh=mesh), N, desc
 
 
 def run_reference(args):
+    """CPU arm: the C++/OpenMP port of the same assembly (oracle/cpu_port: analytic Jacobian from the same generated
+    pointwise integrands, element loops and insertion written independently of the CUDA code) on every host core,
+    on the SAME mesh as one GPU of the GPU arm.  The reference itself (Firedrake/PETSc) is not installable offline
+    (DESIGN.md 5), hence "kind": "port".  Rank 0 alone runs; other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample per step: K steps of `procs` concurrent 48 x 48 meshes end within a few minutes
-    n = args.sample_n if args.sample_n != 96 else 48
-    procs = args.cpu_procs or host_cores()
-    import multiprocessing as mp
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr                 # stdout carries exactly one JSON line
+    import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    pool = mp.get_context("fork").Pool(procs)
-    vals = []
-    for _ in range(args.warmup):
-        cpu_baseline_parallel(n, procs, pool)
-    t0 = time.perf_counter()
-    ndof = 0
+    from oracle.cpu_port import CpuPort
+    from echemfem_b200.workloads import cfg2_state
+    t_setup = time.perf_counter()
+    s, N, desc = build_problem(args, 0, 1)
+    port = CpuPort(s, nthreads=args.cpu_procs or 0)
+    cores = args.cpu_procs or port.lib.cpu_port_max_threads()
+    u = cfg2_state(s.V.node_coords())
+    F, vals = np.zeros(port.ndof), np.zeros(port.nnz)
+    t_setup = time.perf_counter() - t_setup
+    W = max(args.warmup, 1)
+    for _ in range(W):
+        port.assemble(u, out=(F, vals))
+    times = []
     for _ in range(args.steps):
-        v, t, nd = cpu_baseline_parallel(n, procs, pool)
-        ndof = nd * procs
-        vals.append(t)
-    total = time.perf_counter() - t0
-    pool.close()
-    pool.join()
-    value = ndof * args.steps / sum(vals) / 1e6
-    sample = ("%d processes x UnitSquareMesh(%d,%d) DG Q1 = %d dofs per step (numpy oracle, complex-step Jacobian)"
-              % (procs, n, n, ndof))
+        t0 = time.perf_counter()
+        port.assemble(u, out=(F, vals))
+        times.append(time.perf_counter() - t0)
+    ndof = port.nf * port.ncell * port.n
+    ms = 1e3 * sum(times) / len(times)
+    value = ndof / (ms * 1e-3) / 1e6
+    sample = ("%s, DG Q%d: %d dofs, %d non-zeros per step; one residual + one Jacobian (C++/OpenMP port, analytic "
+              "Jacobian), %d threads; the GPU arm's per-GPU mesh" % (desc, args.degree, ndof, port.nnz, cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(vals) / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 MMS 2D DG Q1 electroneutral Nernst-Planck (bounded CPU sample)",
-                       "sample_N": n},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2 MMS 2D DG Q%d electroneutral Nernst-Planck, %s" % (args.degree, desc),
+                       "dofs": ndof, "nnz": port.nnz, "same_config_as_gpu_arm": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": total}
-    print(json.dumps(line))
+            "gpu_launches": 0, "setup_s": t_setup, "best_ms_per_step": 1e3 * min(times)}
+    print(json.dumps(line), file=real_stdout, flush=True)
+
+
+def cpu_baseline(s, desc, deg, reps=3, nthreads=0):
+    """Bounded CPU sample inside the GPU arm: the port on this rank's mesh, `reps` assemblies (about 10-30 s with
+    its set-up)."""
+    import numpy as np
+    from oracle.cpu_port import CpuPort
+    from echemfem_b200.workloads import cfg2_state
+    port = CpuPort(s, nthreads=nthreads)
+    u = cfg2_state(s.V.node_coords())
+    F, vals = np.zeros(port.ndof), np.zeros(port.nnz)
+    port.assemble(u, out=(F, vals))
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        port.assemble(u, out=(F, vals))
+        best = min(best, time.perf_counter() - t0)
+    ndof = port.nf * port.ncell * port.n
+    cores = nthreads or port.lib.cpu_port_max_threads()
+    return {"value": ndof / best / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%s DG Q%d (%d dofs, %d non-zeros), best of %d x (one residual + one Jacobian), C++/OpenMP port "
+                      "with analytic Jacobian, %.2f s per assembly" % (desc, deg, ndof, port.nnz, reps, best)}
 
 
 def main():
@@ -241,19 +231,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--N", type=int, default=0, help="cells per direction (cfg2: 1408 / 944 / 704 for Q1 / Q2 / Q3)")
     ap.add_argument("--degree", type=int, default=1, help="polynomial degree (the headline number is Q1)")
-    ap.add_argument("--sample-n", dest="sample_n", type=int, default=96, help="CPU baseline sample mesh")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-newton", action="store_true", help="skip the Newton solve (assembly + SpMV only)")
     ap.add_argument("--host-chunks", dest="host_chunks", type=int, default=16, help="cell ranges of the e2e "
                     "host-buffer pipeline (ech_set_host_chunks)")
-    ap.add_argument("--cpu-procs", dest="cpu_procs", type=int, default=0, help="processes of the CPU baseline "
-                                                                               "(default: every core of the host)")
-    ap.add_argument("--tile", type=int, default=0, help="number the cells tile by tile (T x T cells) instead of "
-                                                        "lexicographically")
-    ap.add_argument("--extras", action="store_true", help="also time SpMV and one full Newton solve")
-    ap.add_argument("--newton-n", dest="newton_n", type=int, default=1408, help="mesh of the --extras Newton solve "
-                                                                               "(default: the cfg2 mesh itself)")
+    ap.add_argument("--cpu-procs", dest="cpu_procs", type=int, default=0, help="threads of the CPU arm (default: all)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -263,7 +248,6 @@ def main():
 
     import numpy as np
     import torch
-    import ctypes as C
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -273,44 +257,28 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    import product_cases
-    from echemfem_b200.newton import NewtonEngine
     from echemfem_b200 import capi
     from echemfem_b200.capi import ptr
+    from echemfem_b200.newton import NewtonEngine
+    from echemfem_b200.workloads import cfg2_state
 
     W = max(args.warmup, 3)
-    N = args.N or {1: 1408, 2: 944, 3: 704}[args.degree]
     deg = args.degree
-    # The path shards by cells.  Weak scaling: the global mesh is (world*N) x N cells on [0, world] x [0, 1],
-    # rank r owns the r-th strip of N x N cells plus one ghost column per cut; per step the ghost-cell
-    # state is exchanged (NCCL send/recv) before the residual and Jacobian kernels run.
-    if world > 1:
-        from echemfem_b200.partition import strip_partition
-        lmesh, plan = strip_partition([np.linspace(0.0, float(world), world * N + 1), np.linspace(0.0, 1.0, N + 1)],
-                                      rank, world)
-        s = product_cases.AdvectionDiffusionMigrationSolver(0, 1.0, D1=0.5e-5, D2=1.0e-5, mesh=lmesh, p=deg)
-    else:
-        tmesh = None
-        if args.tile:
-            from echemfem_b200.mesh import UnitSquareMesh
-            tmesh = UnitSquareMesh(N, N, tile=args.tile)
-        s = product_cases.AdvectionDiffusionMigrationSolver(N, 1.0, D1=0.5e-5, D2=1.0e-5, p=deg, mesh=tmesh)
-    eng = NewtonEngine(s)
+    s, N, desc = build_problem(args, rank, world)
+    s.init_solver_parameters(pc_type="lu")                 # the reference's default option set (solver.py:929)
+    s.solver_parameters.pop("snes_monitor", None)
+    s._engine = eng = NewtonEngine(s)                      # the engine setup_solver() / solve() will use
     mesh = s.mesh
-    x = s.V.node_coords()
-    pert = 1e-3 * np.sin(7 * x[:, 0] + 3 * x[:, 1])
-    u_host = np.concatenate([np.cos(x[:, 0]) + np.sin(x[:, 1]) + 3 + pert, np.sin(x[:, 0]) + np.cos(x[:, 1]) + 3 + pert])
+    u_host = cfg2_state(s.V.node_coords())
     u = s.u.tensor
     u.copy_(torch.from_numpy(u_host).cuda())
-    aux = eng._aux_tensor()
-    consts = eng._consts()
-    lib = eng.lib
-    st = eng._stream()
+    aux, consts = eng._aux_tensor(), eng._consts()
+    lib, st = eng.lib, eng._stream()
     ndof = eng.nf * eng.ncell * eng.nloc            # owned dofs of this rank
     nstate = eng.ndof                               # owned + ghost
 
     def step():
-        # one Newton-iteration assembly: F(u) and J(u) at the same state, one fused pass
+        # one Newton-iteration assembly: F(u) and J(u) at the same state, one fused pass (+ ghost exchange)
         if eng.halo is not None:
             eng.halo.exchange(u)
         capi.check(lib.ech_residual_jacobian(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr), ptr(eng.vals),
@@ -319,9 +287,7 @@ def main():
     for _ in range(W):
         step()
     torch.cuda.synchronize()
-
-    # per-kernel timings (events on the launching stream)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.ech_launch_count(eng.h)
@@ -330,10 +296,10 @@ def main():
     torch.cuda.synchronize()
     sampler.mark_begin()
     t_wall = time.perf_counter()
+    ev0.record()
     for k in range(args.steps):
-        evs[k][0].record()
         step()
-        evs[k][1].record()
+    ev1.record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -341,101 +307,126 @@ def main():
     sampler.mark_end()
     clocks = sampler.stop()
     launches = lib.ech_launch_count(eng.h) - launches0
-    t_step = evs[0][0].elapsed_time(evs[-1][1]) / args.steps
-    # the two callbacks separately (what PETSc would call one after the other), for the breakdown
-    sep = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    tF = tJ = 0.0
-    for _ in range(3):      # first launches of the two separate kernels (module load, attribute set-up) are not timed
-        capi.check(lib.ech_residual(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.F), st), eng.h)
-        capi.check(lib.ech_jacobian(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr), ptr(eng.vals), st), eng.h)
-    torch.cuda.synchronize()
-    for k in range(args.steps):
-        sep[0].record()
-        capi.check(lib.ech_residual(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.F), st), eng.h)
-        sep[1].record()
-        capi.check(lib.ech_jacobian(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr), ptr(eng.vals), st), eng.h)
-        sep[2].record()
+    t_step = ev0.elapsed_time(ev1) / args.steps
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
         torch.cuda.synchronize()
-        tF += sep[0].elapsed_time(sep[1]) / args.steps
-        tJ += sep[1].elapsed_time(sep[2]) / args.steps
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # the two callbacks separately (what PETSc would call one after the other), for the breakdown
+    tF = timed(lambda: capi.check(lib.ech_residual(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.F), st), eng.h), args.steps)
+    tJ = timed(lambda: capi.check(lib.ech_jacobian(eng.h, ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr), ptr(eng.vals),
+                                                   st), eng.h), args.steps)
+
+    # SpMV with the assembled Jacobian (MatMult of KSPSolve; across ranks: ghost exchange + local product)
+    xv = torch.from_numpy(np.cos(np.arange(nstate) * 0.37)).cuda()
+    yv = torch.empty_like(xv)
+
+    def matvec():
+        if eng.halo is not None:
+            eng.halo.exchange(xv)
+        eng.spmv(xv, yv)
+    t_spmv = timed(matvec, args.steps)
+    del xv, yv
 
     # end to end through the host-buffer C ABI: pinned host state in, residual out, every step
     uh = torch.from_numpy(u_host).pin_memory()
-    capi.check(lib.ech_set_host_chunks(eng.h, args.host_chunks), eng.h)
     Fh = torch.empty(nstate, dtype=torch.float64).pin_memory()
-    for _ in range(2):
+
+    def host_call():
         capi.check(lib.ech_assemble_host(eng.h, ptr(uh), ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr),
                                          ptr(eng.vals), ptr(eng.F), ptr(Fh), st), eng.h)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        capi.check(lib.ech_assemble_host(eng.h, ptr(uh), ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr),
-                                         ptr(eng.vals), ptr(eng.F), ptr(Fh), st), eng.h)
-    e1.record()
-    torch.cuda.synchronize()
-    t_e2e = e0.elapsed_time(e1) / args.steps
-    # the same call without the chunked pipeline (one copy in, one launch, one copy out), for the breakdown
-    capi.check(lib.ech_set_host_chunks(eng.h, 0), eng.h)
-    for _ in range(2):
-        capi.check(lib.ech_assemble_host(eng.h, ptr(uh), ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr),
-                                         ptr(eng.vals), ptr(eng.F), ptr(Fh), st), eng.h)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(min(args.steps, 10)):
-        capi.check(lib.ech_assemble_host(eng.h, ptr(uh), ptr(u), ptr(aux), ptr(consts), ptr(eng.rowptr),
-                                         ptr(eng.vals), ptr(eng.F), ptr(Fh), st), eng.h)
-    e1.record()
-    torch.cuda.synchronize()
-    t_e2e_serial = e0.elapsed_time(e1) / min(args.steps, 10)
     capi.check(lib.ech_set_host_chunks(eng.h, args.host_chunks), eng.h)
+    t_e2e = timed(host_call, args.steps, warm=2)
+    capi.check(lib.ech_set_host_chunks(eng.h, 0), eng.h)
+    t_e2e_serial = timed(host_call, min(args.steps, 10), warm=2)
+    capi.check(lib.ech_set_host_chunks(eng.h, args.host_chunks), eng.h)
+    del uh, Fh
 
-    extras = {}
-    if args.extras:
-        xv = torch.from_numpy(np.cos(np.arange(nstate) * 0.37)).cuda()
-        yv = torch.empty_like(xv)
-        for _ in range(3):
-            eng.spmv(xv, yv)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            eng.spmv(xv, yv)
-        a1.record()
+    # one full Newton solve with the reference's default option set on the same mesh (all ranks together)
+    newton = None
+    if not args.no_newton:
+        torch.cuda.empty_cache()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        s.setup_solver()                                   # bulk initial guess + potential pre-solve (solver.py:645-663)
         torch.cuda.synchronize()
-        extras["spmv_ms"] = a0.elapsed_time(a1) / args.steps
-        if world == 1:
-            del xv, yv
-            torch.cuda.empty_cache()
-            extras["newton"] = newton_step(args.newton_n, deg, args.tile or 8)
+        t_setup = time.perf_counter() - t0
+        for k in eng.timers:
+            eng.timers[k] = 0.0
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        s.solve()
+        torch.cuda.synchronize()
+        t_solve = time.perf_counter() - t0
+        tt = torch.tensor([t_solve, t_setup] + [eng.timers[k] for k in sorted(eng.timers)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tt = [float(v) for v in tt.cpu()]
+        its = max(eng.last["snes_its"], 1)
+        x = s.V.node_coords()
+        no = eng.ncell * eng.nloc
+        un = s.u.numpy()
+        err = torch.tensor([np.abs(un[:no] - (np.cos(x[:no, 0]) + np.sin(x[:no, 1]) + 3)).max(),
+                            np.abs(un[eng.N:eng.N + no] - (np.sin(x[:no, 0]) + np.cos(x[:no, 1]) + 3)).max()],
+                           dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        mg = getattr(eng, "_mg", None) is not None
+        newton = {"newton_step_s": tt[0] / its, "solve_s": tt[0], "setup_solver_s": tt[1],
+                  "snes_its": eng.last["snes_its"], "ksp_its_per_step": eng.last["ksp_its_per_step"],
+                  "dofs_total": world * ndof, "timers_s_max_over_ranks": dict(zip(sorted(eng.timers), [round(v, 4) for v in tt[2:]])),
+                  "max_nodal_error_vs_exact_fields": [float(v) for v in err.cpu()],
+                  "option_set": "init_solver_parameters('lu') (the reference's default, solver.py:929): newtonls + l2 line "
+                                "search; MUMPS is replaced by right-preconditioned GMRES(200) run to ksp_rtol 1e-12",
+                  "preconditioner": ("geometric multigrid V-cycle, block-Jacobi/ILU(0) smoothers on 8x8-cell tiles "
+                                     "(level-scheduled solves), Galerkin coarse operators" +
+                                     ("; one hierarchy per rank (PETSc bjacobi: one block per rank)" if world > 1 else ""))
+                  if mg else "block-Jacobi/ILU(0) (level-scheduled solves)",
+                  "ksp_reductions_last_solve": getattr(eng, "ksp_reductions", None)}
 
-    times = torch.tensor([t_step, tF, tJ, t_e2e], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_step, tF, tJ, t_e2e, t_spmv, t_e2e_serial], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_step, tF, tJ, t_e2e = [float(v) for v in times.cpu()]
+    t_step, tF, tJ, t_e2e, t_spmv, t_e2e_serial = [float(v) for v in times.cpu()]
 
     if rank == 0:
         BJ, BF, BS = algorithmic_bytes(mesh, eng.nf, eng.nloc, eng.nnz)
         peak, peak_src = measured_peak()
         achieved = (BJ + 8 * ndof) / (t_step * 1e-3) / 1e9      # fused kernel: Jacobian bytes + the residual vector
+        spmv_gbs = BS / (t_spmv * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": world * ndof / (t_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": W, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 MMS 2D DG Q%d electroneutral Nernst-Planck, UnitSquareMesh(%d,%d) quads%s" % (
-                           deg, N, N, ", cells numbered in %dx%d tiles" % (args.tile, args.tile) if args.tile else ""),
-                       "cells_per_gpu": getattr(mesh, "num_owned", mesh.num_cells), "dofs_per_gpu": ndof, "nnz_per_gpu": eng.nnz,
+            "steps": args.steps, "warmup": W, "ms_per_step": t_step, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2 MMS 2D DG Q%d electroneutral Nernst-Planck, %s, cells numbered in %dx%d tiles" % (
+                           deg, desc, TILE, TILE),
+                       "cells_per_gpu": eng.ncell, "dofs_per_gpu": ndof, "nnz_per_gpu": eng.nnz,
                        "l2_policy": "outputs (%.1f GB CSR values) exceed the 126 MB L2 every step" % (8 * eng.nnz / 1e9),
                        "parallelism": "cells partitioned in strips, one per GPU; ghost-cell state exchanged by NCCL "
                                       "send/recv every step (%d B per rank); no matrix entries communicated" % (
                                           eng.halo.bytes_per_exchange if eng.halo is not None else 0)},
             "residual_ms": tF, "jacobian_ms": tJ,
             "residual_MDOFs": ndof / (tF * 1e-3) / 1e6, "jacobian_MDOFs": ndof / (tJ * 1e-3) / 1e6,
-            "roofline": {"bound": "hbm", "kernel": "echdg::v2::jacobian_coop2_kernel<true> (fused F + J, 1 launch per step)",
+            "roofline": {"bound": "hbm", "kernel": "fused residual + Jacobian kernel of the DG module (1 launch per step)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes": BJ + 8 * ndof, "traffic": ncu_traffic(deg, N),
                          "jacobian_only_achieved_GBs": BJ / (tJ * 1e-3) / 1e9,
                          "residual_achieved_GBs": BF / (tF * 1e-3) / 1e9},
+            "spmv": {"ms": t_spmv, "achieved_GBs": spmv_gbs, "frac": spmv_gbs / peak, "algorithmic_bytes": BS,
+                     "kernel": "spmv_kernel<8> (CSR, 8 lanes per row)" + (" + ghost exchange" if world > 1 else "")},
+            "newton": newton,
             "e2e": {"value": world * ndof / (t_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": t_e2e,
                     "h2d_bytes_per_step": 8 * nstate, "d2h_bytes_per_step": 8 * nstate,
                     "host_chunks": args.host_chunks, "unchunked_ms_per_step": t_e2e_serial,
@@ -444,16 +435,11 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall,
             "module_compile_s": eng.t_compile,
         }
-        line.update(extras)
-        if extras.get("spmv_ms"):
-            line["spmv_GBs"] = BS / (extras["spmv_ms"] * 1e-3) / 1e9
-        if not args.no_cpu:
-            procs = args.cpu_procs or host_cores()
-            v, t, nd = cpu_baseline_parallel(args.sample_n, procs)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
-                                    "sample": "%d processes x UnitSquareMesh(%d,%d) DG Q1 (%d dofs each), one residual + "
-                                              "one Jacobian (numpy oracle, complex-step Jacobian), %.1f s"
-                                              % (procs, args.sample_n, args.sample_n, nd, t)}
+        if newton is not None:
+            line["newton_step_s"] = newton["newton_step_s"]
+        if not args.no_cpu and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            line["cpu_baseline"] = cpu_baseline(s, desc, deg, nthreads=args.cpu_procs or 0)
         print(json.dumps(line), file=real_stdout, flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -29,7 +29,7 @@ class GmresOpts(C.Structure):
                 ("rows_per_field", c_i64), ("nblocks", c_i64), ("block_cell_ptr", c_p), ("lu", c_p),
                 ("diag_pos", c_p), ("agg", c_p), ("nc", c_i32), ("reserved", c_i32), ("coarse_inv", c_p),
                 ("coarse_work", c_p), ("lcol", c_p), ("passptr", c_p), ("slots", c_p), ("lanes_per_row", c_i32),
-                ("max_block_rows", c_i32)]
+                ("max_block_rows", c_i32), ("refine", c_i32), ("reserved2", c_i32)]
 
 
 EXPORTS = {

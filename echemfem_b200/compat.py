@@ -75,22 +75,52 @@ def _stub_third_party():
             def Get_size(self):
                 return int(__import__("os").environ.get("WORLD_SIZE", "1"))
 
+            # under torchrun (one process per GPU) the collectives go through torch.distributed; a stub that
+            # reports WORLD_SIZE ranks but reduces nothing would make reference scripts print wrong sums silently
+            @staticmethod
+            def _dist():
+                if int(__import__("os").environ.get("WORLD_SIZE", "1")) == 1:
+                    return None
+                import torch.distributed as dist
+                if not dist.is_initialized():
+                    raise RuntimeError("mpi4py stand-in: WORLD_SIZE > 1 but torch.distributed is not initialised")
+                return dist
+
             def Barrier(self):
-                pass
+                d = self._dist()
+                if d is not None:
+                    d.barrier()
 
             barrier = Barrier
 
             def bcast(self, obj, root=0):
-                return obj
+                d = self._dist()
+                if d is None:
+                    return obj
+                box = [obj]
+                d.broadcast_object_list(box, src=root)
+                return box[0]
 
             def allreduce(self, v, op=None):
-                return v
+                d = self._dist()
+                if d is None:
+                    return v
+                vals = [None] * d.get_world_size()
+                d.all_gather_object(vals, v)
+                if op == "max":
+                    return max(vals)
+                if op == "min":
+                    return min(vals)
+                out = vals[0]
+                for x in vals[1:]:
+                    out = out + x
+                return out
         mpi = types.ModuleType("mpi4py")
         MPI = types.ModuleType("mpi4py.MPI")
         MPI.Comm = _Comm
         MPI.COMM_WORLD = _Comm()
         MPI.COMM_SELF = _Comm()
-        MPI.SUM = MPI.MAX = MPI.MIN = None
+        MPI.SUM, MPI.MAX, MPI.MIN = "sum", "max", "min"
         MPI.Wtime = __import__("time").time
         mpi.MPI = MPI
         sys.modules["mpi4py"] = mpi

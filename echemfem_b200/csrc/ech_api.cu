@@ -549,6 +549,12 @@ static int grid_for(int64_t n, int block, int cap = 148 * 16) {
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+// x *= a (in place; axpby_kernel's arguments are __restrict__ and must not alias)
+__global__ void scale_kernel(int64_t n, double a, double *x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] *= a;
+}
+
 extern "C" int ech_axpby(int64_t n, double a, const double *x, double b, double *y, void *stream) {
     if (n == 0) return ECH_OK;
     axpby_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
@@ -1744,7 +1750,8 @@ extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx
             converged = true;
             break;
         }
-        if ((rc = ech_axpby(n, 0.0, V0, 1.0 / beta, V0, s))) return rc;   // V0 *= 1/beta  (a*x + b*y with x==y)
+        scale_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, 1.0 / beta, V0);
+        ++g_launches;
         std::fill(g.begin(), g.end(), 0.0);
         g[0] = beta;
         int j = 0;
@@ -1753,23 +1760,35 @@ extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx
             double *Vn = basis + (int64_t)(j + 1) * n;
             if ((rc = precond(Vj, zt))) return rc;
             if ((rc = ech_spmv(n, rowptr, colidx, vals, zt, w, s))) return rc;
-            // classical Gram-Schmidt + one refinement pass
+            // classical Gram-Schmidt.  One fused reduction gives h = V^T w and w.w, hence the norm of the
+            // orthogonalised vector without a second pass: |w - V h|^2 = w.w - |h|^2 (PETSc's default is CGS without
+            // refinement, KSP_GMRES_CGS_REFINE_NEVER; one device -> host read-back per iteration).  A refinement
+            // pass (and an exact norm) follows only where cancellation makes that difference unreliable, or always
+            // if the caller asks for it (refine = 2).
             if ((rc = multidot(n, j + 1, basis, w, partial, hdev, hcol.data(), s))) return rc;
             for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
             multiaxpy_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, j + 1, basis, n, hdev, w, -1.0);
             ++g_launches;
-            if ((rc = multidot(n, j + 1, basis, w, partial, hdev, hcol.data(), s))) return rc;
-            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] += hcol[i];
-            multiaxpy_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, j + 1, basis, n, hdev, w, -1.0);
-            ++g_launches;
             double corr = 0.0;
             for (int i = 0; i <= j; ++i) corr += hcol[i] * hcol[i];
-            double hn2 = hcol[j + 1] - corr;
-            if (hn2 < 0.0) hn2 = 0.0;
-            // exact norm of the refined vector
-            if ((rc = multidot(n, 0, basis, w, partial, hdev, hcol.data(), s))) return rc;
-            const double hn = sqrt(hcol[0]);
-            (void)hn2;
+            const double ww = hcol[j + 1];
+            double hn2 = ww - corr;
+            const bool refine = o->refine == 2 || (o->refine == 1 && hn2 < 0.5 * ww) || !(hn2 > 1e-6 * ww);
+            double hn;
+            if (refine) {
+                if ((rc = multidot(n, j + 1, basis, w, partial, hdev, hcol.data(), s))) return rc;
+                for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] += hcol[i];
+                multiaxpy_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, j + 1, basis, n, hdev, w, -1.0);
+                ++g_launches;
+                corr = 0.0;
+                for (int i = 0; i <= j; ++i) corr += hcol[i] * hcol[i];
+                hn2 = hcol[j + 1] - corr;
+                if (!(hn2 > 1e-6 * hcol[j + 1])) {        // still cancelling: exact norm of the refined vector
+                    if ((rc = multidot(n, 0, basis, w, partial, hdev, hcol.data(), s))) return rc;
+                    hn2 = hcol[0];
+                }
+            }
+            hn = sqrt(hn2 > 0.0 ? hn2 : 0.0);
             H[(size_t)(j + 1) * m + j] = hn;
             if (hn > 0.0) {
                 if ((rc = ech_axpby(n, 1.0 / hn, w, 0.0, Vn, s))) return rc;
@@ -1812,6 +1831,15 @@ extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx
         if ((rc = ech_axpby(n, 1.0, zt, 1.0, x, s))) return rc;
         CK(nullptr, cudaStreamSynchronize(s));
         if (!converged && k == 0) break;
+        if (converged && its < o->max_it) {
+            // the recurrence says converged: verify with the true residual (Gram-Schmidt without refinement may
+            // have lost orthogonality); if it is not there yet, the outer loop restarts from it
+            if ((rc = ech_spmv(n, rowptr, colidx, vals, x, w, s))) return rc;
+            if ((rc = ech_axpby(n, 1.0, b, -1.0, w, s))) return rc;                   // w = b - A x
+            if ((rc = multidot(n, 0, basis, w, partial, hdev, hcol.data(), s))) return rc;
+            rnorm = sqrt(hcol[0]);
+            if (rnorm > 1.5 * tol) converged = false;
+        }
     }
     if (its_host) *its_host = its;
     if (rnorm_host) *rnorm_host = rnorm;

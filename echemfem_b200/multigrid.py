@@ -73,15 +73,20 @@ class Level:
 class Hierarchy:
     """Levels of a tensor mesh and the scalar prolongations between them (host side)."""
 
-    def __init__(self, mesh, degree, tile=16, coarsest_cells=64, max_levels=12):
-        if not hasattr(mesh, "axes") or getattr(mesh, "halo_plan", None) is not None:
-            raise NotImplementedError("multigrid needs an undistributed tensor-product mesh")
+    def __init__(self, mesh, degree, tile=16, coarsest_cells=64, max_levels=12, fine_rows=None):
+        """fine_rows: rows of the finest prolongation (>= fine dofs): a rank's vectors also hold its ghost cells
+        (after the owned ones), which the hierarchy of the owned cells leaves untouched."""
+        if hasattr(mesh, "owned_axes"):
+            mesh_axes, perm = mesh.owned_axes, getattr(mesh, "cell_perm", None)   # one rank's strip (strip_partition)
+        elif hasattr(mesh, "axes") and getattr(mesh, "halo_plan", None) is None:
+            mesh_axes, perm = mesh.axes, getattr(mesh, "cell_perm", None)
+        else:
+            raise NotImplementedError("multigrid needs a tensor-product mesh (whole, or one strip per rank)")
         self.p = degree
         n1 = degree + 1
-        d = len(mesh.axes)
+        d = len(mesh_axes)
         self.n = n1 ** d
-        axes = [np.asarray(a, dtype=float) for a in mesh.axes]
-        perm = getattr(mesh, "cell_perm", None)
+        axes = [np.asarray(a, dtype=float) for a in mesh_axes]
         self.levels = []
         self.P = []                      # P[l]: level l (fine)  <-  level l + 1 (coarse), scalar dofs
         while True:
@@ -109,8 +114,11 @@ class Hierarchy:
             P = P.tocoo()
             rf = _dof_map(shape, n1, L.inv)
             rc = _dof_map(cshape, n1, cinv)
+            nrow = L.ncell * self.n
+            if len(self.levels) == 1 and fine_rows is not None:
+                nrow = max(nrow, int(fine_rows))
             self.P.append(sp.csr_matrix((P.data, (rf[P.row], rc[P.col])),
-                                        shape=(L.ncell * self.n, int(np.prod(cshape)) * self.n)))
+                                        shape=(nrow, int(np.prod(cshape)) * self.n)))
             axes, perm = cax, cperm
 
     @property
@@ -162,14 +170,18 @@ class Multigrid:
         mesh = engine.solver.mesh
         if engine.family != "DG":
             raise NotImplementedError("multigrid is implemented for DG spaces")
-        self.h = Hierarchy(mesh, engine.solver.W.scalar.degree, tile=tile, coarsest_cells=coarsest_cells)
+        # across ranks every rank builds the hierarchy of its own cells: the V-cycle is then the block solver of
+        # PETSc's bjacobi (one block per rank, echemfem/solver.py:1186), couplings to ghost cells dropped
+        self.distributed = engine.halo is not None
+        self.h = Hierarchy(mesh, engine.solver.W.scalar.degree, tile=tile, coarsest_cells=coarsest_cells,
+                           fine_rows=engine.N)
         if self.h.nlevels < 2:
             raise NotImplementedError("mesh cannot be coarsened")
         n = self.h.n
         self.lv = []
         for l, L in enumerate(self.h.levels):
             D = Level()
-            D.N = L.ncell * n                    # scalar dofs = field stride
+            D.N = L.ncell * n if l else engine.N  # field stride (finest level: owned + ghost cells)
             D.ndof = D.N * self.nf
             # one warp solves one block row by row: small blocks keep the smoother of the coarse levels (few
             # cells, little parallelism) from dominating the cycle; the fine level follows the mesh tiles
@@ -286,4 +298,6 @@ class Multigrid:
         capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(D.s), 1.0, ptr(z), st))
 
     def apply(self, r, z):
+        if self.distributed:
+            z.zero_()          # ghost entries (stale halo values) must not enter the rank-local residuals
         self.vcycle(0, r, z)

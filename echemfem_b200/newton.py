@@ -287,7 +287,7 @@ class NewtonEngine:
         per = 64 if self.cg is None else 256
         nblocks = self.nblocks
         hint = getattr(self.solver.mesh, "block_hint", None)
-        if nblocks is None and hint and self.cg is None and self.halo is None:
+        if nblocks is None and hint and self.cg is None:
             nblocks = max(1, nunits // int(hint))          # tile-numbered mesh: one block per tile
         if nblocks is None:
             # one warp factors / solves one block: enough blocks to fill the machine, >= ~256 rows per field each
@@ -348,15 +348,24 @@ class NewtonEngine:
                 from .multigrid import Multigrid
                 # validated for Q1; higher degrees need a p-coarsening level first (the reference's PMGPC,
                 # examples/mms_scaling.py:211-238), until then they keep the one-level / aggregation path
-                if self.halo is None and self.cg is None and self.solver.W.scalar.degree == 1:
+                local_ok = self.halo is None or hasattr(self.solver.mesh, "owned_axes")
+                if local_ok and self.cg is None and self.solver.W.scalar.degree == 1:
                     self._mg = Multigrid(self, **kw)
             except NotImplementedError:
                 self._mg = None
         return self._mg
 
-    def linear_solve(self, rhs, rtol, atol, restart, max_it, monitor=False, coarse=0, coarse_mode=3, mg=False):
-        """Solve J dx = rhs with right-preconditioned GMRES; returns (dx, iterations)."""
+    def linear_solve(self, rhs, rtol, atol, restart, max_it, monitor=False, coarse=0, coarse_mode=3, mg=False,
+                     refine=None):
+        """Solve J dx = rhs with right-preconditioned GMRES; returns (dx, iterations, converged).
+        refine: Gram-Schmidt refinement, 0 never / 1 if needed / 2 always; None: by tolerance -- classical
+        Gram-Schmidt without refinement (PETSc's default) loses orthogonality like cond^2 * eps, which the
+        reference's iterative option sets (ksp_rtol 1e-2 ... 1e-10 on preconditioned systems) tolerate and the
+        1e-12 solves that stand in for its direct solver do not."""
+        if refine is None:
+            refine = 1 if rtol < 1e-8 else 0
         L = self._linear_plan(restart)
+        restart = int(max(1, min(restart, L["restart"])))        # a cached plan may hold a longer basis
         M = self.multigrid() if mg else None
         if M is not None:
             t0 = time.time()
@@ -364,7 +373,7 @@ class NewtonEngine:
             torch.cuda.synchronize()
             self.timers["PCSetUp"] += time.time() - t0
             t0 = time.time()
-            out = self._gmres(rhs, rtol, atol, max_it, monitor, precond=M.apply)
+            out = self._gmres(rhs, rtol, atol, max_it, monitor, precond=M.apply, restart=restart, refine=refine)
             torch.cuda.synchronize()
             self.timers["KSPSolve"] += time.time() - t0
             return out
@@ -383,13 +392,13 @@ class NewtonEngine:
         self.timers["PCSetUp"] += time.time() - t0
         if self.halo is not None:
             t0 = time.time()
-            out = self._gmres(rhs, rtol, atol, max_it, monitor)
+            out = self._gmres(rhs, rtol, atol, max_it, monitor, restart=restart, refine=refine)
             torch.cuda.synchronize()
             self.timers["KSPSolve"] += time.time() - t0
             return out
-        opts = capi.GmresOpts(rtol, atol, L["restart"], max_it, 1, 1 if monitor else 0, self.nf, self._unit,
+        opts = capi.GmresOpts(rtol, atol, restart, max_it, 1, 1 if monitor else 0, self.nf, self._unit,
                               self.N, L["nblocks"], ptr(L["block_ptr"]), ptr(L["lu"]), ptr(L["diag"]),
-                              None, 0, 0, None, None, None, None, None, 0, 0)
+                              None, 0, 0, None, None, None, None, None, 0, 0, int(refine), 0)
         if L["ilu_plan"] is not None:
             L["ilu_plan"].set_opts(opts)
         if Cz is not None:
@@ -409,15 +418,22 @@ class NewtonEngine:
             capi.check(rc)
         return L["dx"], its.value, rc == 0
 
-    def _gmres(self, b, rtol, atol, max_it, monitor=False, precond=None):
+    def _gmres(self, b, rtol, atol, max_it, monitor=False, precond=None, restart=None, refine=0):
         """Right-preconditioned restarted GMRES driven from Python: the same algorithm as `ech_gmres`, with
         (across ranks) the ghost-dof exchange in front of every SpMV and the Gram-Schmidt dot products
         all-reduced over NCCL (PETSc: VecScatter + MPI_Allreduce inside KSPSolve), and with a pluggable
-        preconditioner (multigrid V-cycle).  Preconditioner blocks never cross ranks."""
+        preconditioner (multigrid V-cycle).  Preconditioner blocks never cross ranks.
+
+        ONE reduction (one all-reduce, one device -> host read-back) per iteration: the fused multi-dot returns
+        h = V^T w together with w.w, and |w - V h|^2 = w.w - |h|^2 (classical Gram-Schmidt without refinement is
+        PETSc's default, KSP_GMRES_CGS_REFINE_NEVER); a refinement pass runs only where that difference cancels
+        (or per `refine`: 1 if needed, 2 always).  Convergence claimed by the recurrence is confirmed with the true
+        residual."""
         import torch.distributed as dist
         distributed = self.halo is not None
         L = self._lin
-        n, m = self.ndof, L["restart"]
+        n = self.ndof
+        m = L["restart"] if restart is None else int(max(1, min(restart, L["restart"])))
         lib, st = self.lib, self._stream()
         V = L["basis"]
         work = L["work"]
@@ -426,11 +442,15 @@ class NewtonEngine:
         partial = work[3 * n + 4096:]
         x = L["dx"]
         x.zero_()
+        own = self._owned_mask() if distributed else None
+        self.ksp_reductions = 0
 
         def mdot(k, vec):
+            # ghost entries of Krylov vectors are zero (rows of ghost cells are empty), so plain sums are owned sums
             capi.check(lib.ech_multidot(n, k, ptr(V), ptr(vec), ptr(partial), ptr(hdev), st))
             if distributed:
                 dist.all_reduce(hdev[:k + 1])
+            self.ksp_reductions += 1
             return hdev[:k + 1].cpu().numpy()
 
         if precond is None:
@@ -448,23 +468,36 @@ class NewtonEngine:
                 self.halo.exchange(src)
             capi.check(lib.ech_spmv(n, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(src), ptr(dst), st))
 
-        bnorm = math.sqrt(max(mdot(0, b)[0], 0.0))
+        def owned_sq(vec):
+            if not distributed:
+                return max(mdot(0, vec)[0], 0.0)
+            torch.mul(vec, own, out=t2)
+            capi.check(lib.ech_multidot(n, 0, ptr(V), ptr(t2), ptr(partial), ptr(hdev), st))
+            dist.all_reduce(hdev[:1])
+            self.ksp_reductions += 1
+            return max(float(hdev[0].item()), 0.0)
+
+        bnorm = math.sqrt(owned_sq(b))
         tol = max(rtol * bnorm, atol)
         its, rnorm, converged = 0, bnorm, False
         H = np.zeros((m + 1, m))
         cs, sn, g = np.zeros(m), np.zeros(m), np.zeros(m + 1)
-        while its < max_it and not converged:
+        rank0 = not distributed or self.halo.plan.rank == 0
+        while its < max_it:
             V0 = V[:n]
             t2.copy_(x)
             matvec(t2, w)
             torch.sub(b, w, out=V0)
+            if distributed:
+                V0.mul_(own)                 # b may carry ghost entries; basis vectors must not
             beta = math.sqrt(max(mdot(0, V0)[0], 0.0))
             rnorm = beta
-            if monitor and (not distributed or self.halo.plan.rank == 0):
+            if monitor and rank0:
                 print("  %3d KSP Residual norm %.12e" % (its, rnorm))
-            if beta <= tol:
+            if beta <= (1.5 * tol if converged else tol):
                 converged = True
                 break
+            converged = False
             V0.mul_(1.0 / beta)
             g[:] = 0.0
             g[0] = beta
@@ -476,10 +509,16 @@ class NewtonEngine:
                 h = mdot(j + 1, w)
                 H[:j + 1, j] = h[:j + 1]
                 capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
-                h = mdot(j + 1, w)                                   # one refinement pass
-                H[:j + 1, j] += h[:j + 1]
-                capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
-                hn = math.sqrt(max(mdot(0, w)[0], 0.0))
+                ww = h[j + 1]
+                hn2 = ww - float(np.dot(h[:j + 1], h[:j + 1]))
+                if refine == 2 or (refine == 1 and hn2 < 0.5 * ww) or not (hn2 > 1e-6 * ww):
+                    h = mdot(j + 1, w)
+                    H[:j + 1, j] += h[:j + 1]
+                    capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
+                    hn2 = h[j + 1] - float(np.dot(h[:j + 1], h[:j + 1]))
+                    if not (hn2 > 1e-6 * h[j + 1]):
+                        hn2 = mdot(0, w)[0]
+                hn = math.sqrt(max(hn2, 0.0))
                 H[j + 1, j] = hn
                 if hn > 0.0:
                     torch.mul(w, 1.0 / hn, out=Vn)
@@ -495,7 +534,7 @@ class NewtonEngine:
                 g[j] = cs[j] * g[j]
                 its += 1
                 rnorm = abs(g[j + 1])
-                if monitor and (not distributed or self.halo.plan.rank == 0):
+                if monitor and rank0:
                     print("  %3d KSP Residual norm %.12e" % (its, rnorm))
                 j += 1
                 if rnorm <= tol or hn == 0.0:
@@ -510,8 +549,9 @@ class NewtonEngine:
             capi.check(lib.ech_multiaxpy(n, k, ptr(V), ptr(hdev), 1.0, ptr(t2), st))
             precond(t2, zt)
             x.add_(zt)
+            # converged by the recurrence: the next pass of the loop checks the true residual and restarts if needed
         if distributed:
-            x.mul_(self._owned_mask())      # ghost entries of the update are refreshed by the next exchange
+            x.mul_(own)      # ghost entries of the update are refreshed by the next exchange
         return x, its, converged
 
     # -- Newton -----------------------------------------------------------------------------
@@ -555,6 +595,9 @@ class NewtonEngine:
         restart = P.get("ksp_gmres_restart", 30) if not direct else 200
         ksp_max_it = P.get("ksp_max_it", 10000)
         linesearch = P.get("snes_linesearch_type", "bt")
+        # PETSc: -ksp_gmres_cgs_refinement_type refine_never (default) | refine_ifneeded | refine_always
+        refine = {None: None, "refine_never": 0, "refine_ifneeded": 1, "refine_always": 2}[
+            P.get("ksp_gmres_cgs_refinement_type")]
         # coarse level: on by default where the reference would factor directly ("lu") and the system is large
         coarse = P.get("pc_coarse_dofs", 4096 if (direct and self.ndof >= 100000) else 0)
         coarse_mode = 2 if P.get("pc_coarse_type", "multiplicative") == "additive" else 3
@@ -615,7 +658,7 @@ class NewtonEngine:
             torch.cuda.synchronize()
             self.timers["JacobianEval"] += time.time() - t0
             y, kits, ok = self.linear_solve(F, ksp_rtol, ksp_atol, restart, ksp_max_it, coarse=coarse,
-                                            coarse_mode=coarse_mode, mg=mg)
+                                            coarse_mode=coarse_mode, mg=mg, refine=refine)
             ksp_hist.append(kits)
             if not ok:
                 print("*** WARNING: linear solve did not reach ksp_rtol in %d iterations" % kits)
@@ -688,16 +731,31 @@ class NewtonEngine:
 
     # -- stats (solver.py:729-792) ---------------------------------------------------------------
     def write_stats(self, path, overwrite):
+        """One CSV row per solve with the reference's columns (echemfem/solver.py:729-792): counts are summed over
+        the ranks (owned cells / dofs only), timers are the maximum over the ranks, rank 0 writes."""
         import pandas
         s = self.solver
-        data = {"num_processes": 1, "num_cells": s.mesh.num_cells, "dimension": 3,
-                "degreeC": s.poly_degree, "degreeU": s.poly_degreeU, "dofs": self.ndof,
+        owned_cells = int(self.ncell)
+        owned_dofs = int(self.nf * self.ncell * self.nloc) if self.cg is None else int(self.ndof)
+        counts = [owned_cells, owned_dofs]
+        timers = [self.timers[k] for k in ("SNESSolve", "KSPSolve", "PCSetUp", "PCApply", "JacobianEval", "FunctionEval")]
+        nproc, rank = 1, 0
+        if self.halo is not None:
+            import torch.distributed as dist
+            nproc, rank = dist.get_world_size(), dist.get_rank()
+            c = torch.tensor(counts, dtype=torch.float64, device=self.dev)
+            t = torch.tensor(timers, dtype=torch.float64, device=self.dev)
+            dist.all_reduce(c)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            counts, timers = [int(v) for v in c.cpu()], [float(v) for v in t.cpu()]
+        if rank != 0:
+            return
+        data = {"num_processes": nproc, "num_cells": counts[0], "dimension": 3,          # literal in the reference (solver.py:764)
+                "degreeC": s.poly_degree, "degreeU": s.poly_degreeU, "dofs": counts[1],
                 "name": "bortels_threeion_extruded_3d_nondim", "snes_its": self.last["snes_its"],
-                "ksp_its": self.last["ksp_its"], "SNESSolve": self.timers["SNESSolve"],
-                "KSPSolve": self.timers["KSPSolve"], "PCSetUp": self.timers["PCSetUp"],
-                "PCApply": self.timers["PCApply"], "JacobianEval": self.timers["JacobianEval"],
-                "FunctionEval": self.timers["FunctionEval"], "mesh_name": s.mesh.name,
-                "csolver": getattr(s, "csolver", "")}
+                "ksp_its": self.last["ksp_its"], "SNESSolve": timers[0], "KSPSolve": timers[1], "PCSetUp": timers[2],
+                "PCApply": timers[3], "JacobianEval": timers[4], "FunctionEval": timers[5],
+                "mesh_name": s.mesh.name, "csolver": getattr(s, "csolver", "")}
         path = os.path.abspath(path)
         os.makedirs(os.path.dirname(path), exist_ok=True)
         mode = "w" if overwrite else "a"

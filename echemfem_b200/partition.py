@@ -176,9 +176,10 @@ def partition_mesh(mesh, rank, size, edges=None, parts=None):
     return local, local.halo_plan
 
 
-def strip_partition(axes, rank, size, name="strip"):
+def strip_partition(axes, rank, size, name="strip", tile=None):
     """Rank `rank`'s part of the tensor mesh over `axes`, split into strips along the first direction,
-    built WITHOUT the global mesh (weak-scaling benchmarks): the strip plus one ghost layer per side."""
+    built WITHOUT the global mesh (weak-scaling benchmarks): the strip plus one ghost layer per side.
+    tile: the owned cells are numbered tile by tile (`mesh.tile_order`), as `UnitSquareMesh(..., tile=)` does."""
     axes = [np.asarray(a, dtype=float) for a in axes]
     nx = len(axes[0]) - 1
     edges = np.linspace(0, nx, size + 1).astype(np.int64)
@@ -192,6 +193,12 @@ def strip_partition(axes, rank, size, name="strip"):
     owned_mask = (col >= i0) & (col < i1)
     gid = (col * per_col + np.arange(ext.num_cells) % per_col).astype(np.int64)
     owned = np.nonzero(owned_mask)[0]
+    oshape = tuple([i1 - i0] + [len(a) - 1 for a in axes[1:]])
+    operm = None
+    if tile is not None and all(n % int(tile) == 0 for n in oshape):
+        from .mesh import tile_order
+        operm = tile_order(oshape, tile)               # owned cells are lexicographic in ext order
+        owned = owned[operm]
     ghosts = np.nonzero(~owned_mask)[0]
     gowner = np.where(col[ghosts] < i0, rank - 1, rank + 1)
     o = np.lexsort((gid[ghosts], gowner))
@@ -199,6 +206,12 @@ def strip_partition(axes, rank, size, name="strip"):
     order = np.concatenate([owned, ghosts])
     local = LocalMesh(ext, order, len(owned), gid[order], gowner, name=name, global_num_cells=nx * per_col)
     local.halo_plan = _halo_plan(local, None, rank, size)
+    # the owned cells are a tensor mesh of their own, numbered lexicographically: a rank-local multigrid hierarchy
+    # (the V-cycle as the block of PETSc's bjacobi) can be built on it
+    local.owned_axes = [axes[0][i0:i1 + 1]] + axes[1:]
+    local.cell_perm = operm
+    if operm is not None:
+        local.block_hint = int(tile) ** len(axes)
     return local, local.halo_plan
 
 

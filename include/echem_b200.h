@@ -183,12 +183,15 @@ typedef struct ech_gmres_opts {
     const int64_t *passptr;
     const uint64_t *slots;
     int32_t lanes_per_row, max_block_rows;
+    /* Gram-Schmidt refinement (PETSc KSPGMRESCGSRefinementType): 0 never (PETSc's default), 1 if needed, 2 always */
+    int32_t refine, reserved2;
 } ech_gmres_opts;
 
-/* Right-preconditioned restarted GMRES (classical Gram-Schmidt with one refinement, unpreconditioned
- * residual norm: PETSc fgmres + fixed PC, solver.py:1181-1189).  basis: (restart+1) * nrows doubles,
- * work: 3 * nrows + 4096 + 2*(restart+2)*1024 doubles.  Synchronises once per iteration
- * (Hessenberg column read-back).  its_host / rnorm_host receive iteration count and final norm. */
+/* Right-preconditioned restarted GMRES (classical Gram-Schmidt, unpreconditioned residual norm: PETSc fgmres +
+ * fixed PC, solver.py:1181-1189).  basis: (restart+1) * nrows doubles, work: 3 * nrows + 4096 +
+ * 2*(restart+2)*1024 doubles.  ONE device -> host read-back per iteration: the fused reduction returns the
+ * Hessenberg column and w.w, from which the norm of the new basis vector follows; convergence claimed by the
+ * recurrence is confirmed with the true residual.  its_host / rnorm_host receive iteration count and final norm. */
 int ech_gmres(int64_t nrows, const int64_t *rowptr, const int32_t *colidx, const double *vals, const double *b,
               double *x, const ech_gmres_opts *opts, double *basis, double *work, int32_t *its_host,
               double *rnorm_host, void *stream);
