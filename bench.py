@@ -242,8 +242,12 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    # stdout carries exactly one JSON line; everything the solver prints goes to stderr
-    real_stdout = sys.stdout
+    # stdout carries exactly one JSON line; everything else -- Python prints and C-level writes such as NCCL's
+    # version banner -- goes to stderr: file descriptor 1 is pointed at stderr, the line is written to a duplicate
+    sys.stdout.flush()
+    real_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(real_fd, "w")
     sys.stdout = sys.stderr
 
     import numpy as np

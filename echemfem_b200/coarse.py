@@ -34,3 +34,25 @@ def box_aggregates(coords, nf, target):
     nagg = int(box.max()) + 1
     agg = np.concatenate([box + f * nagg for f in range(nf)]).astype(np.int32)
     return agg, nagg * nf
+
+
+def box_aggregates_global(coords, nf, target, lo, hi):
+    """Like `box_aggregates`, on a box grid fixed by the GLOBAL bounding box (lo, hi), so that every rank of a
+    partitioned mesh numbers the boxes identically.  Returns (agg[nf * n] int32, nc, nbs): numbers are NOT
+    compressed (nc = nf * number of boxes); the caller removes globally empty boxes."""
+    x = np.asarray(coords, dtype=float)
+    if x.ndim == 1:
+        x = x[:, None]
+    n, dim = x.shape
+    lo, hi = np.asarray(lo, dtype=float), np.asarray(hi, dtype=float)
+    nb = max(1.0, (float(target) / float(nf)) ** (1.0 / dim))
+    span = np.where(hi > lo, hi - lo, 1.0)
+    aspect = span / np.prod(span) ** (1.0 / dim)
+    nbs = np.maximum(1, np.round(nb * aspect).astype(np.int64))
+    idx = np.clip((nbs * (x - lo) / span).astype(np.int64), 0, nbs - 1)
+    lin = idx[:, 0]
+    for k in range(1, dim):
+        lin = lin * nbs[k] + idx[:, k]
+    nbox = int(np.prod(nbs))
+    agg = np.concatenate([lin + f * nbox for f in range(nf)]).astype(np.int32)
+    return agg, nbox * nf, nbs

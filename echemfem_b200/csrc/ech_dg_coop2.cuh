@@ -166,24 +166,45 @@ constexpr int cell_stride() {
 constexpr int CELL_STRIDE = cell_stride();
 constexpr int NCONST_PAD = even(ECH_NCONST);
 
+// ECH_COOP2_PIPE (default 1): staging with the PRODUCER lane numbering (lane = slot * CPW + cell): every lane loads
+// ONE neighbour id and copies that neighbour's data; the eight lanes of a quarter-warp write eight different cells
+// at equal offsets, which the cell stride (10 mod 16 doubles) spreads over distinct bank groups -- the consumer
+// numbering of round 1 wrote 4.3 x the ideal number of shared-memory wavefronts (LDGSTS, ncu source page).
+// ECH_COOP2_NBUF = 2 double-buffers the staged cell data, so that the data of batch i+1 arrives while batch i is
+// evaluated and the ids of batch i+2 are loaded (both dependent round trips of the staging off the critical path).
+// Measured on cfg2 (profiles/r2i_coop2_staging_variants.txt): the extra 7 KB per warp cost the eighth resident
+// warp per SM (2.93 ms against 2.55 ms); with 2 warps per CTA to amortise the per-CTA reserve it is 3.2 ms.  The
+// kernel is occupancy-bound (time ~ 1 / resident warps), so the default is ONE buffer, the next batch staged
+// during the last round, persistent warps over 2 waves: 2.51 ms against 2.61 ms for the round-1 staging.
+#ifndef ECH_COOP2_PIPE
+#define ECH_COOP2_PIPE 1
+#endif
+#ifndef ECH_COOP2_NBUF
+#define ECH_COOP2_NBUF 1
+#endif
+constexpr bool PIPE = ECH_COOP2_PIPE != 0 && G >= NLF;
+constexpr int NBUF = (PIPE && ECH_COOP2_NBUF == 2) ? 2 : 1;       // 1: the next batch is staged during the last round
+constexpr bool EARLY = NBUF == 2;
+
 struct Smem2 {
     double *rec;       // RECLEN * 32
-    double *nbd;       // [CPW][CELL_STRIDE]
-    double *fa;        // [CPW][NLF] facet areas of my cells
+    double *nbd;       // [NBUF][CPW][CELL_STRIDE]
+    double *fa;        // [NBUF][even(CPW * NLF)] facet areas of my cells
     double *kc;        // [NCONST_PAD] runtime constants
     double *acc;       // [NF][NF][NLOC][32] own-block accumulators (SMEM_ACC only)
     int *meta;         // [2][CPW][META_LEN]  (double-buffered: the next batch is staged while this one is consumed)
 };
+constexpr int FA_LEN = even(CPW * NLF);
 __host__ __device__ constexpr int warp_smem2_doubles(int reclen) {
-    return even(reclen * 32 + CPW * CELL_STRIDE + even(CPW * NLF) + NCONST_PAD + ACC_DOUBLES + CPW * META_LEN);
+    return even(reclen * 32 + NBUF * (CPW * CELL_STRIDE + FA_LEN) + NCONST_PAD + ACC_DOUBLES + CPW * META_LEN);
 }
 __device__ __forceinline__ Smem2 warp_smem2(double *smem, int warp, int reclen) {
     double *base = smem + (size_t)warp * warp_smem2_doubles(reclen);
     Smem2 w;
     w.rec = base;
     w.nbd = base + reclen * 32;
-    w.fa = w.nbd + CPW * CELL_STRIDE;
-    w.kc = w.fa + even(CPW * NLF);
+    w.fa = w.nbd + NBUF * CPW * CELL_STRIDE;
+    w.kc = w.fa + NBUF * FA_LEN;
     w.acc = w.kc + NCONST_PAD;
     w.meta = reinterpret_cast<int *>(w.acc + ACC_DOUBLES);
     return w;
@@ -316,6 +337,37 @@ __device__ __forceinline__ void issue_stage(const ech_dg_args &A, const Smem2 &W
             if (nb >= 0) copy_slot<0, 1>(A, W.nbd + g * CELL_STRIDE + lf * SLOT_LEN, nb, fstride, 0);
         }
         copy_slot<1, G>(A, W.nbd + g * CELL_STRIDE + NLF * SLOT_LEN, (int)c, fstride, a);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// ---- staging with the producer lane numbering (PIPE): lane (ge, ae) = (cell of the warp, slot) copies the data of the
+// neighbour across facet ae of cell ge whole, and its share (ae of G) of the cell's own data
+struct StageIds {
+    int nb, code, slot;     // neighbour across facet ae of cell ge (nb = -1: none / boundary class folded below)
+};
+__device__ __forceinline__ StageIds load_ids_e(const ech_dg_args &A, int ae, int64_t ce, bool active_e) {
+    StageIds r{-1, 0, 0};
+    if (active_e && ae < NLF) {
+        r.nb = ldg_s32(A.nbr + ce * NLF + ae);
+        r.code = ldg_u8(A.code + ce * NLF + ae);
+        r.slot = ldg_u8(A.slot + ce * NLF + ae);
+    }
+    return r;
+}
+__device__ __forceinline__ void issue_stage_e(const ech_dg_args &A, const Smem2 &W, int mb, int ge, int ae, int64_t ce,
+                                              bool active_e, const StageIds &id, int64_t fstride) {
+    if (active_e) {
+        double *nbd = W.nbd + (EARLY ? mb : 0) * (CPW * CELL_STRIDE) + ge * CELL_STRIDE;
+        if (ae < NLF) {
+            int *m = W.meta + (mb * CPW + ge) * META_LEN;
+            m[ae] = id.nb;
+            m[NLF + ae] = id.code;
+            m[2 * NLF + ae] = id.slot;
+            cp_async8(W.fa + (EARLY ? mb : 0) * FA_LEN + ge * NLF + ae, A.facet_area + ce * NLF + ae);
+            if (id.nb >= 0) copy_slot<0, 1>(A, nbd + ae * SLOT_LEN, id.nb, fstride, 0);
+        }
+        copy_slot<1, G>(A, nbd + NLF * SLOT_LEN, (int)ce, fstride, ae);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -766,25 +818,34 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
     // producer role: this lane evaluates slot ae of cell ge of the warp
     const int ge = lane % CPW, ae = lane / CPW;
     const RecRef RE{W.rec + 2 * ge};
-    const double *own = W.nbd + ge * CELL_STRIDE + NLF * SLOT_LEN;
 
     int ad[D];      // digits of my test node
 #pragma unroll
     for (int k = 0; k < D; ++k) ad[k] = ((active_lane ? a : 0) / ipow(N1, D - 1 - k)) % N1;
 
-    // PERSISTENT warps: a warp walks over batches of CPW cells; the staging of the next batch (two dependent
-    // global round trips: neighbour ids, then their data) is issued while the current one is being consumed
+    // PERSISTENT warps: a warp walks over batches of CPW cells; the staging of the following batches (two dependent
+    // global round trips: neighbour ids, then their data) is in flight while the current one is evaluated
     const int64_t wstride = (int64_t)gridDim.x * J2WARPS;
     // a launch covers the batches of cells [A.cell_begin, A.ncell) (cell_begin is a multiple of CPW)
     int64_t batch = A.cell_begin / CPW + (int64_t)blockIdx.x * J2WARPS + warp;
     for (int k = lane; k < ECH_NCONST; k += 32) cp_async8(W.kc + k, A.consts + k);
-    int ids[NLF], cs[2 * NLF];
+    int ids[NLF], cs[2 * NLF];                      // (!PIPE) ids of the next batch, consumer numbering
+    StageIds idn{-1, 0, 0};                         // (PIPE) ids of the batch to stage next, producer numbering
     int mb = 0;
     if (batch < nbatch) {
-        const int64_t c0 = batch * CPW + g;
-        const bool act0 = active_lane && c0 < A.ncell;
-        load_ids(A, a, c0, act0, ids, cs);
-        issue_stage(A, W, mb, g, a, c0, act0, ids, cs, fstride);
+        if constexpr (PIPE) {
+            const int64_t ce0 = batch * CPW + ge;
+            const bool act0 = ae < G && ce0 < A.ncell;
+            const StageIds id0 = load_ids_e(A, ae, ce0, act0);
+            issue_stage_e(A, W, 0, ge, ae, ce0, act0, id0, fstride);
+            const int64_t ce1 = (batch + wstride) * CPW + ge;
+            idn = load_ids_e(A, ae, ce1, batch + wstride < nbatch && ae < G && ce1 < A.ncell);
+        } else {
+            const int64_t c0 = batch * CPW + g;
+            const bool act0 = active_lane && c0 < A.ncell;
+            load_ids(A, a, c0, act0, ids, cs);
+            issue_stage(A, W, mb, g, a, c0, act0, ids, cs, fstride);
+        }
     }
 
     for (; batch < nbatch; batch += wstride) {
@@ -797,7 +858,21 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
     const bool has_next = batch + wstride < nbatch;
     const int64_t cn = (batch + wstride) * CPW + g;
     const bool active_n = has_next && active_lane && cn < A.ncell;
-    load_ids(A, a, cn, active_n, ids, cs);          // first round trip of the next batch (registers)
+    const double *nbd_b = W.nbd + (EARLY ? mb : 0) * (CPW * CELL_STRIDE) + ge * CELL_STRIDE;
+    const double *fa_b = W.fa + (EARLY ? mb : 0) * FA_LEN + ge * NLF;
+    const double *own = nbd_b + NLF * SLOT_LEN;
+    if constexpr (EARLY) {
+        if (has_next) {
+            const int64_t cen = (batch + wstride) * CPW + ge;
+            issue_stage_e(A, W, mb ^ 1, ge, ae, cen, ae < G && cen < A.ncell, idn, fstride);     // data of batch i+1
+        }
+        const int64_t cenn = (batch + 2 * wstride) * CPW + ge;
+        idn = load_ids_e(A, ae, cenn, batch + 2 * wstride < nbatch && ae < G && cenn < A.ncell);   // ids of batch i+2
+    } else if constexpr (PIPE) {
+        // single buffer: idn holds the ids of batch i+1 (loaded one batch ahead); its data is staged in the last round
+    } else {
+        load_ids(A, a, cn, active_n, ids, cs);          // first round trip of the next batch (registers)
+    }
 
     int ncol = 0, pos_self = 0;
     int64_t rp[NF];
@@ -809,7 +884,10 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
 #pragma unroll
         for (int i = 0; i < NF; ++i) rp[i] = ldg_s64(A.rowptr + (int64_t)i * rows_per_field + c * NLOC + a);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (EARLY && has_next)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the batch just issued
+    else
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
     double acc[SMEM_ACC ? 1 : NF][SMEM_ACC ? 1 : NF][SMEM_ACC ? 1 : NLOC];
@@ -870,11 +948,11 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
                     for (int k = 0; k < D; ++k) invJn[m][k] = 0.0;
                 if (nb >= 0) {
                     if constexpr (ECH_FAMILY_DG) {
-                        neighbour_side2(W.nbd + ge * CELL_STRIDE + lf * SLOT_LEN, meta_e[NLF + lf], tt, p, invJn);
+                        neighbour_side2(nbd_b + lf * SLOT_LEN, meta_e[NLF + lf], tt, p, invJn);
                     }
                 }
                 own_side2(own, idx, p, gm);
-                p.fa = W.fa[ge * NLF + lf];
+                p.fa = fa_b[lf];
                 facet_normal(gm, lf, p.n, ds);
                 w *= ds;
                 if (nb < 0) {
@@ -918,7 +996,16 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
         }
         __syncwarp();
         // every producer is done with the staged cell data: second round trip of the next batch
-        if (round == NROUND - 1 && has_next) issue_stage(A, W, mb ^ 1, g, a, cn, active_n, ids, cs, fstride);
+        if constexpr (!PIPE) {
+            if (round == NROUND - 1 && has_next) issue_stage(A, W, mb ^ 1, g, a, cn, active_n, ids, cs, fstride);
+        } else if constexpr (!EARLY) {
+            if (round == NROUND - 1 && has_next) {
+                const int64_t cen = (batch + wstride) * CPW + ge;
+                issue_stage_e(A, W, mb ^ 1, ge, ae, cen, ae < G && cen < A.ncell, idn, fstride);
+                const int64_t cenn = (batch + 2 * wstride) * CPW + ge;
+                idn = load_ids_e(A, ae, cenn, batch + 2 * wstride < nbatch && ae < G && cenn < A.ncell);
+            }
+        }
         // ---------------- consume: the records of my cell into my rows (slot = compile-time task)
         if (active) {
             static_for<0, NROUND>([&](auto rc) {
@@ -1122,10 +1209,12 @@ static int launch_jacobian_coop2(const ech_dg_args *a, cudaStream_t s) {
     // against 2.64 ms for one batch per warp (the default, w = 0) -- with 2 warps per scheduler the start-up
     // stagger of short-lived CTAs de-phases the warps better than the software pipeline hides the staging.
 #ifndef ECH_COOP2_WAVES
-#define ECH_COOP2_WAVES 0
+#define ECH_COOP2_WAVES (PIPE ? 2 : 0)
 #endif
-    const int64_t resident = (int64_t)g_coop2_sms * g_coop2_ctas_per_sm[fused] * ECH_COOP2_WAVES;
-    const int64_t grid = (ECH_COOP2_WAVES == 0 || need < resident) ? need : resident;
+    // run-time override for tuning: waves of resident CTAs; 0 = one batch per warp
+    static const int waves = getenv("ECH_COOP2_WAVES") ? atoi(getenv("ECH_COOP2_WAVES")) : ECH_COOP2_WAVES;
+    const int64_t resident = (int64_t)g_coop2_sms * g_coop2_ctas_per_sm[fused] * waves;
+    const int64_t grid = (waves == 0 || need < resident) ? need : resident;
     if (fused)
         jacobian_coop2_kernel<true><<<(unsigned)grid, J2WARPS * 32, J2SMEM, s>>>(*a, nbatch);
     else

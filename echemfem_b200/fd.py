@@ -14,7 +14,8 @@ from .symbolic import coordinate as _coordinate, facet_normal as _facet_normal
 from .symbolic import cell_volume as _cv, cell_diameter as _cd, facet_area as _fa
 from .mesh import (Mesh as _Mesh, TensorMesh, UnitSquareMesh, RectangleMesh, UnitCubeMesh,  # noqa: F401
                    ExtrudedMesh)
-from .function import (Function, FunctionSpace, MixedFunctionSpace, errornorm)  # noqa: F401
+from .function import (Function, FunctionSpace, MixedFunctionSpace, VectorFunctionSpace, VectorFunction,  # noqa: F401
+                       errornorm)
 
 
 def SpatialCoordinate(mesh):

@@ -203,6 +203,69 @@ class Function:
         return sym.FieldRef(kind, j, self.space.mesh.dim)
 
 
+class VectorFunctionSpace:
+    """`VectorFunctionSpace(mesh, family, degree)`: d copies of one scalar space (the velocity space of the
+    reference's flow solvers, echemfem/flow_solver.py:45-60)."""
+
+    def __init__(self, mesh, family, degree=None, dim=None, **kw):
+        self.scalar = family if isinstance(family, FunctionSpace) else FunctionSpace(mesh, family, degree, **kw)
+        self.mesh = mesh
+        self.value_size = int(dim or mesh.dim)
+
+    def dim(self):
+        return self.value_size * self.scalar.num_nodes
+
+
+class VectorFunction:
+    """Discrete vector field: `value_size` scalar `Function`s of one space.  This is what `FlowSolver.vel`
+    is in the reference (flow_solver.py:114) and what `EchemSolver.set_velocity` may assign to `self.vel`
+    (examples/simple_flow_battery.py:98-114): the solver registers the components as data coefficients."""
+
+    def __init__(self, space, name=None):
+        self.space = space
+        self.name = name
+        self.components = [Function(space.scalar, name="%s_%d" % (name or "v", k)) for k in range(space.value_size)]
+
+    def function_space(self):
+        return self.space
+
+    def sub(self, k):
+        return self.components[k]
+
+    @property
+    def subfunctions(self):
+        return tuple(self.components)
+
+    def interpolate(self, expr):
+        comps = list(expr) if not isinstance(expr, VectorFunction) else expr.components
+        if len(comps) != len(self.components):
+            raise ValueError("expected %d components" % len(self.components))
+        for f, e in zip(self.components, comps):
+            if isinstance(e, Function):
+                f.assign(e)
+            else:
+                f.interpolate(e)
+        return self
+
+    def assign(self, other):
+        return self.interpolate(other)
+
+    def rename(self, name):
+        self.name = name
+
+    def numpy(self):
+        return np.stack([f.numpy() for f in self.components], axis=1)
+
+    def __len__(self):
+        return len(self.components)
+
+    def __iter__(self):
+        return iter(self.components)
+
+    def __getitem__(self, k):
+        return self.components[k]
+
+
 class _Scaled:
     def __init__(self, fn, factor):
         self.fn, self.factor = fn, factor

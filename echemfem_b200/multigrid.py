@@ -142,6 +142,16 @@ def spgemm_rows(rowptr, colidx, vals, ncols, B, bnnz_per_row, max_products=1.5e8
     idt = B.crow_indices().dtype
     per_row = max(1.0, nnz / max(nrows, 1)) * max(1.0, bnnz_per_row)
     chunk = int(max(1024, min(nrows, max_products / per_row)))
+    try:
+        return _spgemm_chunks(rowptr, colidx, vals, ncols, B, idt, nrows, chunk)
+    except RuntimeError as err:                       # cuSPARSE work space: retry with smaller row chunks
+        if "insufficient resources" not in str(err) and "out of memory" not in str(err):
+            raise
+        torch.cuda.empty_cache()
+        return _spgemm_chunks(rowptr, colidx, vals, ncols, B, idt, nrows, max(256, chunk // 8))
+
+
+def _spgemm_chunks(rowptr, colidx, vals, ncols, B, idt, nrows, chunk):
     crows, cols, vs = [], [], []
     base = 0
     for r0 in range(0, nrows, chunk):

@@ -340,6 +340,70 @@ class NewtonEngine:
         }
         return self._coarse
 
+    def _global_coarse_plan(self, target):
+        """Coarse space shared by all ranks (multi-GPU): the same box aggregation on the GLOBAL bounding box.
+        Block-Jacobi across ranks (one block per rank, as PETSc's bjacobi) cannot move the smooth global modes of
+        the potential equation; the Galerkin operator of this space is summed over the ranks (one all-reduce per
+        set-up), inverted redundantly, and applied after the rank-local preconditioner (one all-reduce of nc
+        numbers per Krylov iteration).  Ghost dofs take part in the Galerkin product (columns) only."""
+        import torch.distributed as dist
+        from .coarse import box_aggregates_global
+        C_ = getattr(self, "_gcoarse", None)
+        if C_ is not None and C_["target"] == target:
+            return C_
+        dev = self.dev
+        x = self.solver.W.scalar.node_coords()
+        d = x.shape[1]
+        ext = torch.tensor(np.concatenate([x.min(axis=0), -x.max(axis=0)]), dtype=torch.float64, device=dev)
+        dist.all_reduce(ext, op=dist.ReduceOp.MIN)
+        ext = ext.cpu().numpy()
+        agg, nc, _ = box_aggregates_global(x, self.nf, target, ext[:d], -ext[d:])
+        no = self.ncell * self.nloc
+        owned = np.zeros(self.ndof, dtype=bool)
+        for f in range(self.nf):
+            owned[f * self.N:f * self.N + no] = True
+        present = torch.zeros(nc, dtype=torch.float64, device=dev)
+        present[torch.from_numpy(np.unique(agg[owned]).astype(np.int64)).to(dev)] = 1.0
+        dist.all_reduce(present)
+        keep = (present.cpu().numpy() > 0)
+        renum = np.cumsum(keep) - 1                      # globally empty boxes get no coarse dof
+        ncc = int(keep.sum())
+        agg = renum[agg].astype(np.int32)
+        agg_owned = np.where(owned, agg, ncc).astype(np.int32)     # ghost dofs -> bin `ncc`, never read back
+        self._gcoarse = {
+            "target": target, "nc": ncc, "agg": torch.from_numpy(agg).to(dev),
+            "agg_owned": torch.from_numpy(agg_owned).to(dev),
+            "Ac": torch.empty((ncc, ncc), dtype=torch.float64, device=dev), "inv": None,
+            "rc": torch.zeros(ncc + 1, dtype=torch.float64, device=dev),
+            "yc": torch.zeros(ncc + 1, dtype=torch.float64, device=dev),
+            "res": torch.empty(self.ndof, dtype=torch.float64, device=dev),
+        }
+        return self._gcoarse
+
+    def _global_coarse_setup(self, target):
+        import torch.distributed as dist
+        Cz = self._global_coarse_plan(target)
+        capi.check(self.lib.ech_coarse_galerkin(self.ndof, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals),
+                                                ptr(Cz["agg"]), Cz["nc"], ptr(Cz["Ac"]), self._stream()))
+        dist.all_reduce(Cz["Ac"])
+        # dense coarse inverse: a library call (cuSOLVER through torch), once per Newton iteration, on every rank
+        Cz["inv"] = torch.linalg.inv(Cz["Ac"]).contiguous()
+        return Cz
+
+    def _global_coarse_correct(self, Cz, r, z):
+        """z += P Ac^-1 P^T (r - A z)   (multiplicative correction after the rank-local preconditioner)."""
+        import torch.distributed as dist
+        lib, st, n = self.lib, self._stream(), self.ndof
+        self.halo.exchange(z)
+        capi.check(lib.ech_spmv(n, ptr(self.rowptr), ptr(self.colidx), ptr(self.vals), ptr(z), ptr(Cz["res"]), st))
+        capi.check(lib.ech_axpby(n, 1.0, ptr(r), -1.0, ptr(Cz["res"]), st))             # res = r - A z
+        Cz["rc"].zero_()
+        capi.check(lib.ech_coarse_restrict(n, ptr(Cz["agg_owned"]), Cz["nc"] + 1, ptr(Cz["res"]), ptr(Cz["rc"]), st))
+        dist.all_reduce(Cz["rc"][:Cz["nc"]])
+        capi.check(lib.ech_dense_gemv(Cz["nc"], Cz["nc"], ptr(Cz["inv"]), ptr(Cz["rc"]), ptr(Cz["yc"]), st))
+        capi.check(lib.ech_coarse_prolong_add(n, ptr(Cz["agg_owned"]), ptr(Cz["yc"]), ptr(z), st))
+        z.mul_(self._owned_mask())
+
     def multigrid(self, **kw):
         """The geometric multigrid hierarchy of this mesh (built once), or None if the mesh has none."""
         if not hasattr(self, "_mg"):
@@ -372,8 +436,18 @@ class NewtonEngine:
             M.setup()
             torch.cuda.synchronize()
             self.timers["PCSetUp"] += time.time() - t0
+            pre = M.apply
+            if self.halo is not None and coarse:
+                t0 = time.time()
+                Cz = self._global_coarse_setup(int(coarse))
+                torch.cuda.synchronize()
+                self.timers["PCSetUp"] += time.time() - t0
+
+                def pre(src, dst):
+                    M.apply(src, dst)
+                    self._global_coarse_correct(Cz, src, dst)
             t0 = time.time()
-            out = self._gmres(rhs, rtol, atol, max_it, monitor, precond=M.apply, restart=restart, refine=refine)
+            out = self._gmres(rhs, rtol, atol, max_it, monitor, precond=pre, restart=restart, refine=refine)
             torch.cuda.synchronize()
             self.timers["KSPSolve"] += time.time() - t0
             return out

@@ -15,7 +15,7 @@ out per boundary: `_interior_penalty` (SIP), `_weak_dirichlet` (Nitsche),
 """
 from . import symbolic as S
 from .symbolic import (Constant, Expr, inner, dot, grad, avg, jump, conditional,
-                       max_value, sqrt, ln, as_expr)
+                       max_value, sqrt, ln, as_expr, as_vector)
 from .function import Function, FunctionSpace, MixedFunctionSpace
 
 _FLOW_KEYS = ("advection", "diffusion", "migration", "finite size", "electroneutrality",
@@ -164,12 +164,45 @@ class EchemSolver:
 
         if self.flow["advection"]:
             self.set_velocity()
+            self.vel = self._ingest_velocity(self.vel)
         if self.homog_params:
             self.setup_bulk_reactions()
 
         self.setup_forms(us, v)
         self.init_solver_parameters()
         self._engine = None
+
+    def _ingest_velocity(self, vel):
+        """`set_velocity` may leave a symbolic expression in `self.vel` (most examples) or a DISCRETE field, as
+        `FlowSolver.vel` is (flow_solver.py:114; examples/simple_flow_battery.py:98-114): a `VectorFunction`, or a
+        sequence of scalar `Function`s.  Discrete components become data coefficients of the form (auxiliary nodal
+        fields next to U_app), interpolated in the kernels like the unknowns.  They must live on the scalar space
+        of the concentrations -- a field of another space is transferred by nodal interpolation with
+        `VectorFunction(VectorFunctionSpace(mesh, family, p)).interpolate(...)` first."""
+        from .function import VectorFunction
+        comps = None
+        if isinstance(vel, VectorFunction):
+            comps = vel.components
+        elif isinstance(vel, (list, tuple)) and any(isinstance(c, Function) for c in vel):
+            comps = list(vel)
+        if comps is None:
+            return vel
+        d = self.mesh.dim
+        if len(comps) != d:
+            raise ValueError("velocity field has %d components on a %dD mesh" % (len(comps), d))
+        out = []
+        for c in comps:
+            if isinstance(c, Function):
+                sp_ = c.function_space()
+                if (sp_.family, sp_.degree, sp_.num_nodes) != (self.V.family, self.V.degree, self.V.num_nodes):
+                    raise NotImplementedError("discrete velocity components must live on the solver's scalar space "
+                                              "(%s%d); interpolate the flow field there first" % (self.V.family, self.V.degree))
+                self.register_coefficient(c)
+                out.append(c._as_expr())
+            else:
+                out.append(c)
+        self.velocity_field = vel
+        return as_vector(out)
 
     def register_coefficient(self, fn):
         """Make a data `Function` usable inside forms (it becomes auxiliary field a{j})."""

@@ -1,0 +1,92 @@
+"""The reference's own example scripts, executed UNMODIFIED and TO COMPLETION on the GPU: `from firedrake import *`,
+`from echemfem import EchemSolver`, mesh construction (`Mesh('x.msh')` from the .geo), `setup_solver()`, `solve()`
+all resolve to this package through `echemfem_b200.compat`.
+
+The scripts are not part of this repository.  They are read from $ECHEMFEM_REFERENCE_EXAMPLES, else from
+/root/reference/examples (build container), else from gpurun_scratch/reference_examples (an untracked copy made
+by tools/stage_reference_examples.sh so that the GPU box, which has no /root/reference, can run them)."""
+import contextlib
+import io
+import os
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _examples_dir():
+    for d in (os.environ.get("ECHEMFEM_REFERENCE_EXAMPLES"), "/root/reference/examples",
+              os.path.join(ROOT, "gpurun_scratch", "reference_examples")):
+        if d and os.path.isdir(d):
+            return d
+    return None
+
+
+def _run_script(script):
+    import echemfem_b200.compat as compat
+    compat.install(force=True)
+    d = _examples_dir()
+    path = os.path.join(d, script)
+    with open(path) as f:
+        src = f.read()
+    cwd = os.getcwd()
+    g = {"__name__": "__main__", "__file__": path}
+    out = io.StringIO()
+    t0 = time.time()
+    try:
+        os.chdir(d)
+        with contextlib.redirect_stdout(out):
+            exec(compile(src, path, "exec"), g)
+    finally:
+        os.chdir(cwd)
+    return g, out.getvalue(), time.time() - t0
+
+
+needs_examples = pytest.mark.skipif(_examples_dir() is None, reason="reference example scripts not staged")
+
+
+@needs_examples
+def test_bortels_threeion_nondim_runs_unmodified_and_matches_the_oracle():
+    """BASELINE.json configs[0]: examples/bortels_threeion_nondim.py (297 x 49 graded quads from the transfinite
+    .geo, 3 ions, Butler-Volmer electrodes, DG Q1, 174 636 dofs): the solution `solver.u` the script ends with,
+    against the oracle's full-size Newton solution (tests/golden/make_bortels_example.py), 1e-8 relative per field."""
+    g, log, secs = _run_script("bortels_threeion_nondim.py")
+    s = g["solver"]
+    e = s._engine
+    assert e.last["reason"] is not None and e.last["snes_its"] >= 1
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "example_bortels_threeion_nondim.npz"))
+    Ns = int(ref["ndof_scalar"])
+    assert e.N == Ns and e.nf == 3
+    U = s.u.numpy().reshape(3, Ns)
+    stride = int(ref["stride"])
+    assert np.allclose(s.V.node_coords()[::stride], ref["node_coords_samples"], rtol=0, atol=1e-12)
+    for f in range(3):
+        a, b = U[f, ::stride], ref["samples"][f]
+        assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b), "field %d" % f
+        assert abs(np.linalg.norm(U[f]) - ref["norms"][f]) <= 1e-8 * ref["norms"][f]
+    line = "REFERENCE_EXAMPLE bortels_threeion_nondim.py unmodified: %d dofs, snes_its %d, ksp_its %s, %.1f s, " \
+           "matches the oracle solution to 1e-8 per field" % (e.ndof, e.last["snes_its"], e.last["ksp_its_per_step"], secs)
+    print(line)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "reference_examples.log"), "a") as f:
+        f.write(line + "\n")
+
+
+@needs_examples
+@pytest.mark.parametrize("script,nf", [("gupta_advection_migration.py", 5), ("BMCSL.py", 4)])
+def test_other_examples_run_unmodified_to_completion(script, nf):
+    """configs[2] (CG, five species, homogeneous reactions, boundary-layer mesh) and the finite-size BMCSL example:
+    unmodified scripts, Newton converged, finite fields."""
+    g, log, secs = _run_script(script)
+    s = g["solver"]
+    e = s._engine
+    assert e.nf == nf and e.last["reason"] is not None
+    assert np.isfinite(s.u.numpy()).all()
+    line = "REFERENCE_EXAMPLE %s unmodified: %d dofs, snes_its %d, ksp_its %s, %.1f s" % (
+        script, e.ndof, e.last["snes_its"], e.last["ksp_its_per_step"], secs)
+    print(line)
+    with open(os.path.join(ROOT, "gpurun_out", "reference_examples.log"), "a") as f:
+        f.write(line + "\n")
