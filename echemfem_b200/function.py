@@ -138,6 +138,16 @@ class Function:
     def function_space(self):
         return self.space
 
+    @property
+    def dat(self):
+        """`f.dat.data` / `f.dat.data_ro` (PyOP2 Dat of the reference's Functions): host copy of the nodal values."""
+        arr = self.numpy().copy()
+
+        class _Dat:
+            data = arr
+            data_ro = arr
+        return _Dat
+
     # -- storage ------------------------------------------------------------------
     @property
     def tensor(self):

@@ -45,6 +45,7 @@ class Mesh:
         the vertex coordinates, shape (nv,) in 1D and (nv, d) otherwise.  Vertices of tensor meshes are numbered
         lexicographically (left to right in 1D).  Move vertices before the solver is set up."""
         view = self.coords[:, 0] if self.dim == 1 else self.coords
+        dim = self.dim
 
         class _Dat:
             data = view
@@ -52,7 +53,14 @@ class Mesh:
 
         class _Coords:
             dat = _Dat
-        return _Coords
+
+            def __getitem__(self, k):
+                # `mesh.coordinates[k]` inside expressions (examples/BMCSL.py:99): the k-th spatial coordinate
+                return symbolic.coordinate(dim)[k]
+
+            def __iter__(self):
+                return iter(symbolic.coordinate(dim))
+        return _Coords()
 
     # Firedrake-compatible queries used by the reference (solver.py:202, 221, 752)
     def topological_dimension(self):

@@ -5,7 +5,8 @@ one Richardson iteration of block-Jacobi/ILU per level and a direct coarse solve
 (examples/mms_scaling.py:72-76).  Here:
 
 * the hierarchy comes from the tensor structure of the mesh: every other vertex is dropped per direction and
-  level (the inverse of `MeshHierarchy`'s uniform refinement), also for graded axes;
+  level (the inverse of `MeshHierarchy`'s uniform refinement), also for graded axes and odd cell counts (the
+  297 x 49 mesh of examples/bortels_threeion_nondim.py);
 * prolongation is the natural embedding of the coarse DG space into the fine one (the coarse polynomial of the
   parent cell evaluated at the fine nodes), a tensor product of 1D matrices assembled on the host; restriction
   is its transpose;
@@ -99,9 +100,11 @@ class Hierarchy:
                 L.inv = np.empty_like(perm)
                 L.inv[perm] = np.arange(len(perm))
             self.levels.append(L)
-            if len(self.levels) >= max_levels or L.ncell <= coarsest_cells or any(s % 2 or s < 4 for s in shape):
+            if len(self.levels) >= max_levels or L.ncell <= coarsest_cells or any(s < 4 for s in shape):
                 break
-            cax = [a[::2] for a in axes]
+            # every other vertex is dropped; with an odd number of cells the last one keeps itself as parent
+            # (prolongation_1d works from the coordinates, so its block is the identity)
+            cax = [a[::2] if (len(a) - 1) % 2 == 0 else np.append(a[::2], a[-1]) for a in axes]
             cshape = tuple(len(a) - 1 for a in cax)
             cperm = tile_order(cshape, tile) if all(s % tile == 0 and s > tile for s in cshape) else None
             cinv = None

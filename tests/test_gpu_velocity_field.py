@@ -53,6 +53,18 @@ def test_discrete_velocity_matches_symbolic_and_oracle(family):
     N = 5
     prob = mms_cases.adm_problem(1.0, family=family)
     prob.vel = _vel
+
+    def forcing(u, x):            # div((vel - D z grad Uex) Cex) - div(D grad Cex) with THIS velocity (div vel = -0.2)
+        X, Y = x[..., 0], x[..., 1]
+        C = np.cos(X) + np.sin(Y) + 3.0
+        Cx, Cy = -np.sin(X), np.cos(Y)
+        lapC = -np.cos(X) - np.sin(Y)
+        Ux, Uy = np.cos(X), -np.sin(Y)
+        lapU = -np.sin(X) - np.cos(Y)
+        v = _vel(x)
+        adv = v[..., 0] * Cx + v[..., 1] * Cy - 0.2 * C
+        return [adv - D * z * (Cx * Ux + Cy * Uy + C * lapU) - D * lapC for D, z in ((0.5, 2.0), (1.0, -2.0))]
+    prob.physical_params["bulk reaction"] = forcing
     disc = Discretization(unit_square_mesh(N), prob)
     x = disc.node_coords
     pert = 1e-2 * np.sin(7 * x[:, 0] + 3 * x[:, 1])
