@@ -54,6 +54,12 @@ struct ech_handle {
     unsigned long long own_bits[16], nbr_bits[16];   // per equation: bit j
     std::string err;
     int host_chunks = 16;                   // ech_set_host_chunks
+    // ech_set_host_chunks(h, -n): AUTO -- the first calls time the n-chunk pipeline and the single-copy path on
+    // the caller's own buffers and keep the faster one (with several GPUs behind one host bridge the many small
+    // copies of the pipeline lose against one large copy; SCALE_r01: 16.7 ms against 10.7 ms at 8 GPUs)
+    int auto_state = 0;                     // 0 off, 1..2*AUTO_REPS measuring, -1 decided
+    int auto_chunks = 0;
+    double auto_ms[2] = {0.0, 0.0};
     HostPipe pipe;
 };
 
@@ -1856,9 +1862,17 @@ extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx
 
 // =============================================================== host-buffer boundary
 extern "C" int ech_set_host_chunks(ech_handle *h, int nchunks) {
-    if (!h || nchunks < 0 || nchunks > 4096) return fail(h, ECH_ERR_ARG, "ech_set_host_chunks: bad argument");
-    h->host_chunks = nchunks;
+    if (!h || nchunks < -4096 || nchunks > 4096) return fail(h, ECH_ERR_ARG, "ech_set_host_chunks: bad argument");
     pipe_release(h->pipe);
+    if (nchunks < 0) {                      // auto: measure -nchunks chunks against the single-copy path
+        h->auto_chunks = -nchunks;
+        h->host_chunks = -nchunks;
+        h->auto_state = 1;
+        h->auto_ms[0] = h->auto_ms[1] = 0.0;
+        return ECH_OK;
+    }
+    h->auto_state = 0;
+    h->host_chunks = nchunks;
     return ECH_OK;
 }
 
@@ -1979,6 +1993,35 @@ extern "C" int ech_assemble_host(ech_handle *h, const double *u_host, double *u_
     ech_num_rows(h, &nrows);
     if (vals && !rowptr) return fail(h, ECH_ERR_ARG, "ech_assemble_host: vals without rowptr");
     const int align = (h->info[7] != 0 && h->mod.range_align) ? h->mod.range_align() : 0;
+    constexpr int AUTO_REPS = 3;
+    if (h->auto_state > 0) {
+        // measuring: calls 1..AUTO_REPS run the pipeline, the next AUTO_REPS the single-copy path (first of each
+        // batch is a warm-up and not counted); results are identical either way, so every call is a valid call
+        const int k = h->auto_state - 1;
+        const int which = k / AUTO_REPS;
+        h->host_chunks = which == 0 ? h->auto_chunks : 0;
+        h->auto_state = 0;                                  // re-enter as a plain call
+        cudaEvent_t e0, e1;
+        CK(h, cudaEventCreate(&e0));
+        CK(h, cudaEventCreate(&e1));
+        CK(h, cudaEventRecord(e0, s));
+        int rc = ech_assemble_host(h, u_host, u_dev, aux, consts, rowptr, vals, F_dev, F_host, stream);
+        CK(h, cudaEventRecord(e1, s));
+        CK(h, cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (rc) return rc;
+        if (k % AUTO_REPS != 0) h->auto_ms[which] += ms;
+        if (k + 1 == 2 * AUTO_REPS) {
+            h->host_chunks = h->auto_ms[0] <= h->auto_ms[1] ? h->auto_chunks : 0;
+            h->auto_state = -1;
+        } else {
+            h->auto_state = k + 2;
+        }
+        return ECH_OK;
+    }
     if (align > 0 && h->host_chunks > 1 && h->mesh.ncell >= (int64_t)h->host_chunks * align)
         return assemble_host_pipelined(h, align, u_host, u_dev, aux, consts, rowptr, vals, F_dev, F_host, s);
     const int64_t nstate = nrows;

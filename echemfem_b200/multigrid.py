@@ -102,6 +102,8 @@ class Hierarchy:
             self.levels.append(L)
             if len(self.levels) >= max_levels or L.ncell <= coarsest_cells or any(s < 4 for s in shape):
                 break
+            if any(s % 2 for s in shape) and L.ncell <= 256:
+                break           # an odd level small enough for the dense coarse solve is the coarsest one
             # every other vertex is dropped; with an odd number of cells the last one keeps itself as parent
             # (prolongation_1d works from the coordinates, so its block is the identity)
             cax = [a[::2] if (len(a) - 1) % 2 == 0 else np.append(a[::2], a[-1]) for a in axes]

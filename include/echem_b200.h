@@ -207,7 +207,9 @@ int ech_assemble_host(ech_handle *h, const double *u_host, double *u_dev, const 
 /* Chunking of ech_assemble_host for discontinuous spaces (default 16): the owned cells are cut into nchunks
  * contiguous ranges; the state of range k+1 is copied in while range k is assembled and the residual of
  * range k-1 is copied out (three streams).  0 or 1: one copy in, one launch, one copy out.  Results are
- * bit-identical either way. */
+ * bit-identical either way.  nchunks < 0: AUTO -- the first six calls time the (-nchunks)-chunk pipeline and the
+ * single-copy path on the caller's buffers and the faster one is kept (several GPUs sharing one host bridge favour
+ * the single copy). */
 int ech_set_host_chunks(ech_handle *h, int nchunks);
 
 /* number of kernels launched by this library (and the bound module) since ech_create */
