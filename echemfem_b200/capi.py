@@ -58,6 +58,13 @@ EXPORTS = {
                                              c_p, c_p]),
     "ech_bjacobi_ilu0_apply_planned": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_p, c_p, c_p,
                                                  c_i32, c_p, c_p, c_p]),
+    "ech_bjacobi_ilu0_pack_count": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_i32, c_p, c_p,
+                                              c_p, C.POINTER(c_i64), c_p]),
+    "ech_bjacobi_ilu0_pack_fill": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_i32, c_p, c_p,
+                                             c_p, c_p, c_p, c_p, c_p]),
+    "ech_bjacobi_ilu0_pack_values": (C.c_int, [c_i64, c_i32, c_p, c_p, c_p, c_p, c_p]),
+    "ech_bjacobi_ilu0_apply_packed": (C.c_int, [c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
+                                                c_p]),
     "ech_coarse_galerkin": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_i32, c_p, c_p]),
     "ech_coarse_restrict": (C.c_int, [c_i64, c_p, c_i32, c_p, c_p, c_p]),
     "ech_coarse_prolong_add": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),

@@ -1571,6 +1571,456 @@ extern "C" int ech_bjacobi_ilu0_apply_planned(int64_t nrows, int32_t nfields, in
                               (cudaStream_t)stream);
 }
 
+// =============================================================== pass-packed triangular solves (bulk copies)
+// The planned solve above still spends ~150 warp instructions per pass on per-lane loads, predication and address
+// arithmetic.  Here the factors are RE-PACKED after every factorisation into the order the solve consumes them: one
+// contiguous, 16-byte aligned CHUNK per pass,
+//     { uint32 next_size16, nE; uint64 ent_base;  uint16 off[G], len[G], row[G] (padded to 16);
+//       double vals[nE] (padded to 16);  uint16 idx[nE] (padded to 16) }
+// and the solve fetches chunk t + ILU_PD with ONE `cp.async.bulk` (TMA bulk copy, completion on an mbarrier) into a
+// shared-memory ring while chunk t is reduced: no per-lane global loads, exact-length loops, all loads coalesced.
+// For an upper-sweep row the first entry of its segment is the pivot.  idx = position of the column in the block's z.
+constexpr int ILU_PD = 4;                 // ring depth (chunks in flight per warp)
+constexpr int ILU_PWPC = 4;               // blocks (warps) per CTA
+
+__host__ __device__ inline uint32_t pad16(uint32_t b) { return (b + 15u) & ~15u; }
+__host__ __device__ inline uint32_t chunk_bytes(int G, uint32_t nE) {
+    return 16u + pad16(6u * (uint32_t)G) + pad16(8u * nE) + pad16(2u * nE);
+}
+
+// rows of one block sorted by level (natural order inside a level): order[] and, per pass, nothing else -- the
+// callers walk order[] level by level, G rows at a time.  cnt: int[ntot + 2] scratch.  All in shared memory.
+__device__ void pack_sort_rows(const uint16_t *__restrict__ lv, const BlockPlan &B, uint32_t first, uint32_t nrow_f,
+                               uint32_t ntot, int *cnt, uint16_t *order, uint16_t *lev_s, int lane) {
+    for (uint32_t k = lane; k <= ntot + 1; k += 32) cnt[k] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < ntot; i += 32) {
+        const uint32_t f = i / nrow_f, j = i - f * nrow_f;
+        const uint16_t l = lv[(int64_t)f * B.rows_per_field + first + j];
+        lev_s[i] = l;
+        atomicAdd(&cnt[l], 1);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int run = 0;
+        for (uint32_t k = 0; k <= ntot; ++k) {
+            const int c = cnt[k];
+            cnt[k] = run;
+            run += c;
+        }
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < ntot; base += 32) {          // natural order, lane by lane: reproducible
+        const uint32_t i = base + lane;
+        for (int l = 0; l < 32; ++l) {
+            if (lane == l && i < ntot) order[cnt[lev_s[i]]++] = (uint16_t)i;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+}
+
+// half-row of block row i in sweep `upper`: first entry and length INCLUDING the pivot for upper rows
+__device__ __forceinline__ void pack_half_row(const BlockPlan &B, const int64_t *__restrict__ rowptr,
+                                              const int32_t *__restrict__ colidx, uint32_t first, uint32_t nrow_f,
+                                              uint32_t i, bool upper, int64_t &beg, int &len) {
+    const uint32_t f = i / nrow_f, j = i - f * nrow_f;
+    const int64_t r = (int64_t)f * B.rows_per_field + first + j;
+    const int64_t rs = rowptr[r], re = rowptr[r + 1];
+    int64_t lo = rs, hi = re - 1, dpos = rs;
+    while (lo <= hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int32_t cj = colidx[mid];
+        if (cj == r) {
+            dpos = mid;
+            break;
+        }
+        if (cj < r) lo = mid + 1; else hi = mid - 1;
+    }
+    beg = upper ? dpos : rs;
+    len = upper ? (int)(re - dpos) : (int)(dpos - rs);
+}
+
+// MODE 0: sizes per (sweep, block) -> sizes[sweep][{bytes, entries, passes}][nblocks + 1] (unscanned) and the largest
+// chunk;  MODE 1: write the chunks (headers, idx), the source positions of the values and the block descriptors
+template <int MODE>
+__global__ void __launch_bounds__(32) ilu0_pack_plan_kernel(BlockPlan B, const int64_t *__restrict__ rowptr,
+                                                           const int32_t *__restrict__ colidx, int G,
+                                                           const uint16_t *__restrict__ levels, int64_t nrows,
+                                                           int64_t *sizes, unsigned long long *maxchunk,
+                                                           const uint16_t *__restrict__ lcol, uint8_t *packed,
+                                                           uint32_t *src, int64_t *bdesc, uint32_t cap_rows) {
+    extern __shared__ uint16_t sh16[];
+    const int64_t blk = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    const uint32_t nrow_f = (uint32_t)((c1 - c0) * B.nloc), ntot = nrow_f * (uint32_t)B.nf;
+    const uint32_t first = (uint32_t)(c0 * B.nloc);
+    const int64_t NB1 = B.nblocks + 1;
+    if (ntot == 0 || ntot > cap_rows) {
+        if (MODE == 0 && lane == 0)
+            for (int sw = 0; sw < 2; ++sw)
+                for (int q = 0; q < 3; ++q) sizes[(sw * 3 + q) * NB1 + blk] = 0;
+        return;
+    }
+    uint16_t *order = sh16;                                    // [ntot]
+    uint16_t *lev_s = sh16 + ((ntot + 7) & ~7u);               // [ntot]
+    int *cnt = reinterpret_cast<int *>(sh16 + 2 * ((ntot + 7) & ~7u));   // [ntot + 2]
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        pack_sort_rows(levels + (int64_t)sweep * nrows, B, first, nrow_f, ntot, cnt, order, lev_s, lane);
+        // walk the sorted rows: a pass = up to G consecutive rows of one level
+        int64_t bytes = 0, ents = 0, passes = 0;
+        int64_t base_bytes = 0, base_ent = 0;
+        if (MODE == 1) {
+            base_bytes = sizes[(sweep * 3 + 0) * NB1 + blk];
+            base_ent = sizes[(sweep * 3 + 1) * NB1 + blk];
+        }
+        uint8_t *prev_hdr[ILU_PD];                              // headers still waiting for their next_size16
+        for (int d = 0; d < ILU_PD; ++d) prev_hdr[d] = nullptr;
+        uint32_t k = 0;
+        while (k < ntot) {
+            const uint16_t level = lev_s[order[k]];
+            uint32_t kend = k;
+            while (kend < ntot && kend < k + (uint32_t)G && lev_s[order[kend]] == level) ++kend;
+            // lanes 0..G-1 look at their row
+            int64_t beg = 0;
+            int len = 0;
+            uint32_t row = 0xFFFF;
+            int clen = 0;                                       // CSR length of the half-row; len counts the entries
+            if (lane < (int)(kend - k)) {                        // whose column lies INSIDE the block (the others are
+                row = order[k + lane];                           // dropped by block Jacobi and never packed)
+                pack_half_row(B, rowptr, colidx, first, nrow_f, row, sweep == 1, beg, clen);
+                for (int e = 0; e < clen; ++e)
+                    len += ((sweep == 1 && e == 0) || lcol[beg + e] != 0xFFFF) ? 1 : 0;
+            }
+            // exclusive prefix of len over the lanes -> off; nE = total
+            int off = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, off, o);
+                if (lane >= o) off += v;
+            }
+            const uint32_t nE = (uint32_t)__shfl_sync(0xffffffffu, off, 31);
+            off -= len;
+            const uint32_t csz = chunk_bytes(G, nE);
+            if (MODE == 0) {
+                if (lane == 0) atomicMax(maxchunk, (unsigned long long)csz);
+            } else {
+                uint8_t *ch = packed + base_bytes + bytes;
+                uint32_t *h32 = reinterpret_cast<uint32_t *>(ch);
+                if (lane == 0) {
+                    h32[0] = 0;                                    // next_size16: patched ILU_PD passes later
+                    h32[1] = nE;
+                    *reinterpret_cast<unsigned long long *>(ch + 8) = (unsigned long long)(base_ent + ents);
+                }
+                uint16_t *h16 = reinterpret_cast<uint16_t *>(ch + 16);
+                if (lane < G) {
+                    h16[lane] = (uint16_t)off;
+                    h16[G + lane] = (uint16_t)len;
+                    h16[2 * G + lane] = (uint16_t)row;
+                }
+                uint16_t *idx = reinterpret_cast<uint16_t *>(ch + 16 + pad16(6u * G) + pad16(8u * nE));
+                uint32_t *sp = src + base_ent + ents;
+                // entries of every row of the pass, row after row (lanes stride over a row's entries)
+                for (int gq = 0; gq < (int)(kend - k); ++gq) {
+                    const int64_t b_ = __shfl_sync(0xffffffffu, beg, gq);
+                    const int l_ = __shfl_sync(0xffffffffu, clen, gq);
+                    int o_ = __shfl_sync(0xffffffffu, off, gq);
+                    const uint32_t r_ = __shfl_sync(0xffffffffu, row, gq);
+                    for (int e0 = 0; e0 < l_; e0 += 32) {            // compact the in-block entries, order kept
+                        const int e = e0 + lane;
+                        uint16_t k_ = 0xFFFF;
+                        if (e < l_) k_ = (sweep == 1 && e == 0) ? (uint16_t)r_ : lcol[b_ + e];
+                        const unsigned m = __ballot_sync(0xffffffffu, k_ != 0xFFFF);
+                        if (k_ != 0xFFFF) {
+                            const int pos = o_ + __popc(m & ((1u << lane) - 1u));
+                            sp[pos] = (uint32_t)(b_ + e);
+                            idx[pos] = k_;
+                        }
+                        o_ += __popc(m);
+                    }
+                }
+                // patch the header ILU_PD passes back with this chunk's size; first ILU_PD sizes go to the descriptor
+                if (lane == 0) {
+                    if (passes < ILU_PD)
+                        bdesc[((int64_t)sweep * B.nblocks + blk) * 8 + 2 + passes] = csz / 16;
+                    else
+                        reinterpret_cast<uint32_t *>(prev_hdr[passes % ILU_PD])[0] = csz / 16;
+                }
+                prev_hdr[passes % ILU_PD] = ch;
+            }
+            bytes += csz;
+            ents += nE;
+            ++passes;
+            k = kend;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (MODE == 0) {
+                sizes[(sweep * 3 + 0) * NB1 + blk] = bytes;
+                sizes[(sweep * 3 + 1) * NB1 + blk] = ents;
+                sizes[(sweep * 3 + 2) * NB1 + blk] = passes;
+            } else {
+                int64_t *bd = bdesc + ((int64_t)sweep * B.nblocks + blk) * 8;
+                bd[0] = base_bytes;
+                bd[1] = passes;
+                for (int64_t q = passes; q < ILU_PD; ++q) bd[2 + q] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// exclusive scans of the six size arrays (bytes and entries run on from the lower sweep into the upper one)
+__global__ void ilu0_pack_scan_kernel(int64_t nblocks, int64_t *sizes, int64_t *totals) {
+    const int64_t NB1 = nblocks + 1;
+    for (int q = 0; q < 3; ++q) {
+        int64_t run = 0;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            int64_t *p = sizes + (sweep * 3 + q) * NB1;
+            for (int64_t b = 0; b < nblocks; ++b) {
+                const int64_t c = p[b];
+                p[b] = run;
+                run += c;
+            }
+            p[nblocks] = run;
+        }
+        totals[q] = run;
+    }
+}
+
+// values of the current factors into the chunks (after every factorisation)
+__global__ void __launch_bounds__(128) ilu0_pack_values_kernel(int64_t nblocks, int G, const int64_t *__restrict__ bdesc,
+                                                              uint8_t *packed, const uint32_t *__restrict__ src,
+                                                              const double *__restrict__ lu) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // (sweep, block)
+    const int lane = threadIdx.x & 31;
+    if (w >= 2 * nblocks) return;
+    const int64_t *bd = bdesc + w * 8;
+    uint8_t *ch = packed + bd[0];
+    const int64_t npass = bd[1];
+    for (int64_t t = 0; t < npass; ++t) {
+        const uint32_t nE = reinterpret_cast<const uint32_t *>(ch)[1];
+        const unsigned long long eb = *reinterpret_cast<const unsigned long long *>(ch + 8);
+        double *v = reinterpret_cast<double *>(ch + 16 + pad16(6u * G));
+        for (uint32_t e = lane; e < nE; e += 32) v[e] = lu[src[eb + e]];
+        ch += chunk_bytes(G, nE);
+    }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int LPR, bool UPPER>
+__device__ __forceinline__ void ilu0_packed_sweep(const uint8_t *__restrict__ packed, const int64_t *bd, uint8_t *ring,
+                                                  uint32_t ring_stride, uint64_t *bars, uint32_t &uses, double *z,
+                                                  int lane) {
+    constexpr int G = 32 / LPR;
+    const int g = lane / LPR, l = lane - g * LPR;
+    const int64_t npass = bd[1];
+    const uint8_t *next_src = packed + bd[0];
+    // prologue: the first ILU_PD chunks
+    if (lane == 0) {
+        for (int d = 0; d < ILU_PD && d < npass; ++d) {
+            const uint32_t bytes = (uint32_t)bd[2 + d] * 16u;
+            const uint32_t st = (uses + d) % ILU_PD;
+            mbar_expect_tx(bars + st, bytes);
+            bulk_g2s(ring + st * ring_stride, next_src, bytes, bars + st);
+            next_src += bytes;
+        }
+    }
+    for (int64_t t = 0; t < npass; ++t) {
+        const uint32_t u = uses + (uint32_t)t;
+        const uint32_t st = u % ILU_PD;
+        mbar_wait(bars + st, (u / ILU_PD) & 1u);
+        const uint8_t *ch = ring + st * ring_stride;
+        const uint32_t next16 = reinterpret_cast<const uint32_t *>(ch)[0];
+        const uint32_t nE = reinterpret_cast<const uint32_t *>(ch)[1];
+        const uint16_t *h16 = reinterpret_cast<const uint16_t *>(ch + 16);
+        const int off = h16[g], len = h16[G + g];
+        const uint32_t row = h16[2 * G + g];
+        const double *v = reinterpret_cast<const double *>(ch + 16 + pad16(6u * G));
+        const uint16_t *idx = reinterpret_cast<const uint16_t *>(ch + 16 + pad16(6u * G) + pad16(8u * nE));
+        double s0 = 0.0, s1 = 0.0;
+        int e = off + (UPPER ? 1 : 0) + l;
+        const int eend = off + len;
+        for (; e + LPR < eend; e += 2 * LPR) {
+            s0 = fma(v[e], z[idx[e]], s0);
+            s1 = fma(v[e + LPR], z[idx[e + LPR]], s1);
+        }
+        if (e < eend) s0 = fma(v[e], z[idx[e]], s0);
+        double sum = s0 + s1;
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (l == 0 && len > 0) z[row] = UPPER ? (z[row] - sum) / v[off] : z[row] - sum;
+        __syncwarp();
+        if (lane == 0 && t + ILU_PD < npass) {                     // refill this stage with chunk t + ILU_PD
+            const uint32_t bytes = next16 * 16u;
+            mbar_expect_tx(bars + st, bytes);
+            bulk_g2s(ring + st * ring_stride, next_src, bytes, bars + st);
+            next_src += bytes;
+        }
+    }
+    uses += (uint32_t)npass;
+    // stages are used strictly in order, so after the sweep every barrier is complete and idle
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(32 * ILU_PWPC) ilu0_apply_packed_kernel(
+    BlockPlan B, const int64_t *__restrict__ bdesc, const uint8_t *__restrict__ packed,
+    const double *__restrict__ rhs, double *zg, int64_t cap_rows, uint32_t ring_stride) {
+    extern __shared__ __align__(16) uint8_t sm8[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t)blockIdx.x * ILU_PWPC + warp;
+    // per warp: z[cap_rows] | bars[ILU_PD] | ring[ILU_PD][ring_stride]
+    const size_t per_warp = ((size_t)cap_rows * 8 + 15) / 16 * 16 + 64 + (size_t)ILU_PD * ring_stride;
+    uint8_t *base = sm8 + (size_t)warp * per_warp;
+    double *zs = reinterpret_cast<double *>(base);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + ((size_t)cap_rows * 8 + 15) / 16 * 16);
+    uint8_t *ring = reinterpret_cast<uint8_t *>(bars) + 64;
+    if (lane == 0)
+        for (int d = 0; d < ILU_PD; ++d) mbar_init(bars + d, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (blk >= B.nblocks) return;
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    const uint32_t nrow_f = (uint32_t)((c1 - c0) * B.nloc), ntot = nrow_f * (uint32_t)B.nf;
+    const uint32_t first = (uint32_t)(c0 * B.nloc);
+    if (ntot == 0) return;
+    for (int f = 0; f < B.nf; ++f)
+        for (uint32_t j = lane; j < nrow_f; j += 32) zs[f * nrow_f + j] = rhs[(int64_t)f * B.rows_per_field + first + j];
+    __syncwarp();
+    uint32_t uses = 0;
+    ilu0_packed_sweep<LPR, false>(packed, bdesc + blk * 8, ring, ring_stride, bars, uses, zs, lane);
+    ilu0_packed_sweep<LPR, true>(packed, bdesc + (B.nblocks + blk) * 8, ring, ring_stride, bars, uses, zs, lane);
+    for (int f = 0; f < B.nf; ++f)
+        for (uint32_t j = lane; j < nrow_f; j += 32) zg[(int64_t)f * B.rows_per_field + first + j] = zs[f * nrow_f + j];
+}
+
+static size_t pack_plan_smem(int64_t maxrows) { return (size_t)(2 * ((maxrows + 7) & ~7) * 2 + (maxrows + 4) * 4 + 32); }
+
+extern "C" int ech_bjacobi_ilu0_pack_count(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                           int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                           const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row,
+                                           const uint16_t *levels, const uint16_t *lcol, int64_t *sizes,
+                                           int64_t *totals_host, void *stream) {
+    if (!block_cell_ptr || !rowptr || !colidx || !levels || !lcol || !sizes || !totals_host ||
+        !plan_lpr_ok(lanes_per_row) ||
+        max_block_rows <= 0 || max_block_rows > ILU_MAXROWS)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_pack_count: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    const size_t smem = pack_plan_smem(max_block_rows);
+    CK(nullptr, cudaFuncSetAttribute(ilu0_pack_plan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t *dtot = nullptr;
+    CK(nullptr, cudaMalloc(&dtot, 4 * sizeof(int64_t)));
+    CK(nullptr, cudaMemsetAsync(dtot, 0, 4 * sizeof(int64_t), s));
+    ilu0_pack_plan_kernel<0><<<(unsigned)nblocks, 32, smem, s>>>(B, rowptr, colidx, 32 / lanes_per_row, levels, nrows,
+                                                                sizes, reinterpret_cast<unsigned long long *>(dtot + 3),
+                                                                lcol, nullptr, nullptr, nullptr,
+                                                                (uint32_t)max_block_rows);
+    ilu0_pack_scan_kernel<<<1, 1, 0, s>>>(nblocks, sizes, dtot);
+    g_launches += 2;
+    CK(nullptr, cudaMemcpyAsync(totals_host, dtot, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(nullptr, cudaStreamSynchronize(s));
+    cudaFree(dtot);
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;          // totals_host: bytes, entries, passes, largest chunk (bytes)
+}
+
+extern "C" int ech_bjacobi_ilu0_pack_fill(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                          int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                          const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row,
+                                          const uint16_t *levels, const uint16_t *lcol, int64_t *sizes,
+                                          uint8_t *packed, uint32_t *src, int64_t *bdesc, void *stream) {
+    if (!block_cell_ptr || !rowptr || !colidx || !levels || !lcol || !sizes || !packed || !src || !bdesc ||
+        !plan_lpr_ok(lanes_per_row) || max_block_rows <= 0 || max_block_rows > ILU_MAXROWS)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_pack_fill: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    const size_t smem = pack_plan_smem(max_block_rows);
+    CK(nullptr, cudaFuncSetAttribute(ilu0_pack_plan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ilu0_pack_plan_kernel<1><<<(unsigned)nblocks, 32, smem, s>>>(B, rowptr, colidx, 32 / lanes_per_row, levels, nrows,
+                                                                sizes, nullptr, lcol, packed, src, bdesc,
+                                                                (uint32_t)max_block_rows);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_bjacobi_ilu0_pack_values(int64_t nblocks, int32_t lanes_per_row, const int64_t *bdesc,
+                                            uint8_t *packed, const uint32_t *src, const double *lu, void *stream) {
+    if (!bdesc || !packed || !src || !lu || !plan_lpr_ok(lanes_per_row))
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_pack_values: bad argument");
+    if (nblocks == 0) return ECH_OK;
+    const int64_t nthreads = 2 * nblocks * 32;
+    ilu0_pack_values_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        nblocks, 32 / lanes_per_row, bdesc, packed, src, lu);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_bjacobi_ilu0_apply_packed(int32_t nfields, int64_t rows_per_field, int32_t nloc, int64_t nblocks,
+                                             const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                             int32_t max_chunk_bytes, int32_t lanes_per_row, const int64_t *bdesc,
+                                             const uint8_t *packed, const double *r, double *z, void *stream) {
+    if (!block_cell_ptr || !bdesc || !packed || !r || !z || max_block_rows <= 0 || max_chunk_bytes <= 0)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_apply_packed: bad argument");
+    if (nblocks == 0) return ECH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    const uint32_t ring_stride = pad16((uint32_t)max_chunk_bytes);
+    const size_t per_warp = ((size_t)max_block_rows * 8 + 15) / 16 * 16 + 64 + (size_t)ILU_PD * ring_stride;
+    const size_t smem = per_warp * ILU_PWPC;
+    if (smem > 227 * 1024) return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_apply_packed: blocks too large for the ring");
+    const unsigned grid = (unsigned)((nblocks + ILU_PWPC - 1) / ILU_PWPC);
+#define ECH_LAUNCH_PACKED(L)                                                                                         \
+    {                                                                                                                \
+        static size_t attr = 0;                                                                                      \
+        if (smem > attr) {                                                                                           \
+            CK(nullptr, cudaFuncSetAttribute(ilu0_apply_packed_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                            \
+            attr = smem;                                                                                             \
+        }                                                                                                            \
+        ilu0_apply_packed_kernel<L><<<grid, 32 * ILU_PWPC, smem, s>>>(B, bdesc, packed, r, z, max_block_rows,         \
+                                                                     ring_stride);                                   \
+    }
+    if (lanes_per_row == 2) ECH_LAUNCH_PACKED(2)
+    else if (lanes_per_row == 4) ECH_LAUNCH_PACKED(4)
+    else if (lanes_per_row == 8) ECH_LAUNCH_PACKED(8)
+    else if (lanes_per_row == 16) ECH_LAUNCH_PACKED(16)
+    else return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_apply_packed: lanes_per_row");
+#undef ECH_LAUNCH_PACKED
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== coarse space (two-level preconditioner)
 // Piecewise-constant aggregation: fine dof r belongs to coarse dof agg[r].  Ac = P^T A P is accumulated
 // with warp-level pre-reduction (entries of a row that hit the same coarse column are summed with

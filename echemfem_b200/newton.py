@@ -455,6 +455,8 @@ class NewtonEngine:
         capi.check(self.lib.ech_bjacobi_ilu0_factor(self.ndof, self.nf, self.N, self._unit, L["nblocks"],
                                                     ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
                                                     ptr(self.vals), ptr(L["lu"]), ptr(L["diag"]), self._stream()))
+        if L["ilu_plan"] is not None:
+            L["ilu_plan"].refresh(L["lu"], self._stream())
         Cz = None
         if coarse and self.halo is None:
             Cz = self._coarse_plan(int(coarse))

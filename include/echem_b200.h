@@ -150,6 +150,30 @@ int ech_bjacobi_ilu0_apply_planned(int64_t nrows, int32_t nfields, int64_t rows_
                                    const int64_t *passptr, const uint64_t *slots, int32_t lanes_per_row,
                                    const double *r, double *z, void *stream);
 
+/* Pass-packed variant of the level-scheduled solves: after every factorisation the factors are copied into the
+ * order the solve consumes them -- one contiguous 16-byte aligned chunk per pass (header, values, block-local column
+ * positions; entries whose column lies outside the block are dropped) -- and the solve fetches chunk t+4 with ONE cp.async.bulk (TMA bulk copy, mbarrier completion) into a
+ * shared-memory ring while chunk t is reduced.  pack_count (after plan_count: it reads its `levels` and `lcol`)
+ * returns totals_host = {bytes of `packed`, entries of `src`, passes, largest chunk}; pack_fill writes the static
+ * parts (sizes: scratch of 6 * (nblocks + 1) int64 shared by both calls; bdesc: 2 * nblocks * 8 int64);
+ * pack_values refreshes the values from `lu`; apply_packed solves.  pack_count synchronises the stream. */
+int ech_bjacobi_ilu0_pack_count(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row,
+                                const uint16_t *levels, const uint16_t *lcol, int64_t *sizes, int64_t *totals_host,
+                                void *stream);
+int ech_bjacobi_ilu0_pack_fill(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                               int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                               const int64_t *rowptr, const int32_t *colidx, int32_t lanes_per_row,
+                               const uint16_t *levels, const uint16_t *lcol, int64_t *sizes, uint8_t *packed,
+                               uint32_t *src, int64_t *bdesc, void *stream);
+int ech_bjacobi_ilu0_pack_values(int64_t nblocks, int32_t lanes_per_row, const int64_t *bdesc, uint8_t *packed,
+                                 const uint32_t *src, const double *lu, void *stream);
+int ech_bjacobi_ilu0_apply_packed(int32_t nfields, int64_t rows_per_field, int32_t nloc, int64_t nblocks,
+                                  const int64_t *block_cell_ptr, int32_t max_block_rows, int32_t max_chunk_bytes,
+                                  int32_t lanes_per_row, const int64_t *bdesc, const uint8_t *packed, const double *r,
+                                  double *z, void *stream);
+
 /* Coarse space of the optional two-level preconditioner (not in the reference's "ilu" option set; it
  * plays the role of the coarse levels of its gmg/amg sets, solver.py:1190-1213, for meshes on which
  * block-Jacobi/ILU(0) alone stalls).  Piecewise-constant aggregation agg[dof] -> coarse dof:

@@ -94,6 +94,7 @@ def test_block_ilu0_apply_matches_host(case):
         assert plan.ok
         if lpr is not None and lpr != plan.lpr:          # rebuild with another grouping: same result up to rounding
             plan.lpr = lpr
+            plan.packed = None
             G = 32 // lpr
             levels = torch.empty(2 * e.ndof, dtype=torch.int16, device="cuda")
             import ctypes as C
@@ -107,6 +108,15 @@ def test_block_ilu0_apply_matches_host(case):
                                                         ptr(e.rowptr), ptr(e.colidx), lpr, ptr(levels),
                                                         ptr(plan.passptr), ptr(plan.slots), st))
         zz = torch.full_like(rd, float("nan"))
+        if lpr is None:
+            # pass-packed factors fetched with cp.async.bulk (the default path) ...
+            assert plan.packed is not None
+            plan.refresh(lu, st)
+            plan.apply(lu, rd, zz, st)
+            zp["packed"] = zz.cpu().numpy()
+            assert np.isfinite(zp["packed"]).all(), case
+            plan._packed_for = None                       # ... and the register-pipelined planned solve
+            zz = torch.full_like(rd, float("nan"))
         plan.apply(lu, rd, zz, st)
         zp[plan.lpr] = zz.cpu().numpy()
         assert np.isfinite(zp[plan.lpr]).all(), (case, plan.lpr)
