@@ -2137,6 +2137,157 @@ extern "C" int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const dou
     return ECH_OK;
 }
 
+// =============================================================== Galerkin coarse operators of the DG tensor hierarchy
+// A_c = P^T A P for nested tensor meshes, without a general sparse product: A has the DG block-stencil structure
+// (row (i, c, a); per coupled field one n-entry block per cell of {c} U face-neighbours(c)), P maps the n dofs of a
+// coarse cell K to the dofs of its children through one dense n x n block per fine cell.  A coarse block (K, L) is
+//     A_c[(i,K,A),(j,L,B)] = sum over children c of K, fine cells c' in cols(c) with parent(c') = L,
+//                            sum_a sum_b  P_c[a][A] * A[(i,c,a),(j,c',b)] * P_c'[b][B],
+// and L is K or a face neighbour of K: the coarse matrix has the same block-stencil layout, so every level is
+// produced in place, on a fixed pattern, by one kernel (this replaces the two cuSPARSE SpGEMMs per level of round 1).
+struct GalerkinLevel {
+    int32_t nf, nloc, nlf;
+    int64_t ncell_f, ncell_c;              // fine cells that have a parent (owned), coarse cells
+    int64_t fstride_f, fstride_c;          // rows per field
+    const int64_t *rowptr_f;
+    const double *vals_f;
+    const int32_t *nbr_f;                  // [ncell_f][nlf]  (< 0 or >= ncell_f: no coupling kept)
+    const uint8_t *slot_f, *slot_self_f, *ncol_f;
+    const int32_t *parent_f;               // [ncell_f]
+    const double *pblk;                    // [ncell_f][n][n]   P_c[a][A]
+    const int32_t *children;               // [ncell_c][2^d]  (-1: absent)
+    int32_t nchild;
+    const int64_t *rowptr_c;
+    double *vals_c;
+    const int32_t *nbr_c;
+    const uint8_t *slot_c, *slot_self_c, *ncol_c;
+    const uint8_t *own, *nbrm;             // [nf][nf] block masks of the weak form
+};
+
+__device__ __forceinline__ int gal_block_offset(const GalerkinLevel &G, int i, int j, int ncol, int pos) {
+    int off = 0;
+    for (int jj = 0; jj < j; ++jj)
+        if (G.own[i * G.nf + jj]) off += (G.nbrm[i * G.nf + jj] ? ncol : 1) * G.nloc;
+    return off + (G.nbrm[i * G.nf + j] ? pos : 0) * G.nloc;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) galerkin_dg_kernel(GalerkinLevel G) {
+    const int64_t K = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (K >= G.ncell_c) return;
+    const int nf = G.nf, nlf = G.nlf;
+    const int ncolK = G.ncol_c[K];
+    const int selfK = G.slot_self_c[K];
+    // work items of this coarse cell: (i, A, j, p) with p the column-cell slot of K's rows
+    const int nitem = nf * N * nf * ncolK;
+    for (int item = lane; item < nitem; item += 32) {
+        int t = item;
+        const int p = t % ncolK; t /= ncolK;
+        const int j = t % nf; t /= nf;
+        const int A = t % N; t /= N;
+        const int i = t;
+        if (!G.own[i * nf + j]) continue;
+        const bool crosses = G.nbrm[i * nf + j] != 0;
+        if (!crosses && p != selfK) continue;
+        // the coarse cell L behind slot p
+        int64_t L = K;
+        if (p != selfK) {
+            L = -1;
+            for (int lf = 0; lf < nlf; ++lf) {
+                const int nb = G.nbr_c[K * nlf + lf];
+                if (nb >= 0 && G.slot_c[K * nlf + lf] == p) L = nb;
+            }
+            if (L < 0) continue;
+        }
+        double acc[N];
+#pragma unroll
+        for (int B = 0; B < N; ++B) acc[B] = 0.0;
+        for (int q = 0; q < G.nchild; ++q) {
+            const int64_t c = G.children[K * G.nchild + q];
+            if (c < 0) continue;
+            const int ncol = G.ncol_f[c];
+            const double *Pc = G.pblk + c * (N * N);
+            // fine column cells of c whose parent is L: c itself and its face neighbours
+            for (int lf = -1; lf < nlf; ++lf) {
+                int64_t cp;
+                int pos;
+                if (lf < 0) {
+                    cp = c;
+                    pos = G.slot_self_f[c];
+                } else {
+                    cp = G.nbr_f[c * nlf + lf];
+                    pos = G.slot_f[c * nlf + lf];
+                    if (!crosses) continue;
+                }
+                if (cp < 0 || cp >= G.ncell_f || G.parent_f[cp] != L) continue;
+                const double *Pp = G.pblk + cp * (N * N);
+                const int off = gal_block_offset(G, i, j, ncol, pos);
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    const double w = Pc[a * N + A];
+                    if (w == 0.0) continue;
+                    const double *v = G.vals_f + G.rowptr_f[(int64_t)i * G.fstride_f + c * N + a] + off;
+#pragma unroll
+                    for (int b = 0; b < N; ++b) {
+                        const double wv = w * v[b];
+#pragma unroll
+                        for (int B = 0; B < N; ++B) acc[B] = fma(wv, Pp[b * N + B], acc[B]);
+                    }
+                }
+            }
+        }
+        double *out = G.vals_c + G.rowptr_c[(int64_t)i * G.fstride_c + K * N + A] + gal_block_offset(G, i, j, ncolK, p);
+#pragma unroll
+        for (int B = 0; B < N; ++B) out[B] = acc[B];
+    }
+}
+
+extern "C" int ech_galerkin_dg(const int64_t *ip, const void *const *pp, void *stream) {
+    // ip: nf, nloc, nlf, nchild, ncell_f, ncell_c, fstride_f, fstride_c
+    // pp: rowptr_f, vals_f, nbr_f, slot_f, slot_self_f, ncol_f, parent_f, pblk, children, rowptr_c, vals_c, nbr_c,
+    //     slot_c, slot_self_c, ncol_c, own, nbrm
+    if (!ip || !pp) return fail(nullptr, ECH_ERR_ARG, "ech_galerkin_dg: null argument");
+    for (int k = 0; k < 17; ++k)
+        if (!pp[k]) return fail(nullptr, ECH_ERR_ARG, "ech_galerkin_dg: null array");
+    GalerkinLevel G;
+    G.nf = (int32_t)ip[0];
+    G.nloc = (int32_t)ip[1];
+    G.nlf = (int32_t)ip[2];
+    G.nchild = (int32_t)ip[3];
+    G.ncell_f = ip[4];
+    G.ncell_c = ip[5];
+    G.fstride_f = ip[6];
+    G.fstride_c = ip[7];
+    G.rowptr_f = (const int64_t *)pp[0];
+    G.vals_f = (const double *)pp[1];
+    G.nbr_f = (const int32_t *)pp[2];
+    G.slot_f = (const uint8_t *)pp[3];
+    G.slot_self_f = (const uint8_t *)pp[4];
+    G.ncol_f = (const uint8_t *)pp[5];
+    G.parent_f = (const int32_t *)pp[6];
+    G.pblk = (const double *)pp[7];
+    G.children = (const int32_t *)pp[8];
+    G.rowptr_c = (const int64_t *)pp[9];
+    G.vals_c = (double *)pp[10];
+    G.nbr_c = (const int32_t *)pp[11];
+    G.slot_c = (const uint8_t *)pp[12];
+    G.slot_self_c = (const uint8_t *)pp[13];
+    G.ncol_c = (const uint8_t *)pp[14];
+    G.own = (const uint8_t *)pp[15];
+    G.nbrm = (const uint8_t *)pp[16];
+    if (G.ncell_c == 0) return ECH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((G.ncell_c * 32 + 127) / 128);
+    if (G.nloc == 2) galerkin_dg_kernel<2><<<grid, 128, 0, s>>>(G);
+    else if (G.nloc == 4) galerkin_dg_kernel<4><<<grid, 128, 0, s>>>(G);
+    else if (G.nloc == 8) galerkin_dg_kernel<8><<<grid, 128, 0, s>>>(G);
+    else return fail(nullptr, ECH_ERR_ARG, "ech_galerkin_dg: nloc must be 2, 4 or 8 (Q1 in 1, 2 or 3 dimensions)");
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== GMRES
 extern "C" int ech_gmres(int64_t n, const int64_t *rowptr, const int32_t *colidx, const double *vals,
                          const double *b, double *x, const ech_gmres_opts *o, double *basis, double *work,

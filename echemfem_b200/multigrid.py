@@ -71,6 +71,64 @@ class Level:
     pass
 
 
+def dg_pattern(nf, n, ncell, cells_sorted, ncol, own, nbrm, nrows_per_field=None):
+    """Field-blocked AIJ pattern of a DG space: row (i, c, a) holds, for every coupled field j,
+    one n-entry block per cell of sorted({c} U neighbours(c)) if the coupling crosses facets, else the own block.
+    cells_sorted: (ncell, 2d+1) cell ids in ascending order, -1 padded; returns (rowptr int64, colidx int32)."""
+    N = nrows_per_field or ncell * n
+    ncol = np.asarray(ncol, dtype=np.int64)
+    self_pos = np.argmax(cells_sorted == np.arange(ncell)[:, None], axis=1)
+    rowptr_parts, col_parts = [], []
+    base = 0
+    for i in range(nf):
+        nblk = np.zeros(ncell, dtype=np.int64)
+        for j in range(nf):
+            if own[i, j]:
+                nblk += ncol if nbrm[i, j] else 1
+        # block starts per cell, in row order
+        tot = int(nblk.sum())
+        starts = np.empty(tot, dtype=np.int64)
+        cell_off = np.concatenate([[0], np.cumsum(nblk)])[:-1]
+        seg = np.zeros(ncell, dtype=np.int64)
+        for j in range(nf):
+            if not own[i, j]:
+                continue
+            if nbrm[i, j]:
+                for p in range(cells_sorted.shape[1]):
+                    m = p < ncol
+                    starts[(cell_off + seg + p)[m]] = j * N + cells_sorted[m, p] * n
+                seg += ncol
+            else:
+                starts[cell_off + seg] = j * N + np.arange(ncell) * n
+                seg += 1
+        # expand: every row a of the cell repeats the cell's block list; every block is n consecutive columns
+        lens_rows = np.repeat(nblk * n, n)                                        # (ncell * n,)
+        rowptr_parts.append(base + np.concatenate([[0], np.cumsum(lens_rows)])[:-1])
+        # (cell, a, block) order: position of block q of cell c in copy a = n * cell_off[c] + a * nblk[c] + q
+        q_in_cell = np.arange(tot) - np.repeat(cell_off, nblk)
+        out_base = np.repeat(np.concatenate([[0], np.cumsum(nblk * n)])[:-1], nblk)   # in blocks, per cell, all copies
+        blocks_all = np.empty(tot * n, dtype=np.int64)
+        for a in range(n):
+            blocks_all[out_base + a * np.repeat(nblk, nblk) + q_in_cell] = starts
+        cols = (blocks_all[:, None] + np.arange(n)[None, :]).reshape(-1)
+        col_parts.append(cols.astype(np.int32))
+        base += int(lens_rows.sum())
+    rowptr = np.concatenate(rowptr_parts + [[base]]).astype(np.int64)
+    return rowptr, np.concatenate(col_parts)
+
+
+def _sorted_cells(nbr):
+    """(ncell, 2d+1) ascending cell ids of {c} U valid neighbours, -1 padded, and the count."""
+    nbr = np.asarray(nbr, dtype=np.int64)
+    nc = nbr.shape[0]
+    big = np.iinfo(np.int64).max
+    allc = np.concatenate([np.arange(nc, dtype=np.int64)[:, None], np.where(nbr >= 0, nbr, big)], axis=1)
+    allc.sort(axis=1)
+    ncol = (allc < big).sum(axis=1)
+    allc[allc == big] = -1
+    return allc, ncol
+
+
 class Hierarchy:
     """Levels of a tensor mesh and the scalar prolongations between them (host side)."""
 
@@ -119,6 +177,12 @@ class Hierarchy:
             P = P.tocoo()
             rf = _dof_map(shape, n1, L.inv)
             rc = _dof_map(cshape, n1, cinv)
+            # parent (coarse cell, coarse numbering) of every fine cell (fine numbering)
+            lexf = np.arange(L.ncell) if perm is None else np.asarray(perm)
+            multi = np.unravel_index(lexf, shape)
+            lexc = np.ravel_multi_index(tuple(m // 2 for m in multi), cshape)
+            L.parent = (lexc if cinv is None else cinv[lexc]).astype(np.int32)
+            L.cshape, L.ctile = cshape, (tile if cperm is not None else None)
             nrow = L.ncell * self.n
             if len(self.levels) == 1 and fine_rows is not None:
                 nrow = max(nrow, int(fine_rows))
@@ -219,12 +283,68 @@ class Multigrid:
             D.P = _dev_csr(P, self.dev)
             D.R = _dev_csr(P.T, self.dev)
             # block-diagonal (all fields) transfer operators as torch CSR tensors for the Galerkin products
-            D.Pt = self._blockdiag(P)
-            D.Rt = self._blockdiag(P.T.tocsr())
+            if os.environ.get("ECH_MG_SPGEMM", "0") != "0" or n not in (2, 4, 8):
+                # block-diagonal (all fields) transfer operators as torch CSR tensors for the cuSPARSE cross-check path
+                D.Pt = self._blockdiag(P)
+                D.Rt = self._blockdiag(P.T.tocsr())
         self.nlevels = len(self.lv)
+        # own Galerkin kernel (ech_galerkin_dg): fixed block-stencil pattern and cell tables of every coarse level
+        self.own_galerkin = os.environ.get("ECH_MG_SPGEMM", "0") == "0" and n in (2, 4, 8)
+        if self.own_galerkin:
+            self._galerkin_tables(engine)
         self.planned = os.environ.get("ECH_ILU_PLANNED", "1") != "0"
         self.use_graph = os.environ.get("ECH_MG_GRAPH", "1") != "0"
         self._graph = self._gr = self._gz = None
+
+    def _galerkin_tables(self, engine):
+        from .mesh import TensorMesh
+        dev, n, nf = self.dev, self.h.n, self.nf
+        own = np.ascontiguousarray(engine.form.own_mask, dtype=bool)
+        nbm = np.ascontiguousarray(engine.form.nbr_mask, dtype=bool)
+        f = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
+        self._own_d, self._nbm_d = f(own.astype(np.uint8), torch.uint8), f(nbm.astype(np.uint8), torch.uint8)
+        d = len(self.h.levels[0].shape)
+        for l, (L, D) in enumerate(zip(self.h.levels, self.lv)):
+            if l == 0:
+                m = engine.m                      # the engine's own tables (ghost cells lie behind the owned ones)
+                D.tab = {"nbr": m["nbr"], "slot": m["slot"], "slot_self": m["slot_self"], "ncol": m["ncol"]}
+                D.ncell_owned = engine.ncell
+            else:
+                tile = self.h.levels[l - 1].ctile
+                cm = TensorMesh(L.axes, tile=tile)
+                nbr, _, slot, slot_self, ncol = cm.connectivity({})
+                nbr = np.where(nbr >= 0, nbr, -1)
+                cs, nc = _sorted_cells(nbr)
+                rp, ci = dg_pattern(nf, n, L.ncell, cs, nc, own, nbm)
+                D.tab = {"nbr": f(nbr, torch.int32), "slot": f(slot, torch.uint8),
+                         "slot_self": f(slot_self, torch.uint8), "ncol": f(ncol, torch.uint8)}
+                D.ncell_owned = L.ncell
+                D.rowptr, D.colidx = f(rp, torch.int64), f(ci, torch.int32)
+                D.vals = torch.zeros(int(rp[-1]), dtype=torch.float64, device=dev)
+            if l < len(self.h.P):
+                P = self.h.P[l].tocoo()
+                pblk = np.zeros((L.ncell * n, n))
+                keep = P.row < L.ncell * n
+                pblk[P.row[keep], P.col[keep] % n] = P.data[keep]
+                ncc = self.h.levels[l + 1].ncell
+                children = -np.ones((ncc, 2 ** d), dtype=np.int32)
+                order = np.argsort(L.parent, kind="stable")
+                par = L.parent[order]
+                first = np.searchsorted(par, np.arange(ncc))
+                rank = np.arange(L.ncell) - first[par]
+                children[par, rank] = order
+                D.gal = {"parent": f(L.parent, torch.int32), "pblk": f(pblk, torch.float64),
+                         "children": f(children, torch.int32), "nchild": 2 ** d}
+
+    def _galerkin(self, D, Dc):
+        """Dc.vals = P^T D.vals P (ech_galerkin_dg)."""
+        n, nf, d = self.h.n, self.nf, len(self.h.levels[0].shape)
+        ip = (capi.c_i64 * 8)(nf, n, 2 * d, D.gal["nchild"], D.ncell_owned, Dc.ncell_owned, D.N, Dc.N)
+        arrs = [D.rowptr, D.vals, D.tab["nbr"], D.tab["slot"], D.tab["slot_self"], D.tab["ncol"], D.gal["parent"],
+                D.gal["pblk"], D.gal["children"], Dc.rowptr, Dc.vals, Dc.tab["nbr"], Dc.tab["slot"],
+                Dc.tab["slot_self"], Dc.tab["ncol"], self._own_d, self._nbm_d]
+        pp = (capi.c_p * 17)(*[a.data_ptr() for a in arrs])
+        capi.check(self.lib.ech_galerkin_dg(ip, pp, self.e._stream()))
 
     def _blockdiag(self, P):
         P = P.tocsr()
@@ -247,7 +367,10 @@ class Multigrid:
         fine.rowptr, fine.colidx, fine.vals = e.rowptr, e.colidx, e.vals
         for l in range(self.nlevels - 1):
             D, Dc = self.lv[l], self.lv[l + 1]
-            # A P, then P^T (A P), each in row chunks
+            if self.own_galerkin:
+                self._galerkin(D, Dc)
+                continue
+            # cross-check path (ECH_MG_SPGEMM=1): A P, then P^T (A P) through cuSPARSE, each in row chunks
             ap = spgemm_rows(D.rowptr, D.colidx, D.vals, D.ndof, D.Pt, D.Pt.values().numel() / D.ndof)
             AP = torch.sparse_csr_tensor(ap[0].to(D.Pt.crow_indices().dtype), ap[1].to(D.Pt.crow_indices().dtype), ap[2],
                                          size=(D.ndof, Dc.ndof))

@@ -185,6 +185,14 @@ int ech_coarse_prolong_add(int64_t n, const int32_t *agg, const double *yc, doub
 /* y[nr] = M[nr x nc] x (dense, row-major; one warp per row) */
 int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const double *x, double *y, void *stream);
 
+/* Galerkin coarse operator A_c = P^T A P of the DG tensor hierarchy (multigrid set-up; stands in for the coarse-level
+ * assembly of the reference's `gmg` option set on a MeshHierarchy, solver.py:1190-1201).  A and A_c share the DG
+ * block-stencil layout; P is one dense nloc x nloc block per fine cell.  ip[8] = {nfields, nloc (2, 4 or 8), facets
+ * per cell, children per coarse cell, fine cells, coarse cells, fine rows per field, coarse rows per field};
+ * pp[17] = {rowptr_f, vals_f, nbr_f, slot_f, slot_self_f, ncol_f, parent_f, pblk, children, rowptr_c, vals_c, nbr_c,
+ * slot_c, slot_self_c, ncol_c, own_mask, nbr_mask} (device pointers; masks uint8[nf*nf]).  Writes vals_c. */
+int ech_galerkin_dg(const int64_t *ip, const void *const *pp, void *stream);
+
 typedef struct ech_gmres_opts {
     double rtol, atol;
     int32_t restart, max_it;
