@@ -65,6 +65,8 @@ EXPORTS = {
     "ech_bjacobi_ilu0_pack_values": (C.c_int, [c_i64, c_i32, c_p, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_apply_packed": (C.c_int, [c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p,
                                                 c_p]),
+    "ech_halo_pack": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),
+    "ech_halo_unpack": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),
     "ech_galerkin_dg": (C.c_int, [C.POINTER(c_i64), C.POINTER(c_p), c_p]),
     "ech_coarse_galerkin": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_i32, c_p, c_p]),
     "ech_coarse_restrict": (C.c_int, [c_i64, c_p, c_i32, c_p, c_p, c_p]),

@@ -2137,6 +2137,38 @@ extern "C" int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const dou
     return ECH_OK;
 }
 
+// =============================================================== halo pack / unpack (one launch for all peers)
+// buf[k] = u[idx[k]]  and  u[idx[k]] = buf[k]: the send lists of all peers are one index array, the per-peer messages
+// contiguous slices of one buffer (PetscSF pack / unpack of the reference's halo updates).
+__global__ void halo_pack_kernel(int64_t n, const int64_t *__restrict__ idx, const double *__restrict__ u,
+                                 double *__restrict__ buf) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        buf[k] = u[idx[k]];
+}
+__global__ void halo_unpack_kernel(int64_t n, const int64_t *__restrict__ idx, const double *__restrict__ buf,
+                                   double *__restrict__ u) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        u[idx[k]] = buf[k];
+}
+
+extern "C" int ech_halo_pack(int64_t n, const int64_t *idx, const double *u, double *buf, void *stream) {
+    if (n == 0) return ECH_OK;
+    if (!idx || !u || !buf) return fail(nullptr, ECH_ERR_ARG, "ech_halo_pack: null argument");
+    halo_pack_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, idx, u, buf);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_halo_unpack(int64_t n, const int64_t *idx, const double *buf, double *u, void *stream) {
+    if (n == 0) return ECH_OK;
+    if (!idx || !u || !buf) return fail(nullptr, ECH_ERR_ARG, "ech_halo_unpack: null argument");
+    halo_unpack_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, idx, buf, u);
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== Galerkin coarse operators of the DG tensor hierarchy
 // A_c = P^T A P for nested tensor meshes, without a general sparse product: A has the DG block-stencil structure
 // (row (i, c, a); per coupled field one n-entry block per cell of {c} U face-neighbours(c)), P maps the n dofs of a

@@ -216,21 +216,40 @@ def strip_partition(axes, rank, size, name="strip", tile=None):
 
 
 class HaloExchange:
-    """Ghost-cell state exchange for vectors laid out [nf][ncell_total * n] (torch.distributed P2P)."""
+    """Ghost-cell state exchange for vectors laid out [nf][ncell_total * n].  Device side: ONE pack launch gathers
+    the messages of all peers into contiguous slices of one send buffer, grouped NCCL send / recv move the slices
+    (torch.distributed P2P), ONE unpack launch scatters the receive buffer into the ghost entries
+    (`ech_halo_pack` / `ech_halo_unpack`).  Without a CUDA device (gloo tests) the same slices are packed with torch
+    indexing."""
 
     def __init__(self, plan, nf, nloc, ncell_total, device):
         import torch
         self.plan, self.nf, self.nloc, self.ntot = plan, nf, nloc, ncell_total
         self.device = device
-        self.bytes_per_exchange = 0
-        self._send_idx, self._recv_idx, self._sbuf, self._rbuf = {}, {}, {}, {}
-        for peer, cells in plan.send.items():
-            self._send_idx[peer] = self._dof_index(cells).to(device)
-            self._sbuf[peer] = torch.empty(len(cells) * nf * nloc, dtype=torch.float64, device=device)
-        for peer, cells in plan.recv.items():
-            self._recv_idx[peer] = self._dof_index(cells).to(device)
-            self._rbuf[peer] = torch.empty(len(cells) * nf * nloc, dtype=torch.float64, device=device)
-            self.bytes_per_exchange += 8 * len(cells) * nf * nloc
+        self.peers = plan.peers()
+        self._sslice, self._rslice = {}, {}
+        sidx, ridx = [], []
+        so = ro = 0
+        for peer in self.peers:
+            if peer in plan.send:
+                ix = self._dof_index(plan.send[peer])
+                self._sslice[peer] = (so, so + len(ix))
+                so += len(ix)
+                sidx.append(ix)
+            if peer in plan.recv:
+                ix = self._dof_index(plan.recv[peer])
+                self._rslice[peer] = (ro, ro + len(ix))
+                ro += len(ix)
+                ridx.append(ix)
+        cat = lambda parts: torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64)
+        self._sidx, self._ridx = cat(sidx).to(device), cat(ridx).to(device)
+        self._sbuf = torch.empty(so, dtype=torch.float64, device=device)
+        self._rbuf = torch.empty(ro, dtype=torch.float64, device=device)
+        self.bytes_per_exchange = 8 * ro
+        self._lib = None
+        if torch.device(device).type == "cuda":
+            from . import capi
+            self._lib = capi.lib()
 
     def _dof_index(self, cells):
         import torch
@@ -243,16 +262,26 @@ class HaloExchange:
         """Fill the ghost-cell entries of `u` with the owners' values."""
         import torch
         import torch.distributed as dist
-        if self.plan.size == 1 or not self.plan.peers():
+        if self.plan.size == 1 or not self.peers:
             return
+        if self._lib is not None:
+            from . import capi
+            from .capi import ptr
+            st = capi.C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            capi.check(self._lib.ech_halo_pack(self._sidx.numel(), ptr(self._sidx), ptr(u), ptr(self._sbuf), st))
+        else:
+            torch.index_select(u, 0, self._sidx, out=self._sbuf)
         ops = []
-        for peer in self.plan.peers():
-            if peer in self._send_idx:
-                torch.index_select(u, 0, self._send_idx[peer], out=self._sbuf[peer])
-                ops.append(dist.P2POp(dist.isend, self._sbuf[peer], peer))
-            if peer in self._recv_idx:
-                ops.append(dist.P2POp(dist.irecv, self._rbuf[peer], peer))
+        for peer in self.peers:
+            if peer in self._sslice:
+                a, b = self._sslice[peer]
+                ops.append(dist.P2POp(dist.isend, self._sbuf[a:b], peer))
+            if peer in self._rslice:
+                a, b = self._rslice[peer]
+                ops.append(dist.P2POp(dist.irecv, self._rbuf[a:b], peer))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        for peer, idx in self._recv_idx.items():
-            u.index_copy_(0, idx, self._rbuf[peer])
+        if self._lib is not None:
+            capi.check(self._lib.ech_halo_unpack(self._ridx.numel(), ptr(self._ridx), ptr(self._rbuf), ptr(u), st))
+        else:
+            u.index_copy_(0, self._ridx, self._rbuf)

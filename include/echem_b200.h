@@ -185,6 +185,12 @@ int ech_coarse_prolong_add(int64_t n, const int32_t *agg, const double *yc, doub
 /* y[nr] = M[nr x nc] x (dense, row-major; one warp per row) */
 int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const double *x, double *y, void *stream);
 
+/* Ghost-dof exchange, device side (VecScatter / PetscSF pack and unpack of the reference's halo updates): the send
+ * lists of ALL peers are one index array, their messages contiguous slices of one buffer; the transport between
+ * the slices is the caller's (NCCL send / recv through torch.distributed). */
+int ech_halo_pack(int64_t n, const int64_t *idx, const double *u, double *buf, void *stream);
+int ech_halo_unpack(int64_t n, const int64_t *idx, const double *buf, double *u, void *stream);
+
 /* Galerkin coarse operator A_c = P^T A P of the DG tensor hierarchy (multigrid set-up; stands in for the coarse-level
  * assembly of the reference's `gmg` option set on a MeshHierarchy, solver.py:1190-1201).  A and A_c share the DG
  * block-stencil layout; P is one dense nloc x nloc block per fine cell.  ip[8] = {nfields, nloc (2, 4 or 8), facets
