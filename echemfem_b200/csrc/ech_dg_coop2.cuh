@@ -182,7 +182,9 @@ constexpr int NCONST_PAD = even(ECH_NCONST);
 #ifndef ECH_COOP2_NBUF
 #define ECH_COOP2_NBUF 1
 #endif
-constexpr bool PIPE = ECH_COOP2_PIPE != 0 && G >= NLF;
+// (only where the lanes of a warp divide evenly among the cells: for Q2, G = 9, the remapped staging measured
+// 12 % slower than the round-1 one -- profiles/r2q_bench_cfg2_Q2.json -- and is not used)
+constexpr bool PIPE = ECH_COOP2_PIPE != 0 && G >= NLF && (32 % G == 0);
 constexpr int NBUF = (PIPE && ECH_COOP2_NBUF == 2) ? 2 : 1;       // 1: the next batch is staged during the last round
 constexpr bool EARLY = NBUF == 2;
 

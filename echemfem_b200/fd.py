@@ -88,8 +88,14 @@ def set_log_level(level):
 
 class AssembledPC:
     """Base class of the reference's custom PETSc preconditioners (examples/mms_scaling.py:24-62).  Python-level
-    PETSc preconditioners have no counterpart on the device path: the classes can be defined, but selecting them
-    (`pc_type: python`) falls back to the option sets of `init_solver_parameters`."""
+    PETSc preconditioners have no counterpart on the device path: the classes can be DEFINED (so that such scripts
+    import), but instantiating one -- which is what selecting `pc_type: python` does -- raises instead of silently
+    solving with a different preconditioner."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("Python-level PETSc preconditioners (%s) have no counterpart on the device path; "
+                                  "use the option sets of init_solver_parameters ('lu', 'ilu', 'gmg')"
+                                  % type(self).__name__)
 
 
 class PMGPC(AssembledPC):

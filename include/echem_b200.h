@@ -250,7 +250,8 @@ int ech_assemble_host(ech_handle *h, const double *u_host, double *u_dev, const 
  * the single copy). */
 int ech_set_host_chunks(ech_handle *h, int nchunks);
 
-/* number of kernels launched by this library (and the bound module) since ech_create */
+/* number of kernels launched by this library (and the bound modules) in this PROCESS since it was loaded -- one
+ * counter for all handles; callers take differences around the region they count */
 int64_t ech_launch_count(const ech_handle *h);
 
 #ifdef __cplusplus
