@@ -140,3 +140,28 @@ def test_pipelined_host_assembly_with_ghost_cells(size, how):
             Fk, Jk, _ = _host_call(e, s, u, chunks)
             assert np.array_equal(Fk[owned], F_dev[owned]), (rank, chunks)
             assert np.array_equal(Jk, J_dev), (rank, chunks)
+
+
+def test_auto_mode_decides_between_pipeline_and_single_copy():
+    """`ech_set_host_chunks(h, -k)`: the first six calls time the k-chunk pipeline and the single-copy path, every one
+    of them a valid call (bit-identical results); afterwards the faster mode stays selected."""
+    s, e, u = _setup(UnitSquareMesh(40, 40))
+    s.u.tensor.copy_(torch.from_numpy(u).cuda())
+    F_dev = e.residual_jacobian(s.u.tensor)[0].cpu().numpy().copy()
+    J_dev = e.vals.cpu().numpy().copy()
+    lib = e.lib
+    capi.check(lib.ech_set_host_chunks(e.h, -4), e.h)
+    uh = torch.from_numpy(u.copy()).pin_memory()
+    Fh = torch.empty(u.size, dtype=torch.float64).pin_memory()
+    aux, consts = e._aux_tensor(), e._consts()
+    launches = []
+    for k in range(9):
+        Fh.fill_(float("nan"))
+        e.vals.fill_(float("nan"))
+        n0 = lib.ech_launch_count(e.h)
+        capi.check(lib.ech_assemble_host(e.h, ptr(uh), ptr(s.u.tensor), ptr(aux), ptr(consts), ptr(e.rowptr),
+                                         ptr(e.vals), ptr(e.F), ptr(Fh), e._stream()), e.h)
+        launches.append(lib.ech_launch_count(e.h) - n0)
+        assert np.array_equal(Fh.numpy(), F_dev) and np.array_equal(e.vals.cpu().numpy(), J_dev), k
+    assert all(2 <= n <= 4 for n in launches[:3]) and launches[3:6] == [1, 1, 1]        # measured both modes
+    assert len(set(launches[6:])) == 1                                                   # then one mode, kept
