@@ -144,6 +144,10 @@ def build_problem(args, rank, world):
     deg = args.degree
     N = args.N or CFG2_N[deg]
     tile = TILE if N % TILE == 0 else None
+    if getattr(args, "tile", None):
+        tile = tuple(int(v) for v in args.tile.split("x"))
+        if any(N % t for t in tile):
+            raise SystemExit("--tile must divide N")
     if world == 1:
         mesh = TensorMesh([np.linspace(0.0, 1.0, N + 1), np.linspace(0.0, 1.0, N + 1)], name="unit_square", tile=tile)
         desc = "UnitSquareMesh(%d,%d) quads" % (N, N)
@@ -234,6 +238,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--N", type=int, default=0, help="cells per direction (cfg2: 1408 / 944 / 704 for Q1 / Q2 / Q3)")
     ap.add_argument("--degree", type=int, default=1, help="polynomial degree (the headline number is Q1)")
+    ap.add_argument("--tile", default="", help="cell-numbering tile, e.g. 32x2 (default 8x8): one preconditioner block per tile")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-newton", action="store_true", help="skip the Newton solve (assembly + SpMV only)")
     ap.add_argument("--host-chunks", dest="host_chunks", type=int, default=16, help="cell ranges of the e2e "

@@ -2169,6 +2169,74 @@ extern "C" int ech_halo_unpack(int64_t n, const int64_t *idx, const double *buf,
     return ECH_OK;
 }
 
+// =============================================================== Galerkin operator of the conforming auxiliary space
+// A_aux = Q^T A Q for the continuous-Q1 subspace of a DG-Q1 space (echemfem_b200/auxspace.py).  Q restricted to one
+// cell is the same dense NV x NV matrix W for every cell (continuous hat functions at the DG nodes of the reference
+// cell), so every cell block B (rows of cell c, columns of cell c') of A contributes W^T B W to the NV x NV block
+// between the vertices of c and the vertices of c'.  One thread per cell block; dst holds, per block, the NV*NV
+// positions in A_aux (computed once per sparsity pattern).  All rows of a cell share their column pattern, so the
+// block sits at the same offset `off` from the row start in each of its NV rows.
+template <int NV>
+__global__ void __launch_bounds__(128)
+aux_galerkin_kernel(int64_t nblk, const int64_t *__restrict__ row0, const int32_t *__restrict__ off,
+                    const int32_t *__restrict__ dst, const int64_t *__restrict__ rowptr, const double *__restrict__ vals,
+                    const double *__restrict__ W, double *__restrict__ out) {
+    __shared__ double Ws[NV * NV];
+    for (int i = threadIdx.x; i < NV * NV; i += blockDim.x) Ws[i] = W[i];
+    __syncthreads();
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nblk; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r0 = row0[k];
+        const int32_t o = off[k];
+        double T[NV][NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) T[i][j] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+            const double *p = vals + rowptr[r0 + a] + o;
+            double c[NV];                                    // c[vb] = sum_b B[a][b] W[b][vb]
+#pragma unroll
+            for (int j = 0; j < NV; ++j) c[j] = 0.0;
+#pragma unroll
+            for (int b = 0; b < NV; ++b) {
+                const double v = p[b];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) c[j] = fma(v, Ws[b * NV + j], c[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) T[i][j] = fma(Ws[a * NV + i], c[j], T[i][j]);
+        }
+        const int32_t *d = dst + k * (NV * NV);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) atomicAdd(out + d[i * NV + j], T[i][j]);
+    }
+}
+
+extern "C" int ech_aux_galerkin(int32_t nv, int64_t nblk, const int64_t *row0, const int32_t *off, const int32_t *dst,
+                                const int64_t *rowptr, const double *vals, const double *W, int64_t nout, double *out,
+                                void *stream) {
+    if (!out || nout < 0) return fail(nullptr, ECH_ERR_ARG, "ech_aux_galerkin: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(nullptr, cudaMemsetAsync(out, 0, sizeof(double) * (size_t)nout, s));
+    if (nblk == 0) return ECH_OK;
+    if (!row0 || !off || !dst || !rowptr || !vals || !W) return fail(nullptr, ECH_ERR_ARG, "ech_aux_galerkin: null argument");
+    const unsigned grid = grid_for(nblk, 128);
+    switch (nv) {
+    case 2: aux_galerkin_kernel<2><<<grid, 128, 0, s>>>(nblk, row0, off, dst, rowptr, vals, W, out); break;
+    case 4: aux_galerkin_kernel<4><<<grid, 128, 0, s>>>(nblk, row0, off, dst, rowptr, vals, W, out); break;
+    case 8: aux_galerkin_kernel<8><<<grid, 128, 0, s>>>(nblk, row0, off, dst, rowptr, vals, W, out); break;
+    default: return fail(nullptr, ECH_ERR_ARG, "ech_aux_galerkin: 2, 4 or 8 vertices per cell");
+    }
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== Galerkin coarse operators of the DG tensor hierarchy
 // A_c = P^T A P for nested tensor meshes, without a general sparse product: A has the DG block-stencil structure
 // (row (i, c, a); per coupled field one n-entry block per cell of {c} U face-neighbours(c)), P maps the n dofs of a

@@ -145,6 +145,13 @@ constexpr bool SMEM_ACC = !STRADDLE && (NF * NF * NLOC > 48);
 constexpr bool SMEM_ACC = false;
 #endif
 constexpr int ACC_DOUBLES = SMEM_ACC ? NF * NF * NLOC * 32 : 0;
+// neighbour blocks one equation at a time (see the consumer).  Measured on the 3D three-ion case (12.6 M dofs):
+// stack 7 KB -> 1.5-1.9 KB per thread, but 27.3 ms against 24.3 ms (the recomputed neighbour basis costs more than the
+// spills it removes), so it is off by default
+#ifndef ECH_NBR_PER_EQ
+#define ECH_NBR_PER_EQ 0
+#endif
+constexpr bool NBR_PER_EQ = ECH_NBR_PER_EQ != 0 && !SMEM_ACC && !STRADDLE && (NF * NF * NLOC > 48);
 
 
 // ---------------------------------------------------------------- staged cell data (asynchronous copies)
@@ -1041,7 +1048,51 @@ __global__ void ECH_COOP2_BOUNDS jacobian_coop2_kernel(const ech_dg_args A, int6
                         }
                     });
                     // interior facets, facet by facet
-                    if constexpr (ECH_FAMILY_DG) {
+                    if constexpr (ECH_FAMILY_DG && NBR_PER_EQ) {
+                        // large elements: the neighbour-block accumulators of ALL equations (NF*NF*NLOC doubles) next to
+                        // the own-block ones do not fit the register file (3D, three fields: 7 KB of spills per
+                        // thread).  Own part for all equations first, then the neighbour part one equation at a time
+                        // (NF*NLOC accumulators), the neighbour's reference basis recomputed per equation.
+                        static_for<0, NLF>([&](auto lc) {
+                            constexpr int lf = decltype(lc)::value;
+                            constexpr int r0 = facet_first_round(lf);
+                            if constexpr (RD == r0) {
+                                if (meta[lf] >= 0) {
+                                    static_for<0, NQF>([&](auto qc) {
+                                        constexpr int qf = decltype(qc)::value;
+                                        constexpr int TK = NQC + lf * NQF + qf;
+                                        constexpr int s = TK - RD * G;
+                                        double pa, da[D];
+                                        test_values<TK>(ad, pa, da);
+                                        double phi2[NLOC], d2[NLOC][D];      // unused on the own side
+                                        take_all2<MIP, TK>(R, s, RC::OFF_JP, pa, da, phi2, d2, accR);
+                                    });
+                                    static_for<0, NF>([&](auto ic) {
+                                        constexpr int I = decltype(ic)::value;
+                                        double accnI[NF][NLOC];
+                                        static_for<0, NF>([&](auto jc) {
+                                            constexpr int j = decltype(jc)::value;
+                                            if constexpr (NBR_BLOCK[I][j]) {
+#pragma unroll
+                                                for (int b = 0; b < NLOC; ++b) accnI[j][b] = 0.0;
+                                            }
+                                        });
+                                        static_for<0, NQF>([&](auto qc) {
+                                            constexpr int qf = decltype(qc)::value;
+                                            constexpr int TK = NQC + lf * NQF + qf;
+                                            constexpr int s = TK - RD * G;
+                                            double pa, da[D];
+                                            test_values<TK>(ad, pa, da);
+                                            double phi2[NLOC], d2[NLOC][D];
+                                            nb_basis<TK>(meta[NLF + lf], phi2, d2);
+                                            take_row2<MIM, I, -1>(R, s, RC::OFF_JM, pa, da, phi2, d2, accnI);
+                                        });
+                                        store_row_blocks<false, I>(A.out, rp[I], ncol, meta[2 * NLF + lf], accnI);
+                                    });
+                                }
+                            }
+                        });
+                    } else if constexpr (ECH_FAMILY_DG) {
                         static_for<0, NLF>([&](auto lc) {
                             constexpr int lf = decltype(lc)::value;
                             constexpr int r0 = facet_first_round(lf), r1 = facet_last_round(lf);

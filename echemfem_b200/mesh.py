@@ -222,6 +222,7 @@ def TensorMesh(axes, name="tensor", marker_of_facet=None, layers=None, tile=None
         t = tuple(int(v) for v in (tile if np.ndim(tile) else (tile,) * d))
         if all(n % k == 0 for n, k in zip(shape, t)):
             m.block_hint = int(np.prod(t))      # cells per preconditioner block = one tile
+            m.tile_shape = t
     return m
 
 

@@ -129,6 +129,18 @@ def _sorted_cells(nbr):
     return allc, ncol
 
 
+def _fit_tile(shape, tile):
+    """Tile of a coarse level: `tile` itself if it divides the level (None -> lexicographic numbering otherwise);
+    a per-direction tile (tuple, e.g. elongated along the flow) is halved per direction until it divides."""
+    if not np.ndim(tile):
+        return tile if all(s % tile == 0 and s > tile for s in shape) else None
+    t = [int(v) for v in tile]
+    for k, s in enumerate(shape):
+        while t[k] > 1 and (s % t[k] or s < t[k]):
+            t[k] //= 2
+    return tuple(t) if int(np.prod(t)) > 1 else None
+
+
 class Hierarchy:
     """Levels of a tensor mesh and the scalar prolongations between them (host side)."""
 
@@ -166,7 +178,8 @@ class Hierarchy:
             # (prolongation_1d works from the coordinates, so its block is the identity)
             cax = [a[::2] if (len(a) - 1) % 2 == 0 else np.append(a[::2], a[-1]) for a in axes]
             cshape = tuple(len(a) - 1 for a in cax)
-            cperm = tile_order(cshape, tile) if all(s % tile == 0 and s > tile for s in cshape) else None
+            ctile = _fit_tile(cshape, tile)
+            cperm = tile_order(cshape, ctile) if ctile is not None else None
             cinv = None
             if cperm is not None:
                 cinv = np.empty_like(cperm)
@@ -182,7 +195,7 @@ class Hierarchy:
             multi = np.unravel_index(lexf, shape)
             lexc = np.ravel_multi_index(tuple(m // 2 for m in multi), cshape)
             L.parent = (lexc if cinv is None else cinv[lexc]).astype(np.int32)
-            L.cshape, L.ctile = cshape, (tile if cperm is not None else None)
+            L.cshape, L.ctile = cshape, ctile
             nrow = L.ncell * self.n
             if len(self.levels) == 1 and fine_rows is not None:
                 nrow = max(nrow, int(fine_rows))
@@ -252,6 +265,9 @@ class Multigrid:
         # across ranks every rank builds the hierarchy of its own cells: the V-cycle is then the block solver of
         # PETSc's bjacobi (one block per rank, echemfem/solver.py:1186), couplings to ghost cells dropped
         self.distributed = engine.halo is not None
+        if getattr(mesh, "tile_shape", None) is not None and len(set(mesh.tile_shape)) > 1:
+            tile = mesh.tile_shape          # elongated tiles (blocks along the flow): coarse levels follow the mesh
+            cells_per_block = int(np.prod(tile))
         self.h = Hierarchy(mesh, engine.solver.W.scalar.degree, tile=tile, coarsest_cells=coarsest_cells,
                            fine_rows=engine.N)
         if self.h.nlevels < 2:
@@ -293,6 +309,15 @@ class Multigrid:
         if self.own_galerkin:
             self._galerkin_tables(engine)
         self.planned = os.environ.get("ECH_ILU_PLANNED", "1") != "0"
+        # continuous-Q1 auxiliary space for the potential fields (auxspace.py: why the nested DG hierarchy alone is
+        # a weak preconditioner for the elliptic block, and what this buys)
+        self.aux = None
+        if os.environ.get("ECH_MG_AUX", "1") != "0" and self.h.p == 1:
+            s = engine.solver
+            fields = [getattr(s, nm) for nm in ("i_Ul", "i_Us") if getattr(s, nm, None) is not None]
+            if fields:
+                from .auxspace import AuxSpaceCG
+                self.aux = AuxSpaceCG(self, fields)
         self.use_graph = os.environ.get("ECH_MG_GRAPH", "1") != "0"
         self._graph = self._gr = self._gz = None
 
@@ -365,6 +390,8 @@ class Multigrid:
         self._graph = None                     # level matrices are rebuilt: the captured cycle points at old buffers
         fine = self.lv[0]
         fine.rowptr, fine.colidx, fine.vals = e.rowptr, e.colidx, e.vals
+        if self.aux is not None:
+            self.aux.setup(fine.rowptr, fine.colidx, fine.vals, st)
         for l in range(self.nlevels - 1):
             D, Dc = self.lv[l], self.lv[l + 1]
             if self.own_galerkin:
@@ -431,10 +458,15 @@ class Multigrid:
         self._smooth(D, r, z)                                                  # pre-smoothing
         self._spmv(D, z, D.t)
         capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(r), -1.0, ptr(D.t), st))      # t = r - A z
+        aux = self.aux if l == 0 else None
+        if aux is not None:
+            aux.restrict_and_solve(D.t, st)                                     # conforming correction, same residual
         self._transfer(D.R, Dc.N, D.t, D.N, Dc.r, Dc.N)                         # restrict
         self.vcycle(l + 1, Dc.r, Dc.z)
         self._transfer(D.P, D.N, Dc.z, Dc.N, D.t, D.N)                          # prolongate
         capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(D.t), 1.0, ptr(z), st))       # z += P z_c
+        if aux is not None:
+            aux.prolong_add(z, D.s, st)                                         # z_phi += Q z_aux
         self._spmv(D, z, D.t)
         capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(r), -1.0, ptr(D.t), st))      # t = r - A z
         self._smooth(D, D.t, D.s)                                               # post-smoothing

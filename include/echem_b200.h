@@ -191,6 +191,16 @@ int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const double *x, dou
 int ech_halo_pack(int64_t n, const int64_t *idx, const double *u, double *buf, void *stream);
 int ech_halo_unpack(int64_t n, const int64_t *idx, const double *buf, double *u, void *stream);
 
+/* A_aux = Q^T A Q for the continuous-Q1 subspace of a DG-Q1 space (the conforming auxiliary space of the potential
+ * fields in the multigrid preconditioner; the reference reaches conforming coarse spaces through its `gmg` / `amg`
+ * option sets, solver.py:1190-1213).  Q on one cell is the dense nv x nv matrix W (row-major [dg node][vertex]) for
+ * every cell.  Per cell block k of A: row0[k] = first of its nv rows, off[k] = offset of the block from each row
+ * start, dst[k*nv*nv + i*nv + j] = position in A_aux of (vertex i of the row cell, vertex j of the column cell).
+ * out[0..nout) is zeroed first. */
+int ech_aux_galerkin(int32_t nv, int64_t nblk, const int64_t *row0, const int32_t *off, const int32_t *dst,
+                     const int64_t *rowptr, const double *vals, const double *W, int64_t nout, double *out,
+                     void *stream);
+
 /* Galerkin coarse operator A_c = P^T A P of the DG tensor hierarchy (multigrid set-up; stands in for the coarse-level
  * assembly of the reference's `gmg` option set on a MeshHierarchy, solver.py:1190-1201).  A and A_c share the DG
  * block-stencil layout; P is one dense nloc x nloc block per fine cell.  ip[8] = {nfields, nloc (2, 4 or 8), facets

@@ -1,0 +1,57 @@
+"""Host-side pieces of the continuous-Q1 auxiliary space (echemfem_b200/auxspace.py): the (cell, corner) -> vertex
+table and the embedding block against the node coordinates of the DG space, and the coordinate-based linear
+interpolation between vertex sets."""
+import numpy as np
+import pytest
+
+from echemfem_b200.auxspace import dg_to_cg_nodes, embedding_block, interpolation_1d
+from echemfem_b200.function import FunctionSpace
+from echemfem_b200.mesh import TensorMesh, ExtrudedMesh
+from echemfem_b200.multigrid import Hierarchy
+
+
+@pytest.mark.parametrize("tile", [None, 4, (8, 2)])
+def test_dg_dofs_map_to_their_vertices(tile):
+    ax = [np.linspace(0.0, 2.0, 17) ** 1.3, np.linspace(-1.0, 1.0, 13)]
+    mesh = TensorMesh(ax, tile=tile)
+    V = FunctionSpace(mesh, "DG", 1)
+    h = Hierarchy(mesh, 1, tile=tile if tile is not None else 4)
+    nrows = V.dim() + 8                                    # ghost rows behind the owned ones stay unmapped
+    vtab = dg_to_cg_nodes(mesh.shape, h.levels[0].inv, nrows)
+    assert np.all(vtab[V.dim():] == -1) and np.all(vtab[:V.dim()] >= 0)
+    g = np.meshgrid(*ax, indexing="ij")
+    verts = np.stack([a.reshape(-1) for a in g], axis=1)
+    # the embedding of the coordinate functions (continuous, linear per direction) gives the DG node coordinates
+    W = embedding_block(2)
+    np.testing.assert_allclose(W.sum(axis=1), 1.0, rtol=0, atol=1e-15)
+    corners = verts[vtab[:V.dim()].reshape(-1, 4)]               # (cells, corner, 2)
+    np.testing.assert_allclose(np.einsum("av,cvk->cak", W, corners).reshape(-1, 2), V.node_coords(), rtol=0, atol=1e-14)
+    # every vertex is a corner of as many cells as surround it
+    hits = np.bincount(vtab[:V.dim()], minlength=len(verts)).reshape(len(ax[0]), len(ax[1]))
+    assert hits[0, 0] == 1 and hits[0, 1] == 2 and hits[1, 1] == 4
+
+
+def test_dg_dofs_map_to_their_vertices_3d():
+    base = TensorMesh([np.linspace(0, 1, 5), np.linspace(0, 2, 7)])
+    mesh = ExtrudedMesh(base, 4, 0.25)
+    if not hasattr(mesh, "axes"):
+        pytest.skip("extruded mesh does not expose tensor axes")
+    V = FunctionSpace(mesh, "DG", 1)
+    h = Hierarchy(mesh, 1, tile=2)
+    vtab = dg_to_cg_nodes(mesh.shape, h.levels[0].inv, V.dim())
+    g = np.meshgrid(*mesh.axes, indexing="ij")
+    verts = np.stack([a.reshape(-1) for a in g], axis=1)
+    corners = verts[vtab.reshape(-1, 8)]
+    np.testing.assert_allclose(np.einsum("av,cvk->cak", embedding_block(3), corners).reshape(-1, 3), V.node_coords(),
+                               rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("n", [8, 9, 11])
+def test_interpolation_reproduces_linear_functions(n):
+    ax_f = np.linspace(0.0, 1.0, n + 1) ** 1.5
+    ax_c = ax_f[::2] if n % 2 == 0 else np.append(ax_f[::2], ax_f[-1])
+    P = interpolation_1d(ax_f, ax_c)
+    assert P.shape == (n + 1, len(ax_c))
+    np.testing.assert_allclose(P @ (3.0 * ax_c - 1.0), 3.0 * ax_f - 1.0, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(np.asarray(P.sum(axis=1)).ravel(), 1.0, rtol=0, atol=1e-14)
+    assert P.nnz <= 2 * (n + 1) and P.data.min() > 0.0

@@ -93,3 +93,45 @@ def test_multigrid_on_extruded_hexes():
     assert ok1 and ok2 and its2 < its1
     b = F.cpu().numpy()
     assert np.linalg.norm(A @ dx2.cpu().numpy() - b) <= 1e-8 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("tile", [None, 8])
+def test_auxiliary_space_operator_and_iteration_count(tile, monkeypatch):
+    """The conforming auxiliary space of the potential (auxspace.py): A_aux = Q^T A_phiphi Q and its coarse levels
+    against scipy, and the V-cycle with it needs fewer GMRES iterations than the nested DG hierarchy alone."""
+    from echemfem_b200.multigrid import Multigrid
+    eng, A, F = _system(32, tile)
+    M = Multigrid(eng, tile=4, cells_per_block=16, coarsest_cells=16)
+    aux = M.aux
+    assert aux is not None and aux.fields == [1]
+    M.setup()
+    N = eng.N
+    Q = sp.csr_matrix(tuple(t.cpu().numpy() for t in aux.Q)[::-1], shape=(N, aux.ncg))
+    App = A[N:2 * N][:, N:2 * N]
+    want = (Q.T @ App @ Q).tocsr()
+    L0 = aux.lv[0]
+    got = sp.csr_matrix((L0.vals.cpu().numpy(), L0.colidx.cpu().numpy(), L0.rowptr.cpu().numpy()), shape=want.shape)
+    assert abs(got - want).max() <= 1e-12 * abs(want).max()
+    # a continuous function has no jumps: the embedding of a linear vertex function is linear at the DG nodes
+    x = eng.solver.V.node_coords()
+    g = np.meshgrid(np.linspace(0, 1, 33), np.linspace(0, 1, 33), indexing="ij")
+    np.testing.assert_allclose(Q @ (2 * g[0].ravel() - 3 * g[1].ravel()), 2 * x[:, 0] - 3 * x[:, 1], atol=1e-13)
+    # next conforming level: P^T A P with the host interpolation
+    P = sp.csr_matrix(tuple(t.cpu().numpy() for t in L0.P)[::-1], shape=(L0.nnode, aux.lv[1].nnode))
+    L1 = aux.lv[1]
+    got1 = sp.csr_matrix((L1.vals.cpu().numpy(), L1.colidx.cpu().numpy(), L1.rowptr.cpu().numpy()), shape=(L1.n, L1.n))
+    want1 = (P.T @ want @ P).tocsr()
+    assert abs(got1 - want1).max() <= 1e-11 * abs(want1).max()
+    # iteration counts: with / without the auxiliary correction, same solution
+    b = F.cpu().numpy()
+    dx2, its2, ok2 = eng.linear_solve(F, 1e-11, 1e-50, 200, 2000, mg=True)
+    dx2 = dx2.clone()
+    monkeypatch.setenv("ECH_MG_AUX", "0")
+    del eng._mg
+    dx1, its1, ok1 = eng.linear_solve(F, 1e-11, 1e-50, 200, 2000, mg=True)
+    assert eng._mg.aux is None
+    assert ok1 and ok2
+    for dx in (dx1, dx2):
+        assert np.linalg.norm(A @ dx.cpu().numpy() - b) <= 1e-9 * np.linalg.norm(b)
+    assert its2 < its1, (its1, its2)
+    print("GMRES iterations N=32: nested DG hierarchy %d, with the conforming auxiliary space %d" % (its1, its2))
