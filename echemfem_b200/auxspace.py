@@ -183,10 +183,15 @@ class AuxSpaceCG:
         self.dst = inv.to(torch.int32).contiguous()
         self._pattern = (int(rowptr.data_ptr()), int(colidx.numel()))
 
-    def setup(self, rowptr, colidx, vals, stream):
-        """Level operators for the current fine matrix (called from Multigrid.setup, once per Jacobian)."""
+    def prepare(self, rowptr, colidx):
+        """Pattern-only part of the set-up (block lists and the pattern of A_aux): done once per sparsity pattern,
+        with the hierarchy, like the tables of the DG Galerkin kernel."""
         if self._pattern != (int(rowptr.data_ptr()), int(colidx.numel())):
             self._symbolic(rowptr, colidx)
+
+    def setup(self, rowptr, colidx, vals, stream):
+        """Level operators for the current fine matrix (called from Multigrid.setup, once per Jacobian)."""
+        self.prepare(rowptr, colidx)
         A = self.lv[0]
         capi.check(self.lib.ech_aux_galerkin(self.nv, self.row0.numel(), ptr(self.row0), ptr(self.off), ptr(self.dst),
                                              ptr(rowptr), ptr(vals), ptr(self.Wd), A.vals.numel(), ptr(A.vals), stream))

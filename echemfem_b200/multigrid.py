@@ -318,6 +318,8 @@ class Multigrid:
             if fields:
                 from .auxspace import AuxSpaceCG
                 self.aux = AuxSpaceCG(self, fields)
+                if getattr(engine, "rowptr", None) is not None:
+                    self.aux.prepare(engine.rowptr, engine.colidx)
         self.use_graph = os.environ.get("ECH_MG_GRAPH", "1") != "0"
         self._graph = self._gr = self._gz = None
 

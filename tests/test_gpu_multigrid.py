@@ -100,7 +100,7 @@ def test_auxiliary_space_operator_and_iteration_count(tile, monkeypatch):
     """The conforming auxiliary space of the potential (auxspace.py): A_aux = Q^T A_phiphi Q and its coarse levels
     against scipy, and the V-cycle with it needs fewer GMRES iterations than the nested DG hierarchy alone."""
     from echemfem_b200.multigrid import Multigrid
-    eng, A, F = _system(32, tile)
+    eng, A, F = _system(64, tile)
     M = Multigrid(eng, tile=4, cells_per_block=16, coarsest_cells=16)
     aux = M.aux
     assert aux is not None and aux.fields == [1]
@@ -114,7 +114,7 @@ def test_auxiliary_space_operator_and_iteration_count(tile, monkeypatch):
     assert abs(got - want).max() <= 1e-12 * abs(want).max()
     # a continuous function has no jumps: the embedding of a linear vertex function is linear at the DG nodes
     x = eng.solver.V.node_coords()
-    g = np.meshgrid(np.linspace(0, 1, 33), np.linspace(0, 1, 33), indexing="ij")
+    g = np.meshgrid(np.linspace(0, 1, 65), np.linspace(0, 1, 65), indexing="ij")
     np.testing.assert_allclose(Q @ (2 * g[0].ravel() - 3 * g[1].ravel()), 2 * x[:, 0] - 3 * x[:, 1], atol=1e-13)
     # next conforming level: P^T A P with the host interpolation
     P = sp.csr_matrix(tuple(t.cpu().numpy() for t in L0.P)[::-1], shape=(L0.nnode, aux.lv[1].nnode))
@@ -134,4 +134,4 @@ def test_auxiliary_space_operator_and_iteration_count(tile, monkeypatch):
     for dx in (dx1, dx2):
         assert np.linalg.norm(A @ dx.cpu().numpy() - b) <= 1e-9 * np.linalg.norm(b)
     assert its2 < its1, (its1, its2)
-    print("GMRES iterations N=32: nested DG hierarchy %d, with the conforming auxiliary space %d" % (its1, its2))
+    print("GMRES iterations N=64: nested DG hierarchy %d, with the conforming auxiliary space %d" % (its1, its2))

@@ -36,6 +36,19 @@ for l, D in enumerate(M.lv[:-1]):
         l, D.ndof, D.nblocks, timed(lambda: M._smooth(D, D.r if l else r, D.z)), timed(lambda: M._spmv(D, D.z, D.t)),
         timed(lambda: M._transfer(D.R, M.lv[l + 1].N, D.t, D.N, M.lv[l + 1].r, M.lv[l + 1].N)),
         timed(lambda: M._transfer(D.P, D.N, M.lv[l + 1].z, M.lv[l + 1].N, D.t, D.N))))
+if M.aux is not None:
+    A = M.aux
+    st = eng._stream()
+    print("aux: restrict + V-cycle %.3f ms   prolong-add %.3f ms   (%d conforming levels, %d vertices, %d nnz)" % (
+        timed(lambda: A.restrict_and_solve(M.lv[0].t, st)), timed(lambda: A.prolong_add(z, M.lv[0].s, st)),
+        len(A.lv), A.ncg, A.lv[0].vals.numel()))
+    t0 = time.time(); A.setup(eng.rowptr, eng.colidx, eng.vals, st); torch.cuda.synchronize()
+    print("aux set-up (numeric) %.3f s" % (time.time() - t0))
+    print("aux: Q^T A Q kernel %.3f ms" % timed(lambda: capi.check(eng.lib.ech_aux_galerkin(
+        A.nv, A.row0.numel(), ptr(A.row0), ptr(A.off), ptr(A.dst), ptr(eng.rowptr), ptr(eng.vals), ptr(A.Wd),
+        A.lv[0].vals.numel(), ptr(A.lv[0].vals), st))))
+    for l, D in enumerate(A.lv[:-1]):
+        print("  aux level %d: n %8d nnz %9d" % (l, D.n, D.vals.numel()))
 L = eng._linear_plan(200)
 V = L["basis"]; n = eng.ndof; work = L["work"]; hdev = work[3 * n:3 * n + 202]; partial = work[3 * n + 4096:]
 for k in (10, 50, 100):
