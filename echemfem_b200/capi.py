@@ -67,7 +67,11 @@ EXPORTS = {
                                                 c_p]),
     "ech_halo_pack": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),
     "ech_halo_unpack": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),
+    "ech_dg_prolong_add": (C.c_int, [c_i32, c_i32, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    "ech_dg_restrict": (C.c_int, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "ech_aux_galerkin": (C.c_int, [c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
+    "ech_aux_galerkin_global": (C.c_int, [c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i32, c_p, c_p, c_p,
+                                          c_i64, c_p, c_p]),
     "ech_galerkin_dg": (C.c_int, [C.POINTER(c_i64), C.POINTER(c_p), c_p]),
     "ech_coarse_galerkin": (C.c_int, [c_i64, c_p, c_p, c_p, c_p, c_i32, c_p, c_p]),
     "ech_coarse_restrict": (C.c_int, [c_i64, c_p, c_i32, c_p, c_p, c_p]),

@@ -2169,6 +2169,87 @@ extern "C" int ech_halo_unpack(int64_t n, const int64_t *idx, const double *buf,
     return ECH_OK;
 }
 
+// =============================================================== transfers of the nested DG hierarchy
+// Prolongation and restriction between a DG level and its parent level straight from the tables of the Galerkin
+// kernel (parent cell per fine cell, children per coarse cell, one dense n x n block per fine cell) instead of a
+// general CSR product with four entries per row: z_f += P z_c and r_c = P^T r_f, all fields in one launch.
+template <int NL>
+__global__ void dg_prolong_add_kernel(int64_t ncell, int32_t nf, int64_t fs_f, int64_t fs_c,
+                                      const int32_t *__restrict__ parent, const double *__restrict__ pblk,
+                                      const double *__restrict__ zc, double *__restrict__ z) {
+    const int64_t nrow = ncell * NL;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t K = parent[r / NL];
+        double w[NL];
+#pragma unroll
+        for (int A = 0; A < NL; ++A) w[A] = pblk[r * NL + A];
+        for (int f = 0; f < nf; ++f) {
+            const double *src = zc + f * fs_c + K * NL;
+            double s = 0.0;
+#pragma unroll
+            for (int A = 0; A < NL; ++A) s = fma(w[A], src[A], s);
+            z[f * fs_f + r] += s;
+        }
+    }
+}
+
+template <int NL>
+__global__ void dg_restrict_kernel(int64_t ncc, int32_t nf, int32_t nchild, int64_t fs_f, int64_t fs_c,
+                                   const int32_t *__restrict__ children, const double *__restrict__ pblk,
+                                   const double *__restrict__ r, double *__restrict__ rc) {
+    const int64_t nrow = ncc * NL;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nrow; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t K = q / NL;
+        const int A = (int)(q % NL);
+        for (int f = 0; f < nf; ++f) {
+            double s = 0.0;
+            for (int k = 0; k < nchild; ++k) {
+                const int64_t c = children[K * nchild + k];
+                if (c < 0) continue;
+                const double *src = r + f * fs_f + c * NL;
+                const double *w = pblk + c * NL * NL + A;
+#pragma unroll
+                for (int a = 0; a < NL; ++a) s = fma(w[a * NL], src[a], s);
+            }
+            rc[f * fs_c + q] = s;
+        }
+    }
+}
+
+extern "C" int ech_dg_prolong_add(int32_t nloc, int32_t nf, int64_t ncell_f, int64_t fs_f, int64_t fs_c,
+                                  const int32_t *parent, const double *pblk, const double *zc, double *z, void *stream) {
+    if (ncell_f == 0) return ECH_OK;
+    if (!parent || !pblk || !zc || !z) return fail(nullptr, ECH_ERR_ARG, "ech_dg_prolong_add: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = grid_for(ncell_f * nloc, 256);
+    switch (nloc) {
+    case 2: dg_prolong_add_kernel<2><<<grid, 256, 0, s>>>(ncell_f, nf, fs_f, fs_c, parent, pblk, zc, z); break;
+    case 4: dg_prolong_add_kernel<4><<<grid, 256, 0, s>>>(ncell_f, nf, fs_f, fs_c, parent, pblk, zc, z); break;
+    case 8: dg_prolong_add_kernel<8><<<grid, 256, 0, s>>>(ncell_f, nf, fs_f, fs_c, parent, pblk, zc, z); break;
+    default: return fail(nullptr, ECH_ERR_ARG, "ech_dg_prolong_add: 2, 4 or 8 dofs per cell");
+    }
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+extern "C" int ech_dg_restrict(int32_t nloc, int32_t nf, int32_t nchild, int64_t ncell_c, int64_t fs_f, int64_t fs_c,
+                               const int32_t *children, const double *pblk, const double *r, double *rc, void *stream) {
+    if (ncell_c == 0) return ECH_OK;
+    if (!children || !pblk || !r || !rc) return fail(nullptr, ECH_ERR_ARG, "ech_dg_restrict: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = grid_for(ncell_c * nloc, 256);
+    switch (nloc) {
+    case 2: dg_restrict_kernel<2><<<grid, 256, 0, s>>>(ncell_c, nf, nchild, fs_f, fs_c, children, pblk, r, rc); break;
+    case 4: dg_restrict_kernel<4><<<grid, 256, 0, s>>>(ncell_c, nf, nchild, fs_f, fs_c, children, pblk, r, rc); break;
+    case 8: dg_restrict_kernel<8><<<grid, 256, 0, s>>>(ncell_c, nf, nchild, fs_f, fs_c, children, pblk, r, rc); break;
+    default: return fail(nullptr, ECH_ERR_ARG, "ech_dg_restrict: 2, 4 or 8 dofs per cell");
+    }
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== Galerkin operator of the conforming auxiliary space
 // A_aux = Q^T A Q for the continuous-Q1 subspace of a DG-Q1 space (echemfem_b200/auxspace.py).  Q restricted to one
 // cell is the same dense NV x NV matrix W for every cell (continuous hat functions at the DG nodes of the reference
@@ -2232,6 +2313,101 @@ extern "C" int ech_aux_galerkin(int32_t nv, int64_t nblk, const int64_t *row0, c
     case 8: aux_galerkin_kernel<8><<<grid, 128, 0, s>>>(nblk, row0, off, dst, rowptr, vals, W, out); break;
     default: return fail(nullptr, ECH_ERR_ARG, "ech_aux_galerkin: 2, 4 or 8 vertices per cell");
     }
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+// Same product for a conforming space on a COARSER global vertex grid shared by all ranks (auxspace.py,
+// GlobalConformingCoarse): the embedding block depends on where the fine cell sits in its coarse cell (Wc, one
+// NV x NV block per local cell, ghost cells included), and the result is accumulated into an ELL layout addressed by
+// vertex offsets, so no pattern table is needed: row (ia, I), entry (ja, s) with s the offset J - I in {-2..2}^D.
+// cI: coarse cell multi-index per local cell; vd: coarse vertices per direction; fidx: field -> position in the
+// auxiliary field list (-1: not an auxiliary field).
+template <int NV, int D>
+__global__ void __launch_bounds__(128)
+aux_galerkin_global_kernel(int64_t nblk, const int64_t *__restrict__ row0, const int32_t *__restrict__ off,
+                           const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                           const double *__restrict__ vals, int64_t N, const int32_t *__restrict__ fidx, int32_t na,
+                           const double *__restrict__ Wc, const int32_t *__restrict__ cI,
+                           const int32_t *__restrict__ vd, double *__restrict__ out) {
+    constexpr int S1 = 5;
+    int S = 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) S *= S1;
+    int64_t nvert = 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) nvert *= vd[k];
+    for (int64_t kb = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; kb < nblk; kb += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r0 = row0[kb];
+        const int32_t o = off[kb];
+        const int64_t col0 = colidx[rowptr[r0] + o];
+        const int64_t c = (r0 % N) / NV, cc = (col0 % N) / NV;
+        const int32_t ia = fidx[r0 / N], ja = fidx[col0 / N];
+        const double *Wr = Wc + c * (NV * NV), *Wk = Wc + cc * (NV * NV);
+        double T[NV][NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) T[i][j] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+            const double *p = vals + rowptr[r0 + a] + o;
+            double t[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) t[j] = 0.0;
+#pragma unroll
+            for (int b = 0; b < NV; ++b) {
+                const double v = p[b];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) t[j] = fma(v, Wk[b * NV + j], t[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double w = Wr[a * NV + i];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) T[i][j] = fma(w, t[j], T[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            int64_t I = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) I = I * vd[k] + cI[c * D + k] + ((i >> (D - 1 - k)) & 1);
+            double *row = out + ((int64_t)ia * nvert + I) * ((int64_t)na * S) + (int64_t)ja * S;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                int sidx = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const int dk = (cI[cc * D + k] + ((j >> (D - 1 - k)) & 1)) - (cI[c * D + k] + ((i >> (D - 1 - k)) & 1));
+                    sidx = sidx * S1 + dk + 2;
+                }
+                atomicAdd(row + sidx, T[i][j]);
+            }
+        }
+    }
+}
+
+extern "C" int ech_aux_galerkin_global(int32_t nv, int32_t d, int64_t nblk, const int64_t *row0, const int32_t *off,
+                                       const int64_t *rowptr, const int32_t *colidx, const double *vals, int64_t N,
+                                       const int32_t *fidx, int32_t na, const double *Wc, const int32_t *cI,
+                                       const int32_t *vd, int64_t nout, double *out, void *stream) {
+    if (!out || nout < 0) return fail(nullptr, ECH_ERR_ARG, "ech_aux_galerkin_global: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(nullptr, cudaMemsetAsync(out, 0, sizeof(double) * (size_t)nout, s));
+    if (nblk == 0) return ECH_OK;
+    if (!row0 || !off || !rowptr || !colidx || !vals || !fidx || !Wc || !cI || !vd)
+        return fail(nullptr, ECH_ERR_ARG, "ech_aux_galerkin_global: null argument");
+    const unsigned grid = grid_for(nblk, 128);
+    if (nv == 2 && d == 1)
+        aux_galerkin_global_kernel<2, 1><<<grid, 128, 0, s>>>(nblk, row0, off, rowptr, colidx, vals, N, fidx, na, Wc, cI, vd, out);
+    else if (nv == 4 && d == 2)
+        aux_galerkin_global_kernel<4, 2><<<grid, 128, 0, s>>>(nblk, row0, off, rowptr, colidx, vals, N, fidx, na, Wc, cI, vd, out);
+    else if (nv == 8 && d == 3)
+        aux_galerkin_global_kernel<8, 3><<<grid, 128, 0, s>>>(nblk, row0, off, rowptr, colidx, vals, N, fidx, na, Wc, cI, vd, out);
+    else
+        return fail(nullptr, ECH_ERR_ARG, "ech_aux_galerkin_global: nv must be 2^d, d = 1, 2 or 3");
     ++g_launches;
     CK(nullptr, cudaGetLastError());
     return ECH_OK;

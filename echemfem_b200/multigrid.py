@@ -449,6 +449,25 @@ class Multigrid:
                                          capi.C.c_void_p(x.data_ptr() + f * xstride * es),
                                          capi.C.c_void_p(y.data_ptr() + f * ystride * es), self.e._stream()))
 
+    def _restrict(self, D, Dc, rf, rc):
+        """rc = P^T rf (all fields)."""
+        if hasattr(D, "gal"):
+            g = D.gal
+            capi.check(self.lib.ech_dg_restrict(self.h.n, self.nf, g["nchild"], Dc.ncell_owned, D.N, Dc.N,
+                                                ptr(g["children"]), ptr(g["pblk"]), ptr(rf), ptr(rc), self.e._stream()))
+        else:
+            self._transfer(D.R, Dc.N, rf, D.N, rc, Dc.N)
+
+    def _prolong_add(self, D, Dc, zc, z):
+        """z += P zc (all fields; rows behind the owned cells untouched)."""
+        if hasattr(D, "gal"):
+            g = D.gal
+            capi.check(self.lib.ech_dg_prolong_add(self.h.n, self.nf, D.ncell_owned, D.N, Dc.N, ptr(g["parent"]),
+                                                   ptr(g["pblk"]), ptr(zc), ptr(z), self.e._stream()))
+        else:
+            self._transfer(D.P, D.N, zc, Dc.N, D.t, D.N)
+            capi.check(self.lib.ech_axpby(D.ndof, 1.0, ptr(D.t), 1.0, ptr(z), self.e._stream()))
+
     def vcycle(self, l, r, z):
         """z = V-cycle(r) on level l; r is not modified."""
         lib, st = self.lib, self.e._stream()
@@ -463,10 +482,9 @@ class Multigrid:
         aux = self.aux if l == 0 else None
         if aux is not None:
             aux.restrict_and_solve(D.t, st)                                     # conforming correction, same residual
-        self._transfer(D.R, Dc.N, D.t, D.N, Dc.r, Dc.N)                         # restrict
+        self._restrict(D, Dc, D.t, Dc.r)
         self.vcycle(l + 1, Dc.r, Dc.z)
-        self._transfer(D.P, D.N, Dc.z, Dc.N, D.t, D.N)                          # prolongate
-        capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(D.t), 1.0, ptr(z), st))       # z += P z_c
+        self._prolong_add(D, Dc, Dc.z, z)                                       # z += P z_c
         if aux is not None:
             aux.prolong_add(z, D.s, st)                                         # z_phi += Q z_aux
         self._spmv(D, z, D.t)

@@ -404,6 +404,20 @@ class NewtonEngine:
         capi.check(lib.ech_coarse_prolong_add(n, ptr(Cz["agg_owned"]), ptr(Cz["yc"]), ptr(z), st))
         z.mul_(self._owned_mask())
 
+    def _global_conforming(self, M):
+        """The conforming coarse space shared by all ranks (built once), or None if the mesh has no global axes
+        or the problem no potential field."""
+        if not hasattr(self, "_gconf"):
+            self._gconf = None
+            axes = getattr(self.solver.mesh, "global_axes", None)
+            if axes is not None and getattr(M, "aux", None) is not None:
+                from .auxspace import GlobalConformingCoarse
+                try:
+                    self._gconf = GlobalConformingCoarse(self, M.aux.fields, axes)
+                except NotImplementedError:
+                    self._gconf = None
+        return self._gconf
+
     def multigrid(self, **kw):
         """The geometric multigrid hierarchy of this mesh (built once), or None if the mesh has none."""
         if not hasattr(self, "_mg"):
@@ -438,14 +452,25 @@ class NewtonEngine:
             self.timers["PCSetUp"] += time.time() - t0
             pre = M.apply
             if self.halo is not None and coarse:
+                # coarse space shared by all ranks, applied after the rank-local V-cycles: continuous Q1 on the
+                # global vertex grid for the potential fields (auxspace.GlobalConformingCoarse) where the mesh
+                # knows its global axes, else (or with ECH_GCOARSE=box / both) the box aggregation of section 3.4
+                mode = os.environ.get("ECH_GCOARSE", "cg")
+                G = self._global_conforming(M) if mode in ("cg", "both") else None
                 t0 = time.time()
-                Cz = self._global_coarse_setup(int(coarse))
+                Cz = self._global_coarse_setup(int(coarse)) if (G is None or mode == "both") else None
+                if G is not None:
+                    G.setup(self._stream())
                 torch.cuda.synchronize()
                 self.timers["PCSetUp"] += time.time() - t0
 
                 def pre(src, dst):
                     M.apply(src, dst)
-                    self._global_coarse_correct(Cz, src, dst)
+                    if Cz is not None:
+                        self._global_coarse_correct(Cz, src, dst)
+                    if G is not None:
+                        G.correct(src, dst)
+                        dst.mul_(self._owned_mask())
             t0 = time.time()
             out = self._gmres(rhs, rtol, atol, max_it, monitor, precond=pre, restart=restart, refine=refine)
             torch.cuda.synchronize()

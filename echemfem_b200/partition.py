@@ -209,6 +209,7 @@ def strip_partition(axes, rank, size, name="strip", tile=None):
     # the owned cells are a tensor mesh of their own, numbered lexicographically: a rank-local multigrid hierarchy
     # (the V-cycle as the block of PETSc's bjacobi) can be built on it
     local.owned_axes = [axes[0][i0:i1 + 1]] + axes[1:]
+    local.global_axes = axes                 # the coarse space shared by all ranks lives on the global vertex grid
     local.cell_perm = operm
     if operm is not None:
         local.block_hint = int(tile) ** len(axes)

@@ -191,6 +191,15 @@ int ech_dense_gemv(int32_t nr, int32_t nc, const double *M, const double *x, dou
 int ech_halo_pack(int64_t n, const int64_t *idx, const double *u, double *buf, void *stream);
 int ech_halo_unpack(int64_t n, const int64_t *idx, const double *buf, double *u, void *stream);
 
+/* Transfers of the nested DG hierarchy from the tables of ech_galerkin_dg (PCMG's interpolation / restriction on the
+ * reference's MeshHierarchy, solver.py:1190-1201): z_f[f][c*nloc + a] += sum_A pblk[c][a][A] zc[f][parent[c]*nloc + A],
+ * and rc[f][K*nloc + A] = sum over the children c of K (children[K*nchild + k], -1: none) and a of
+ * pblk[c][a][A] r[f][c*nloc + a]; fs_f / fs_c: entries per field of the fine / coarse vectors. */
+int ech_dg_prolong_add(int32_t nloc, int32_t nf, int64_t ncell_f, int64_t fs_f, int64_t fs_c, const int32_t *parent,
+                       const double *pblk, const double *zc, double *z, void *stream);
+int ech_dg_restrict(int32_t nloc, int32_t nf, int32_t nchild, int64_t ncell_c, int64_t fs_f, int64_t fs_c,
+                    const int32_t *children, const double *pblk, const double *r, double *rc, void *stream);
+
 /* A_aux = Q^T A Q for the continuous-Q1 subspace of a DG-Q1 space (the conforming auxiliary space of the potential
  * fields in the multigrid preconditioner; the reference reaches conforming coarse spaces through its `gmg` / `amg`
  * option sets, solver.py:1190-1213).  Q on one cell is the dense nv x nv matrix W (row-major [dg node][vertex]) for
@@ -200,6 +209,17 @@ int ech_halo_unpack(int64_t n, const int64_t *idx, const double *buf, double *u,
 int ech_aux_galerkin(int32_t nv, int64_t nblk, const int64_t *row0, const int32_t *off, const int32_t *dst,
                      const int64_t *rowptr, const double *vals, const double *W, int64_t nout, double *out,
                      void *stream);
+
+/* E^T A E for the conforming space on a coarser GLOBAL vertex grid shared by all ranks (the coarse space of the
+ * multi-GPU preconditioner; complete owned rows, ghost columns included).  Wc: one nv x nv embedding block per local
+ * cell ([dg node][coarse corner]); cI: coarse cell multi-index per local cell (int32[d]); vd: coarse vertices per
+ * direction; fidx[nfields]: position of a field among the `na` auxiliary fields or -1; N: rows per field.  Output in
+ * ELL layout, zeroed first: out[((ia * nvert + I) * na + ja) * 5^d + s], s = lexicographic offset J - I + 2 per
+ * direction. */
+int ech_aux_galerkin_global(int32_t nv, int32_t d, int64_t nblk, const int64_t *row0, const int32_t *off,
+                            const int64_t *rowptr, const int32_t *colidx, const double *vals, int64_t N,
+                            const int32_t *fidx, int32_t na, const double *Wc, const int32_t *cI, const int32_t *vd,
+                            int64_t nout, double *out, void *stream);
 
 /* Galerkin coarse operator A_c = P^T A P of the DG tensor hierarchy (multigrid set-up; stands in for the coarse-level
  * assembly of the reference's `gmg` option set on a MeshHierarchy, solver.py:1190-1201).  A and A_c share the DG

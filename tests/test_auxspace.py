@@ -55,3 +55,31 @@ def test_interpolation_reproduces_linear_functions(n):
     np.testing.assert_allclose(P @ (3.0 * ax_c - 1.0), 3.0 * ax_f - 1.0, rtol=0, atol=1e-14)
     np.testing.assert_allclose(np.asarray(P.sum(axis=1)).ravel(), 1.0, rtol=0, atol=1e-14)
     assert P.nnz <= 2 * (n + 1) and P.data.min() > 0.0
+
+
+def test_coarse_embedding_on_two_strips_agrees_on_shared_vertices():
+    """The coarse space shared by all ranks is addressed by coordinates: two strips of one mesh (ghost layers
+    included) embed the same global vertex function, each reproducing it at its own DG nodes."""
+    from echemfem_b200.auxspace import coarse_embedding
+    from echemfem_b200.partition import strip_partition
+    axes = [np.linspace(0.0, 2.0, 33) ** 1.2, np.linspace(0.0, 1.0, 17)]
+    cax = [a[::4] for a in axes]
+    g = np.meshgrid(*cax, indexing="ij")
+    f = (1.5 * g[0] - 0.5 * g[1] + g[0] * g[1]).ravel()            # bilinear per coarse cell: in the coarse space
+    seen = np.zeros(f.size, dtype=int)
+    for rank in range(2):
+        mesh, _ = strip_partition(axes, rank, 2, tile=8)
+        assert mesh.global_axes is axes or all(np.array_equal(a, b) for a, b in zip(mesh.global_axes, axes))
+        V = FunctionSpace(mesh, "DG", 1)
+        x = V.node_coords()
+        cI, W, vert = coarse_embedding(x, 4, cax)
+        assert cI.shape == (mesh.num_cells, 2) and W.shape == (len(x), 4)
+        np.testing.assert_allclose(W.sum(axis=1), 1.0, atol=1e-14)
+        # the coarse function is bilinear on each coarse cell only in the reference coordinates of the coarse cell;
+        # with a graded axis check the two affine parts and the product through the coarse cell's own coordinates
+        np.testing.assert_allclose((W * g[0].ravel()[vert]).sum(axis=1), x[:, 0], atol=1e-13)
+        np.testing.assert_allclose((W * g[1].ravel()[vert]).sum(axis=1), x[:, 1], atol=1e-13)
+        np.testing.assert_allclose((W * (g[0] * g[1]).ravel()[vert]).sum(axis=1), x[:, 0] * x[:, 1], atol=1e-13)
+        seen[np.unique(vert)] += 1
+    # vertices on and next to the cut are used by both ranks (owned cells of one, ghost cells of the other)
+    assert seen.min() >= 1 and (seen == 2).sum() >= 2 * len(cax[1])

@@ -43,6 +43,17 @@ def test_galerkin_levels_and_vcycle_solution(tile, p):
     got = sp.csr_matrix((D.vals.cpu().numpy(), D.colidx.cpu().numpy(), D.rowptr.cpu().numpy()), shape=Ac.shape)
     assert got.has_sorted_indices
     assert abs(got - Ac).max() <= 1e-11 * abs(Ac).max()
+    # transfers (ech_dg_restrict / ech_dg_prolong_add) against the host prolongation
+    D0, D1 = M.lv[0], M.lv[1]
+    rng = np.random.default_rng(3)
+    rf, zc = rng.standard_normal(D0.ndof), rng.standard_normal(D1.ndof)
+    z0 = rng.standard_normal(D0.ndof)
+    rc_d = torch.zeros(D1.ndof, dtype=torch.float64, device="cuda")
+    M._restrict(D0, D1, torch.from_numpy(rf).cuda(), rc_d)
+    np.testing.assert_allclose(rc_d.cpu().numpy(), P.T @ rf, rtol=0, atol=1e-13 * np.abs(rf).max() * 16)
+    z_d = torch.from_numpy(z0).cuda()
+    M._prolong_add(D0, D1, torch.from_numpy(zc).cuda(), z_d)
+    np.testing.assert_allclose(z_d.cpu().numpy(), z0 + P @ zc, rtol=0, atol=1e-13 * 16)
     # preconditioned GMRES solves the system (true residual) and beats the one-level preconditioner
     dx1, its1, ok1 = eng.linear_solve(F, 1e-11, 1e-50, 200, 2000)
     dx1 = dx1.clone()
@@ -135,3 +146,25 @@ def test_auxiliary_space_operator_and_iteration_count(tile, monkeypatch):
         assert np.linalg.norm(A @ dx.cpu().numpy() - b) <= 1e-9 * np.linalg.norm(b)
     assert its2 < its1, (its1, its2)
     print("GMRES iterations N=64: nested DG hierarchy %d, with the conforming auxiliary space %d" % (its1, its2))
+
+
+def test_global_conforming_coarse_operator():
+    """E^T A E of the coarse space shared by all ranks (auxspace.GlobalConformingCoarse): the kernel's ELL result on the
+    CSR pattern of level 0 against scipy, on one rank (no ghosts); the multi-rank sum is covered by the 2-rank run of
+    tests/test_gpu_distributed.py."""
+    from echemfem_b200.auxspace import GlobalConformingCoarse
+    eng, A, F = _system(32, 8)
+    axes = [np.linspace(0.0, 1.0, 33), np.linspace(0.0, 1.0, 33)]
+    G = GlobalConformingCoarse(eng, [1], axes, level=2)
+    assert G.level == 2 and G.vdims == [9, 9]
+    vals = G.local_operator(eng._stream()).cpu().numpy()
+    L0 = G.h.lv[0]
+    got = sp.csr_matrix((vals, L0.colidx.cpu().numpy(), L0.rowptr.cpu().numpy()), shape=(81, 81))
+    N = eng.N
+    E = sp.csr_matrix(tuple(t.cpu().numpy() for t in G.E)[::-1], shape=(N, 81))
+    want = (E.T @ A[N:2 * N][:, N:2 * N] @ E).tocsr()
+    assert abs(got - want).max() <= 1e-12 * abs(want).max()
+    # E evaluates coarse vertex functions at the DG nodes: linear functions are reproduced
+    x = eng.solver.V.node_coords()
+    g = np.meshgrid(axes[0][::4], axes[1][::4], indexing="ij")
+    np.testing.assert_allclose(E @ (g[0].ravel() - 2 * g[1].ravel()), x[:, 0] - 2 * x[:, 1], atol=1e-13)

@@ -34,8 +34,8 @@ print("V-cycle total      %.2f ms" % timed(lambda: M.apply(r, z)))
 for l, D in enumerate(M.lv[:-1]):
     print("level %d: ndof %9d nblocks %6d  smooth %.3f ms  spmv %.3f ms  restrict %.3f ms  prolong %.3f ms" % (
         l, D.ndof, D.nblocks, timed(lambda: M._smooth(D, D.r if l else r, D.z)), timed(lambda: M._spmv(D, D.z, D.t)),
-        timed(lambda: M._transfer(D.R, M.lv[l + 1].N, D.t, D.N, M.lv[l + 1].r, M.lv[l + 1].N)),
-        timed(lambda: M._transfer(D.P, D.N, M.lv[l + 1].z, M.lv[l + 1].N, D.t, D.N))))
+        timed(lambda: M._restrict(D, M.lv[l + 1], D.t, M.lv[l + 1].r)),
+        timed(lambda: M._prolong_add(D, M.lv[l + 1], M.lv[l + 1].z, D.s))))
 if M.aux is not None:
     A = M.aux
     st = eng._stream()
