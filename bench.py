@@ -387,10 +387,15 @@ def main():
             eng.timers[k] = 0.0
         if dist is not None:
             dist.barrier()
+        nsampler = ClockSampler(local)
+        nsampler.start()
+        nsampler.mark_begin()
         t0 = time.perf_counter()
         s.solve()
         torch.cuda.synchronize()
         t_solve = time.perf_counter() - t0
+        nsampler.mark_end()
+        newton_clocks = nsampler.stop()
         tt = torch.tensor([t_solve, t_setup] + [eng.timers[k] for k in sorted(eng.timers)], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -415,7 +420,8 @@ def main():
                                      "(level-scheduled solves), Galerkin coarse operators" +
                                      ("; one hierarchy per rank (PETSc bjacobi: one block per rank)" if world > 1 else ""))
                   if mg else "block-Jacobi/ILU(0) (level-scheduled solves)",
-                  "ksp_reductions_last_solve": getattr(eng, "ksp_reductions", None)}
+                  "ksp_reductions_last_solve": getattr(eng, "ksp_reductions", None),
+                  "clocks_during_solve": newton_clocks}
 
     times = torch.tensor([t_step, tF, tJ, t_e2e, t_spmv, t_e2e_serial, t_e2e_chunked], dtype=torch.float64, device="cuda")
     if dist is not None:

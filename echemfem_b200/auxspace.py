@@ -182,9 +182,15 @@ class ConformingHierarchy:
             idt = D.Pt.crow_indices().dtype
             At = torch.sparse_csr_tensor(D.rowptr.to(idt), D.colidx.to(idt), D.vals, size=(D.n, D.n))
             Ac = torch.sparse.mm(D.Rt, torch.sparse.mm(At, D.Pt))
-            Dc.rowptr = Ac.crow_indices().to(torch.int64).contiguous()
-            Dc.colidx = Ac.col_indices().to(torch.int32).contiguous()
-            Dc.vals = Ac.values().contiguous()
+            if getattr(Dc, "vals", None) is not None and Dc.vals.numel() == Ac.values().numel():
+                # same pattern as at the last set-up: update in place, so that a captured V-cycle stays valid
+                Dc.rowptr.copy_(Ac.crow_indices())
+                Dc.colidx.copy_(Ac.col_indices())
+                Dc.vals.copy_(Ac.values())
+            else:
+                Dc.rowptr = Ac.crow_indices().to(torch.int64).contiguous()
+                Dc.colidx = Ac.col_indices().to(torch.int32).contiguous()
+                Dc.vals = Ac.values().contiguous()
             del At, Ac
         for D in self.lv[:-1]:
             # damped Jacobi as a diagonal CSR matrix: the smoother is one ech_spmv
@@ -195,13 +201,29 @@ class ConformingHierarchy:
             diag[rows[sel]] = D.vals[sel]
             if bool((diag == 0).any()):
                 raise RuntimeError("auxiliary space: zero diagonal entry in a conforming level operator")
-            D.w = (self.omega / diag).contiguous()
+            if getattr(D, "w", None) is not None and D.w.numel() == D.n:
+                torch.div(self.omega, diag, out=D.w)
+            else:
+                D.w = (self.omega / diag).contiguous()
             if not hasattr(D, "wrow") or D.wrow.numel() != D.n + 1:
                 D.wrow = torch.arange(D.n + 1, dtype=torch.int64, device=self.dev)
                 D.wcol = torch.arange(D.n, dtype=torch.int32, device=self.dev)
         C = self.lv[-1]
         dense = torch.sparse_csr_tensor(C.rowptr, C.colidx.to(torch.int64), C.vals, size=(C.n, C.n)).to_dense()
-        C.inv = torch.linalg.inv(dense).contiguous()
+        if getattr(C, "inv", None) is not None and C.inv.shape == dense.shape:
+            C.inv.copy_(torch.linalg.inv(dense))
+        else:
+            C.inv = torch.linalg.inv(dense).contiguous()
+
+    def pointers(self):
+        """Addresses of everything a captured cycle reads (a CUDA graph stays valid while these do not move)."""
+        out = []
+        for D in self.lv:
+            for name in ("rowptr", "colidx", "vals", "w", "inv"):
+                t = getattr(D, name, None)
+                if t is not None:
+                    out.append(t.data_ptr())
+        return out
 
     def _spmv(self, rp, ci, v, n, x, y, st):
         capi.check(self.lib.ech_spmv(n, ptr(rp), ptr(ci), ptr(v), ptr(x), ptr(y), st))

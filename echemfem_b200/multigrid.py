@@ -389,7 +389,6 @@ class Multigrid:
     # -- setup: Galerkin products + ILU factors, once per Newton iteration -------------------------------
     def setup(self):
         e, lib, st = self.e, self.lib, self.e._stream()
-        self._graph = None                     # level matrices are rebuilt: the captured cycle points at old buffers
         fine = self.lv[0]
         fine.rowptr, fine.colidx, fine.vals = e.rowptr, e.colidx, e.vals
         if self.aux is not None:
@@ -426,7 +425,30 @@ class Multigrid:
                 D.ilu_plan.refresh(D.lu, st)
         C = self.lv[-1]
         dense = torch.sparse_csr_tensor(C.rowptr, C.colidx.to(torch.int64), C.vals, size=(C.ndof, C.ndof)).to_dense()
-        C.inv = torch.linalg.inv(dense).contiguous()
+        if getattr(C, "inv", None) is not None and C.inv.shape == dense.shape:
+            C.inv.copy_(torch.linalg.inv(dense))
+        else:
+            C.inv = torch.linalg.inv(dense).contiguous()
+        # the captured cycle reads fixed buffers: it stays valid while none of them moved (instantiating a graph of
+        # ~250 kernels costs 30 - 650 ms, measured, against 12.8 ms per replay -- re-capturing per Newton iteration
+        # was up to a quarter of a solve)
+        sig = self._pointers()
+        if sig != getattr(self, "_graph_sig", None):
+            self._graph = None
+            self._graph_sig = sig
+
+    def _pointers(self):
+        out = []
+        for D in self.lv:
+            for name in ("rowptr", "colidx", "vals", "lu", "diag", "inv"):
+                t = getattr(D, name, None)
+                if t is not None:
+                    out.append(t.data_ptr())
+            if getattr(D, "ilu_plan", None) is not None:
+                out.append(id(D.ilu_plan))
+        if self.aux is not None:
+            out += self.aux.h.pointers()
+        return out
 
     # -- apply ---------------------------------------------------------------------------------------------
     def _smooth(self, D, r, z):

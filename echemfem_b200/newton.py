@@ -14,6 +14,7 @@ well below the 1e-8 solution tolerance of BASELINE.json.
 import ctypes as C
 import math
 import os
+import sys
 import time
 
 import numpy as np
@@ -578,6 +579,8 @@ class NewtonEngine:
             self.ksp_reductions += 1
             return max(float(hdev[0].item()), 0.0)
 
+        # ECH_KSP_PROFILE=1: synchronising wall-clock split of the iteration (diagnostic; slows the solve down)
+        prof = {"precond": 0.0, "matvec": 0.0, "its": 0, "t0": time.perf_counter()} if os.environ.get("ECH_KSP_PROFILE") else None
         bnorm = math.sqrt(owned_sq(b))
         tol = max(rtol * bnorm, atol)
         its, rnorm, converged = 0, bnorm, False
@@ -613,8 +616,22 @@ class NewtonEngine:
             j = 0
             while j < m and its < max_it:
                 Vj, Vn = V[j * n:(j + 1) * n], V[(j + 1) * n:(j + 2) * n]
-                precond(Vj, zt)
-                matvec(zt, w)
+                if prof is not None:
+                    torch.cuda.synchronize()
+                    tp0 = time.perf_counter()
+                    precond(Vj, zt)
+                    torch.cuda.synchronize()
+                    tp1 = time.perf_counter()
+                    matvec(zt, w)
+                    torch.cuda.synchronize()
+                    tp2 = time.perf_counter()
+                    prof["precond"] += tp1 - tp0
+                    prof.setdefault("pc", []).append(1e3 * (tp1 - tp0))
+                    prof["matvec"] += tp2 - tp1
+                    prof["its"] += 1
+                else:
+                    precond(Vj, zt)
+                    matvec(zt, w)
                 h = mdot(j + 1, w)
                 H[:j + 1, j] = h[:j + 1]
                 capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
@@ -661,6 +678,16 @@ class NewtonEngine:
             # converged by the recurrence: the next pass of the loop checks the true residual and restarts if needed
         if distributed:
             x.mul_(own)      # ghost entries of the update are refreshed by the next exchange
+        if prof is not None and rank0 and prof["its"]:
+            torch.cuda.synchronize()
+            tot = time.perf_counter() - prof["t0"]
+            k = prof["its"]
+            print("KSP profile: %d its, %.2f ms/it total; preconditioner %.2f ms, SpMV (+exchange) %.2f ms, "
+                  "orthogonalisation + host %.2f ms" % (k, 1e3 * tot / k, 1e3 * prof["precond"] / k, 1e3 * prof["matvec"] / k,
+                                                       1e3 * (tot - prof["precond"] - prof["matvec"]) / k), file=sys.stderr)
+            pc = prof["pc"]
+            print("KSP profile: preconditioner ms per application: first %s ... min %.2f median %.2f max %.2f" % (
+                ["%.1f" % v for v in pc[:6]], min(pc), sorted(pc)[len(pc) // 2], max(pc)), file=sys.stderr)
         return x, its, converged
 
     # -- Newton -----------------------------------------------------------------------------

@@ -1,0 +1,9 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+ECH_KSP_PROFILE=1 python bench.py --no-cpu --steps 5 > gpurun_out/r2x_bench_prof.json 2> gpurun_out/r2x_bench_prof.err
+grep "KSP profile" gpurun_out/r2x_bench_prof.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2x_bench_prof.json").read().strip().splitlines()[-1]); n=d["newton"]
+print(n["newton_step_s"], n["ksp_its_per_step"], n["timers_s_max_over_ranks"], n["clocks_during_solve"])
+PY

@@ -54,3 +54,16 @@ V = L["basis"]; n = eng.ndof; work = L["work"]; hdev = work[3 * n:3 * n + 202]; 
 for k in (10, 50, 100):
     print("multidot k=%d %.2f ms   multiaxpy %.2f ms" % (k, timed(lambda: capi.check(eng.lib.ech_multidot(n, k, ptr(V), ptr(r), ptr(partial), ptr(hdev), eng._stream()))),
           timed(lambda: capi.check(eng.lib.ech_multiaxpy(n, k, ptr(V), ptr(hdev), -1.0, ptr(z), eng._stream())))))
+
+# does the cycle cost depend on WHICH set-up produced it?  (KSP profile: 13.4 / 18.8 ms per application in
+# consecutive Newton iterations)
+for rep in range(4):
+    eng.jacobian(s.u.tensor)
+    M.setup(); torch.cuda.synchronize()
+    D = M.lv[0]
+    line = "set-up %d: V-cycle %.2f ms  fine smooth %.3f  fine spmv %.3f  level-1 smooth %.3f" % (
+        rep, timed(lambda: M.apply(r, z)), timed(lambda: M._smooth(D, r, D.z)), timed(lambda: M._spmv(D, D.z, D.t)),
+        timed(lambda: M._smooth(M.lv[1], M.lv[1].r, M.lv[1].z)))
+    if M.aux is not None:
+        line += "  aux cycle %.3f" % timed(lambda: M.aux.restrict_and_solve(D.t, eng._stream()))
+    print(line + "  eager V-cycle %.2f" % timed(lambda: M._apply_eager(r, z)))
