@@ -418,7 +418,11 @@ def main():
                                 "search; MUMPS is replaced by right-preconditioned GMRES(200) run to ksp_rtol 1e-12",
                   "preconditioner": ("geometric multigrid V-cycle, block-Jacobi/ILU(0) smoothers on 8x8-cell tiles "
                                      "(level-scheduled solves), Galerkin coarse operators" +
-                                     ("; one hierarchy per rank (PETSc bjacobi: one block per rank)" if world > 1 else ""))
+                                     ("; continuous-Q1 auxiliary space for the potential" if getattr(eng._mg, "aux", None) is not None else "") +
+                                     ("; one hierarchy per rank (PETSc bjacobi: one block per rank)" +
+                                      ("; continuous-Q1 coarse space on the global vertex grid shared by all ranks"
+                                       if getattr(eng, "_gconf", None) is not None else "; global box-aggregation coarse space")
+                                      if world > 1 else ""))
                   if mg else "block-Jacobi/ILU(0) (level-scheduled solves)",
                   "ksp_reductions_last_solve": getattr(eng, "ksp_reductions", None),
                   "clocks_during_solve": newton_clocks}

@@ -67,3 +67,22 @@ for rep in range(4):
     if M.aux is not None:
         line += "  aux cycle %.3f" % timed(lambda: M.aux.restrict_and_solve(D.t, eng._stream()))
     print(line + "  eager V-cycle %.2f" % timed(lambda: M._apply_eager(r, z)))
+
+# where a set-up (PCSetUp, once per Newton iteration) goes
+lib, st = eng.lib, eng._stream()
+def factor(D):
+    capi.check(lib.ech_bjacobi_ilu0_factor(D.ndof, M.nf, D.N, M.h.n, D.nblocks, ptr(D.block_ptr), ptr(D.rowptr),
+                                           ptr(D.colidx), ptr(D.vals), ptr(D.lu), ptr(D.diag), st))
+print("set-up parts: " + "  ".join(
+    ["factor L%d %.1f ms" % (l, timed(lambda: factor(D), 2)) for l, D in enumerate(M.lv[:-1])]))
+print("set-up parts: " + "  ".join(
+    ["pack L%d %.2f ms" % (l, timed(lambda: D.ilu_plan.refresh(D.lu, st), 2)) for l, D in enumerate(M.lv[:-1]) if D.ilu_plan is not None]))
+if M.own_galerkin:
+    print("set-up parts: " + "  ".join(
+        ["galerkin L%d->L%d %.2f ms" % (l, l + 1, timed(lambda: M._galerkin(M.lv[l], M.lv[l + 1]), 2)) for l in range(M.nlevels - 1)]))
+C_ = M.lv[-1]
+def inv():
+    dense = torch.sparse_csr_tensor(C_.rowptr, C_.colidx.to(torch.int64), C_.vals, size=(C_.ndof, C_.ndof)).to_dense()
+    return torch.linalg.inv(dense)
+print("set-up parts: dense inverse of the coarsest level (%d) %.1f ms" % (C_.ndof, timed(inv, 2)))
+t0 = time.time(); M.setup(); torch.cuda.synchronize(); print("whole set-up %.3f s" % (time.time() - t0))
