@@ -341,11 +341,10 @@ class AuxSpaceCG:
         """z_f += Q z_aux for every auxiliary field f; tmp: scratch of at least N entries."""
         D = self.lv[0]
         es = z.element_size()
-        rp, ci, v = self.Q
         for a, f in enumerate(self.fields):
-            capi.check(self.lib.ech_spmv(self.N, ptr(rp), ptr(ci), ptr(v), capi.C.c_void_p(D.z.data_ptr() + a * self.ncg * es),
-                                         ptr(tmp), st))
-            capi.check(self.lib.ech_axpby(self.N, 1.0, ptr(tmp), 1.0, capi.C.c_void_p(z.data_ptr() + f * self.N * es), st))
+            capi.check(self.lib.ech_aux_prolong_add(self.nv, self.N, ptr(self.vtab), ptr(self.Wd),
+                                                    capi.C.c_void_p(D.z.data_ptr() + a * self.ncg * es),
+                                                    capi.C.c_void_p(z.data_ptr() + f * self.N * es), st))
 
 
 class GlobalConformingCoarse:

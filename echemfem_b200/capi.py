@@ -51,6 +51,9 @@ EXPORTS = {
     "ech_multidot": (C.c_int, [c_i64, c_i32, c_p, c_p, c_p, c_p, c_p]),
     "ech_multiaxpy": (C.c_int, [c_i64, c_i32, c_p, c_p, C.c_double, c_p, c_p]),
     "ech_bjacobi_ilu0_factor": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ech_bjacobi_ilu0_factor_async": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_p,
+                                                c_p, c_p]),
+    "ech_bjacobi_ilu0_factor_status": (C.c_int, [c_i32]),
     "ech_bjacobi_ilu0_apply": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_plan_count": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_i32, c_p, c_p,
                                               c_p, C.POINTER(c_i64), c_p]),
@@ -69,6 +72,7 @@ EXPORTS = {
     "ech_halo_unpack": (C.c_int, [c_i64, c_p, c_p, c_p, c_p]),
     "ech_dg_prolong_add": (C.c_int, [c_i32, c_i32, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "ech_dg_restrict": (C.c_int, [c_i32, c_i32, c_i32, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    "ech_aux_prolong_add": (C.c_int, [c_i32, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "ech_aux_galerkin": (C.c_int, [c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
     "ech_aux_galerkin_global": (C.c_int, [c_i32, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i32, c_p, c_p, c_p,
                                           c_i64, c_p, c_p]),

@@ -1123,6 +1123,33 @@ __global__ void __launch_bounds__(32) ilu0_apply_kernel(BlockPlan B, const int64
         ilu0_solve_block<false>(B, rowptr, colidx, lu, diag_pos, rhs, zg, zs, c0, c1, lane);
 }
 
+// launches only: lu = vals, diagonal positions, factorisation; *flag (device) becomes 1 on a zero pivot, 2 on a shift
+static int ilu0_factor_launch(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc, int64_t nblocks,
+                              const int64_t *block_cell_ptr, const int64_t *rowptr, const int32_t *colidx,
+                              const double *vals, double *lu, int32_t *diag_pos, int64_t nnz, int *flag,
+                              cudaStream_t s) {
+    CK(nullptr, cudaMemcpyAsync(lu, vals, sizeof(double) * nnz, cudaMemcpyDeviceToDevice, s));
+    diag_pos_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, s>>>(nrows, rowptr, colidx, diag_pos);
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    CK(nullptr, cudaMemsetAsync(flag, 0, sizeof(int), s));
+    const int block = 128;
+    const int64_t nthreads = nblocks * 32;
+    ilu0_factor_kernel<<<(unsigned)((nthreads + block - 1) / block), block, 0, s>>>(B, rowptr, colidx, lu, diag_pos,
+                                                                                  flag);
+    g_launches += 2;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+static int ilu0_factor_report(int hflag) {
+    if (hflag == 1) return fail(nullptr, ECH_ERR_BREAKDOWN, "ech_bjacobi_ilu0_factor: zero pivot");
+    if (hflag == 2) {
+        static int warned = 0;
+        if (!warned++) fprintf(stderr, "echem_b200: ILU(0) met negligible pivots; shifted (PETSc shift_type nonzero)\n");
+    }
+    return ECH_OK;
+}
+
 extern "C" int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
                                        int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
                                        const int32_t *colidx, const double *vals, double *lu, int32_t *diag_pos,
@@ -1133,29 +1160,35 @@ extern "C" int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t r
     int64_t nnz = 0;
     CK(nullptr, cudaMemcpyAsync(&nnz, rowptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CK(nullptr, cudaStreamSynchronize(s));
-    CK(nullptr, cudaMemcpyAsync(lu, vals, sizeof(double) * nnz, cudaMemcpyDeviceToDevice, s));
-    diag_pos_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, s>>>(nrows, rowptr, colidx, diag_pos);
-    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
     int *flag = nullptr;
     CK(nullptr, cudaMalloc(&flag, sizeof(int)));
-    CK(nullptr, cudaMemsetAsync(flag, 0, sizeof(int), s));
-    const int block = 128;
-    const int64_t nthreads = nblocks * 32;
-    ilu0_factor_kernel<<<(unsigned)((nthreads + block - 1) / block), block, 0, s>>>(B, rowptr, colidx, lu, diag_pos,
-                                                                                  flag);
-    g_launches += 2;
+    int rc = ilu0_factor_launch(nrows, nfields, rows_per_field, nloc, nblocks, block_cell_ptr, rowptr, colidx, vals, lu,
+                                diag_pos, nnz, flag, s);
+    if (rc) {
+        cudaFree(flag);
+        return rc;
+    }
     int hflag = 0;
     CK(nullptr, cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(nullptr, cudaStreamSynchronize(s));
     cudaFree(flag);
     CK(nullptr, cudaGetLastError());
-    if (hflag == 1) return fail(nullptr, ECH_ERR_BREAKDOWN, "ech_bjacobi_ilu0_factor: zero pivot");
-    if (hflag == 2) {
-        static int warned = 0;
-        if (!warned++) fprintf(stderr, "echem_b200: ILU(0) met negligible pivots; shifted (PETSc shift_type nonzero)\n");
-    }
-    return ECH_OK;
+    return ilu0_factor_report(hflag);
 }
+
+// The same without any host synchronisation: nnz and the device flag come from the caller, who reads the flag
+// after joining the stream (the levels of a multigrid hierarchy are factored concurrently on separate streams).
+extern "C" int ech_bjacobi_ilu0_factor_async(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                             int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
+                                             const int32_t *colidx, const double *vals, int64_t nnz, double *lu,
+                                             int32_t *diag_pos, int32_t *flag, void *stream) {
+    if (!block_cell_ptr || !rowptr || !colidx || !vals || !lu || !diag_pos || !flag)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_factor_async: null argument");
+    return ilu0_factor_launch(nrows, nfields, rows_per_field, nloc, nblocks, block_cell_ptr, rowptr, colidx, vals, lu,
+                              diag_pos, nnz, (int *)flag, (cudaStream_t)stream);
+}
+
+extern "C" int ech_bjacobi_ilu0_factor_status(int32_t flag) { return ilu0_factor_report(flag); }
 
 static int ilu0_apply(const BlockPlan &B, const int64_t *rowptr, const int32_t *colidx, const double *lu,
                       const int32_t *diag_pos, const double *r, double *z, cudaStream_t s) {
@@ -2244,6 +2277,42 @@ extern "C" int ech_dg_restrict(int32_t nloc, int32_t nf, int32_t nchild, int64_t
     case 4: dg_restrict_kernel<4><<<grid, 256, 0, s>>>(ncell_c, nf, nchild, fs_f, fs_c, children, pblk, r, rc); break;
     case 8: dg_restrict_kernel<8><<<grid, 256, 0, s>>>(ncell_c, nf, nchild, fs_f, fs_c, children, pblk, r, rc); break;
     default: return fail(nullptr, ECH_ERR_ARG, "ech_dg_restrict: 2, 4 or 8 dofs per cell");
+    }
+    ++g_launches;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
+// z[r] += sum_v W[a][v] * zc[vtab[cell * NV + v]] for DG row r = cell * NV + a (rows whose cell has no vertices,
+// vtab < 0, are skipped): the embedding of the conforming auxiliary space applied without a CSR copy of it.
+template <int NV>
+__global__ void aux_prolong_add_kernel(int64_t nrow, const int64_t *__restrict__ vtab, const double *__restrict__ W,
+                                       const double *__restrict__ zc, double *__restrict__ z) {
+    __shared__ double Ws[NV * NV];
+    for (int i = threadIdx.x; i < NV * NV; i += blockDim.x) Ws[i] = W[i];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t *vt = vtab + (r / NV) * NV;
+        if (vt[0] < 0) continue;
+        const int a = (int)(r % NV);
+        double s = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s = fma(Ws[a * NV + v], zc[vt[v]], s);
+        z[r] += s;
+    }
+}
+
+extern "C" int ech_aux_prolong_add(int32_t nv, int64_t nrow, const int64_t *vtab, const double *W, const double *zc,
+                                   double *z, void *stream) {
+    if (nrow == 0) return ECH_OK;
+    if (!vtab || !W || !zc || !z) return fail(nullptr, ECH_ERR_ARG, "ech_aux_prolong_add: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = grid_for(nrow, 256);
+    switch (nv) {
+    case 2: aux_prolong_add_kernel<2><<<grid, 256, 0, s>>>(nrow, vtab, W, zc, z); break;
+    case 4: aux_prolong_add_kernel<4><<<grid, 256, 0, s>>>(nrow, vtab, W, zc, z); break;
+    case 8: aux_prolong_add_kernel<8><<<grid, 256, 0, s>>>(nrow, vtab, W, zc, z); break;
+    default: return fail(nullptr, ECH_ERR_ARG, "ech_aux_prolong_add: 2, 4 or 8 vertices per cell");
     }
     ++g_launches;
     CK(nullptr, cudaGetLastError());

@@ -406,7 +406,12 @@ class Multigrid:
             Dc.rowptr, Dc.colidx, Dc.vals = spgemm_rows(Rt.crow_indices().to(torch.int64), Rt.col_indices().to(torch.int32),
                                                         Rt.values(), D.ndof, AP, ap[2].numel() / D.ndof)
             del ap, AP
-        for l, D in enumerate(self.lv[:-1]):
+        ready = all(hasattr(D, "lu") and D.lu.numel() == D.vals.numel() and (D.ilu_plan is not None or not self.planned)
+                    for D in self.lv[:-1])
+        concurrent = ready and os.environ.get("ECH_MG_CONCURRENT_FACTOR", "1") != "0"
+        if concurrent:
+            self._factor_concurrently()
+        for l, D in enumerate([] if concurrent else self.lv[:-1]):
             if not hasattr(D, "lu") or D.lu.numel() != D.vals.numel():
                 D.lu = torch.empty_like(D.vals)
                 D.diag = torch.empty(D.ndof, dtype=torch.int32, device=self.dev)
@@ -436,6 +441,34 @@ class Multigrid:
         if sig != getattr(self, "_graph_sig", None):
             self._graph = None
             self._graph_sig = sig
+
+    def _factor_concurrently(self):
+        """ILU(0) of all levels at once, one stream per level: a level's factorisation is one warp per tile walking
+        512 rows in sequence, so the small levels are pure latency (10 ms each whatever their size) and hide behind the
+        fine level's 106 ms (189 ms one after the other at cfg2 size).  Buffers and plans exist (not the first set-up)."""
+        lib = self.lib
+        main = torch.cuda.current_stream()
+        nl = len(self.lv) - 1
+        if getattr(self, "_fstreams", None) is None or len(self._fstreams) != nl:
+            self._fstreams = [torch.cuda.Stream(device=self.dev) for _ in range(nl)]
+            self._fflags = torch.zeros(nl, dtype=torch.int32, device=self.dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        es = self._fflags.element_size()
+        for l, D in enumerate(self.lv[:-1]):
+            sl = self._fstreams[l]
+            sl.wait_event(ev)
+            st = capi.C.c_void_p(sl.cuda_stream)
+            capi.check(lib.ech_bjacobi_ilu0_factor_async(D.ndof, self.nf, D.N, self.h.n, D.nblocks, ptr(D.block_ptr),
+                                                         ptr(D.rowptr), ptr(D.colidx), ptr(D.vals), int(D.vals.numel()),
+                                                         ptr(D.lu), ptr(D.diag),
+                                                         capi.C.c_void_p(self._fflags.data_ptr() + l * es), st))
+            if D.ilu_plan is not None:
+                D.ilu_plan.refresh(D.lu, st)
+        for sl in self._fstreams:
+            main.wait_stream(sl)
+        for flag in self._fflags.cpu().tolist():
+            capi.check(lib.ech_bjacobi_ilu0_factor_status(int(flag)))
 
     def _pointers(self):
         out = []

@@ -124,6 +124,14 @@ int ech_bjacobi_ilu0_factor(int64_t nrows, int32_t nfields, int64_t rows_per_fie
                             int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
                             const int32_t *colidx, const double *vals, double *lu, int32_t *diag_pos,
                             void *stream);
+/* The same without host synchronisation: `nnz` and a device flag word from the caller (0 ok, 1 zero pivot, 2 shifted
+ * pivot; pass it to ech_bjacobi_ilu0_factor_status after joining the stream).  Lets the levels of a multigrid
+ * hierarchy factor concurrently on separate streams. */
+int ech_bjacobi_ilu0_factor_async(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc, int64_t nblocks,
+                                  const int64_t *block_cell_ptr, const int64_t *rowptr, const int32_t *colidx,
+                                  const double *vals, int64_t nnz, double *lu, int32_t *diag_pos, int32_t *flag,
+                                  void *stream);
+int ech_bjacobi_ilu0_factor_status(int32_t flag);
 int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
                            int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
                            const int32_t *colidx, const double *lu, const int32_t *diag_pos, const double *r,
@@ -199,6 +207,11 @@ int ech_dg_prolong_add(int32_t nloc, int32_t nf, int64_t ncell_f, int64_t fs_f, 
                        const double *pblk, const double *zc, double *z, void *stream);
 int ech_dg_restrict(int32_t nloc, int32_t nf, int32_t nchild, int64_t ncell_c, int64_t fs_f, int64_t fs_c,
                     const int32_t *children, const double *pblk, const double *r, double *rc, void *stream);
+
+/* z[r] += sum_v W[a][v] zc[vtab[cell*nv + v]] for the DG rows r = cell*nv + a of one field (cells with vtab < 0 are
+ * skipped): prolongation from the conforming auxiliary space, fused with the update. */
+int ech_aux_prolong_add(int32_t nv, int64_t nrow, const int64_t *vtab, const double *W, const double *zc, double *z,
+                        void *stream);
 
 /* A_aux = Q^T A Q for the continuous-Q1 subspace of a DG-Q1 space (the conforming auxiliary space of the potential
  * fields in the multigrid preconditioner; the reference reaches conforming coarse spaces through its `gmg` / `amg`
