@@ -54,6 +54,8 @@ EXPORTS = {
     "ech_bjacobi_ilu0_factor_async": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_p,
                                                 c_p, c_p]),
     "ech_bjacobi_ilu0_factor_status": (C.c_int, [c_i32]),
+    "ech_bjacobi_ilu0_factor_planned": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_p, c_i64,
+                                                  c_p, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_apply": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_plan_count": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p, c_p, c_i32, c_p, c_p,
                                               c_p, C.POINTER(c_i64), c_p]),

@@ -1604,6 +1604,159 @@ extern "C" int ech_bjacobi_ilu0_apply_planned(int64_t nrows, int32_t nfields, in
                               (cudaStream_t)stream);
 }
 
+// =============================================================== ILU(0) factorisation on the plan's local columns
+// ilu0_factor_kernel above finds every update target with a binary search over global column indices and walks
+// the lower entries of a row strictly one after the other, each with its own chain of dependent global loads
+// (column -> row pointer -> pivot -> entries): ~20 us per row, 10 ms for a 512-row tile whatever the level size.
+// Here (IKJ form with a work row):
+//   * the row being eliminated lives in a shared-memory work vector indexed by the plan's LOCAL column (lcol), with
+//     a tag per local column saying which row put it there, so an update is `if (tag[j] == row) w[j] -= l * u_kj`;
+//   * the meta data of up to 32 lower entries (pivot row, its diagonal position, length of its upper part, its
+//     pivot) are fetched by 32 lanes at once -- one round of latency per row instead of one per entry;
+//   * the upper part of the NEXT pivot row is loaded while the current one is applied.
+// Same arithmetic in the same order as ilu0_factor_kernel (tests/test_gpu_ilu.py compares the factors).
+constexpr int ILUF_WPC = 4;
+
+__global__ void __launch_bounds__(32 * ILUF_WPC) ilu0_factor_lcol_kernel(
+    BlockPlan B, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, double *lu,
+    const int32_t *__restrict__ diag_pos, const uint16_t *__restrict__ lcol, int64_t cap_rows, int *flag) {
+    extern __shared__ __align__(16) uint8_t smf[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t)blockIdx.x * ILUF_WPC + warp;
+    if (blk >= B.nblocks) return;
+    const size_t per_warp = ((size_t)cap_rows * 10 + 15) / 16 * 16;
+    double *w = reinterpret_cast<double *>(smf + warp * per_warp);
+    uint16_t *tag = reinterpret_cast<uint16_t *>(smf + warp * per_warp + (size_t)cap_rows * 8);
+    const int64_t c0 = B.cell_ptr[blk], c1 = B.cell_ptr[blk + 1];
+    const uint32_t first = (uint32_t)(c0 * B.nloc), nrow_f = (uint32_t)((c1 - c0) * B.nloc), ntot = nrow_f * B.nf;
+    for (uint32_t k = lane; k < ntot; k += 32) tag[k] = 0xFFFF;
+    __syncwarp();
+    for (uint32_t li = 0; li < ntot; ++li) {
+        const uint32_t f = li / nrow_f, jr = li - f * nrow_f;
+        const int64_t r = (int64_t)f * B.rows_per_field + first + jr;
+        const int64_t rs = rowptr[r], re = rowptr[r + 1];
+        const int64_t rd = rs + diag_pos[r];
+        for (int64_t q = rs + lane; q < re; q += 32) {
+            const uint16_t lc = lcol[q];
+            if (lc != 0xFFFF) {
+                w[lc] = lu[q];
+                tag[lc] = (uint16_t)li;
+            }
+        }
+        __syncwarp();
+        for (int64_t base = rs; base < rd; base += 32) {
+            const int64_t pk = base + lane;
+            uint32_t lck = 0xFFFF;
+            long long kd = 0;
+            int klen = 0;
+            double piv = 1.0;
+            if (pk < rd) {
+                lck = lcol[pk];
+                if (lck != 0xFFFF) {
+                    const int64_t k = colidx[pk];
+                    const int64_t ks = rowptr[k];
+                    kd = ks + diag_pos[k];
+                    klen = (int)(rowptr[k + 1] - kd - 1);
+                    piv = lu[kd];
+                }
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, lck != 0xFFFF);
+            // upper part of the first pivot row
+            uint16_t jn = 0xFFFF;
+            double un = 0.0;
+            if (todo) {
+                const int t0 = __ffs(todo) - 1;
+                const long long kd0 = __shfl_sync(0xffffffffu, kd, t0);
+                const int len0 = __shfl_sync(0xffffffffu, klen, t0);
+                if (lane < len0) {
+                    jn = lcol[kd0 + 1 + lane];
+                    un = lu[kd0 + 1 + lane];
+                }
+            }
+            while (todo) {
+                const int t = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t lct = __shfl_sync(0xffffffffu, lck, t);
+                const long long kdt = __shfl_sync(0xffffffffu, kd, t);
+                const int lent = __shfl_sync(0xffffffffu, klen, t);
+                const double pv = __shfl_sync(0xffffffffu, piv, t);
+                const uint16_t jc = jn;
+                const double uc = un;
+                jn = 0xFFFF;
+                if (todo) {                                  // next pivot row's upper part: in flight during this one
+                    const int t1 = __ffs(todo) - 1;
+                    const long long kd1 = __shfl_sync(0xffffffffu, kd, t1);
+                    const int len1 = __shfl_sync(0xffffffffu, klen, t1);
+                    if (lane < len1) {
+                        jn = lcol[kd1 + 1 + lane];
+                        un = lu[kd1 + 1 + lane];
+                    }
+                }
+                const double l = w[lct] / pv;
+                __syncwarp();
+                if (lane == 0) w[lct] = l;
+                if (lane < lent && jc != 0xFFFF && tag[jc] == (uint16_t)li) w[jc] -= l * uc;
+                for (int e = 32 + lane; e < lent; e += 32) {
+                    const uint16_t j = lcol[kdt + 1 + e];
+                    if (j != 0xFFFF && tag[j] == (uint16_t)li) w[j] -= l * lu[kdt + 1 + e];
+                }
+                __syncwarp();
+            }
+        }
+        for (int64_t q = rs + lane; q < re; q += 32) {
+            const uint16_t lc = lcol[q];
+            if (lc != 0xFFFF) lu[q] = w[lc];
+        }
+        __syncwarp();
+        {
+            double rmax = 0.0;
+            for (int64_t q = rs + lane; q < re; q += 32) rmax = fmax(rmax, fabs(lu[q]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+            if (lane == 0) {
+                const double pivr = lu[rd];
+                if (!(fabs(pivr) > 1e-13 * rmax)) {
+                    if (rmax == 0.0 || pivr != pivr) {
+                        atomicExch(flag, 1);
+                    } else {
+                        lu[rd] = (pivr < 0.0 ? -1.0 : 1.0) * 1e-10 * rmax;
+                        atomicMax(flag, 2);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// lu = vals, then the factorisation above; no host synchronisation (flag: device word, see ..._factor_async)
+extern "C" int ech_bjacobi_ilu0_factor_planned(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                               int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                               const int64_t *rowptr, const int32_t *colidx, const double *vals,
+                                               int64_t nnz, const uint16_t *lcol, double *lu, int32_t *diag_pos,
+                                               int32_t *flag, void *stream) {
+    if (!block_cell_ptr || !rowptr || !colidx || !vals || !lcol || !lu || !diag_pos || !flag || max_block_rows <= 0)
+        return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_factor_planned: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t per_warp = ((size_t)max_block_rows * 10 + 15) / 16 * 16;
+    const size_t smem = per_warp * ILUF_WPC;
+    if (smem > 200 * 1024) return fail(nullptr, ECH_ERR_ARG, "ech_bjacobi_ilu0_factor_planned: blocks too large");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CK(nullptr, cudaFuncSetAttribute(ilu0_factor_lcol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    CK(nullptr, cudaMemcpyAsync(lu, vals, sizeof(double) * nnz, cudaMemcpyDeviceToDevice, s));
+    diag_pos_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, s>>>(nrows, rowptr, colidx, diag_pos);
+    BlockPlan B{nfields, nloc, rows_per_field, nblocks, block_cell_ptr};
+    CK(nullptr, cudaMemsetAsync(flag, 0, sizeof(int), s));
+    ilu0_factor_lcol_kernel<<<(unsigned)((nblocks + ILUF_WPC - 1) / ILUF_WPC), 32 * ILUF_WPC, smem, s>>>(
+        B, rowptr, colidx, lu, diag_pos, lcol, max_block_rows, (int *)flag);
+    g_launches += 2;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // =============================================================== pass-packed triangular solves (bulk copies)
 // The planned solve above still spends ~150 warp instructions per pass on per-lane loads, predication and address
 // arithmetic.  Here the factors are RE-PACKED after every factorisation into the order the solve consumes them: one

@@ -73,6 +73,23 @@ class IluPlan:
                                                   ptr(self.bdesc), stream))
         self._packed_for = None
 
+    def factor_async(self, rowptr, colidx, vals, lu, diag, flag_ptr, stream):
+        """lu = ILU(0)(vals) block by block on the plan's local columns (`ech_bjacobi_ilu0_factor_planned`), then the
+        packed copy of the factors; no host synchronisation: `flag_ptr` is a device int32 the caller reads later and
+        hands to `ech_bjacobi_ilu0_factor_status`."""
+        capi.check(self.lib.ech_bjacobi_ilu0_factor_planned(self.ndof, self.nf, self.N, self.unit, self.nblocks,
+                                                            ptr(self.block_ptr), self.max_rows, ptr(rowptr), ptr(colidx),
+                                                            ptr(vals), int(vals.numel()), ptr(self.lcol), ptr(lu),
+                                                            ptr(diag), flag_ptr, stream))
+        self.refresh(lu, stream)
+
+    def factor(self, rowptr, colidx, vals, lu, diag, stream):
+        """Synchronous form of `factor_async` (reads the status word back)."""
+        if getattr(self, "_flag", None) is None:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=lu.device)
+        self.factor_async(rowptr, colidx, vals, lu, diag, ptr(self._flag), stream)
+        capi.check(self.lib.ech_bjacobi_ilu0_factor_status(int(self._flag.item())))
+
     def refresh(self, lu, stream):
         """After every factorisation: the values of `lu` into the packed chunks."""
         if self.packed is not None:

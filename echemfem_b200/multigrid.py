@@ -406,28 +406,20 @@ class Multigrid:
             Dc.rowptr, Dc.colidx, Dc.vals = spgemm_rows(Rt.crow_indices().to(torch.int64), Rt.col_indices().to(torch.int32),
                                                         Rt.values(), D.ndof, AP, ap[2].numel() / D.ndof)
             del ap, AP
-        ready = all(hasattr(D, "lu") and D.lu.numel() == D.vals.numel() and (D.ilu_plan is not None or not self.planned)
-                    for D in self.lv[:-1])
-        concurrent = ready and os.environ.get("ECH_MG_CONCURRENT_FACTOR", "1") != "0"
-        if concurrent:
-            self._factor_concurrently()
-        for l, D in enumerate([] if concurrent else self.lv[:-1]):
+        for l, D in enumerate(self.lv[:-1]):
             if not hasattr(D, "lu") or D.lu.numel() != D.vals.numel():
                 D.lu = torch.empty_like(D.vals)
                 D.diag = torch.empty(D.ndof, dtype=torch.int32, device=self.dev)
-            capi.check(lib.ech_bjacobi_ilu0_factor(D.ndof, self.nf, D.N, self.h.n, D.nblocks, ptr(D.block_ptr),
-                                                   ptr(D.rowptr), ptr(D.colidx), ptr(D.vals), ptr(D.lu), ptr(D.diag),
-                                                   st))
             if self.planned and (D.ilu_plan is None or D.ilu_plan.lcol.numel() != D.vals.numel()):
-                # level-scheduled solves: the plan follows the pattern (fixed after the first Galerkin product)
+                # level-scheduled solves and the factorisation on local columns: the plan follows the pattern
+                # (fixed after the first Galerkin product)
                 from .ilu import IluPlan
                 D.ilu_plan = IluPlan(lib, self.dev, st, D.ndof, self.nf, D.N, self.h.n, D.block_edges, D.block_ptr,
                                      D.rowptr, D.colidx, int(D.vals.numel()))
                 if not D.ilu_plan.ok:
                     D.ilu_plan = None
                     self.planned = False
-            if D.ilu_plan is not None:
-                D.ilu_plan.refresh(D.lu, st)
+        self._factor_levels()
         C = self.lv[-1]
         dense = torch.sparse_csr_tensor(C.rowptr, C.colidx.to(torch.int64), C.vals, size=(C.ndof, C.ndof)).to_dense()
         if getattr(C, "inv", None) is not None and C.inv.shape == dense.shape:
@@ -442,13 +434,16 @@ class Multigrid:
             self._graph = None
             self._graph_sig = sig
 
-    def _factor_concurrently(self):
-        """ILU(0) of all levels at once, one stream per level: a level's factorisation is one warp per tile walking
-        512 rows in sequence, so the small levels are pure latency (10 ms each whatever their size) and hide behind the
-        fine level's 106 ms (189 ms one after the other at cfg2 size).  Buffers and plans exist (not the first set-up)."""
+    def _factor_levels(self):
+        """ILU(0) of all levels at once, one stream per level (`ECH_MG_CONCURRENT_FACTOR=0`: one after the other on
+        the current stream): the factorisation of a level is one warp per tile walking its rows in sequence, so the
+        small levels are pure latency and hide behind the fine level.  With a plan the factorisation runs on the
+        plan's local columns (`ech_bjacobi_ilu0_factor_planned`; `ECH_ILU_FACTOR_PLANNED=0`: the search-based kernel)."""
         lib = self.lib
         main = torch.cuda.current_stream()
         nl = len(self.lv) - 1
+        concurrent = os.environ.get("ECH_MG_CONCURRENT_FACTOR", "1") != "0"
+        planned = os.environ.get("ECH_ILU_FACTOR_PLANNED", "1") != "0"
         if getattr(self, "_fstreams", None) is None or len(self._fstreams) != nl:
             self._fstreams = [torch.cuda.Stream(device=self.dev) for _ in range(nl)]
             self._fflags = torch.zeros(nl, dtype=torch.int32, device=self.dev)
@@ -456,17 +451,22 @@ class Multigrid:
         ev.record(main)
         es = self._fflags.element_size()
         for l, D in enumerate(self.lv[:-1]):
-            sl = self._fstreams[l]
-            sl.wait_event(ev)
+            sl = self._fstreams[l] if concurrent else main
+            if concurrent:
+                sl.wait_event(ev)
             st = capi.C.c_void_p(sl.cuda_stream)
+            flag = capi.C.c_void_p(self._fflags.data_ptr() + l * es)
+            if D.ilu_plan is not None and planned:
+                D.ilu_plan.factor_async(D.rowptr, D.colidx, D.vals, D.lu, D.diag, flag, st)
+                continue
             capi.check(lib.ech_bjacobi_ilu0_factor_async(D.ndof, self.nf, D.N, self.h.n, D.nblocks, ptr(D.block_ptr),
                                                          ptr(D.rowptr), ptr(D.colidx), ptr(D.vals), int(D.vals.numel()),
-                                                         ptr(D.lu), ptr(D.diag),
-                                                         capi.C.c_void_p(self._fflags.data_ptr() + l * es), st))
+                                                         ptr(D.lu), ptr(D.diag), flag, st))
             if D.ilu_plan is not None:
                 D.ilu_plan.refresh(D.lu, st)
-        for sl in self._fstreams:
-            main.wait_stream(sl)
+        if concurrent:
+            for sl in self._fstreams:
+                main.wait_stream(sl)
         for flag in self._fflags.cpu().tolist():
             capi.check(lib.ech_bjacobi_ilu0_factor_status(int(flag)))
 

@@ -478,11 +478,14 @@ class NewtonEngine:
             self.timers["KSPSolve"] += time.time() - t0
             return out
         t0 = time.time()
-        capi.check(self.lib.ech_bjacobi_ilu0_factor(self.ndof, self.nf, self.N, self._unit, L["nblocks"],
-                                                    ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
-                                                    ptr(self.vals), ptr(L["lu"]), ptr(L["diag"]), self._stream()))
-        if L["ilu_plan"] is not None:
-            L["ilu_plan"].refresh(L["lu"], self._stream())
+        if L["ilu_plan"] is not None and os.environ.get("ECH_ILU_FACTOR_PLANNED", "1") != "0":
+            L["ilu_plan"].factor(self.rowptr, self.colidx, self.vals, L["lu"], L["diag"], self._stream())
+        else:
+            capi.check(self.lib.ech_bjacobi_ilu0_factor(self.ndof, self.nf, self.N, self._unit, L["nblocks"],
+                                                        ptr(L["block_ptr"]), ptr(self.rowptr), ptr(self.colidx),
+                                                        ptr(self.vals), ptr(L["lu"]), ptr(L["diag"]), self._stream()))
+            if L["ilu_plan"] is not None:
+                L["ilu_plan"].refresh(L["lu"], self._stream())
         Cz = None
         if coarse and self.halo is None:
             Cz = self._coarse_plan(int(coarse))

@@ -132,6 +132,12 @@ int ech_bjacobi_ilu0_factor_async(int64_t nrows, int32_t nfields, int64_t rows_p
                                   const double *vals, int64_t nnz, double *lu, int32_t *diag_pos, int32_t *flag,
                                   void *stream);
 int ech_bjacobi_ilu0_factor_status(int32_t flag);
+/* The factorisation on the plan's local column indices (`lcol` of ech_bjacobi_ilu0_plan_count): work row in shared
+ * memory, no searches; same factors as ech_bjacobi_ilu0_factor.  Asynchronous like ..._factor_async. */
+int ech_bjacobi_ilu0_factor_planned(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
+                                    int64_t nblocks, const int64_t *block_cell_ptr, int32_t max_block_rows,
+                                    const int64_t *rowptr, const int32_t *colidx, const double *vals, int64_t nnz,
+                                    const uint16_t *lcol, double *lu, int32_t *diag_pos, int32_t *flag, void *stream);
 int ech_bjacobi_ilu0_apply(int64_t nrows, int32_t nfields, int64_t rows_per_field, int32_t nloc,
                            int64_t nblocks, const int64_t *block_cell_ptr, const int64_t *rowptr,
                            const int32_t *colidx, const double *lu, const int32_t *diag_pos, const double *r,

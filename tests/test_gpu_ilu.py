@@ -109,6 +109,15 @@ def test_block_ilu0_apply_matches_host(case):
                                                         ptr(plan.passptr), ptr(plan.slots), st))
         zz = torch.full_like(rd, float("nan"))
         if lpr is None:
+            # the factorisation on the plan's local columns gives the factors of the search-based kernel (same
+            # arithmetic in the same order; a ragged last block and blocks of any field count included)
+            lu2 = torch.full_like(lu, float("nan"))
+            diag2 = torch.empty_like(diag)
+            plan.factor(e.rowptr, e.colidx, e.vals, lu2, diag2, st)
+            assert torch.equal(diag, diag2)
+            a, b2 = lu.cpu().numpy(), lu2.cpu().numpy()
+            assert np.isfinite(b2).all()
+            assert np.abs(a - b2).max() <= 1e-14 * np.abs(a).max(), (case, np.abs(a - b2).max())
             # pass-packed factors fetched with cp.async.bulk (the default path) ...
             assert plan.packed is not None
             plan.refresh(lu, st)

@@ -75,6 +75,10 @@ def factor(D):
                                            ptr(D.colidx), ptr(D.vals), ptr(D.lu), ptr(D.diag), st))
 print("set-up parts: " + "  ".join(
     ["factor L%d %.1f ms" % (l, timed(lambda: factor(D), 2)) for l, D in enumerate(M.lv[:-1])]))
+flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+print("set-up parts (factorisation on local columns): " + "  ".join(
+    ["factor L%d %.1f ms" % (l, timed(lambda: D.ilu_plan.factor_async(D.rowptr, D.colidx, D.vals, D.lu, D.diag, ptr(flag), st), 2))
+     for l, D in enumerate(M.lv[:-1]) if D.ilu_plan is not None]))
 print("set-up parts: " + "  ".join(
     ["pack L%d %.2f ms" % (l, timed(lambda: D.ilu_plan.refresh(D.lu, st), 2)) for l, D in enumerate(M.lv[:-1]) if D.ilu_plan is not None]))
 if M.own_galerkin:
