@@ -359,7 +359,8 @@ class GlobalConformingCoarse:
 
     Measured, 2 GPUs, 2 x 1408^2 cells (cfg2 physics, ksp_rtol 1e-12): box aggregation (4096 constants) 416 Krylov
     iterations; this space coarsened 8x / 4x / 2x / 1x per direction: 125 / 100 / 87 / 87 (one GPU, same physics on
-    1408^2: 58).  Default 4x (level 2), coarsened further while it has more than 1.2 M vertices."""
+    1408^2: 58).  Default 2x (level 1), coarsened further while it has more than 1.2 M vertices (4x at 4 and 8 GPUs of the
+    weak-scaling benchmark)."""
 
     S1 = 5                    # vertex offsets -2..2 per direction between vertices of face-adjacent coarse cells
 
@@ -367,7 +368,7 @@ class GlobalConformingCoarse:
         import os
         import torch.distributed as dist
         if level is None:
-            level = int(os.environ.get("ECH_GCOARSE_LEVEL", "2"))
+            level = int(os.environ.get("ECH_GCOARSE_LEVEL", "1"))
         if max_vertices is None:
             max_vertices = int(os.environ.get("ECH_GCOARSE_MAX_VERTICES", "1200000"))
         self.e, self.lib, self.dev = engine, engine.lib, engine.dev

@@ -320,6 +320,8 @@ class Multigrid:
                 self.aux = AuxSpaceCG(self, fields)
                 if getattr(engine, "rowptr", None) is not None:
                     self.aux.prepare(engine.rowptr, engine.colidx)
+        self.aux_overlap = os.environ.get("ECH_MG_AUX_OVERLAP", "1") != "0"
+        self._side = None
         self.use_graph = os.environ.get("ECH_MG_GRAPH", "1") != "0"
         self._graph = self._gr = self._gz = None
 
@@ -535,12 +537,25 @@ class Multigrid:
         self._spmv(D, z, D.t)
         capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(r), -1.0, ptr(D.t), st))      # t = r - A z
         aux = self.aux if l == 0 else None
+        side = None
         if aux is not None:
-            aux.restrict_and_solve(D.t, st)                                     # conforming correction, same residual
+            # conforming correction from the same residual.  It is independent of the DG coarse-grid correction and
+            # both are chains of small latency-bound kernels: run it on a second stream (a parallel branch of the
+            # captured graph) unless the CSR transfer path, which overwrites D.t, is in use
+            if self.aux_overlap and hasattr(D, "gal"):
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.dev)
+                side = self._side
+                side.wait_stream(torch.cuda.current_stream())
+                aux.restrict_and_solve(D.t, capi.C.c_void_p(side.cuda_stream))
+            else:
+                aux.restrict_and_solve(D.t, st)
         self._restrict(D, Dc, D.t, Dc.r)
         self.vcycle(l + 1, Dc.r, Dc.z)
         self._prolong_add(D, Dc, Dc.z, z)                                       # z += P z_c
         if aux is not None:
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
             aux.prolong_add(z, D.s, st)                                         # z_phi += Q z_aux
         self._spmv(D, z, D.t)
         capi.check(lib.ech_axpby(D.ndof, 1.0, ptr(r), -1.0, ptr(D.t), st))      # t = r - A z
