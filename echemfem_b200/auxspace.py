@@ -20,9 +20,16 @@ Everything in the apply path is this package's own kernels (`ech_spmv`, `ech_axp
 uses `ech_aux_galerkin` for Q^T A Q (cell block by cell block, fixed pattern) and cuSPARSE SpGEMM through `torch.sparse.mm`
 for the small conforming coarse levels (<= 1/16 of the fine matrix in total).
 """
+import warnings
+
 import numpy as np
 import scipy.sparse as sp
 import torch
+
+# torch announces on first use that sparse CSR tensors are a beta feature and that invariant checks are off; the
+# matrices here are built from sorted, duplicate-free scipy CSR data
+warnings.filterwarnings("ignore", message=".*Sparse CSR tensor support is in beta.*")
+warnings.filterwarnings("ignore", message=".*Sparse invariant checks are implicitly disabled.*")
 
 from . import capi
 from .capi import ptr

@@ -582,6 +582,9 @@ class NewtonEngine:
             self.ksp_reductions += 1
             return max(float(hdev[0].item()), 0.0)
 
+        # refinement threshold of "if needed": a second Gram-Schmidt pass when |w - V h|^2 < eta2 |w|^2
+        # (0.5 = PETSc's 1/sqrt(2) criterion on the norms)
+        eta2 = float(os.environ.get("ECH_GMRES_REFINE_ETA2", "0.5"))
         # ECH_KSP_PROFILE=1: synchronising wall-clock split of the iteration (diagnostic; slows the solve down)
         prof = {"precond": 0.0, "matvec": 0.0, "its": 0, "t0": time.perf_counter()} if os.environ.get("ECH_KSP_PROFILE") else None
         bnorm = math.sqrt(owned_sq(b))
@@ -640,7 +643,7 @@ class NewtonEngine:
                 capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
                 ww = h[j + 1]
                 hn2 = ww - float(np.dot(h[:j + 1], h[:j + 1]))
-                if refine == 2 or (refine == 1 and hn2 < 0.5 * ww) or not (hn2 > 1e-6 * ww):
+                if refine == 2 or (refine == 1 and hn2 < eta2 * ww) or not (hn2 > 1e-6 * ww):
                     h = mdot(j + 1, w)
                     H[:j + 1, j] += h[:j + 1]
                     capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
