@@ -50,6 +50,7 @@ EXPORTS = {
     "ech_dot": (C.c_int, [c_i64, c_p, c_p, c_p, C.POINTER(C.c_double), c_p]),
     "ech_multidot": (C.c_int, [c_i64, c_i32, c_p, c_p, c_p, c_p, c_p]),
     "ech_multiaxpy": (C.c_int, [c_i64, c_i32, c_p, c_p, C.c_double, c_p, c_p]),
+    "ech_multiaxpy_dot": (C.c_int, [c_i64, c_i32, c_p, c_p, C.c_double, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_factor": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ech_bjacobi_ilu0_factor_async": (C.c_int, [c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_p,
                                                 c_p, c_p]),

@@ -636,6 +636,72 @@ __global__ void multiaxpy_kernel(int64_t n, int k, const double *__restrict__ V,
     }
 }
 
+// Fused update + projection for the second Gram-Schmidt pass: w += sign * sum_j h[j] V[j], and in the same sweep
+// partial sums of V[j].w_new (j < k) and w_new.w_new.  The second read of V[j][i] comes right after the first by the
+// same thread (L1), so classical Gram-Schmidt with refinement reads the basis three times per iteration instead
+// of four.  One accumulator per column and thread: k <= KMAX (16 / 32 / 64), above that the caller uses the two
+// separate kernels.  partial layout as multidot_kernel's, with gridDim.x blocks.
+template <int KMAX>
+__global__ void __launch_bounds__(256) multiaxpy_dot_kernel(int64_t n, int k, const double *__restrict__ V, int64_t ldv,
+                                                            const double *__restrict__ h, double sign,
+                                                            double *__restrict__ w, double *__restrict__ partial) {
+    __shared__ double hs[KMAX];
+    __shared__ double red[8];
+    if (threadIdx.x < KMAX) hs[threadIdx.x] = threadIdx.x < k ? h[threadIdx.x] : 0.0;
+    __syncthreads();
+    double acc[KMAX], ww = 0.0;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) acc[j] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < k) s = fma(hs[j], V[j * ldv + i], s);
+        const double wn = w[i] + sign * s;
+        w[i] = wn;
+        ww = fma(wn, wn, ww);
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < k) acc[j] = fma(V[j * ldv + i], wn, acc[j]);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j <= KMAX; ++j) {
+        if (j < k || j == KMAX) {
+            double v = j == KMAX ? ww : acc[j < KMAX ? j : 0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) red[wid] = v;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int q = 0; q < 8; ++q) t += red[q];
+                partial[(int64_t)(j == KMAX ? k : j) * gridDim.x + blockIdx.x] = t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int ech_multiaxpy_dot(int64_t n, int32_t k, const double *V, const double *h, double sign, double *w,
+                                 double *work, double *out, void *stream) {
+    if (!V || !h || !w || !work || !out) return fail(nullptr, ECH_ERR_ARG, "ech_multiaxpy_dot: null argument");
+    if (k < 1 || k > 64) return fail(nullptr, ECH_ERR_ARG, "ech_multiaxpy_dot: 1 <= k <= 64");
+    if (n == 0) return ECH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = 148 * 2;
+    if (k <= 16)
+        multiaxpy_dot_kernel<16><<<nb, 256, 0, s>>>(n, k, V, n, h, sign, w, work);
+    else if (k <= 32)
+        multiaxpy_dot_kernel<32><<<nb, 256, 0, s>>>(n, k, V, n, h, sign, w, work);
+    else
+        multiaxpy_dot_kernel<64><<<nb, 256, 0, s>>>(n, k, V, n, h, sign, w, work);
+    multidot_finish_kernel<<<k + 1, 256, 0, s>>>(k + 1, nb, work, out);
+    g_launches += 2;
+    CK(nullptr, cudaGetLastError());
+    return ECH_OK;
+}
+
 // hdev[0..k-1] = V^T w, hdev[k] = w.w ; copied to host (synchronises)
 static int multidot(int64_t n, int k, const double *V, const double *w, double *partial, double *hdev,
                     double *hhost, cudaStream_t s) {

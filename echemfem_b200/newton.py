@@ -585,6 +585,10 @@ class NewtonEngine:
         # refinement threshold of "if needed": a second Gram-Schmidt pass when |w - V h|^2 < eta2 |w|^2
         # (0.5 = PETSc's 1/sqrt(2) criterion on the norms)
         eta2 = float(os.environ.get("ECH_GMRES_REFINE_ETA2", "0.5"))
+        # ech_multiaxpy_dot (update of pass one fused with the projection of pass two: three reads of the basis
+        # instead of four).  Measured at cfg2 size: SLOWER, 5.6 instead of 3.6 ms per iteration -- one accumulator
+        # per basis vector and thread costs the occupancy the streaming kernels live on.  Opt-in.
+        fused = os.environ.get("ECH_GMRES_FUSED_CGS2", "0") != "0"
         # ECH_KSP_PROFILE=1: synchronising wall-clock split of the iteration (diagnostic; slows the solve down)
         prof = {"precond": 0.0, "matvec": 0.0, "its": 0, "t0": time.perf_counter()} if os.environ.get("ECH_KSP_PROFILE") else None
         bnorm = math.sqrt(owned_sq(b))
@@ -640,11 +644,22 @@ class NewtonEngine:
                     matvec(zt, w)
                 h = mdot(j + 1, w)
                 H[:j + 1, j] = h[:j + 1]
-                capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
                 ww = h[j + 1]
                 hn2 = ww - float(np.dot(h[:j + 1], h[:j + 1]))
-                if refine == 2 or (refine == 1 and hn2 < eta2 * ww) or not (hn2 > 1e-6 * ww):
-                    h = mdot(j + 1, w)
+                second = refine == 2 or (refine == 1 and hn2 < eta2 * ww) or not (hn2 > 1e-6 * ww)
+                if second and fused and j + 1 <= 64:
+                    # the update of the first pass and the projection of the second in one sweep over the basis
+                    capi.check(lib.ech_multiaxpy_dot(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), ptr(partial),
+                                                     ptr(hdev), st))
+                    if distributed:
+                        dist.all_reduce(hdev[:j + 2])
+                    self.ksp_reductions += 1
+                    h = hdev[:j + 2].cpu().numpy()
+                else:
+                    capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
+                    if second:
+                        h = mdot(j + 1, w)
+                if second:
                     H[:j + 1, j] += h[:j + 1]
                     capi.check(lib.ech_multiaxpy(n, j + 1, ptr(V), ptr(hdev), -1.0, ptr(w), st))
                     hn2 = h[j + 1] - float(np.dot(h[:j + 1], h[:j + 1]))

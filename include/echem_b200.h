@@ -116,6 +116,11 @@ int ech_dot(int64_t n, const double *x, const double *y, double *work, double *r
  * work holds >= (k + 1) * 1024 doubles.   w += sign * sum_j h[j] V_j. */
 int ech_multidot(int64_t n, int32_t k, const double *V, const double *w, double *work, double *out, void *stream);
 int ech_multiaxpy(int64_t n, int32_t k, const double *V, const double *h, double sign, double *w, void *stream);
+/* w += sign * sum_{j<k} h[j] V[j], and of the UPDATED w: out[j] = V[j].w (j < k), out[k] = w.w -- the update of one
+ * Gram-Schmidt pass fused with the projection of the next (refinement) pass; 1 <= k <= 64.  h and out may be the same
+ * buffer; work as for ech_multidot. */
+int ech_multiaxpy_dot(int64_t n, int32_t k, const double *V, const double *h, double sign, double *w, double *work,
+                      double *out, void *stream);
 
 /* Block-Jacobi with ILU(0) inside each block.  Block b owns the cells
  * [block_cell_ptr[b], block_cell_ptr[b+1]) (all fields of those cells); couplings
