@@ -301,7 +301,6 @@ class NewtonEngine:
         if m < restart:
             print("*** WARNING: ksp_gmres_restart %d capped to %d by device memory" % (restart, m))
         dev = self.dev
-        import os
         from .ilu import IluPlan
         block_ptr = torch.from_numpy(edges).to(dev)
         plan = None
