@@ -2,23 +2,27 @@
 
 Why.  The Galerkin coarse operators of nested DG spaces inherit the interior-penalty term of the FINE mesh
 (sigma / h_fine on every coarse face), so on level l the jump penalty is 2^l times too strong for that level and the
-smoothers only see the jump modes: the V-cycle of `multigrid.py` loses a constant factor per level on the elliptic
-(potential) block -- measured on the cfg2 problem: GMRES iterations 42 / 75 / 142 at N = 32 / 64 / 128, the potential
-block alone 70 / 118 at N = 64 / 128, the (advective) concentration block alone 12 / 22.  A CONTINUOUS coarse function
-has no jumps, so the Galerkin operator of the conforming subspace carries no penalty at all and its multigrid
-hierarchy (bilinear interpolation, damped Jacobi) is the textbook one.  The correction
+smoothers mostly see jump modes: the V-cycle of `multigrid.py` is not h-independent on the elliptic (potential)
+block.  On the device, cfg2 physics: 27 / 39 / 77 / 130 GMRES iterations per solve at N = 128 / 256 / 512 / 1408.
+A scipy prototype of the same cycle on oracle Jacobians (tests/mg_prototype.py, random right-hand side, rtol 1e-12)
+shows the same growth, 23 / 30 / 45 at N = 32 / 64 / 128, the potential block alone 28 / 36 at N = 64 / 128, the
+(advective) concentration block alone 12 / 22.  A CONTINUOUS coarse function has no jumps, so the Galerkin
+operator of the conforming subspace carries no penalty at all and its multigrid hierarchy (bilinear interpolation,
+damped Jacobi) is the textbook one.  The correction
         z_phi += Q V_cg(Q^T r_phi),      Q: continuous Q1 vertex values -> values at the DG nodes (the embedding),
 is added at the finest level next to the DG coarse-grid correction (same residual: no extra fine-level SpMV).  With it
-a scipy prototype of the same cycle needs 19 / 24 iterations at N = 64 / 128 (73 / 142 without).  Only the potential fields
-get it: for the advection-dominated concentration fields the conforming Galerkin operator is the central (unstable)
-discretisation and the correction diverges (measured), their nested DG hierarchy keeps the upwinding.
+the prototype needs 25 / 27 / 32 iterations at N = 32 / 64 / 128 -- nearly flat -- and the device 58 / 61 instead of
+130 / 140 at N = 1408.  Only the potential fields get it: for the advection-dominated concentration field the
+conforming Galerkin operator is the central (unstable) discretisation and GMRES no longer converges (prototype: 300+
+iterations; tests/test_mg_prototype.py), their nested DG hierarchy keeps the upwinding.  Rediscretising the coarse
+DG levels instead of Galerkin products is worse (47 / 64 against 30 / 45).
 
 The reference reaches the same kind of hierarchy through PETSc (`gmg`: geometric multigrid on a MeshHierarchy, `amg`:
 hypre on the assembled operator, echemfem/solver.py:1190-1213); this is the hand-built equivalent for tensor meshes.
 
-Everything in the apply path is this package's own kernels (`ech_spmv`, `ech_axpby`, `ech_dense_gemv`); the set-up
-uses `ech_aux_galerkin` for Q^T A Q (cell block by cell block, fixed pattern) and cuSPARSE SpGEMM through `torch.sparse.mm`
-for the small conforming coarse levels (<= 1/16 of the fine matrix in total).
+Everything in the apply path is this package's own kernels (`ech_spmv`, `ech_axpby`, `ech_dense_gemv`,
+`ech_aux_prolong_add`); the set-up uses `ech_aux_galerkin` for Q^T A Q (cell block by cell block, fixed pattern) and
+cuSPARSE SpGEMM through `torch.sparse.mm` for the small conforming coarse levels (<= 1/16 of the fine matrix in total).
 """
 import warnings
 
