@@ -5,13 +5,13 @@ Why.  The Galerkin coarse operators of nested DG spaces inherit the interior-pen
 smoothers mostly see jump modes: the V-cycle of `multigrid.py` is not h-independent on the elliptic (potential)
 block.  On the device, cfg2 physics: 27 / 39 / 77 / 130 GMRES iterations per solve at N = 128 / 256 / 512 / 1408.
 A scipy prototype of the same cycle on oracle Jacobians (tests/mg_prototype.py, random right-hand side, rtol 1e-12)
-shows the same growth, 23 / 30 / 45 at N = 32 / 64 / 128, the potential block alone 28 / 36 at N = 64 / 128, the
+shows the same growth, 23 / 30 / 45 / 69 at N = 32 / 64 / 128 / 256, the potential block alone 28 / 36 at N = 64 / 128, the
 (advective) concentration block alone 12 / 22.  A CONTINUOUS coarse function has no jumps, so the Galerkin
 operator of the conforming subspace carries no penalty at all and its multigrid hierarchy (bilinear interpolation,
 damped Jacobi) is the textbook one.  The correction
         z_phi += Q V_cg(Q^T r_phi),      Q: continuous Q1 vertex values -> values at the DG nodes (the embedding),
 is added at the finest level next to the DG coarse-grid correction (same residual: no extra fine-level SpMV).  With it
-the prototype needs 25 / 27 / 32 iterations at N = 32 / 64 / 128 -- nearly flat -- and the device 58 / 61 instead of
+the prototype needs 25 / 27 / 32 / 40 iterations at N = 32 / 64 / 128 / 256 and the device 58 / 61 instead of
 130 / 140 at N = 1408.  Only the potential fields get it: for the advection-dominated concentration field the
 conforming Galerkin operator is the central (unstable) discretisation and GMRES no longer converges (prototype: 300+
 iterations; tests/test_mg_prototype.py), their nested DG hierarchy keeps the upwinding.  Rediscretising the coarse
