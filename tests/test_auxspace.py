@@ -83,3 +83,27 @@ def test_coarse_embedding_on_two_strips_agrees_on_shared_vertices():
         seen[np.unique(vert)] += 1
     # vertices on and next to the cut are used by both ranks (owned cells of one, ghost cells of the other)
     assert seen.min() >= 1 and (seen == 2).sum() >= 2 * len(cax[1])
+
+
+def test_hierarchy_with_elongated_tiles():
+    """Per-direction tiles (blocks elongated along the flow): the coarse levels keep the tile shape while it
+    divides them and halve it per direction where it does not; prolongations stay exact embeddings."""
+    from echemfem_b200.multigrid import _fit_tile
+    assert _fit_tile((64, 64), 8) == 8 and _fit_tile((12, 64), 8) is None          # scalar tiles: all or nothing
+    assert _fit_tile((64, 64), (32, 2)) == (32, 2)
+    assert _fit_tile((16, 8), (32, 2)) == (16, 2)
+    assert _fit_tile((3, 3), (32, 2)) is None
+    ax = [np.linspace(0.0, 1.0, 65), np.linspace(0.0, 1.0, 33)]
+    mesh = TensorMesh(ax, tile=(16, 4))
+    assert mesh.tile_shape == (16, 4) and mesh.block_hint == 64
+    h = Hierarchy(mesh, 1, tile=(16, 4), coarsest_cells=16)
+    assert [L.shape for L in h.levels][:3] == [(64, 32), (32, 16), (16, 8)]
+    assert h.levels[0].ctile == (16, 4) and h.levels[1].ctile == (16, 4)
+    V = FunctionSpace(mesh, "DG", 1)
+    x = V.node_coords()
+    P = h.P[0]
+    # coarse level 1 numbered in its own tiles: compare through a function both levels represent exactly
+    cm = TensorMesh(h.levels[1].axes, tile=h.levels[0].ctile)
+    xc = FunctionSpace(cm, "DG", 1).node_coords()
+    f = lambda p: 1.0 + 2.0 * p[:, 0] - p[:, 1] + 0.5 * p[:, 0] * p[:, 1]
+    np.testing.assert_allclose(P @ f(xc), f(x), rtol=0, atol=1e-13)
