@@ -312,6 +312,35 @@ def rediscretised_iterations(N, tile=(8, 8), maxit=300):
     return gmres_iterations(c.A[0], b, c.vcycle, maxit=maxit)
 
 
+def two_rank_iterations(N, maxit=300):
+    """The mesh cut into two strips along x, as two ranks would hold it: (one rank, block Jacobi of the two
+    rank-local cycles -- couplings across the cut dropped, local conforming spaces included --, the same plus the
+    conforming space on the GLOBAL vertex grid applied multiplicatively afterwards)."""
+    c = Cycle(N, aux_fields=(1,))
+    A = c.A[0]
+    rank_of_dof = np.tile(np.repeat(cell_ij(c.discs[0], N)[:, 0] // (N // 2), 4), 2)
+    Ac = A.tocoo()
+    keep = rank_of_dof[Ac.row] == rank_of_dof[Ac.col]
+    Aloc = sp.csr_matrix((Ac.data[keep], (Ac.row[keep], Ac.col[keep])), shape=A.shape)
+    loc = Cycle.__new__(Cycle)
+    loc.Ns, loc.discs, loc.P, loc.Pa = c.Ns, c.discs, c.P, c.Pa
+    loc.A = [Aloc]
+    for P in c.P:
+        loc.A.append((P.T @ loc.A[-1] @ P).tocsr())
+    loc.S = [TileILU(loc.A[l], tiles(c.discs[l], c.Ns[l], min(8, c.Ns[l]), min(8, c.Ns[l]))) for l in range(len(c.Ns) - 1)]
+    loc.coarse = spla.splu(loc.A[-1].tocsc())
+    loc.aux = ConformingMG(c.Pa.T @ Aloc @ c.Pa, N)
+    G = ConformingMG(c.Pa.T @ A @ c.Pa, N)
+
+    def with_global(r):
+        z = loc.vcycle(r)
+        return z + c.Pa @ G.solve(c.Pa.T @ (r - A @ z))
+
+    b = np.random.default_rng(0).standard_normal(A.shape[0])
+    return (gmres_iterations(A, b, c.vcycle, maxit=maxit), gmres_iterations(A, b, loc.vcycle, maxit=maxit),
+            gmres_iterations(A, b, with_global, maxit=maxit))
+
+
 def iterations(N, aux_fields=(), tile=(8, 8), maxit=300):
     c = Cycle(N, tile=tile, aux_fields=aux_fields)
     b = np.random.default_rng(0).standard_normal(c.A[0].shape[0])

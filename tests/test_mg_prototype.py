@@ -34,3 +34,12 @@ def test_auxiliary_space_flattens_the_iteration_growth():
 
 def test_conforming_space_for_the_concentration_field_breaks_the_cycle():
     assert mp.iterations(32, (0, 1), maxit=120) == 120
+
+
+def test_global_conforming_space_removes_the_penalty_of_the_rank_cut():
+    """Two strips: block Jacobi of the rank-local cycles needs several times the iterations of one rank; the
+    conforming space on the global vertex grid (auxspace.GlobalConformingCoarse) brings them back (N = 64: 27 / 133 / 26)."""
+    one, bj, shared = mp.two_rank_iterations(32)
+    print("prototype, two strips at N = 32: one rank %d, block Jacobi %d, + shared conforming space %d" % (one, bj, shared))
+    assert bj >= 2 * one
+    assert shared <= one + 3
