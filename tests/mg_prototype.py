@@ -83,11 +83,16 @@ def _ilu_lib():
 D1, D2 = 0.5e-5, 1.0e-5
 
 
-def make_disc(N):
+def make_disc(N, R=1):
+    """cfg2 physics on [0, R] x [0, 1] with (R N) x N square cells (R = 1: the unit square of the benchmark; R > 1: the
+    domain of the weak-scaling runs, R strips side by side along the flow)."""
     import mms_cases
-    from oracle.mesh import unit_square_mesh
+    from oracle.mesh import tensor_mesh
     from oracle.assemble import Discretization
-    return Discretization(unit_square_mesh(N), mms_cases.adm_problem(1.0, D1=D1, D2=D2))
+    d = Discretization(tensor_mesh([np.linspace(0.0, float(R), R * N + 1), np.linspace(0.0, 1.0, N + 1)]),
+                       mms_cases.adm_problem(1.0, D1=D1, D2=D2))
+    d.R = R
+    return d
 
 
 def state(disc):
@@ -99,13 +104,13 @@ def state(disc):
 
 def cell_ij(disc, N):
     xc = disc.Xc.mean(axis=1)
-    return np.minimum((xc * N).astype(int), N - 1)
+    return np.minimum((xc * N).astype(int), np.array([getattr(disc, "R", 1) * N - 1, N - 1]))
 
 
 def dg_prolongation(fd, Nf, cd, Nc):
     """Scalar embedding of the coarse DG-Q1 space (2 x 2 merged cells): coarse bilinear basis at the fine nodes."""
     fij, cij = cell_ij(fd, Nf), cell_ij(cd, Nc)
-    cmap = -np.ones((Nc, Nc), dtype=int)
+    cmap = -np.ones((getattr(cd, "R", 1) * Nc, Nc), dtype=int)
     cmap[cij[:, 0], cij[:, 1]] = np.arange(len(cij))
     parent = cmap[fij[:, 0] // 2, fij[:, 1] // 2]
     xf = fd.node_coords.reshape(-1, 4, 2)
@@ -141,7 +146,7 @@ def cg_embedding(disc, N):
             cols.append((ij[:, 0] + vx) * (N + 1) + ij[:, 1] + vy)
             vals.append((xi[:, 0] if vx else 1 - xi[:, 0]) * (xi[:, 1] if vy else 1 - xi[:, 1]))
     return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
-                         shape=(len(x), (N + 1) ** 2))
+                         shape=(len(x), (getattr(disc, "R", 1) * N + 1) * (N + 1)))
 
 
 def tiles(disc, N, tx, ty):
@@ -203,11 +208,10 @@ def interp1d(Nf):
 class ConformingMG:
     """Bilinear interpolation, Galerkin operators, damped Jacobi V(1,1), exact coarsest level."""
 
-    def __init__(self, A, N, nfields=1, omega=0.8, coarsest=8):
+    def __init__(self, A, N, nfields=1, omega=0.8, coarsest=8, R=1):
         self.A, self.P, self.omega = [A.tocsr()], [], omega
         while N > coarsest and N % 2 == 0:
-            P1 = interp1d(N)
-            P = sp.kron(P1, P1, format="csr")
+            P = sp.kron(interp1d(R * N), interp1d(N), format="csr")
             P = sp.block_diag([P] * nfields, format="csr") if nfields > 1 else P
             self.P.append(P)
             self.A.append((P.T @ self.A[-1] @ P).tocsr())
@@ -224,11 +228,12 @@ class ConformingMG:
 
 
 class Cycle:
-    def __init__(self, N, tile=(8, 8), aux_fields=(), coarsest=8):
-        discs, Ns = [make_disc(N)], [N]
+    def __init__(self, N, tile=(8, 8), aux_fields=(), coarsest=8, R=1):
+        discs, Ns = [make_disc(N, R)], [N]
         while Ns[-1] > coarsest:
             Ns.append(Ns[-1] // 2)
-            discs.append(make_disc(Ns[-1]))
+            discs.append(make_disc(Ns[-1], R))
+        self.R = R
         self.discs, self.Ns = discs, Ns
         self.A = [discs[0].jacobian(state(discs[0])).tocsr()]
         self.P = []
@@ -244,7 +249,7 @@ class Cycle:
             Q = cg_embedding(discs[0], N)
             Z = sp.csr_matrix(Q.shape)
             self.Pa = sp.vstack([sp.hstack([(Q if f == g else Z) for g in aux_fields]) for f in range(2)]).tocsr()
-            self.aux = ConformingMG(self.Pa.T @ self.A[0] @ self.Pa, N, nfields=len(aux_fields))
+            self.aux = ConformingMG(self.Pa.T @ self.A[0] @ self.Pa, N, nfields=len(aux_fields), R=R)
 
     def vcycle(self, b, l=0):
         if l == len(self.Ns) - 1:
@@ -312,13 +317,14 @@ def rediscretised_iterations(N, tile=(8, 8), maxit=300):
     return gmres_iterations(c.A[0], b, c.vcycle, maxit=maxit)
 
 
-def two_rank_iterations(N, maxit=300):
-    """The mesh cut into two strips along x, as two ranks would hold it: (one rank, block Jacobi of the two
-    rank-local cycles -- couplings across the cut dropped, local conforming spaces included --, the same plus the
-    conforming space on the GLOBAL vertex grid applied multiplicatively afterwards)."""
-    c = Cycle(N, aux_fields=(1,))
+def two_rank_iterations(N, maxit=300, ranks=2, R=1):
+    """The mesh cut into `ranks` strips along x, as the ranks would hold it: (one rank, block Jacobi of the
+    rank-local cycles -- couplings across the cuts dropped, local conforming spaces included --, the same plus the
+    conforming space on the GLOBAL vertex grid applied multiplicatively afterwards).  R: domain [0, R] x [0, 1]
+    (R = ranks: the weak-scaling layout, one N x N strip per rank)."""
+    c = Cycle(N, aux_fields=(1,), R=R)
     A = c.A[0]
-    rank_of_dof = np.tile(np.repeat(cell_ij(c.discs[0], N)[:, 0] // (N // 2), 4), 2)
+    rank_of_dof = np.tile(np.repeat(cell_ij(c.discs[0], N)[:, 0] // (R * N // ranks), 4), 2)
     Ac = A.tocoo()
     keep = rank_of_dof[Ac.row] == rank_of_dof[Ac.col]
     Aloc = sp.csr_matrix((Ac.data[keep], (Ac.row[keep], Ac.col[keep])), shape=A.shape)
@@ -329,8 +335,8 @@ def two_rank_iterations(N, maxit=300):
         loc.A.append((P.T @ loc.A[-1] @ P).tocsr())
     loc.S = [TileILU(loc.A[l], tiles(c.discs[l], c.Ns[l], min(8, c.Ns[l]), min(8, c.Ns[l]))) for l in range(len(c.Ns) - 1)]
     loc.coarse = spla.splu(loc.A[-1].tocsc())
-    loc.aux = ConformingMG(c.Pa.T @ Aloc @ c.Pa, N)
-    G = ConformingMG(c.Pa.T @ A @ c.Pa, N)
+    loc.aux = ConformingMG(c.Pa.T @ Aloc @ c.Pa, N, R=R)
+    G = ConformingMG(c.Pa.T @ A @ c.Pa, N, R=R)
 
     def with_global(r):
         z = loc.vcycle(r)

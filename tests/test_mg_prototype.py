@@ -36,10 +36,14 @@ def test_conforming_space_for_the_concentration_field_breaks_the_cycle():
     assert mp.iterations(32, (0, 1), maxit=120) == 120
 
 
-def test_global_conforming_space_removes_the_penalty_of_the_rank_cut():
-    """Two strips: block Jacobi of the rank-local cycles needs several times the iterations of one rank; the
-    conforming space on the global vertex grid (auxspace.GlobalConformingCoarse) brings them back (N = 64: 27 / 133 / 26)."""
-    one, bj, shared = mp.two_rank_iterations(32)
-    print("prototype, two strips at N = 32: one rank %d, block Jacobi %d, + shared conforming space %d" % (one, bj, shared))
+@pytest.mark.parametrize("ranks,R", [(2, 1), (2, 2)])
+def test_global_conforming_space_removes_the_penalty_of_the_rank_cut(ranks, R):
+    """Strips along x (R = 1: the unit square cut; R = ranks: the weak-scaling layout, one N x N strip per rank):
+    block Jacobi of the rank-local cycles needs several times the iterations of one rank on the same domain; the
+    conforming space on the global vertex grid (auxspace.GlobalConformingCoarse) brings them back
+    (N = 64: 27 / 133 / 26 and 30 / 136 / 29)."""
+    one, bj, shared = mp.two_rank_iterations(32, ranks=ranks, R=R)
+    print("prototype, %d strips of [0, %d] x [0, 1] at N = 32: one rank %d, block Jacobi %d, + shared conforming space %d"
+          % (ranks, R, one, bj, shared))
     assert bj >= 2 * one
     assert shared <= one + 3
